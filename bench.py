@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — decoded shots/s of the BP decode hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one pass of the hot path over one batch of synthetic code-capacity syndromes
+(``--shots`` per GPU, default 2^20) of the workload BASELINE.json quotes the metric on:
+configs[1], the ~1.6k-qubit random (3,4) hypergraph-product code, BP (min-sum, alpha schedule,
+iteration cap 32, early exit) at p = 0.05, prior 2p/3 (scripts/p_sweep.py:4-8 of the reference).
+
+Printed JSON (one line, rank 0):
+  value      whole-job decoded shots/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the public host API (bp_decoder.decode_batch: pinned host
+             syndromes -> H2D -> decode -> D2H corrections/flags), copies inside the timed region
+  roofline   HBM roofline of the dominant kernel (bp_kernel) from algorithmic bytes / event time;
+             roofline_smem adds the shared-memory roofline that actually bounds it
+  cpu_baseline  the CPU oracle (port of the reference decoder) timed on this host's cores
+``--impl reference`` times that CPU port alone (the reference's own decoder, the third-party
+`ldpc` package, is not installable here: see DESIGN.md).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (qecc file, p, bp options)
+    "hgp_34_n1600": ("hgp_34_n1600.qecc", 0.05, dict(max_iter=32, bp_method="ms", ms_scaling_factor=0.0)),
+    "hgp_34_n6400": ("hgp_34_n6400.qecc", 0.05, dict(max_iter=32, bp_method="ms", ms_scaling_factor=0.0)),
+    "hgp_34_n225": ("hgp_34_n225.qecc", 0.05, dict(max_iter=32, bp_method="ms", ms_scaling_factor=0.0)),
+}
+
+
+def probabilities(p):
+    """depolarizing_noise(p, pm=p) with rounds=0 (noise_model.py:117-123) and the 2p/3 prior."""
+    return 2.0 * p / 3.0 + p - 4.0 / 3.0 * p * p, 2.0 * p / 3.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()          # exact PID we started
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_throughput(code, p, opts, target_seconds=12.0, threads=0):
+    """Time the CPU oracle (the port of the reference's decoder) on a bounded sample of the same
+    workload; returns (shots/s, cores, sample description, mean iterations)."""
+    from oracle import pyoracle as po
+    q, prior = probabilities(p)
+    cores = po.num_threads() if threads <= 0 else threads
+    kw = dict(decoder="bp", max_iter=opts["max_iter"], bp_method=opts["bp_method"],
+              ms_scaling_factor=opts["ms_scaling_factor"], seed=0, threads=cores)
+    probe = 64 * cores
+    t0 = time.perf_counter()
+    po.run_code_capacity(code.checks.z, code.logicals.z, q, prior, shots=probe, **kw)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    shots = int(max(probe, min(5_000_000, probe * target_seconds / dt)))
+    t0 = time.perf_counter()
+    r = po.run_code_capacity(code.checks.z, code.logicals.z, q, prior, shots=shots, shot0=probe, **kw)
+    dt = time.perf_counter() - t0
+    return shots / dt, cores, f"{shots} shots of the same workload, {dt:.1f} s wall on {cores} threads", r["iters_total"] / shots
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="hgp_34_n1600", choices=sorted(WORKLOADS))
+    ap.add_argument("--shots", type=int, default=1 << 20, help="shots per GPU per step")
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--p", type=float, default=None)
+    ap.add_argument("--max-iter", type=int, default=None)
+    ap.add_argument("--bp-method", default=None)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--slots", type=int, default=0)
+    ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from exp_ldpc_b200.codes import load_code
+    fname, p, opts = WORKLOADS[args.workload]
+    opts = dict(opts)
+    if args.p is not None:
+        p = args.p
+    if args.max_iter is not None:
+        opts["max_iter"] = args.max_iter
+    if args.bp_method is not None:
+        opts["bp_method"] = args.bp_method
+    code = load_code(os.path.join(ROOT, "codes", fname))
+    m, n = code.checks.z.shape
+    nnz = int(code.checks.z.nnz)
+    q, prior = probabilities(p)
+    config = {"workload": f"{args.workload}: (3,4) HGP n={n} m={m} nnz={nnz} k={code.num_logicals}, code capacity, "
+                          f"BP {opts['bp_method']} alpha={'1-2^-it' if opts['ms_scaling_factor'] == 0 else opts['ms_scaling_factor']} "
+                          f"max_iter={opts['max_iter']} early-exit, p={p} (flip q={q:.5f}, prior 2p/3)",
+              "shots_per_step_per_gpu": args.shots, "p": p, "max_iter": opts["max_iter"], "bp_method": opts["bp_method"],
+              "precision": args.precision, "parallelism": f"shots sharded over {world} rank(s), one all-reduce of int64[4] per step",
+              "l2": "inputs larger than L2 (no flush needed)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU port)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        rates = []
+        cores = 0
+        sample = ""
+        per_step = max(2.0, min(20.0, 120.0 / (args.steps + args.warmup)))
+        for i in range(args.warmup + args.steps):
+            r, cores, sample, _ = cpu_port_throughput(code, p, opts, target_seconds=per_step if i >= args.warmup else 1.0)
+            if i >= args.warmup:
+                rates.append(r)
+        v = statistics.mean(rates)
+        line = {"metric": "decoded shots/sec (BP, fixed p and iteration cap)", "value": v, "unit": "shots/s",
+                "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "shots/s", "cores": cores, "kind": "port",
+                                 "sample": sample + " per step (oracle/qldpc_oracle.c; the reference's own decoder `ldpc` is not installable here)"},
+                "e2e": {"value": v, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from exp_ldpc_b200.decoders import Logicals, Sampler, TannerGraph, bp_decoder, row_words
+    graph = TannerGraph(code.checks.z, device=local_rank)
+    logicals = Logicals(code.logicals.z, device=local_rank)
+    sampler = Sampler(q, n, device=local_rank)
+    dec = bp_decoder(graph, error_rate=prior, precision=args.precision, **opts)
+    if args.threads or args.slots or args.ctas:
+        dec.configure(args.threads, args.slots, args.ctas)
+    cfg = dec.config()
+    config["launch"] = cfg
+
+    shots = args.shots
+    es, ss = row_words(n), row_words(m)
+    stream = torch.cuda.current_stream().cuda_stream
+    d_err = torch.empty((shots, es), dtype=torch.int32, device=dev)
+    d_syn = torch.empty((shots, ss), dtype=torch.int32, device=dev)
+    d_cor = torch.empty((shots, es), dtype=torch.int32, device=dev)
+    d_fail = torch.empty(shots, dtype=torch.uint8, device=dev)
+    d_conv = torch.empty(shots, dtype=torch.uint8, device=dev)
+    d_it = torch.empty(shots, dtype=torch.int32, device=dev)
+    d_cnt = torch.zeros((args.steps + 1, 4), dtype=torch.int64, device=dev)   # one counter row per step
+    shot0 = rank * shots * (args.steps + args.warmup + 1)
+
+    def make_inputs(step):
+        sampler.run_device(0, 0, shot0 + step * shots, shots, d_err, es, stream)
+        graph.syndrome_batch_device(d_err, es, shots, d_syn, ss, stream)
+
+    def decode_step(row):
+        cnt_row = d_cnt[row]
+        dec.decode_batch_device(d_syn, ss, shots, d_cor, es, d_conv, d_it, None, d_err, es, logicals, d_fail, cnt_row, stream)
+        if world > 1:
+            dist.all_reduce(cnt_row)   # the one collective of the path: sum of the 4 counters
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    make_inputs(0)
+    for _ in range(args.warmup):
+        decode_step(args.steps)
+    barrier()
+    d_cnt.zero_()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    time.sleep(0.25)
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(args.steps):
+        cnt_row = d_cnt[i]
+        k_ev[i][0].record()
+        dec.decode_batch_device(d_syn, ss, shots, d_cor, es, d_conv, d_it, None, d_err, es, logicals, d_fail, cnt_row, stream)
+        k_ev[i][1].record()
+        if world > 1:
+            dist.all_reduce(cnt_row)
+    stop.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clk = clocks.stop()
+    ms_total = start.elapsed_time(stop)
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in k_ev)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    cnt = d_cnt[:args.steps].sum(dim=0).cpu().numpy().astype(np.int64)
+    total_shots = shots * world * args.steps
+    value = total_shots / (ms_total * 1e-3)
+    mean_iters = float(cnt[3]) / max(1, int(cnt[1]))
+
+    # ------------------------------------------------------------------ e2e through the host API
+    e2e = None
+    if not args.no_e2e:
+        h_syn = torch.empty((shots, ss), dtype=torch.int32, pin_memory=True)
+        h_syn.copy_(d_syn)
+        torch.cuda.synchronize()
+        h_np = h_syn.numpy().view(np.uint32)
+        for _ in range(2):
+            dec.decode_batch(h_np[: max(1, shots // 8)], packed=True, return_packed=True)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            corr, conv, its = dec.decode_batch(h_np, packed=True, return_packed=True)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": shots * world * e2e_steps / float(tt.item()), "unit": "shots/s",
+               "h2d_bytes_per_step": int(shots * ss * 4), "d2h_bytes_per_step": int(shots * (es * 4 + 1 + 4)),
+               "api": "bp_decoder.decode_batch(packed host syndromes) -> qd_bp_decode_batch_host", "steps": e2e_steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------ rooflines (rank 0's kernel)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_per_shot = 4 * ((m + 31) // 32) + 4 * ((n + 31) // 32) + 1          # SURVEY.md §8(d) B_dec
+    achieved = bytes_per_shot * shots / (kernel_ms * 1e-3) / 1e9
+    msg_bytes = 8 if args.precision == "f64" else 4
+    smem_bytes_per_shot = mean_iters * nnz * 4 * msg_bytes                      # SURVEY.md §8(d) B_smem
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_mhz = clk.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    smem_peak = sm_count * 128 * sm_mhz * 1e6 / 1e9
+    smem_achieved = smem_bytes_per_shot * shots / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "kernel": "bp_kernel", "kernel_ms": kernel_ms,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_shot": bytes_per_shot,
+                "note": "HBM is touched for I/O only; the kernel is bound by shared memory / issue, see roofline_smem"}
+    roofline_smem = {"bound": "shared-memory", "achieved": smem_achieved, "peak": smem_peak, "unit": "GB/s",
+                     "frac": smem_achieved / smem_peak, "algorithmic_bytes_per_shot": smem_bytes_per_shot,
+                     "mean_iterations": mean_iters, "edge_updates_per_s": 2.0 * nnz * mean_iters * shots / (kernel_ms * 1e-3),
+                     "peak_source": f"{sm_count} SMs x 128 B/clk x {sm_mhz:.0f} MHz (median SM clock during the timed region)"}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, cores, sample, cpu_iters = cpu_port_throughput(code, p, opts, target_seconds=12.0)
+        cpu = {"value": v, "unit": "shots/s", "cores": cores, "kind": "port", "sample": sample,
+               "mean_iterations": cpu_iters}
+
+    line = {"metric": "decoded shots/sec (BP, fixed p and iteration cap)", "value": value, "unit": "shots/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": config, "e2e": e2e, "gpu_launches": args.steps, "clocks": clk, "roofline": roofline,
+            "roofline_smem": roofline_smem, "cpu_baseline": cpu,
+            "counters": {"failures": int(cnt[0]), "shots": int(cnt[1]), "non_converged": int(cnt[2]),
+                         "iterations": int(cnt[3])},
+            "wall_s_timed_region": t_wall}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,924 @@
+// qldpc_b200.cu — C ABI (include/qldpc_b200.h) + bit-packed utility kernels + host orchestration.
+// sm_100a only.  No CPU fallback: without a usable device every entry point returns QD_ENODEV.
+
+#include "../../include/qldpc_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "bp_kernel.cuh"
+#include "ssf_kernel.cuh"
+
+namespace qd {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+// =============================================================================================
+// small utility kernels (HBM-bound, bit-packed, shot-major)
+// =============================================================================================
+
+// one thread per output word: 32 Bernoulli bits = 8 Philox blocks
+__global__ void sample_kernel(const uint32_t *__restrict__ thr, int nbits, int nw, uint32_t k0, uint32_t k1,
+                              uint32_t stream_id, long long shot0, long long shots, uint32_t *__restrict__ out,
+                              int stride)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= shots * stride) return;
+    const long long s = idx / stride;
+    const int w = (int)(idx - s * stride);
+    uint32_t word = 0u;
+    if (w < nw) {
+        const unsigned long long g = (unsigned long long)(shot0 + s);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int j0 = w * 32 + b * 4;
+            if (j0 < nbits) {
+                uint32_t r[4];
+                philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(j0 >> 2), stream_id, k0, k1, r);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (j0 + t < nbits && r[t] < __ldg(thr + j0 + t)) word |= 1u << (b * 4 + t);
+            }
+        }
+    }
+    out[idx] = word;
+}
+
+// one thread per syndrome word (32 checks) of one shot
+__global__ void syndrome_kernel(GraphDev g, const uint32_t *__restrict__ vec, int vstride, long long shots,
+                                uint32_t *__restrict__ synd, int sstride)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= shots * sstride) return;
+    const long long s = idx / sstride;
+    const int w = (int)(idx - s * sstride);
+    uint32_t word = 0u;
+    if (w < g.nwm) {
+        const uint32_t *v = vec + s * (long long)vstride;
+        const int c1 = min(g.m, w * 32 + 32);
+        for (int c = w * 32; c < c1; ++c) {
+            uint32_t par = 0u;
+            for (int e = __ldg(g.row_ptr + c); e < __ldg(g.row_ptr + c + 1); ++e) {
+                const int col = __ldg(g.col_idx + e);
+                par ^= v[col >> 5] >> (col & 31);
+            }
+            word |= (par & 1u) << (c & 31);
+        }
+    }
+    synd[idx] = word;
+}
+
+// one warp per shot: fail = any_i parity(L_i & (a ^ b))
+__global__ void logical_fail_kernel(const uint32_t *__restrict__ lzT, int k, int nwn, const uint32_t *__restrict__ a,
+                                    const uint32_t *__restrict__ b, int stride, long long shots,
+                                    uint8_t *__restrict__ fail_out, unsigned long long *fail_count)
+{
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= shots) return;
+    const uint32_t *ra = a + warp * (long long)stride;
+    const uint32_t *rb = b ? b + warp * (long long)stride : nullptr;
+    int f = 0;
+    for (int i = lane; i < ((k + 31) & ~31); i += 32) {
+        uint32_t acc = 0u;
+        if (i < k)
+            for (int w = 0; w < nwn; ++w) {
+                const uint32_t r = ra[w] ^ (rb ? rb[w] : 0u);
+                acc ^= __ldg(lzT + (size_t)w * k + i) & r;
+            }
+        f |= __popc(acc) & 1;
+    }
+    f = __any_sync(0xffffffffu, f);
+    if (lane == 0) {
+        if (fail_out) fail_out[warp] = (uint8_t)f;
+        if (fail_count && f) atomicAdd(fail_count, 1ULL);
+    }
+}
+
+// =============================================================================================
+// host-side handles
+// =============================================================================================
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n)
+    {
+        if (p) { cudaFree(p); p = nullptr; }
+        bytes = n;
+        if (n == 0) return 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) { p = nullptr; return fail(QD_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+        return 0;
+    }
+    int ensure(size_t n) { return n <= bytes && p ? 0 : alloc(n); }
+    template <typename T> T *as() { return static_cast<T *>(p); }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    int ensure(size_t n)
+    {
+        if (n <= bytes && p) return 0;
+        if (p) { cudaFreeHost(p); p = nullptr; }
+        bytes = n;
+        cudaError_t e = cudaMallocHost(&p, n ? n : 1);
+        if (e != cudaSuccess) { p = nullptr; return fail(QD_ENOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
+        return 0;
+    }
+    template <typename T> T *as() { return static_cast<T *>(p); }
+};
+
+template <typename T>
+static int upload(DevBuf &b, const std::vector<T> &v)
+{
+    int rc = b.alloc(std::max<size_t>(v.size(), 1) * sizeof(T));
+    if (rc) return rc;
+    if (!v.empty()) QD_CUDA(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int use_device(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(QD_ENODEV, std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0"));
+    if (device < 0 || device >= count) return fail(QD_EINVAL, "device index out of range");
+    QD_CUDA(cudaSetDevice(device));
+    return 0;
+}
+
+}  // namespace qd
+
+using namespace qd;
+
+struct qd_graph {
+    int device = 0;
+    GraphDev dev{};
+    std::vector<int32_t> row_ptr, col_idx, col_ptr;
+    std::vector<uint32_t> row_desc, col_desc, csc_pos, csc_row;
+    DevBuf d_row_desc, d_col_desc, d_csc_pos, d_csc_row, d_row_ptr, d_col_idx;
+    int sm_count = 0, smem_optin = 0;
+};
+
+struct qd_logicals {
+    int device = 0;
+    int k = 0, n = 0, nwn = 0;
+    DevBuf d_lzT;   // [nwn][k]
+};
+
+struct qd_sampler {
+    int device = 0;
+    int nbits = 0;
+    DevBuf d_thr;
+};
+
+typedef void (*bp_kernel_fn)(const BpParams);
+
+struct qd_bp {
+    qd_graph *g = nullptr;
+    int max_iter = 0, method = 0, precision = 64;
+    int vmax = 4;
+    int threads = 0, slots = 0, ctas_per_sm = 0;
+    size_t smem = 0;
+    DevBuf d_prior, d_alpha, d_next;
+    // host-buffer pipeline state
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    DevBuf d_in[2], d_out[2], d_conv[2], d_it[2];
+    PinBuf h_in[2], h_out[2], h_conv[2], h_it[2];
+    ~qd_bp()
+    {
+        for (int i = 0; i < 2; ++i) {
+            if (streams[i]) cudaStreamDestroy(streams[i]);
+            if (done[i]) cudaEventDestroy(done[i]);
+        }
+    }
+};
+
+struct qd_ssf {
+    qd_graph *g = nullptr;
+    SsfDev dev{};
+    int max_rounds = 0;
+    int threads = 128;
+    size_t smem = 0;
+    DevBuf d_gen_ptr, d_gen_idx, d_win_ptr, d_win_chk, d_qmask, d_next;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    DevBuf d_in[2], d_out[2], d_conv[2], d_it[2];
+    PinBuf h_in[2], h_out[2], h_conv[2], h_it[2];
+    ~qd_ssf()
+    {
+        for (int i = 0; i < 2; ++i) {
+            if (streams[i]) cudaStreamDestroy(streams[i]);
+            if (done[i]) cudaEventDestroy(done[i]);
+        }
+    }
+};
+
+// =============================================================================================
+// misc
+// =============================================================================================
+extern "C" int qd_abi_version(void) { return QD_ABI_VERSION; }
+extern "C" const char *qd_last_error(void) { return g_err.c_str(); }
+
+extern "C" int qd_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    return count;
+}
+
+extern "C" int qd_device_info(int device, int *sm_count, int *smem_per_block_optin, int *clock_khz)
+{
+    int rc = use_device(device);
+    if (rc) return rc;
+    int v = 0;
+    if (sm_count) { QD_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device)); *sm_count = v; }
+    if (smem_per_block_optin) {
+        QD_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        *smem_per_block_optin = v;
+    }
+    if (clock_khz) { QD_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, device)); *clock_khz = v; }
+    return 0;
+}
+
+// =============================================================================================
+// graph
+// =============================================================================================
+extern "C" int qd_graph_create(int32_t m, int32_t n, int64_t nnz, const int32_t *h_row_ptr,
+                               const int32_t *h_col_idx, int device, qd_graph **out)
+{
+    if (!out) return fail(QD_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (m < 0 || n <= 0 || nnz < 0 || !h_row_ptr || (nnz > 0 && !h_col_idx)) return fail(QD_EINVAL, "bad graph arguments");
+    if (h_row_ptr[0] != 0 || h_row_ptr[m] != nnz) return fail(QD_EINVAL, "row_ptr does not span [0, nnz]");
+    if (nnz >= (1 << 24)) return fail(QD_EUNSUP, "more than 2^24 edges");
+    int rc = use_device(device);
+    if (rc) return rc;
+    std::unique_ptr<qd_graph> g(new qd_graph);
+    g->device = device;
+    g->row_ptr.assign(h_row_ptr, h_row_ptr + m + 1);
+    g->col_idx.assign(h_col_idx, h_col_idx + nnz);
+    int max_row = 0;
+    for (int i = 0; i < m; ++i) {
+        const int lo = h_row_ptr[i], hi = h_row_ptr[i + 1];
+        if (hi < lo) return fail(QD_EINVAL, "row_ptr not monotone");
+        max_row = std::max(max_row, hi - lo);
+        for (int e = lo; e < hi; ++e) {
+            if (h_col_idx[e] < 0 || h_col_idx[e] >= n) return fail(QD_EINVAL, "column index out of range");
+            if (e > lo && h_col_idx[e] <= h_col_idx[e - 1]) return fail(QD_EINVAL, "column indices must be sorted and unique");
+        }
+    }
+    if (max_row > 255) return fail(QD_EUNSUP, "row degree > 255");
+    // message layout: rows padded to an odd pitch when that wastes < 1/3 of the array
+    int pitch = max_row | 1;
+    const bool padded = m > 0 && (int64_t)pitch * m <= nnz + nnz / 3 + 64;
+    g->row_desc.resize(std::max(m, 1));
+    std::vector<int> pos_of_edge(std::max<int64_t>(nnz, 1));
+    for (int i = 0; i < m; ++i) {
+        const int lo = h_row_ptr[i], deg = h_row_ptr[i + 1] - lo;
+        const int pos0 = padded ? i * pitch : lo;
+        g->row_desc[i] = (uint32_t)pos0 | ((uint32_t)deg << 24);
+        for (int k = 0; k < deg; ++k) pos_of_edge[lo + k] = pos0 + k;
+    }
+    const int npos = padded ? pitch * m : (int)nnz;
+    if (npos >= (1 << 24)) return fail(QD_EUNSUP, "message array too large");
+    // CSC: column lists with rows ascending
+    g->col_ptr.assign(n + 1, 0);
+    for (int64_t e = 0; e < nnz; ++e) g->col_ptr[h_col_idx[e] + 1]++;
+    int max_col = 0;
+    for (int j = 0; j < n; ++j) {
+        max_col = std::max(max_col, g->col_ptr[j + 1]);
+        g->col_ptr[j + 1] += g->col_ptr[j];
+    }
+    if (max_col > 255) return fail(QD_EUNSUP, "column degree > 255");
+    g->csc_pos.resize(std::max<int64_t>(nnz, 1));
+    g->csc_row.resize(std::max<int64_t>(nnz, 1));
+    g->col_desc.resize(n);
+    {
+        std::vector<int> fill(g->col_ptr.begin(), g->col_ptr.end() - 1);
+        for (int i = 0; i < m; ++i)
+            for (int e = h_row_ptr[i]; e < h_row_ptr[i + 1]; ++e) {
+                const int t = fill[h_col_idx[e]]++;
+                g->csc_pos[t] = (uint32_t)pos_of_edge[e];
+                g->csc_row[t] = (uint32_t)i;
+            }
+        for (int j = 0; j < n; ++j)
+            g->col_desc[j] = (uint32_t)g->col_ptr[j] | ((uint32_t)(g->col_ptr[j + 1] - g->col_ptr[j]) << 24);
+    }
+    if ((rc = upload(g->d_row_desc, g->row_desc))) return rc;
+    if ((rc = upload(g->d_col_desc, g->col_desc))) return rc;
+    if ((rc = upload(g->d_csc_pos, g->csc_pos))) return rc;
+    if ((rc = upload(g->d_csc_row, g->csc_row))) return rc;
+    if ((rc = upload(g->d_row_ptr, g->row_ptr))) return rc;
+    if ((rc = upload(g->d_col_idx, g->col_idx))) return rc;
+    GraphDev &d = g->dev;
+    d.m = m; d.n = n; d.nnz = (int)nnz;
+    d.nwm = words_for(m); d.nwn = words_for(n);
+    d.npos = npos;
+    d.max_row_deg = max_row; d.max_col_deg = max_col;
+    d.row_desc = g->d_row_desc.as<uint32_t>();
+    d.col_desc = g->d_col_desc.as<uint32_t>();
+    d.csc_pos = g->d_csc_pos.as<uint32_t>();
+    d.csc_row = g->d_csc_row.as<uint32_t>();
+    d.row_ptr = g->d_row_ptr.as<int32_t>();
+    d.col_idx = g->d_col_idx.as<int32_t>();
+    QD_CUDA(cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device));
+    QD_CUDA(cudaDeviceGetAttribute(&g->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    *out = g.release();
+    return 0;
+}
+
+extern "C" int qd_graph_destroy(qd_graph *g)
+{
+    if (g) { cudaSetDevice(g->device); delete g; }
+    return 0;
+}
+
+// =============================================================================================
+// logicals, sampler
+// =============================================================================================
+extern "C" int qd_logicals_create(int32_t k, int32_t n, const uint8_t *h_dense, int device, qd_logicals **out)
+{
+    if (!out) return fail(QD_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (k < 0 || n <= 0 || (k > 0 && !h_dense)) return fail(QD_EINVAL, "bad logicals arguments");
+    int rc = use_device(device);
+    if (rc) return rc;
+    std::unique_ptr<qd_logicals> l(new qd_logicals);
+    l->device = device; l->k = k; l->n = n; l->nwn = words_for(n);
+    std::vector<uint32_t> t((size_t)l->nwn * std::max(k, 1), 0u);
+    for (int i = 0; i < k; ++i)
+        for (int j = 0; j < n; ++j)
+            if (h_dense[(size_t)i * n + j] & 1) t[(size_t)(j >> 5) * k + i] |= 1u << (j & 31);
+    if ((rc = upload(l->d_lzT, t))) return rc;
+    *out = l.release();
+    return 0;
+}
+
+extern "C" int qd_logicals_destroy(qd_logicals *l)
+{
+    if (l) { cudaSetDevice(l->device); delete l; }
+    return 0;
+}
+
+extern "C" int qd_sampler_create(int32_t nbits, const uint32_t *h_threshold, int device, qd_sampler **out)
+{
+    if (!out) return fail(QD_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (nbits <= 0 || !h_threshold) return fail(QD_EINVAL, "bad sampler arguments");
+    int rc = use_device(device);
+    if (rc) return rc;
+    std::unique_ptr<qd_sampler> s(new qd_sampler);
+    s->device = device; s->nbits = nbits;
+    std::vector<uint32_t> thr(h_threshold, h_threshold + nbits);
+    if ((rc = upload(s->d_thr, thr))) return rc;
+    *out = s.release();
+    return 0;
+}
+
+extern "C" int qd_sampler_destroy(qd_sampler *s)
+{
+    if (s) { cudaSetDevice(s->device); delete s; }
+    return 0;
+}
+
+static inline unsigned grid_for(long long items, int block) { return (unsigned)((items + block - 1) / block); }
+
+extern "C" int qd_sampler_run(qd_sampler *s, uint64_t seed, uint32_t stream_id, int64_t shot0, int64_t shots,
+                              uint32_t *d_bits, int32_t stride, void *stream)
+{
+    if (!s || !d_bits || shots < 0) return fail(QD_EINVAL, "bad sampler_run arguments");
+    const int nw = words_for(s->nbits);
+    if (stride < nw) return fail(QD_EINVAL, "stride smaller than ceil(nbits/32)");
+    if (shots == 0) return 0;
+    int rc = use_device(s->device);
+    if (rc) return rc;
+    const long long items = (long long)shots * stride;
+    sample_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
+        s->d_thr.as<uint32_t>(), s->nbits, nw, (uint32_t)seed, (uint32_t)(seed >> 32), stream_id, shot0, shots, d_bits, stride);
+    QD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int qd_syndrome_batch(qd_graph *g, const uint32_t *d_vec, int32_t vec_stride, int64_t shots,
+                                 uint32_t *d_synd, int32_t synd_stride, void *stream)
+{
+    if (!g || !d_vec || !d_synd || shots < 0) return fail(QD_EINVAL, "bad syndrome_batch arguments");
+    if (vec_stride < g->dev.nwn || synd_stride < g->dev.nwm) return fail(QD_EINVAL, "stride too small");
+    if (shots == 0) return 0;
+    int rc = use_device(g->device);
+    if (rc) return rc;
+    const long long items = (long long)shots * synd_stride;
+    syndrome_kernel<<<grid_for(items, 128), 128, 0, (cudaStream_t)stream>>>(g->dev, d_vec, vec_stride, shots, d_synd, synd_stride);
+    QD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int qd_logical_fail_batch(qd_logicals *l, const uint32_t *d_a, const uint32_t *d_b, int32_t stride,
+                                     int64_t shots, uint8_t *d_fail, unsigned long long *d_fail_count, void *stream)
+{
+    if (!l || !d_a || shots < 0) return fail(QD_EINVAL, "bad logical_fail_batch arguments");
+    if (stride < l->nwn) return fail(QD_EINVAL, "stride too small");
+    if (shots == 0) return 0;
+    int rc = use_device(l->device);
+    if (rc) return rc;
+    logical_fail_kernel<<<grid_for((long long)shots * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        l->d_lzT.as<uint32_t>(), l->k, l->nwn, d_a, d_b, stride, shots, d_fail, d_fail_count);
+    QD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// =============================================================================================
+// BP
+// =============================================================================================
+template <typename real, int METHOD>
+static bp_kernel_fn pick_bp(int vmax, int threads)
+{
+    const bool small = threads <= 256;
+    switch (vmax) {
+    case 4:  return small ? bp_kernel<real, METHOD, 4, 256> : bp_kernel<real, METHOD, 4, 1024>;
+    case 8:  return small ? bp_kernel<real, METHOD, 8, 256> : bp_kernel<real, METHOD, 8, 1024>;
+    default: return small ? bp_kernel<real, METHOD, 16, 256> : bp_kernel<real, METHOD, 16, 1024>;
+    }
+}
+
+static bp_kernel_fn bp_kernel_for(const qd_bp *d)
+{
+    if (d->precision == QD_PREC_F64)
+        return d->method == QD_BP_MIN_SUM ? pick_bp<double, QD_BP_MIN_SUM>(d->vmax, d->threads)
+                                          : pick_bp<double, QD_BP_PRODUCT_SUM>(d->vmax, d->threads);
+    return d->method == QD_BP_MIN_SUM ? pick_bp<float, QD_BP_MIN_SUM>(d->vmax, d->threads)
+                                      : pick_bp<float, QD_BP_PRODUCT_SUM>(d->vmax, d->threads);
+}
+
+static size_t bp_smem(const qd_bp *d, int slots)
+{
+    const GraphDev &g = d->g->dev;
+    return d->precision == QD_PREC_F64 ? bp_smem_bytes<double>(g.npos, g.nwn, g.nwm, slots)
+                                       : bp_smem_bytes<float>(g.npos, g.nwn, g.nwm, slots);
+}
+
+// default launch geometry: fill shared memory with shots, keep >= 1024 threads per SM resident
+static int bp_default_config(qd_bp *d)
+{
+    const GraphDev &g = d->g->dev;
+    const size_t budget = (size_t)d->g->smem_optin;            // per CTA (227 KB on B200)
+    const size_t sm_budget = budget;                           // per SM, minus 1 KB/CTA reserved
+    const size_t per_slot = bp_smem(d, 1);
+    if (per_slot > budget)
+        return fail(QD_EUNSUP, "Tanner graph too large for the shared-memory BP kernel (" + std::to_string(per_slot) +
+                                   " B per shot > " + std::to_string(budget) + " B)");
+    const int work = std::max(g.n, g.m);
+    int threads = 128;
+    while (threads < 1024 && threads * 2 <= ((work + 31) & ~31)) threads *= 2;   // <= one item per thread per slot
+    int total_slots = (int)std::min<size_t>(32, sm_budget / (per_slot + 64));
+    int ctas = std::max(1, std::min(total_slots, 1024 / threads));
+    ctas = std::min(ctas, 8);
+    int slots = std::max(1, std::min(8, total_slots / ctas));
+    while (ctas > 1 && (bp_smem(d, slots) + 1024) * ctas > sm_budget) --ctas;
+    d->threads = threads; d->slots = slots; d->ctas_per_sm = ctas;
+    d->smem = bp_smem(d, slots);
+    return 0;
+}
+
+extern "C" int qd_bp_create(qd_graph *g, const double *h_channel_probs, int32_t max_iter, int32_t method,
+                            double ms_scaling_factor, int32_t precision, qd_bp **out)
+{
+    if (!out) return fail(QD_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!g || !h_channel_probs) return fail(QD_EINVAL, "graph or channel_probs is NULL");
+    if (method != QD_BP_PRODUCT_SUM && method != QD_BP_MIN_SUM) return fail(QD_EINVAL, "unknown bp method");
+    if (precision != QD_PREC_F64 && precision != QD_PREC_F32) return fail(QD_EINVAL, "precision must be 64 or 32");
+    if (max_iter < 0) return fail(QD_EINVAL, "max_iter < 0");
+    int rc = use_device(g->device);
+    if (rc) return rc;
+    const GraphDev &gd = g->dev;
+    std::unique_ptr<qd_bp> d(new qd_bp);
+    d->g = g;
+    d->max_iter = max_iter > 0 ? max_iter : gd.n;   // ldpc convention: 0 -> n
+    d->method = method;
+    d->precision = precision;
+    d->vmax = gd.max_col_deg <= 4 ? 4 : gd.max_col_deg <= 8 ? 8 : 16;
+    if (gd.max_col_deg > 16) return fail(QD_EUNSUP, "column degree > 16 not supported by the shared-memory BP kernel");
+    const int dmax = d->vmax == 4 ? 8 : 16;
+    if (method == QD_BP_PRODUCT_SUM && gd.max_row_deg > dmax)
+        return fail(QD_EUNSUP, "product-sum: row degree exceeds the register tile for this column class");
+    // priors in the decoder's domain, computed in double with the host libm (same as the oracle)
+    std::vector<double> pr(gd.n), al(d->max_iter + 1, 0.0);
+    for (int j = 0; j < gd.n; ++j) {
+        const double p = h_channel_probs[j];
+        if (!(p > 0.0) || !(p < 1.0)) return fail(QD_EINVAL, "channel probabilities must lie in (0, 1)");
+        pr[j] = method == QD_BP_MIN_SUM ? std::log((1.0 - p) / p) : p / (1.0 - p);
+    }
+    for (int it = 1; it <= d->max_iter; ++it)
+        al[it] = ms_scaling_factor == 0.0 ? 1.0 - std::pow(2.0, -1.0 * it / 1.0) : ms_scaling_factor;
+    if (precision == QD_PREC_F64) {
+        if ((rc = upload(d->d_prior, pr))) return rc;
+        if ((rc = upload(d->d_alpha, al))) return rc;
+    } else {
+        std::vector<float> prf(pr.begin(), pr.end()), alf(al.begin(), al.end());
+        if ((rc = upload(d->d_prior, prf))) return rc;
+        if ((rc = upload(d->d_alpha, alf))) return rc;
+    }
+    if ((rc = d->d_next.alloc(sizeof(unsigned long long) * 2))) return rc;
+    if ((rc = bp_default_config(d.get()))) return rc;
+    *out = d.release();
+    return 0;
+}
+
+extern "C" int qd_bp_destroy(qd_bp *d)
+{
+    if (d) { cudaSetDevice(d->g->device); delete d; }
+    return 0;
+}
+
+extern "C" int qd_bp_configure(qd_bp *d, int32_t threads, int32_t slots, int32_t ctas_per_sm)
+{
+    if (!d) return fail(QD_EINVAL, "NULL handle");
+    int t = threads > 0 ? threads : d->threads, s = slots > 0 ? slots : d->slots, c = ctas_per_sm > 0 ? ctas_per_sm : d->ctas_per_sm;
+    if (t % 32 || t > 1024 || s > 64) return fail(QD_EINVAL, "threads must be a multiple of 32 <= 1024, slots <= 64");
+    if (s > t) return fail(QD_EINVAL, "slots must not exceed threads");
+    const size_t smem = bp_smem(d, s);
+    if (smem > (size_t)d->g->smem_optin) return fail(QD_EUNSUP, "configuration does not fit shared memory");
+    d->threads = t; d->slots = s; d->ctas_per_sm = c; d->smem = smem;
+    return 0;
+}
+
+extern "C" int qd_bp_get_config(qd_bp *d, int32_t *threads, int32_t *slots, int32_t *ctas_per_sm, int32_t *smem_bytes,
+                                int32_t *grid)
+{
+    if (!d) return fail(QD_EINVAL, "NULL handle");
+    if (threads) *threads = d->threads;
+    if (slots) *slots = d->slots;
+    if (ctas_per_sm) *ctas_per_sm = d->ctas_per_sm;
+    if (smem_bytes) *smem_bytes = (int32_t)d->smem;
+    if (grid) *grid = d->g->sm_count * d->ctas_per_sm;
+    return 0;
+}
+
+static int bp_launch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int64_t shots, uint32_t *d_corr,
+                     int32_t corr_stride, uint8_t *d_converged, int32_t *d_iters, double *d_llr, const uint32_t *d_err,
+                     int32_t err_stride, qd_logicals *logicals, uint8_t *d_fail, int64_t *d_counters, void *stream,
+                     int queue)
+{
+    if (!d || !d_synd || !d_corr || shots < 0) return fail(QD_EINVAL, "bad bp_decode_batch arguments");
+    const GraphDev &g = d->g->dev;
+    if (synd_stride < g.nwm || corr_stride < g.nwn) return fail(QD_EINVAL, "stride too small");
+    if (d_err && (!logicals || err_stride < g.nwn)) return fail(QD_EINVAL, "fused epilogue needs logicals and err_stride >= ceil(n/32)");
+    if (logicals && logicals->n != g.n) return fail(QD_EINVAL, "logicals act on a different number of qubits");
+    if (shots == 0) return 0;
+    int rc = use_device(d->g->device);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    BpParams p{};
+    p.g = g;
+    p.prior = d->d_prior.p; p.alpha = d->d_alpha.p;
+    p.max_iter = d->max_iter; p.slots = d->slots;
+    p.synd = d_synd; p.synd_stride = synd_stride; p.shots = shots;
+    p.corr = d_corr; p.corr_stride = corr_stride;
+    p.conv = d_converged; p.iters = d_iters; p.llr = d_llr;
+    p.err = d_err; p.err_stride = err_stride;
+    p.lzT = d_err ? logicals->d_lzT.as<uint32_t>() : nullptr;
+    p.k = d_err ? logicals->k : 0;
+    p.fail = d_fail;
+    p.counters = (long long *)d_counters;
+    p.next_shot = d->d_next.as<unsigned long long>() + queue;
+    bp_kernel_fn fn = bp_kernel_for(d);
+    QD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem));
+    QD_CUDA(cudaMemsetAsync(p.next_shot, 0, sizeof(unsigned long long), st));
+    long long want = (shots + d->slots - 1) / d->slots;
+    unsigned grid = (unsigned)std::min<long long>((long long)d->g->sm_count * d->ctas_per_sm, want);
+    fn<<<grid, d->threads, d->smem, st>>>(p);
+    QD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int qd_bp_decode_batch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int64_t shots,
+                                  uint32_t *d_corr, int32_t corr_stride, uint8_t *d_converged, int32_t *d_iters,
+                                  double *d_llr, const uint32_t *d_err, int32_t err_stride, qd_logicals *logicals,
+                                  uint8_t *d_fail, int64_t *d_counters, void *stream)
+{
+    return bp_launch(d, d_synd, synd_stride, shots, d_corr, corr_stride, d_converged, d_iters, d_llr, d_err, err_stride,
+                     logicals, d_fail, d_counters, stream, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer pipeline shared by BP and SSF: chunks alternate between two streams so that the
+// H2D copy / decode / D2H copy of one chunk overlap the staging of the next.
+// ---------------------------------------------------------------------------------------------
+template <typename H, typename Launch>
+static int host_pipeline(H *d, int device, int nwm, int nwn, const uint32_t *h_synd, int synd_stride, int64_t shots,
+                         uint32_t *h_corr, int corr_stride, uint8_t *h_conv, int32_t *h_it, Launch launch)
+{
+    int rc = use_device(device);
+    if (rc) return rc;
+    for (int i = 0; i < 2; ++i) {
+        if (!d->streams[i]) QD_CUDA(cudaStreamCreateWithFlags(&d->streams[i], cudaStreamNonBlocking));
+        if (!d->done[i]) QD_CUDA(cudaEventCreateWithFlags(&d->done[i], cudaEventDisableTiming));
+    }
+    const int is = (nwm + 3) & ~3, os = (nwn + 3) & ~3;   // device strides: 16-byte rows
+    const int64_t per_shot = 4LL * (is + os) + 5;
+    int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(1 << 18, (64LL << 20) / per_shot));
+    chunk = std::min(chunk, std::max<int64_t>(shots, 1));
+    for (int i = 0; i < 2; ++i) {
+        if ((rc = d->d_in[i].ensure((size_t)chunk * is * 4))) return rc;
+        if ((rc = d->d_out[i].ensure((size_t)chunk * os * 4))) return rc;
+        if ((rc = d->d_conv[i].ensure((size_t)chunk))) return rc;
+        if ((rc = d->d_it[i].ensure((size_t)chunk * 4))) return rc;
+        if ((rc = d->h_in[i].ensure((size_t)chunk * is * 4))) return rc;
+        if ((rc = d->h_out[i].ensure((size_t)chunk * os * 4))) return rc;
+        if ((rc = d->h_conv[i].ensure((size_t)chunk))) return rc;
+        if ((rc = d->h_it[i].ensure((size_t)chunk * 4))) return rc;
+    }
+    const int64_t nchunks = (shots + chunk - 1) / chunk;
+    auto drain = [&](int64_t c) -> int {   // copy chunk c's results from pinned staging to the caller
+        const int b = (int)(c & 1);
+        QD_CUDA(cudaEventSynchronize(d->done[b]));
+        const int64_t s0 = c * chunk, ns = std::min(chunk, shots - s0);
+        const uint32_t *src = d->h_out[b].template as<uint32_t>();
+        for (int64_t s = 0; s < ns; ++s) {
+            uint32_t *dst = h_corr + (s0 + s) * corr_stride;
+            std::memcpy(dst, src + s * os, (size_t)nwn * 4);
+            for (int w = nwn; w < corr_stride; ++w) dst[w] = 0u;
+        }
+        if (h_conv) std::memcpy(h_conv + s0, d->h_conv[b].p, (size_t)ns);
+        if (h_it) std::memcpy(h_it + s0, d->h_it[b].p, (size_t)ns * 4);
+        return 0;
+    };
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int b = (int)(c & 1);
+        if (c >= 2 && (rc = drain(c - 2))) return rc;
+        const int64_t s0 = c * chunk, ns = std::min(chunk, shots - s0);
+        uint32_t *stage = d->h_in[b].template as<uint32_t>();
+        for (int64_t s = 0; s < ns; ++s) {
+            std::memcpy(stage + s * is, h_synd + (s0 + s) * synd_stride, (size_t)nwm * 4);
+            for (int w = nwm; w < is; ++w) stage[s * is + w] = 0u;
+        }
+        cudaStream_t st = d->streams[b];
+        QD_CUDA(cudaMemcpyAsync(d->d_in[b].p, stage, (size_t)ns * is * 4, cudaMemcpyHostToDevice, st));
+        if ((rc = launch(d->d_in[b].template as<uint32_t>(), is, ns, d->d_out[b].template as<uint32_t>(), os,
+                         d->d_conv[b].template as<uint8_t>(), d->d_it[b].template as<int32_t>(), st)))
+            return rc;
+        QD_CUDA(cudaMemcpyAsync(d->h_out[b].p, d->d_out[b].p, (size_t)ns * os * 4, cudaMemcpyDeviceToHost, st));
+        if (h_conv) QD_CUDA(cudaMemcpyAsync(d->h_conv[b].p, d->d_conv[b].p, (size_t)ns, cudaMemcpyDeviceToHost, st));
+        if (h_it) QD_CUDA(cudaMemcpyAsync(d->h_it[b].p, d->d_it[b].p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
+        QD_CUDA(cudaEventRecord(d->done[b], st));
+    }
+    for (int64_t c = std::max<int64_t>(0, nchunks - 2); c < nchunks; ++c)
+        if ((rc = drain(c))) return rc;
+    return 0;
+}
+
+extern "C" int qd_bp_decode_batch_host(qd_bp *d, const uint32_t *h_synd, int32_t synd_stride, int64_t shots,
+                                       uint32_t *h_corr, int32_t corr_stride, uint8_t *h_converged, int32_t *h_iters)
+{
+    if (!d || !h_synd || !h_corr || shots < 0) return fail(QD_EINVAL, "bad bp_decode_batch_host arguments");
+    const GraphDev &g = d->g->dev;
+    if (synd_stride < g.nwm || corr_stride < g.nwn) return fail(QD_EINVAL, "stride too small");
+    if (shots == 0) return 0;
+    int which = 0;   // the two in-flight chunks use separate work-queue counters
+    auto launch = [&](const uint32_t *in, int is, int64_t ns, uint32_t *out, int os, uint8_t *conv, int32_t *it,
+                      cudaStream_t st) -> int {
+        int rc = bp_launch(d, in, is, ns, out, os, conv, it, nullptr, nullptr, 0, nullptr, nullptr, nullptr, st, which);
+        which ^= 1;
+        return rc;
+    };
+    return host_pipeline(d, d->g->device, g.nwm, g.nwn, h_synd, synd_stride, shots, h_corr, corr_stride, h_converged,
+                         h_iters, launch);
+}
+
+extern "C" int qd_bp_decode_one(qd_bp *d, const uint8_t *h_syndrome, uint8_t *h_decoding, int32_t *converged,
+                                int32_t *iters, double *h_llr)
+{
+    if (!d || !h_syndrome || !h_decoding) return fail(QD_EINVAL, "bad bp_decode_one arguments");
+    const GraphDev &g = d->g->dev;
+    int rc = use_device(d->g->device);
+    if (rc) return rc;
+    std::vector<uint32_t> s(g.nwm, 0u), c(g.nwn, 0u);
+    for (int i = 0; i < g.m; ++i)
+        if (h_syndrome[i] & 1) s[i >> 5] |= 1u << (i & 31);
+    DevBuf ds, dc, dv, di, dl;
+    if ((rc = ds.alloc((size_t)g.nwm * 4 + 4))) return rc;
+    if ((rc = dc.alloc((size_t)g.nwn * 4))) return rc;
+    if ((rc = dv.alloc(4))) return rc;
+    if ((rc = di.alloc(4))) return rc;
+    if (h_llr && (rc = dl.alloc((size_t)g.n * 8))) return rc;
+    QD_CUDA(cudaMemcpy(ds.p, s.data(), (size_t)g.nwm * 4, cudaMemcpyHostToDevice));
+    rc = qd_bp_decode_batch(d, ds.as<uint32_t>(), g.nwm, 1, dc.as<uint32_t>(), g.nwn, dv.as<uint8_t>(), di.as<int32_t>(),
+                            h_llr ? dl.as<double>() : nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    QD_CUDA(cudaDeviceSynchronize());
+    uint8_t cv = 0;
+    int32_t it = 0;
+    QD_CUDA(cudaMemcpy(c.data(), dc.p, (size_t)g.nwn * 4, cudaMemcpyDeviceToHost));
+    QD_CUDA(cudaMemcpy(&cv, dv.p, 1, cudaMemcpyDeviceToHost));
+    QD_CUDA(cudaMemcpy(&it, di.p, 4, cudaMemcpyDeviceToHost));
+    if (h_llr) QD_CUDA(cudaMemcpy(h_llr, dl.p, (size_t)g.n * 8, cudaMemcpyDeviceToHost));
+    for (int j = 0; j < g.n; ++j) h_decoding[j] = (uint8_t)((c[j >> 5] >> (j & 31)) & 1u);
+    if (converged) *converged = cv;
+    if (iters) *iters = it;
+    return 0;
+}
+
+// =============================================================================================
+// SSF
+// =============================================================================================
+extern "C" int qd_ssf_create(qd_graph *hz, int32_t num_generators, const int32_t *h_gen_row_ptr,
+                             const int32_t *h_gen_col_idx, int32_t max_rounds, qd_ssf **out)
+{
+    if (!out) return fail(QD_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!hz || num_generators <= 0 || !h_gen_row_ptr || !h_gen_col_idx || max_rounds < 0)
+        return fail(QD_EINVAL, "bad ssf_create arguments");
+    int rc = use_device(hz->device);
+    if (rc) return rc;
+    const GraphDev &g = hz->dev;
+    const int mg = num_generators;
+    const int gnnz = h_gen_row_ptr[mg];
+    std::vector<int32_t> gen_ptr(h_gen_row_ptr, h_gen_row_ptr + mg + 1), gen_idx(h_gen_col_idx, h_gen_col_idx + gnnz);
+    std::vector<int32_t> win_ptr(mg + 1, 0), win_chk;
+    std::vector<unsigned long long> qmask(std::max(gnnz, 1), 0ULL);
+    int max_w = 0;
+    for (int gi = 0; gi < mg; ++gi) {
+        const int lo = gen_ptr[gi], w = gen_ptr[gi + 1] - lo;
+        if (w <= 0 || w > SSF_MAX_W) return fail(QD_EUNSUP, "SSF: generator weight must be in [1, 12]");
+        max_w = std::max(max_w, w);
+        std::vector<int32_t> win;
+        for (int t = lo; t < lo + w; ++t) {
+            const int q = gen_idx[t];
+            if (q < 0 || q >= g.n) return fail(QD_EINVAL, "SSF: generator qubit out of range");
+            for (int u = hz->col_ptr[q]; u < hz->col_ptr[q + 1]; ++u) {
+                const int c = (int)hz->csc_row[u];
+                int pos = -1;
+                for (size_t z = 0; z < win.size(); ++z) if (win[z] == c) { pos = (int)z; break; }
+                if (pos < 0) {
+                    if (win.size() == 64) return fail(QD_EUNSUP, "SSF: check window of a generator exceeds 64");
+                    pos = (int)win.size();
+                    win.push_back(c);
+                }
+                qmask[t] ^= 1ULL << pos;
+            }
+        }
+        win_chk.insert(win_chk.end(), win.begin(), win.end());
+        win_ptr[gi + 1] = (int)win_chk.size();
+    }
+    std::unique_ptr<qd_ssf> d(new qd_ssf);
+    d->g = hz;
+    d->max_rounds = max_rounds;
+    if ((rc = upload(d->d_gen_ptr, gen_ptr))) return rc;
+    if ((rc = upload(d->d_gen_idx, gen_idx))) return rc;
+    if ((rc = upload(d->d_win_ptr, win_ptr))) return rc;
+    if ((rc = upload(d->d_win_chk, win_chk))) return rc;
+    if ((rc = upload(d->d_qmask, qmask))) return rc;
+    if ((rc = d->d_next.alloc(sizeof(unsigned long long) * 2))) return rc;
+    SsfDev &s = d->dev;
+    s.m = g.m; s.n = g.n; s.nwm = g.nwm; s.nwn = g.nwn; s.mg = mg; s.max_w = max_w;
+    s.gen_ptr = d->d_gen_ptr.as<int32_t>(); s.gen_idx = d->d_gen_idx.as<int32_t>();
+    s.win_ptr = d->d_win_ptr.as<int32_t>(); s.win_chk = d->d_win_chk.as<int32_t>();
+    s.qmask = d->d_qmask.as<unsigned long long>();
+    d->threads = 128;
+    d->smem = ssf_smem_bytes(g.nwn, g.nwm, d->threads);
+    *out = d.release();
+    return 0;
+}
+
+extern "C" int qd_ssf_destroy(qd_ssf *d)
+{
+    if (d) { cudaSetDevice(d->g->device); delete d; }
+    return 0;
+}
+
+static int ssf_launch(qd_ssf *d, const uint32_t *d_synd, int32_t synd_stride, int64_t shots, uint32_t *d_corr,
+                      int32_t corr_stride, uint8_t *d_converged, int32_t *d_rounds, const uint32_t *d_err,
+                      int32_t err_stride, qd_logicals *logicals, uint8_t *d_fail, int64_t *d_counters, void *stream,
+                      int queue)
+{
+    if (!d || !d_synd || !d_corr || shots < 0) return fail(QD_EINVAL, "bad ssf_decode_batch arguments");
+    const GraphDev &g = d->g->dev;
+    if (synd_stride < g.nwm || corr_stride < g.nwn) return fail(QD_EINVAL, "stride too small");
+    if (d_err && (!logicals || err_stride < g.nwn)) return fail(QD_EINVAL, "fused epilogue needs logicals and err_stride >= ceil(n/32)");
+    if (logicals && logicals->n != g.n) return fail(QD_EINVAL, "logicals act on a different number of qubits");
+    if (shots == 0) return 0;
+    int rc = use_device(d->g->device);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    SsfParams p{};
+    p.s = d->dev;
+    p.max_rounds = d->max_rounds;
+    p.synd = d_synd; p.synd_stride = synd_stride; p.shots = shots;
+    p.corr = d_corr; p.corr_stride = corr_stride;
+    p.conv = d_converged; p.rounds = d_rounds;
+    p.err = d_err; p.err_stride = err_stride;
+    p.lzT = d_err ? logicals->d_lzT.as<uint32_t>() : nullptr;
+    p.k = d_err ? logicals->k : 0;
+    p.fail = d_fail;
+    p.counters = (long long *)d_counters;
+    p.next_shot = d->d_next.as<unsigned long long>() + queue;
+    QD_CUDA(cudaFuncSetAttribute(ssf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem));
+    QD_CUDA(cudaMemsetAsync(p.next_shot, 0, sizeof(unsigned long long), st));
+    int per_sm = 0;
+    QD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ssf_kernel, d->threads, d->smem));
+    per_sm = std::max(1, per_sm);
+    unsigned grid = (unsigned)std::min<long long>((long long)d->g->sm_count * per_sm, shots);
+    ssf_kernel<<<grid, d->threads, d->smem, st>>>(p);
+    QD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int qd_ssf_decode_batch(qd_ssf *d, const uint32_t *d_synd, int32_t synd_stride, int64_t shots,
+                                   uint32_t *d_corr, int32_t corr_stride, uint8_t *d_converged, int32_t *d_rounds,
+                                   const uint32_t *d_err, int32_t err_stride, qd_logicals *logicals, uint8_t *d_fail,
+                                   int64_t *d_counters, void *stream)
+{
+    return ssf_launch(d, d_synd, synd_stride, shots, d_corr, corr_stride, d_converged, d_rounds, d_err, err_stride,
+                      logicals, d_fail, d_counters, stream, 0);
+}
+
+extern "C" int qd_ssf_decode_batch_host(qd_ssf *d, const uint32_t *h_synd, int32_t synd_stride, int64_t shots,
+                                        uint32_t *h_corr, int32_t corr_stride, uint8_t *h_converged, int32_t *h_rounds)
+{
+    if (!d || !h_synd || !h_corr || shots < 0) return fail(QD_EINVAL, "bad ssf_decode_batch_host arguments");
+    const GraphDev &g = d->g->dev;
+    if (synd_stride < g.nwm || corr_stride < g.nwn) return fail(QD_EINVAL, "stride too small");
+    if (shots == 0) return 0;
+    int which = 0;
+    auto launch = [&](const uint32_t *in, int is, int64_t ns, uint32_t *out, int os, uint8_t *conv, int32_t *it,
+                      cudaStream_t st) -> int {
+        int rc = ssf_launch(d, in, is, ns, out, os, conv, it, nullptr, 0, nullptr, nullptr, nullptr, st, which);
+        which ^= 1;
+        return rc;
+    };
+    return host_pipeline(d, d->g->device, g.nwm, g.nwn, h_synd, synd_stride, shots, h_corr, corr_stride, h_converged,
+                         h_rounds, launch);
+}
+
+// =============================================================================================
+// code-capacity experiment
+// =============================================================================================
+extern "C" int qd_code_capacity_run(qd_graph *hz, qd_bp *bp, qd_ssf *ssf, qd_sampler *sampler, qd_logicals *logicals,
+                                    uint64_t seed, int64_t shot0, int64_t shots, int64_t *h_counters, uint32_t *h_corr,
+                                    int32_t corr_stride, uint8_t *h_fail, uint8_t *h_converged, int32_t *h_iters)
+{
+    if (!hz || !sampler || !logicals || !h_counters || shots < 0) return fail(QD_EINVAL, "bad code_capacity_run arguments");
+    if ((bp == nullptr) == (ssf == nullptr)) return fail(QD_EINVAL, "exactly one of bp / ssf must be given");
+    const GraphDev &g = hz->dev;
+    if (sampler->nbits != g.n || logicals->n != g.n) return fail(QD_EINVAL, "sampler / logicals size mismatch");
+    if ((bp && bp->g != hz) || (ssf && ssf->g != hz)) return fail(QD_EINVAL, "decoder was built on a different graph");
+    if (h_corr && corr_stride < g.nwn) return fail(QD_EINVAL, "corr_stride too small");
+    int rc = use_device(hz->device);
+    if (rc) return rc;
+    const int es = (g.nwn + 3) & ~3, ss = (g.nwm + 3) & ~3;
+    const int64_t per_shot = 4LL * (2 * es + ss) + 6;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(shots, std::min<int64_t>(1 << 22, (512LL << 20) / per_shot)));
+    DevBuf d_err, d_syn, d_cor, d_fail, d_conv, d_it, d_cnt;
+    if ((rc = d_err.alloc((size_t)chunk * es * 4))) return rc;
+    if ((rc = d_syn.alloc((size_t)chunk * ss * 4))) return rc;
+    if ((rc = d_cor.alloc((size_t)chunk * es * 4))) return rc;
+    if ((rc = d_fail.alloc((size_t)chunk))) return rc;
+    if ((rc = d_conv.alloc((size_t)chunk))) return rc;
+    if ((rc = d_it.alloc((size_t)chunk * 4))) return rc;
+    if ((rc = d_cnt.alloc(4 * sizeof(int64_t)))) return rc;
+    QD_CUDA(cudaMemset(d_cnt.p, 0, 4 * sizeof(int64_t)));
+    std::vector<uint32_t> tmp;
+    for (int64_t s0 = 0; s0 < shots; s0 += chunk) {
+        const int64_t ns = std::min(chunk, shots - s0);
+        if ((rc = qd_sampler_run(sampler, seed, 0u, shot0 + s0, ns, d_err.as<uint32_t>(), es, nullptr))) return rc;
+        if ((rc = qd_syndrome_batch(hz, d_err.as<uint32_t>(), es, ns, d_syn.as<uint32_t>(), ss, nullptr))) return rc;
+        if (bp)
+            rc = qd_bp_decode_batch(bp, d_syn.as<uint32_t>(), ss, ns, d_cor.as<uint32_t>(), es, d_conv.as<uint8_t>(),
+                                    d_it.as<int32_t>(), nullptr, d_err.as<uint32_t>(), es, logicals, d_fail.as<uint8_t>(),
+                                    d_cnt.as<int64_t>(), nullptr);
+        else
+            rc = qd_ssf_decode_batch(ssf, d_syn.as<uint32_t>(), ss, ns, d_cor.as<uint32_t>(), es, d_conv.as<uint8_t>(),
+                                     d_it.as<int32_t>(), d_err.as<uint32_t>(), es, logicals, d_fail.as<uint8_t>(),
+                                     d_cnt.as<int64_t>(), nullptr);
+        if (rc) return rc;
+        if (h_corr) {
+            tmp.resize((size_t)ns * es);
+            QD_CUDA(cudaMemcpy(tmp.data(), d_cor.p, (size_t)ns * es * 4, cudaMemcpyDeviceToHost));
+            for (int64_t s = 0; s < ns; ++s) {
+                uint32_t *dst = h_corr + (s0 + s) * corr_stride;
+                std::memcpy(dst, tmp.data() + s * es, (size_t)g.nwn * 4);
+                for (int w = g.nwn; w < corr_stride; ++w) dst[w] = 0u;
+            }
+        }
+        if (h_fail) QD_CUDA(cudaMemcpy(h_fail + s0, d_fail.p, (size_t)ns, cudaMemcpyDeviceToHost));
+        if (h_converged) QD_CUDA(cudaMemcpy(h_converged + s0, d_conv.p, (size_t)ns, cudaMemcpyDeviceToHost));
+        if (h_iters) QD_CUDA(cudaMemcpy(h_iters + s0, d_it.p, (size_t)ns * 4, cudaMemcpyDeviceToHost));
+    }
+    QD_CUDA(cudaMemcpy(h_counters, d_cnt.p, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return 0;
+}

@@ -1,0 +1,192 @@
+// ssf_kernel.cuh — small-set-flip as an integer kernel (specification: SURVEY.md Appendix C;
+// CPU restatement: oracle/qldpc_oracle.c orc_ssf_decode; the reference itself has no SSF).
+//
+// One CTA per shot in flight (persistent, shots pulled from a global atomic queue).  Per round:
+//   * every thread scans its generators: the syndrome restricted to the generator's check window
+//     is gathered into one 64-bit word; the 2^w - 1 candidate subsets are walked in Gray-code
+//     order, one XOR + two popcounts each:  delta = 2 popc(local & T) - popc(T);
+//   * candidates are ranked by an exact integer key  (delta * 27720 / |F|, lowest generator,
+//     lowest subset mask)  — 27720 = lcm(1..12) makes the ratio an integer, so the arg-max is a
+//     plain 64-bit max and ties break exactly like the serial oracle;
+//   * warp shuffles + one shared-memory stage pick the CTA-wide winner, which is flipped.
+// Integer arithmetic only => results are bit-identical to the oracle.
+#pragma once
+
+#include "common.cuh"
+
+namespace qd {
+
+constexpr int SSF_MAX_W = 12;
+
+struct SsfDev {
+    int m, n, nwm, nwn, mg, max_w;
+    const int32_t *gen_ptr, *gen_idx;        // generator supports (rows of Hx)
+    const int32_t *win_ptr, *win_chk;        // per generator: its window of adjacent checks (<= 64)
+    const unsigned long long *qmask;         // per support entry: toggle mask in window coordinates
+};
+
+struct SsfParams {
+    SsfDev s;
+    int max_rounds;
+    const uint32_t *synd; int synd_stride;
+    long long shots;
+    uint32_t *corr; int corr_stride;
+    uint8_t *conv; int32_t *rounds;
+    const uint32_t *err; int err_stride;
+    const uint32_t *lzT; int k;
+    uint8_t *fail;
+    long long *counters;
+    unsigned long long *next_shot;
+};
+
+__host__ __device__ inline size_t ssf_smem_bytes(int nwn, int nwm, int threads)
+{
+    return (size_t)4 * (nwn + nwm) + 8 * (size_t)(threads / 32 + 2) + 32;
+}
+
+// 27720 / size for size in 1..12
+__constant__ unsigned inv_size[13] = {0, 27720, 13860, 9240, 6930, 5544, 4620, 3960, 3465, 3080, 2772, 2520, 2310};
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = other > v ? other : v;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256) ssf_kernel(const SsfParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SsfDev &s = p.s;
+    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+    unsigned long long *red = reinterpret_cast<unsigned long long *>(smem_raw);   // [nwarps + 2]
+    uint32_t *sigma = reinterpret_cast<uint32_t *>(red + nwarps + 2);              // [nwm]
+    uint32_t *dec = sigma + s.nwm;                                                // [nwn]
+    __shared__ long long sh_shot;
+    __shared__ int sh_weight;
+
+
+    long long c_fail = 0, c_shots = 0, c_nc = 0, c_it = 0;
+
+    for (;;) {
+        if (tid == 0) {
+            const unsigned long long id = atomicAdd(p.next_shot, 1ULL);
+            sh_shot = id < (unsigned long long)p.shots ? (long long)id : -1;
+            sh_weight = 0;
+        }
+        __syncthreads();
+        const long long shot = sh_shot;
+        if (shot < 0) break;
+        {
+            const uint32_t *src = p.synd + shot * (long long)p.synd_stride;
+            int w8 = 0;
+            for (int w = tid; w < s.nwm; w += NT) { const uint32_t v = src[w]; sigma[w] = v; w8 += __popc(v); }
+            w8 = warp_sum(w8);
+            if (lane == 0 && w8) atomicAdd(&sh_weight, w8);
+            for (int w = tid; w < s.nwn; w += NT) dec[w] = 0u;
+        }
+        __syncthreads();
+        int weight = sh_weight;
+        int rounds = 0;
+        while (weight > 0 && (p.max_rounds == 0 || rounds < p.max_rounds)) {
+            unsigned long long best = 0ULL;
+            for (int g = tid; g < s.mg; g += NT) {
+                const int lo = s.gen_ptr[g], w = s.gen_ptr[g + 1] - lo;
+                const int wlo = s.win_ptr[g], nw = s.win_ptr[g + 1] - wlo;
+                unsigned long long local = 0ULL;
+                for (int z = 0; z < nw; ++z) {
+                    const int c = s.win_chk[wlo + z];
+                    local |= (unsigned long long)((sigma[c >> 5] >> (c & 31)) & 1u) << z;
+                }
+                if (!local) continue;
+                unsigned long long qm[SSF_MAX_W];
+#pragma unroll
+                for (int t = 0; t < SSF_MAX_W; ++t) qm[t] = t < w ? s.qmask[lo + t] : 0ULL;
+                unsigned long long T = 0ULL;
+                unsigned gray = 0u;
+                const unsigned long long gkey = (unsigned long long)(0xFFFFFFu - (unsigned)g) << 16;
+                for (unsigned i = 1; i < (1u << w); ++i) {
+                    const int b = __ffs(i) - 1;
+                    gray ^= 1u << b;
+                    unsigned long long q = qm[0];
+#pragma unroll
+                    for (int t = 1; t < SSF_MAX_W; ++t) q = (b == t) ? qm[t] : q;
+                    T ^= q;
+                    const int delta = 2 * __popcll(local & T) - __popcll(T);
+                    if (delta > 0) {
+                        const unsigned long long key =
+                            ((unsigned long long)((unsigned)delta * inv_size[__popc(gray)]) << 40) | gkey |
+                            (unsigned long long)(0xFFFFu - gray);
+                        best = key > best ? key : best;
+                    }
+                }
+            }
+            best = warp_max_u64(best);
+            if (lane == 0) red[warp] = best;
+            __syncthreads();
+            if (warp == 0) {
+                unsigned long long v = lane < nwarps ? red[lane] : 0ULL;
+                v = warp_max_u64(v);
+                if (lane == 0) red[nwarps] = v;
+            }
+            __syncthreads();
+            const unsigned long long win = red[nwarps];
+            if (win == 0ULL) break;                              // no subset lowers the syndrome weight
+            const int g = (int)(0xFFFFFFu - (unsigned)((win >> 16) & 0xFFFFFFu));
+            const unsigned mask = 0xFFFFu - (unsigned)(win & 0xFFFFu);
+            const int size = __popc(mask);
+            const int delta = (int)((unsigned)(win >> 40) / inv_size[size]);
+            const int lo = s.gen_ptr[g], wlo = s.win_ptr[g], nw = s.win_ptr[g + 1] - wlo;
+            if (tid < SSF_MAX_W && ((mask >> tid) & 1u)) {
+                const int q = s.gen_idx[lo + tid];
+                atomicXor(&dec[q >> 5], 1u << (q & 31));
+            }
+            unsigned long long T = 0ULL;
+            for (int t = 0; t < SSF_MAX_W; ++t)
+                if ((mask >> t) & 1u) T ^= s.qmask[lo + t];
+            if (tid >= 32 && tid - 32 < nw && ((T >> (tid - 32)) & 1ULL)) {
+                const int c = s.win_chk[wlo + tid - 32];
+                atomicXor(&sigma[c >> 5], 1u << (c & 31));
+            }
+            weight -= delta;
+            ++rounds;
+            __syncthreads();
+        }
+
+        // ---- retire the shot
+        uint32_t *dst = p.corr + shot * (long long)p.corr_stride;
+        for (int w = tid; w < p.corr_stride; w += NT) dst[w] = w < s.nwn ? dec[w] : 0u;
+        int f = 0;
+        if (p.err) {
+            const uint32_t *e = p.err + shot * (long long)p.err_stride;
+            __syncthreads();
+            for (int w = tid; w < s.nwn; w += NT) dec[w] ^= e[w];
+            __syncthreads();
+            for (int i = tid; i < p.k; i += NT) {
+                uint32_t acc = 0u;
+                for (int w = 0; w < s.nwn; ++w) acc ^= p.lzT[(size_t)w * p.k + i] & dec[w];
+                f |= __popc(acc) & 1;
+            }
+            f = __syncthreads_or(f);
+        }
+        if (tid == 0) {
+            const int conv = weight == 0;
+            if (p.conv) p.conv[shot] = (uint8_t)conv;
+            if (p.rounds) p.rounds[shot] = rounds;
+            if (p.fail) p.fail[shot] = (uint8_t)f;
+            c_fail += f; c_shots += 1; c_nc += !conv; c_it += rounds;
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && p.counters && c_shots) {
+        atomicAdd((unsigned long long *)&p.counters[0], (unsigned long long)c_fail);
+        atomicAdd((unsigned long long *)&p.counters[1], (unsigned long long)c_shots);
+        atomicAdd((unsigned long long *)&p.counters[2], (unsigned long long)c_nc);
+        atomicAdd((unsigned long long *)&p.counters[3], (unsigned long long)c_it);
+    }
+}
+
+}  // namespace qd

@@ -1,0 +1,173 @@
+"""The batch seam: ``run_simulation`` and ``p_sweep`` on the GPU.
+
+Host-side mirror of ``python/qldpc/misc/_experiment.py:154-210`` (``run_simulation``) and
+``python/qldpc/misc/p_sweep.py:17-40`` (``p_sweep``): same positional/keyword arguments, same
+return types (``list[bool]`` of per-shot logical failures; a pandas DataFrame with the reference's
+columns), with
+
+* the Stim sampler replaced by the Philox code-capacity sampler on the device (``rounds = 0``);
+* the per-shot Python loop replaced by ``qd_code_capacity_run``
+  (sample -> syndrome -> decode -> residual -> logical flag, all on the GPU);
+* ``multiprocessing.Pool(cpu_count())`` + ``sum`` replaced by one rank per GPU and a single
+  ``all_reduce(SUM)`` of ``int64[4] = {failures, shots, non_converged, iterations}`` per p-value.
+
+Supported ``decoder_mode``: ``'bp'`` (the first, pure-BP stage of the reference's
+``bposd_hybrid``; prior on every bit = ``data_prior``) and ``'ssf'``.  The OSD-based modes of the
+reference need the OSD post-processor, which is a "next" row; they raise
+``NotImplementedError`` rather than silently decoding differently.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+from dataclasses import dataclass
+from typing import Callable, Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from .codes import QuantumCode
+from .decoders import Logicals, Sampler, TannerGraph, bp_decoder, row_words, ssf_decoder, unpack_bits
+
+__all__ = ["depolarizing_noise", "NoiseModel", "CodeCapacityExperiment", "run_simulation", "p_sweep",
+           "shard_range", "binomial_ci"]
+
+
+@dataclass(frozen=True)
+class NoiseModel:
+    """What the circuit-rewriting noise models of ``noise_model.py`` amount to for ``rounds = 0``."""
+    name: str
+    p: float
+    pm: float
+
+    def code_capacity_flip_probability(self) -> float:
+        """Marginal probability that a data-qubit Z-basis readout is flipped.
+
+        ``depolarizing_noise(p, pm)`` (``noise_model.py:117-123``) puts ``DEPOLARIZE1(p)`` on the data
+        qubits before the only measurement step of the rounds=0 circuit and rewrites ``MZ`` into
+        ``MZ(pm)``: X or Y with probability 2p/3, then an independent readout flip pm."""
+        a = 2.0 * self.p / 3.0
+        return a + self.pm - 2.0 * a * self.pm
+
+
+def depolarizing_noise(p: float, pm: float) -> NoiseModel:
+    return NoiseModel("depolarizing", float(p), float(pm))
+
+
+def shard_range(total: int, rank: int, world: int):
+    """Rank r decodes global shots [r*ceil(N/R), min(N, (r+1)*ceil(N/R)))."""
+    per = math.ceil(total / world) if world > 0 else total
+    lo = min(total, rank * per)
+    hi = min(total, lo + per)
+    return lo, hi
+
+
+def binomial_ci(failures: int, shots: int, z: float = 1.959963984540054):
+    """Wilson 95 % interval for a failure probability."""
+    if shots == 0:
+        return 0.0, 1.0
+    ph = failures / shots
+    den = 1.0 + z * z / shots
+    mid = (ph + z * z / (2 * shots)) / den
+    half = z * math.sqrt(ph * (1 - ph) / shots + z * z / (4.0 * shots * shots)) / den
+    return max(0.0, mid - half), min(1.0, mid + half)
+
+
+class CodeCapacityExperiment:
+    """Device pipeline for one (code, p, decoder) point: owns the graph, sampler, logicals, decoder."""
+
+    def __init__(self, code: QuantumCode, flip_probability: float, prior: float, decoder_mode: str = "bp",
+                 bp_options: Optional[Dict] = None, device: int = 0, precision: str = "f64"):
+        self.code = code
+        self.device = int(device)
+        self.n = code.num_qubits
+        hz = code.checks.z
+        self.graph = TannerGraph(hz, device)
+        self.logicals = Logicals(code.logicals.z, device)
+        self.sampler = Sampler(flip_probability, self.n, device)
+        self.decoder_mode = decoder_mode
+        opts = dict(bp_options or {})
+        if decoder_mode == "bp":
+            self.decoder = bp_decoder(self.graph, error_rate=prior, max_iter=opts.get("max_iter", 0),
+                                      bp_method=opts.get("bp_method", "ps"),
+                                      ms_scaling_factor=opts.get("ms_scaling_factor", 0.0), precision=precision)
+            self._bp, self._ssf = self.decoder.handle, None
+        elif decoder_mode == "ssf":
+            self.decoder = ssf_decoder(self.graph, code.checks.x, max_rounds=opts.get("max_rounds", 0))
+            self._bp, self._ssf = None, self.decoder.handle
+        elif decoder_mode in ("bposd", "bposd_single_shot", "bposd_hybrid", "bpd_detector"):
+            raise NotImplementedError(
+                f"decoder_mode '{decoder_mode}' needs the OSD post-processor / Stim DEM (SURVEY.md §8 f1-f2)")
+        else:
+            raise RuntimeError("Unknown decoder operation mode")   # _experiment.py:189
+
+    def run(self, shots: int, seed: int = 0, shot0: int = 0, per_shot: bool = False) -> dict:
+        counters = np.zeros(4, dtype=np.int64)
+        corr = fail = conv = its = None
+        cs = row_words(self.n)
+        if per_shot:
+            corr = np.zeros((shots, cs), dtype=np.uint32)
+            fail = np.zeros(shots, dtype=np.uint8)
+            conv = np.zeros(shots, dtype=np.uint8)
+            its = np.zeros(shots, dtype=np.int32)
+        _lib.check(_lib.lib().qd_code_capacity_run(
+            self.graph.handle, self._bp, self._ssf, self.sampler.handle, self.logicals.handle, int(seed), int(shot0),
+            int(shots), _lib.ptr(counters), _lib.ptr(corr), cs, _lib.ptr(fail), _lib.ptr(conv), _lib.ptr(its)))
+        out = dict(failures=int(counters[0]), shots=int(counters[1]), non_converged=int(counters[2]),
+                   iters_total=int(counters[3]))
+        if per_shot:
+            out.update(decodings=unpack_bits(corr, self.n), fail=fail, converged=conv, iters=its)
+        return out
+
+
+def run_simulation(samples, code, meas_prior, data_prior, noise_model, noise_model_args, bp_osd_options, rounds,
+                   decoder_mode, seed: int = 0, shot0: int = 0, device: int = 0, precision: str = "f64"):
+    """``run_simulation`` of ``_experiment.py:154-210`` for the code-capacity path (``rounds = 0``).
+    Returns ``list[bool]``: the logical-failure flag of every shot."""
+    if rounds != 0:
+        raise NotImplementedError("multi-round storage simulation needs the circuit sampler (SURVEY.md §8 f2)")
+    checks = code.checks
+    x_steps = int(max(checks.x.sum(axis=0).max(), checks.x.sum(axis=1).max()))   # _experiment.py:160-161
+    z_steps = int(max(checks.z.sum(axis=0).max(), checks.z.sum(axis=1).max()))
+    nm = noise_model(**noise_model_args)
+    _ = meas_prior(x_steps, z_steps)
+    prior = data_prior(x_steps, z_steps)
+    exp = CodeCapacityExperiment(code, nm.code_capacity_flip_probability(), prior, decoder_mode, bp_osd_options,
+                                 device=device, precision=precision)
+    res = exp.run(int(samples), seed=seed, shot0=shot0, per_shot=True)
+    return [bool(v) for v in res["fail"]]
+
+
+def p_sweep(samples, p_values, noise_model, noise_model_args, meas_prior, data_prior, *, code, rounds, decoder_mode,
+            bp_osd_options, seed: int = 0, device: Optional[int] = None, precision: str = "f64", group=None):
+    """``p_sweep`` of ``misc/p_sweep.py:17-40``: one row per p with the reference's columns
+    (``p_ph, failures, samples, walltime, rounds, decoder_mode`` + the BP options), plus
+    ``non_converged`` / ``iters_total`` / ``n_gpus``.  Under ``torch.distributed`` every rank
+    decodes its own shot range and the four counters are combined by one all-reduce per p."""
+    import pandas as pd
+    import torch
+
+    dist = torch.distributed
+    world, rank = (dist.get_world_size(group), dist.get_rank(group)) if dist.is_available() and dist.is_initialized() else (1, 0)
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    if rounds != 0:
+        raise NotImplementedError("multi-round storage simulation needs the circuit sampler (SURVEY.md §8 f2)")
+    lo, hi = shard_range(int(samples), rank, world)
+    rows = []
+    for p_ph in p_values:
+        t0 = time.time()
+        nm = noise_model(**noise_model_args(p_ph))
+        exp = CodeCapacityExperiment(code, nm.code_capacity_flip_probability(), data_prior(p_ph, 0, 0), decoder_mode,
+                                     bp_osd_options, device=device, precision=precision)
+        res = exp.run(hi - lo, seed=seed, shot0=lo)
+        counters = torch.tensor([res["failures"], res["shots"], res["non_converged"], res["iters_total"]],
+                                dtype=torch.int64, device=f"cuda:{device}" if torch.cuda.is_available() else "cpu")
+        if world > 1:
+            dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=group)
+        f, s, nc, it = (int(v) for v in counters.tolist())
+        row = {"p_ph": float(p_ph), "failures": f, "samples": s, "walltime": time.time() - t0, "rounds": rounds,
+               "decoder_mode": decoder_mode, **bp_osd_options, "non_converged": nc, "iters_total": it, "n_gpus": world}
+        rows.append(row)
+    return pd.DataFrame.from_records(rows)

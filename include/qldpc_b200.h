@@ -1,0 +1,152 @@
+/*
+ * qldpc_b200.h — C ABI of libqldpc_b200.so, the B200 (sm_100a) batched qLDPC decoding engine.
+ *
+ * This is the drop-in boundary for the decode hot path of qldpc/exp_ldpc.  The reference has no
+ * FFI of its own for this path: its seam is the Python duck type of the third-party `ldpc`
+ * decoder objects plus `run_simulation`.  Every entry point below names the reference interface
+ * it stands in for (paths relative to the reference tree):
+ *
+ *   qd_bp_create          <- ldpc.bp_decoder(H, channel_probs=|error_rate=, max_iter=, bp_method=,
+ *                            ms_scaling_factor=)            python/qldpc/misc/_experiment.py:110-113,137-140
+ *   qd_bp_decode_one      <- bp_decoder.decode(syndrome)     python/qldpc/misc/_experiment.py:117,149
+ *   qd_bp_decode_batch*   <- the `for i in range(samples)` loop around .decode()
+ *                                                            python/qldpc/misc/_experiment.py:200-209
+ *   qd_syndrome_batch     <- (checks @ readout) % 2          python/qldpc/misc/_experiment.py:47,58,124
+ *                                                            python/qldpc/spacetime_code.py:109
+ *   qd_logical_fail_batch <- np.any(GF2(Lz) @ GF2(readout ^ corr) != 0)
+ *                                                            python/qldpc/misc/_experiment.py:208-209
+ *   qd_sampler_*          <- stim sampler.sample(samples) restricted to the code-capacity circuit
+ *                            (rounds = 0)                    python/qldpc/misc/_experiment.py:193-197
+ *   qd_code_capacity_run  <- run_simulation(samples, ...) for rounds = 0, returning the counts that
+ *                            p_sweep sums                    python/qldpc/misc/_experiment.py:154-210
+ *                                                            python/qldpc/misc/p_sweep.py:28-32
+ *   qd_ssf_*              <- (absent from the reference; SURVEY.md Appendix C is the specification)
+ *
+ * Conventions
+ *   - All functions return 0 on success and a negative QD_E* code on failure; the message is
+ *     available from qd_last_error() (thread-local).
+ *   - Bit vectors are packed shot-major: shot s starts at word s*stride; bit j of a shot is bit
+ *     (j & 31) of word (j >> 5).  `stride` is in 32-bit words and must be >= ceil(bits/32);
+ *     padding bits must be zero on input and are written as zero on output.
+ *   - Pointers named d_* are device pointers on the handle's device; h_* are host pointers.
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Handles are not thread-safe; use one handle per host thread / per stream.
+ *   - There is no CPU fallback: every entry point fails with QD_ENODEV when no CUDA device is
+ *     usable.
+ */
+#ifndef QLDPC_B200_H
+#define QLDPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QD_ABI_VERSION 1
+
+#define QD_EINVAL   (-1)   /* bad argument                       */
+#define QD_ENODEV   (-2)   /* no usable CUDA device              */
+#define QD_ECUDA    (-3)   /* CUDA runtime error                 */
+#define QD_ENOMEM   (-4)   /* allocation failure                 */
+#define QD_EUNSUP   (-5)   /* graph geometry not supported       */
+
+#define QD_BP_PRODUCT_SUM 0   /* bp_method "ps"         */
+#define QD_BP_MIN_SUM     3   /* bp_method "ms" / "msl" */
+
+#define QD_PREC_F64 64       /* reproduces the fp64 operation order of the reference decoder  */
+#define QD_PREC_F32 32       /* faster, not bit-reproducible                                  */
+
+typedef struct qd_graph    qd_graph;
+typedef struct qd_logicals qd_logicals;
+typedef struct qd_sampler  qd_sampler;
+typedef struct qd_bp       qd_bp;
+typedef struct qd_ssf      qd_ssf;
+
+int         qd_abi_version(void);
+const char *qd_last_error(void);
+int         qd_device_count(void);
+/* multiprocessor count, max opt-in shared memory per block (bytes), clock (kHz) of a device */
+int         qd_device_info(int device, int *sm_count, int *smem_per_block_optin, int *clock_khz);
+
+/* ---- Tanner graph: H (m x n) in CSR with sorted column indices, host arrays ---------------- */
+int qd_graph_create(int32_t m, int32_t n, int64_t nnz, const int32_t *h_row_ptr,
+                    const int32_t *h_col_idx, int device, qd_graph **out);
+int qd_graph_destroy(qd_graph *g);
+
+/* ---- logical operators: dense k x n 0/1 bytes (host) -------------------------------------- */
+int qd_logicals_create(int32_t k, int32_t n, const uint8_t *h_dense, int device, qd_logicals **out);
+int qd_logicals_destroy(qd_logicals *l);
+
+/* ---- Philox4x32-10 Bernoulli sampler: bit j of shot g = philox(key=seed,
+ *      ctr=(g_lo, g_hi, j/4, stream_id))[j%4] < h_threshold[j] ------------------------------ */
+int qd_sampler_create(int32_t nbits, const uint32_t *h_threshold, int device, qd_sampler **out);
+int qd_sampler_destroy(qd_sampler *s);
+int qd_sampler_run(qd_sampler *s, uint64_t seed, uint32_t stream_id, int64_t shot0, int64_t shots,
+                   uint32_t *d_bits, int32_t stride, void *stream);
+
+/* ---- H @ v mod 2, batched and bit-packed --------------------------------------------------- */
+int qd_syndrome_batch(qd_graph *g, const uint32_t *d_vec, int32_t vec_stride, int64_t shots,
+                      uint32_t *d_synd, int32_t synd_stride, void *stream);
+
+/* ---- fail[s] = any(L @ (a[s] ^ b[s]) mod 2); d_b may be NULL; d_fail_count (nullable) is
+ *      incremented by the number of failing shots ------------------------------------------- */
+int qd_logical_fail_batch(qd_logicals *l, const uint32_t *d_a, const uint32_t *d_b, int32_t stride,
+                          int64_t shots, uint8_t *d_fail, unsigned long long *d_fail_count,
+                          void *stream);
+
+/* ---- belief propagation -------------------------------------------------------------------- */
+/* h_channel_probs: n priors.  max_iter == 0 -> n.  ms_scaling_factor == 0 -> 1 - 2^-iteration. */
+int qd_bp_create(qd_graph *g, const double *h_channel_probs, int32_t max_iter, int32_t method,
+                 double ms_scaling_factor, int32_t precision, qd_bp **out);
+int qd_bp_destroy(qd_bp *d);
+/* launch geometry override for tuning (threads per CTA, shots in flight per CTA, CTAs per SM);
+ * 0 keeps the heuristic value.  Fails if the configuration does not fit shared memory. */
+int qd_bp_configure(qd_bp *d, int32_t threads, int32_t slots, int32_t ctas_per_sm);
+int qd_bp_get_config(qd_bp *d, int32_t *threads, int32_t *slots, int32_t *ctas_per_sm,
+                     int32_t *smem_bytes, int32_t *grid);
+
+/* Decode `shots` packed syndromes.  Required: d_synd, d_corr.  Optional (NULL to skip):
+ *   d_converged[shots], d_iters[shots], d_llr[shots*n] (posterior log-ratio of the last
+ *   iteration), and the fused failure epilogue: d_err (the sampled error / readout the syndrome
+ *   came from) + logicals -> d_fail[shots] = any(L (err ^ corr)), and d_counters[4] +=
+ *   {failures, shots, non_converged, iterations}.                                             */
+int qd_bp_decode_batch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int64_t shots,
+                       uint32_t *d_corr, int32_t corr_stride, uint8_t *d_converged,
+                       int32_t *d_iters, double *d_llr, const uint32_t *d_err, int32_t err_stride,
+                       qd_logicals *logicals, uint8_t *d_fail, int64_t *d_counters, void *stream);
+/* Same with HOST buffers: chunked, double-buffered H2D -> decode -> D2H; returns when done. */
+int qd_bp_decode_batch_host(qd_bp *d, const uint32_t *h_synd, int32_t synd_stride, int64_t shots,
+                            uint32_t *h_corr, int32_t corr_stride, uint8_t *h_converged,
+                            int32_t *h_iters);
+/* One shot, byte-per-bit host I/O: the literal bp_decoder.decode() replacement. */
+int qd_bp_decode_one(qd_bp *d, const uint8_t *h_syndrome, uint8_t *h_decoding, int32_t *converged,
+                     int32_t *iters, double *h_llr);
+
+/* ---- small-set-flip ------------------------------------------------------------------------ */
+/* hz: graph of the checks whose syndrome is decoded; generators: rows of Hx (host CSR).        */
+int qd_ssf_create(qd_graph *hz, int32_t num_generators, const int32_t *h_gen_row_ptr,
+                  const int32_t *h_gen_col_idx, int32_t max_rounds, qd_ssf **out);
+int qd_ssf_destroy(qd_ssf *d);
+int qd_ssf_decode_batch(qd_ssf *d, const uint32_t *d_synd, int32_t synd_stride, int64_t shots,
+                        uint32_t *d_corr, int32_t corr_stride, uint8_t *d_converged,
+                        int32_t *d_rounds, const uint32_t *d_err, int32_t err_stride,
+                        qd_logicals *logicals, uint8_t *d_fail, int64_t *d_counters, void *stream);
+int qd_ssf_decode_batch_host(qd_ssf *d, const uint32_t *h_synd, int32_t synd_stride, int64_t shots,
+                             uint32_t *h_corr, int32_t corr_stride, uint8_t *h_converged,
+                             int32_t *h_rounds);
+
+/* ---- code-capacity experiment: sample -> syndrome -> decode -> residual -> logical flag ---- */
+/* Exactly one of bp / ssf is non-NULL.  Decodes global shots [shot0, shot0+shots) drawn from
+ * `sampler` with key `seed`; h_counters[4] = {failures, shots, non_converged, iterations}.
+ * Optional per-shot host outputs (NULL to skip): h_corr (packed, stride words), h_fail,
+ * h_converged, h_iters. */
+int qd_code_capacity_run(qd_graph *hz, qd_bp *bp, qd_ssf *ssf, qd_sampler *sampler,
+                         qd_logicals *logicals, uint64_t seed, int64_t shot0, int64_t shots,
+                         int64_t *h_counters, uint32_t *h_corr, int32_t corr_stride,
+                         uint8_t *h_fail, uint8_t *h_converged, int32_t *h_iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QLDPC_B200_H */

@@ -1,0 +1,124 @@
+"""The drop-in boundary: the C-ABI library loads on a CPU-only box and exports every symbol
+include/qldpc_b200.h declares; compute entry points fail loudly (no CPU fallback) without a GPU;
+the product package never touches oracle/.  CPU only."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "qldpc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qd_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_all_exported(built):
+    from exp_ldpc_b200 import _lib
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/qldpc_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes signature table out of sync with the header"
+    assert L.qd_abi_version() == 1
+
+
+def test_exports_are_plain_c(built):
+    from exp_ldpc_b200 import _lib
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    for name in _declared_symbols():
+        assert name in exported
+
+
+def test_library_is_sm100a_only(built):
+    from exp_ldpc_b200 import _lib
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback_without_gpu(built, code225):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from exp_ldpc_b200 import _lib
+    from exp_ldpc_b200.decoders import TannerGraph, bp_decoder
+    assert _lib.lib().qd_device_count() == 0
+    with pytest.raises(_lib.QdError) as ei:
+        TannerGraph(code225.checks.z)
+    assert ei.value.code == _lib.QD_ENODEV
+    with pytest.raises(_lib.QdError):
+        bp_decoder(code225.checks.z, error_rate=0.01)
+
+
+def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
+    from exp_ldpc_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="CUDA extension not built"):
+        _lib.lib()
+
+
+def test_product_never_imports_the_oracle():
+    """No product source may import, include, link, dlopen or call anything under oracle/
+    (comments that cite the oracle as documentation are stripped first)."""
+    pkg = os.path.join(ROOT, "exp_ldpc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            path = os.path.join(dirpath, f)
+            if f.endswith(".py"):
+                code = re.sub(r'"""(.|\n)*?"""', "", open(path).read())
+                code = re.sub(r"#.*", "", code)
+                assert not re.search(r"pyoracle|libqldpc_oracle|import\s+oracle\b|from\s+oracle\b|orc_", code), path
+            elif f.endswith((".cu", ".cuh", ".h", ".cpp")):
+                code = re.sub(r"/\*(.|\n)*?\*/", "", open(path).read())
+                code = re.sub(r"//.*", "", code)
+                assert not re.search(r"oracle|orc_", code), path
+    # and the built library does not link it
+    from exp_ldpc_b200 import _lib
+    if os.path.exists(_lib.LIB_PATH):
+        out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+        assert "oracle" not in out
+
+
+def test_pack_unpack_roundtrip():
+    from exp_ldpc_b200.decoders import bernoulli_thresholds, pack_bits, row_words, unpack_bits
+    rng = np.random.default_rng(0)
+    for nbits in (1, 31, 32, 33, 108, 225, 1600):
+        b = rng.integers(0, 2, size=(7, nbits)).astype(np.uint8)
+        p = pack_bits(b)
+        assert p.dtype == np.uint32 and p.shape == (7, row_words(nbits)) and p.shape[1] % 4 == 0
+        assert np.array_equal(unpack_bits(p, nbits), b)
+        j = nbits - 1
+        assert ((p[:, j >> 5] >> (j & 31)) & 1).tolist() == b[:, j].tolist()
+    from oracle import pyoracle as po
+    q = np.array([0.0, 1e-12, 0.05, 0.5, 1.0])
+    assert np.array_equal(bernoulli_thresholds(q), po.thresholds(q))
+
+
+def test_shard_range_covers_everything():
+    from exp_ldpc_b200.experiment import binomial_ci, shard_range
+    for total in (0, 1, 10, 1000, 12345):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    lo, hi = binomial_ci(50, 1000)
+    assert lo < 0.05 < hi and 0.03 < lo and hi < 0.07
+
+
+def test_noise_model_flip_probability():
+    from exp_ldpc_b200.experiment import depolarizing_noise
+    nm = depolarizing_noise(0.03, 0.03)
+    assert abs(nm.code_capacity_flip_probability() - (0.02 + 0.03 - 2 * 0.02 * 0.03)) < 1e-15
+    assert abs(depolarizing_noise(0.03, 0.0).code_capacity_flip_probability() - 0.02) < 1e-15

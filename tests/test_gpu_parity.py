@@ -1,0 +1,248 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on identical
+seeded inputs and against the committed golden vectors.  Bar: bit-exact for syndromes, logical
+flags, SSF and the fp64 BP path (hard decisions, iteration counts, convergence flags);
+>= 99.99 % is the north-star floor for BP — the fp64 path is held to 100 %."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(built):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def codes(code225, code1600):
+    return {"hgp225": code225, "hgp1600": code1600}
+
+
+def test_sampler_bit_exact(gpu, code225):
+    import torch
+    from exp_ldpc_b200.decoders import Sampler, row_words, unpack_bits
+    from oracle import pyoracle as po
+    for n, q in ((225, 0.05), (37, 0.3), (1600, 0.01)):
+        stride = row_words(n)
+        smp = Sampler(q, n)
+        for shot0, shots, seed, stream in ((0, 300, 0, 0), (2 ** 33 + 5, 64, 12345678901234567, 3)):
+            d = torch.full((shots, stride), 0xFFFFFFFF - 2 ** 32, dtype=torch.int32, device=gpu)
+            smp.run_device(seed, stream, shot0, shots, d, stride)
+            torch.cuda.synchronize()
+            got = d.cpu().numpy().view(np.uint32)
+            want = po.sample_bits(seed, stream, shot0, shots, po.thresholds(q, n))
+            assert np.array_equal(unpack_bits(got, n), want)
+            assert not (got[:, (n + 31) // 32:] != 0).any()                       # padding words are zero
+            if n % 32:
+                assert not (got[:, n // 32] >> (n % 32)).any()                    # padding bits are zero
+
+
+@pytest.mark.parametrize("which", ["hgp225", "hgp1600"])
+def test_syndrome_and_logical_flag_bit_exact(gpu, codes, which):
+    import torch
+    from exp_ldpc_b200.decoders import Logicals, TannerGraph, pack_bits, row_words, unpack_bits
+    from oracle import pyoracle as po
+    code = codes[which]
+    hz, lz = code.checks.z, code.logicals.z
+    m, n = hz.shape
+    shots = 257
+    rng = np.random.default_rng(1)
+    e = rng.integers(0, 2, size=(shots, n)).astype(np.uint8)
+    e[0] = 0
+    e[1] = 1
+    c = rng.integers(0, 2, size=(shots, n)).astype(np.uint8)
+    g = TannerGraph(hz)
+    L = Logicals(lz)
+    es, ss = row_words(n), row_words(m)
+    d_e = torch.from_numpy(pack_bits(e, es).view(np.int32)).to(gpu)
+    d_c = torch.from_numpy(pack_bits(c, es).view(np.int32)).to(gpu)
+    d_s = torch.empty((shots, ss), dtype=torch.int32, device=gpu)
+    d_f = torch.empty(shots, dtype=torch.uint8, device=gpu)
+    d_n = torch.zeros(1, dtype=torch.int64, device=gpu)
+    g.syndrome_batch_device(d_e, es, shots, d_s, ss)
+    L.fail_batch_device(d_e, d_c, es, shots, d_f, d_n)
+    torch.cuda.synchronize()
+    got = unpack_bits(d_s.cpu().numpy().view(np.uint32), m)
+    want = np.stack([po.syndrome(hz, e[s]) for s in range(shots)])
+    assert np.array_equal(got, want)
+    wantf = np.array([po.logical_fail(lz, e[s] ^ c[s]) for s in range(shots)], dtype=np.uint8)
+    assert np.array_equal(d_f.cpu().numpy(), wantf) and int(d_n.item()) == int(wantf.sum())
+    # linearity: syndrome(a ^ b) = syndrome(a) ^ syndrome(b)
+    d_x = torch.bitwise_xor(d_e, d_c)
+    d_s2 = torch.empty_like(d_s)
+    d_s3 = torch.empty_like(d_s)
+    g.syndrome_batch_device(d_c, es, shots, d_s2, ss)
+    g.syndrome_batch_device(d_x, es, shots, d_s3, ss)
+    torch.cuda.synchronize()
+    assert torch.equal(d_s3, torch.bitwise_xor(d_s, d_s2))
+
+
+def _run_gpu_case(name, codes, precision="f64", config=None):
+    from exp_ldpc_b200.experiment import CodeCapacityExperiment
+    from tests_golden_cases import CASES, case_probabilities
+    key, decoder, opts, p, shots, seed = CASES[name]
+    q, prior = case_probabilities(p)
+    exp = CodeCapacityExperiment(codes[key], q, prior, decoder, opts, precision=precision)
+    if config and decoder == "bp":
+        exp.decoder.configure(**config)
+    return exp.run(shots, seed=seed, per_shot=True)
+
+
+def _all_case_names():
+    from tests_golden_cases import CASES
+    return list(CASES)
+
+
+@pytest.mark.parametrize("name", _all_case_names())
+def test_decoders_match_committed_golden_vectors(gpu, codes, name):
+    g = np.load(os.path.join(GOLDEN, "decoder_vectors.npz"))
+    out = _run_gpu_case(name, codes)
+    assert np.array_equal(np.packbits(out["decodings"], axis=1), g[name + "_dec"])
+    assert np.array_equal(out["iters"], g[name + "_iters"])
+    assert np.array_equal(out["fail"], g[name + "_fail"])
+    assert np.array_equal(out["converged"], g[name + "_conv"])
+    assert out["failures"] == int(g[name + "_fail"].sum()) and out["shots"] == len(g[name + "_fail"])
+    assert out["non_converged"] == int((g[name + "_conv"] == 0).sum()) and out["iters_total"] == int(g[name + "_iters"].sum())
+
+
+@pytest.mark.parametrize("name", ["ms_sched_225", "ps_225", "ms_sched_1600"])
+@pytest.mark.parametrize("config", [dict(threads=32, slots=1, ctas_per_sm=1), dict(threads=96, slots=3, ctas_per_sm=2),
+                                    dict(threads=1024, slots=1, ctas_per_sm=1), dict(threads=256, slots=5, ctas_per_sm=1)])
+def test_bp_result_independent_of_launch_geometry(gpu, codes, name, config):
+    g = np.load(os.path.join(GOLDEN, "decoder_vectors.npz"))
+    out = _run_gpu_case(name, codes, config=config)
+    assert np.array_equal(np.packbits(out["decodings"], axis=1), g[name + "_dec"])
+    assert np.array_equal(out["iters"], g[name + "_iters"])
+
+
+@pytest.mark.parametrize("method,alpha,p", [("ms", 0.0, 0.01), ("ms", 0.0, 0.04), ("ms", 0.8, 0.02), ("ps", 0.0, 0.03)])
+def test_bp_fresh_seeds_against_live_oracle(gpu, code225, method, alpha, p):
+    from exp_ldpc_b200.experiment import CodeCapacityExperiment
+    from oracle import pyoracle as po
+    q, prior = 2 * p / 3 + p - 4 / 3 * p * p, 2 * p / 3
+    shots = 5000
+    opts = dict(max_iter=40, bp_method=method, ms_scaling_factor=alpha)
+    got = CodeCapacityExperiment(code225, q, prior, "bp", opts).run(shots, seed=99, shot0=10 ** 6, per_shot=True)
+    ref = po.run_code_capacity(code225.checks.z, code225.logicals.z, q, prior, decoder="bp", max_iter=40, bp_method=method,
+                               ms_scaling_factor=alpha, seed=99, shot0=10 ** 6, shots=shots, per_shot=True)
+    agree = (got["decodings"] == ref["decodings"]).all(axis=1).mean()
+    assert agree == 1.0, f"hard decisions agree on {agree:.6%} of shots"
+    assert np.array_equal(got["iters"], ref["iters"]) and np.array_equal(got["fail"], ref["fail"])
+    assert got["failures"] == ref["failures"]
+
+
+def test_bp_decoder_duck_type_matches_oracle(gpu, code225):
+    """The ldpc.bp_decoder call shape used at _experiment.py:110-117."""
+    from exp_ldpc_b200.decoders import bp_decoder
+    from oracle import pyoracle as po
+    hz = code225.checks.z
+    m, n = hz.shape
+    probs = np.linspace(0.01, 0.05, n)
+    opts = dict(max_iter=n, bp_method="ps", ms_scaling_factor=0, osd_method="osd_cs", osd_order=7)   # OSD keys ignored
+    dec = bp_decoder(hz.tocoo(), channel_probs=probs, **opts)
+    ref = po.OracleBP(hz, channel_probs=probs, max_iter=n, bp_method="ps", ms_scaling_factor=0)
+    errs = po.sample_bits(1, 0, 0, 20, po.thresholds(0.03, n))
+    for e in errs:
+        s = po.syndrome(hz, e).astype(np.float64)            # the reference hands in float64 0/1
+        out = dec.decode(s)
+        want = ref.decode(s)
+        assert out.shape == (n,) and out.dtype.kind == "i" and np.array_equal(out, want)
+        assert dec.converge == ref.converge and dec.iter == ref.iter
+        assert np.allclose(dec.log_prob_ratios, ref.log_prob_ratios, rtol=1e-12, atol=1e-12)
+    zero = dec.decode(np.zeros(m))
+    assert not zero.any() and dec.converge == 1 and dec.iter == 1
+    with pytest.raises(ValueError):
+        dec.decode(np.zeros(m + 1))
+    with pytest.raises(ValueError):
+        bp_decoder(hz, channel_probs=np.full(n + 1, 0.1))
+    with pytest.raises(ValueError):
+        bp_decoder(hz)
+    with pytest.raises(ValueError):
+        bp_decoder(hz, error_rate=0.1, bp_method="nope")
+
+
+def test_decode_batch_host_api(gpu, code225):
+    from exp_ldpc_b200.decoders import bp_decoder, ssf_decoder
+    from oracle import pyoracle as po
+    hz, hx = code225.checks.z, code225.checks.x
+    m, n = hz.shape
+    errs = po.sample_bits(8, 0, 0, 3000, po.thresholds(0.03, n))
+    synd = np.stack([po.syndrome(hz, e) for e in errs])
+    dec = bp_decoder(hz, error_rate=0.02, max_iter=25, bp_method="ms", ms_scaling_factor=0.0)
+    ref = po.OracleBP(hz, error_rate=0.02, max_iter=25, bp_method="ms", ms_scaling_factor=0.0)
+    corr, conv, its = dec.decode_batch(synd)
+    assert corr.shape == (3000, n)
+    for s in range(0, 3000, 17):
+        want = ref.decode(synd[s])
+        assert np.array_equal(corr[s], want) and conv[s] == ref.converge and its[s] == ref.iter
+    # converged shots reproduce the syndrome (H c = s)
+    ok = conv.astype(bool)
+    assert np.array_equal((hz @ corr[ok].T.astype(np.int64)).T % 2, synd[ok])
+    # empty and single-shot batches
+    c0, v0, i0 = dec.decode_batch(np.zeros((0, m), dtype=np.uint8))
+    assert c0.shape == (0, n) and v0.shape == (0,)
+    c1, v1, i1 = dec.decode_batch(synd[5])
+    assert np.array_equal(c1[0], corr[5])
+    # SSF through the same host API
+    sd = ssf_decoder(hz, hx)
+    rs = po.OracleSSF(hz, hx)
+    scorr, sconv, srounds = sd.decode_batch(synd[:400])
+    for s in range(400):
+        want = rs.decode(synd[s])
+        assert np.array_equal(scorr[s], want) and sconv[s] == rs.converge and srounds[s] == rs.rounds
+
+
+def test_run_simulation_signature_and_counts(gpu, code225):
+    from exp_ldpc_b200.experiment import depolarizing_noise, run_simulation
+    from oracle import pyoracle as po
+    p = 0.02
+    prior = lambda p_, *_: 2 / 3 * p_                                         # scripts/p_sweep.py:4-5
+    from functools import partial
+    opts = {"max_iter": 30, "bp_method": "ms", "ms_scaling_factor": 0.0, "osd_method": "osd_cs", "osd_order": 7}
+    flags = run_simulation(1000, code225, partial(prior, p), partial(prior, p), depolarizing_noise, {"p": p, "pm": p},
+                           opts, 0, "bp", seed=3)
+    assert isinstance(flags, list) and len(flags) == 1000 and isinstance(flags[0], bool)
+    q = 2 * p / 3 + p - 4 / 3 * p * p
+    ref = po.run_code_capacity(code225.checks.z, code225.logicals.z, q, 2 * p / 3, decoder="bp", max_iter=30,
+                               bp_method="ms", seed=3, shots=1000, per_shot=True)
+    assert flags == [bool(v) for v in ref["fail"]]
+    with pytest.raises(RuntimeError):
+        run_simulation(10, code225, partial(prior, p), partial(prior, p), depolarizing_noise, {"p": p, "pm": p}, opts, 0, "nope")
+    with pytest.raises(NotImplementedError):
+        run_simulation(10, code225, partial(prior, p), partial(prior, p), depolarizing_noise, {"p": p, "pm": p}, opts, 0, "bposd")
+
+
+def test_full_size_properties_n6400(gpu, code6400):
+    """BASELINE config 2 at full code size, size-independent properties: converged shots satisfy
+    H c = s; counters add up; results do not depend on how the batch is split."""
+    import torch
+    from exp_ldpc_b200.experiment import CodeCapacityExperiment
+    p = 0.01
+    q, prior = 2 * p / 3 + p - 4 / 3 * p * p, 2 * p / 3
+    exp = CodeCapacityExperiment(code6400, q, prior, "bp", dict(max_iter=32, bp_method="ms", ms_scaling_factor=0.0))
+    shots = 3000
+    a = exp.run(shots, seed=1, per_shot=True)
+    hz = code6400.checks.z
+    ok = a["converged"].astype(bool)
+    assert ok.sum() > 0 and a["shots"] == shots and a["non_converged"] == int((~ok).sum())
+    from oracle import pyoracle as po
+    errs = po.sample_bits(1, 0, 0, 64, po.thresholds(q, hz.shape[1]))
+    for s in range(64):
+        synd = po.syndrome(hz, errs[s])
+        if ok[s]:
+            assert np.array_equal(po.syndrome(hz, a["decodings"][s].astype(np.uint8)), synd)
+    b1 = exp.run(1000, seed=1, shot0=0, per_shot=True)
+    b2 = exp.run(2000, seed=1, shot0=1000, per_shot=True)
+    assert np.array_equal(np.concatenate([b1["decodings"], b2["decodings"]]), a["decodings"])
+    assert b1["failures"] + b2["failures"] == a["failures"] and a["iters_total"] == int(a["iters"].sum())
+    # spot-check against the oracle on the first shots
+    ref = po.run_code_capacity(hz, code6400.logicals.z, q, prior, decoder="bp", max_iter=32, bp_method="ms", seed=1,
+                               shots=48, per_shot=True)
+    assert np.array_equal(ref["decodings"], a["decodings"][:48]) and np.array_equal(ref["iters"], a["iters"][:48])
