@@ -167,8 +167,8 @@ struct qd_graph {
     int device = 0;
     GraphDev dev{};
     std::vector<int32_t> row_ptr, col_idx, col_ptr;
-    std::vector<uint32_t> row_desc, col_desc, csc_pos, csc_row;
-    DevBuf d_row_desc, d_col_desc, d_csc_pos, d_csc_row, d_row_ptr, d_col_idx;
+    std::vector<uint32_t> row_desc, col_desc, csc_pos, csc_row, fpos_of_pos;
+    DevBuf d_row_desc, d_col_desc, d_csc_pos, d_csc_row, d_row_ptr, d_col_idx, d_fpos;
     int sm_count = 0, smem_optin = 0;
 };
 
@@ -189,10 +189,13 @@ typedef void (*bp_kernel_fn)(const BpParams);
 struct qd_bp {
     qd_graph *g = nullptr;
     int max_iter = 0, method = 0, precision = 64;
-    int vmax = 4;
+    int vmax = 4;          // register tile of a column
+    int rd = 0;            // compile-time row degree of the selected kernel (0 = generic rows)
+    int idx_bytes = 2;     // bytes per message position in vidx
+    int stage_idx = 0;     // vidx + priors staged in shared memory
     int threads = 0, slots = 0, ctas_per_sm = 0;
     size_t smem = 0;
-    DevBuf d_prior, d_alpha, d_next;
+    DevBuf d_prior, d_alpha, d_next, d_vidx, d_chunk_deg;
     // host-buffer pipeline state
     cudaStream_t streams[2] = {nullptr, nullptr};
     cudaEvent_t done[2] = {nullptr, nullptr};
@@ -282,19 +285,27 @@ extern "C" int qd_graph_create(int32_t m, int32_t n, int64_t nnz, const int32_t 
         }
     }
     if (max_row > 255) return fail(QD_EUNSUP, "row degree > 255");
+    int min_row = max_row;
+    for (int i = 0; i < m; ++i) min_row = std::min(min_row, h_row_ptr[i + 1] - h_row_ptr[i]);
+    const int regular_deg = (m > 0 && min_row == max_row) ? max_row : 0;
     // message layout: rows padded to an odd pitch when that wastes < 1/3 of the array
     int pitch = max_row | 1;
-    const bool padded = m > 0 && (int64_t)pitch * m <= nnz + nnz / 3 + 64;
+    const bool padded = m > 0 && (regular_deg > 0 || (int64_t)pitch * m <= nnz + nnz / 3 + 64);
+    const int fb = std::max(8, (max_row + 7) / 8 * 8);     // decision-flip flag bytes per row
     g->row_desc.resize(std::max(m, 1));
     std::vector<int> pos_of_edge(std::max<int64_t>(nnz, 1));
+    const int npos = padded ? pitch * m : (int)nnz;
+    if (npos >= (1 << 24)) return fail(QD_EUNSUP, "message array too large");
+    g->fpos_of_pos.assign(std::max(npos, 1), 0u);
     for (int i = 0; i < m; ++i) {
         const int lo = h_row_ptr[i], deg = h_row_ptr[i + 1] - lo;
         const int pos0 = padded ? i * pitch : lo;
         g->row_desc[i] = (uint32_t)pos0 | ((uint32_t)deg << 24);
-        for (int k = 0; k < deg; ++k) pos_of_edge[lo + k] = pos0 + k;
+        for (int k = 0; k < deg; ++k) {
+            pos_of_edge[lo + k] = pos0 + k;
+            g->fpos_of_pos[pos0 + k] = (uint32_t)(i * fb + k);
+        }
     }
-    const int npos = padded ? pitch * m : (int)nnz;
-    if (npos >= (1 << 24)) return fail(QD_EUNSUP, "message array too large");
     // CSC: column lists with rows ascending
     g->col_ptr.assign(n + 1, 0);
     for (int64_t e = 0; e < nnz; ++e) g->col_ptr[h_col_idx[e] + 1]++;
@@ -324,10 +335,15 @@ extern "C" int qd_graph_create(int32_t m, int32_t n, int64_t nnz, const int32_t 
     if ((rc = upload(g->d_csc_row, g->csc_row))) return rc;
     if ((rc = upload(g->d_row_ptr, g->row_ptr))) return rc;
     if ((rc = upload(g->d_col_idx, g->col_idx))) return rc;
+    if ((rc = upload(g->d_fpos, g->fpos_of_pos))) return rc;
     GraphDev &d = g->dev;
     d.m = m; d.n = n; d.nnz = (int)nnz;
     d.nwm = words_for(m); d.nwn = words_for(n);
     d.npos = npos;
+    d.pitch = padded ? pitch : 0;
+    d.regular_deg = regular_deg;
+    d.fb = fb;
+    d.fpos_of_pos = g->d_fpos.as<uint32_t>();
     d.max_row_deg = max_row; d.max_col_deg = max_col;
     d.row_desc = g->d_row_desc.as<uint32_t>();
     d.col_desc = g->d_col_desc.as<uint32_t>();
@@ -444,53 +460,75 @@ extern "C" int qd_logical_fail_batch(qd_logicals *l, const uint32_t *d_a, const 
 // =============================================================================================
 // BP
 // =============================================================================================
-template <typename real, int METHOD>
-static bp_kernel_fn pick_bp(int vmax, int threads)
+// ---- kernel instantiation table ---------------------------------------------------------------
+// specialised: regular row degree RD in {6,7,8,9}, column tile 4 or 8, 16-bit message positions;
+// generic:     any row degree (<= 255; <= 16 for product-sum), column tile 8 or 16, 32-bit positions.
+template <typename real, int METHOD, int MAXT>
+static bp_kernel_fn pick_bp_rd(int rd, int vmax)
 {
-    const bool small = threads <= 256;
-    switch (vmax) {
-    case 4:  return small ? bp_kernel<real, METHOD, 4, 256> : bp_kernel<real, METHOD, 4, 1024>;
-    case 8:  return small ? bp_kernel<real, METHOD, 8, 256> : bp_kernel<real, METHOD, 8, 1024>;
-    default: return small ? bp_kernel<real, METHOD, 16, 256> : bp_kernel<real, METHOD, 16, 1024>;
+#ifdef QD_FAST_BUILD
+    if (rd == 7 && vmax == 4) return bp_kernel<real, METHOD, 7, 4, uint16_t, MAXT>;
+    return vmax <= 8 ? bp_kernel<real, METHOD, 0, 8, uint32_t, MAXT> : bp_kernel<real, METHOD, 0, 16, uint32_t, MAXT>;
+#else
+    switch (rd * 100 + vmax) {
+    case 604: return bp_kernel<real, METHOD, 6, 4, uint16_t, MAXT>;
+    case 608: return bp_kernel<real, METHOD, 6, 8, uint16_t, MAXT>;
+    case 704: return bp_kernel<real, METHOD, 7, 4, uint16_t, MAXT>;
+    case 708: return bp_kernel<real, METHOD, 7, 8, uint16_t, MAXT>;
+    case 804: return bp_kernel<real, METHOD, 8, 4, uint16_t, MAXT>;
+    case 808: return bp_kernel<real, METHOD, 8, 8, uint16_t, MAXT>;
+    case 904: return bp_kernel<real, METHOD, 9, 4, uint16_t, MAXT>;
+    case 908: return bp_kernel<real, METHOD, 9, 8, uint16_t, MAXT>;
+    case 8:   return bp_kernel<real, METHOD, 0, 8, uint32_t, MAXT>;
+    default:  return bp_kernel<real, METHOD, 0, 16, uint32_t, MAXT>;
     }
+#endif
+}
+
+template <typename real, int METHOD>
+static bp_kernel_fn pick_bp(int rd, int vmax, int threads)
+{
+    if (threads <= 512) return pick_bp_rd<real, METHOD, 512>(rd, vmax);
+    if (threads <= 768) return pick_bp_rd<real, METHOD, 768>(rd, vmax);
+    return pick_bp_rd<real, METHOD, 1024>(rd, vmax);
 }
 
 static bp_kernel_fn bp_kernel_for(const qd_bp *d)
 {
     if (d->precision == QD_PREC_F64)
-        return d->method == QD_BP_MIN_SUM ? pick_bp<double, QD_BP_MIN_SUM>(d->vmax, d->threads)
-                                          : pick_bp<double, QD_BP_PRODUCT_SUM>(d->vmax, d->threads);
-    return d->method == QD_BP_MIN_SUM ? pick_bp<float, QD_BP_MIN_SUM>(d->vmax, d->threads)
-                                      : pick_bp<float, QD_BP_PRODUCT_SUM>(d->vmax, d->threads);
+        return d->method == QD_BP_MIN_SUM ? pick_bp<double, QD_BP_MIN_SUM>(d->rd, d->vmax, d->threads)
+                                          : pick_bp<double, QD_BP_PRODUCT_SUM>(d->rd, d->vmax, d->threads);
+    return d->method == QD_BP_MIN_SUM ? pick_bp<float, QD_BP_MIN_SUM>(d->rd, d->vmax, d->threads)
+                                      : pick_bp<float, QD_BP_PRODUCT_SUM>(d->rd, d->vmax, d->threads);
 }
 
-static size_t bp_smem(const qd_bp *d, int slots)
+static size_t bp_smem(const qd_bp *d, int slots, bool stage)
 {
     const GraphDev &g = d->g->dev;
-    return d->precision == QD_PREC_F64 ? bp_smem_bytes<double>(g.npos, g.nwn, g.nwm, slots)
-                                       : bp_smem_bytes<float>(g.npos, g.nwn, g.nwm, slots);
+    return bp_smem_layout(g.npos, g.m, g.n, g.fb, g.nwn, g.nwm, slots, d->precision == QD_PREC_F64 ? 8 : 4,
+                          d->vmax * d->idx_bytes, stage).total;
 }
 
-// default launch geometry: fill shared memory with shots, keep >= 1024 threads per SM resident
+// default launch geometry: stage the column index + priors in shared memory when that still
+// leaves room for a shot, then fill the rest of shared memory with shots
 static int bp_default_config(qd_bp *d)
 {
-    const GraphDev &g = d->g->dev;
     const size_t budget = (size_t)d->g->smem_optin;            // per CTA (227 KB on B200)
-    const size_t sm_budget = budget;                           // per SM, minus 1 KB/CTA reserved
-    const size_t per_slot = bp_smem(d, 1);
-    if (per_slot > budget)
-        return fail(QD_EUNSUP, "Tanner graph too large for the shared-memory BP kernel (" + std::to_string(per_slot) +
-                                   " B per shot > " + std::to_string(budget) + " B)");
-    const int work = std::max(g.n, g.m);
-    int threads = 128;
-    while (threads < 1024 && threads * 2 <= ((work + 31) & ~31)) threads *= 2;   // <= one item per thread per slot
-    int total_slots = (int)std::min<size_t>(32, sm_budget / (per_slot + 64));
-    int ctas = std::max(1, std::min(total_slots, 1024 / threads));
-    ctas = std::min(ctas, 8);
-    int slots = std::max(1, std::min(8, total_slots / ctas));
-    while (ctas > 1 && (bp_smem(d, slots) + 1024) * ctas > sm_budget) --ctas;
+    if (bp_smem(d, 1, false) > budget)
+        return fail(QD_EUNSUP, "Tanner graph too large for the shared-memory BP kernel (" +
+                                   std::to_string(bp_smem(d, 1, false)) + " B per shot > " + std::to_string(budget) + " B)");
+    d->stage_idx = bp_smem(d, 1, true) <= budget ? 1 : 0;
+    int slots = 1;
+    while (slots < 16 && bp_smem(d, slots + 1, d->stage_idx) <= budget) ++slots;
+    int ctas = 1;
+    // small graphs: several CTAs per SM instead of very many slots per CTA
+    while (slots >= 8 && ctas < 4) { slots /= 2; ctas *= 2; }
+    const GraphDev &g = d->g->dev;
+    const long long work = (long long)slots * std::max(g.n, g.m);
+    int threads = ctas > 1 ? 512 : 1024;
+    while (threads > 128 && (long long)threads * 2 > work) threads /= 2;
     d->threads = threads; d->slots = slots; d->ctas_per_sm = ctas;
-    d->smem = bp_smem(d, slots);
+    d->smem = bp_smem(d, slots, d->stage_idx);
     return 0;
 }
 
@@ -511,11 +549,25 @@ extern "C" int qd_bp_create(qd_graph *g, const double *h_channel_probs, int32_t 
     d->max_iter = max_iter > 0 ? max_iter : gd.n;   // ldpc convention: 0 -> n
     d->method = method;
     d->precision = precision;
-    d->vmax = gd.max_col_deg <= 4 ? 4 : gd.max_col_deg <= 8 ? 8 : 16;
     if (gd.max_col_deg > 16) return fail(QD_EUNSUP, "column degree > 16 not supported by the shared-memory BP kernel");
-    const int dmax = d->vmax == 4 ? 8 : 16;
-    if (method == QD_BP_PRODUCT_SUM && gd.max_row_deg > dmax)
-        return fail(QD_EUNSUP, "product-sum: row degree exceeds the register tile for this column class");
+    const bool special = gd.regular_deg >= 6 && gd.regular_deg <= 9 && gd.max_col_deg <= 8 && gd.npos < 65535 &&
+                         gd.pitch == (gd.regular_deg | 1);
+#ifdef QD_FAST_BUILD
+    const bool have_special = special && gd.regular_deg == 7 && gd.max_col_deg <= 4;
+#else
+    const bool have_special = special;
+#endif
+    if (have_special) {
+        d->rd = gd.regular_deg;
+        d->vmax = gd.max_col_deg <= 4 ? 4 : 8;
+        d->idx_bytes = 2;
+    } else {
+        d->rd = 0;
+        d->vmax = gd.max_col_deg <= 8 ? 8 : 16;
+        d->idx_bytes = 4;
+        if (method == QD_BP_PRODUCT_SUM && gd.max_row_deg > 16)
+            return fail(QD_EUNSUP, "product-sum: row degree > 16 not supported by the shared-memory BP kernel");
+    }
     // priors in the decoder's domain, computed in double with the host libm (same as the oracle)
     std::vector<double> pr(gd.n), al(d->max_iter + 1, 0.0);
     for (int j = 0; j < gd.n; ++j) {
@@ -523,8 +575,13 @@ extern "C" int qd_bp_create(qd_graph *g, const double *h_channel_probs, int32_t 
         if (!(p > 0.0) || !(p < 1.0)) return fail(QD_EINVAL, "channel probabilities must lie in (0, 1)");
         pr[j] = method == QD_BP_MIN_SUM ? std::log((1.0 - p) / p) : p / (1.0 - p);
     }
+    // al[0] = the fixed scaling factor (0 selects the 1 - 2^-it schedule, formed exactly on the device);
+    // al[1..] = the schedule as the host computes it (reference values, checked against the device formula)
+    al[0] = ms_scaling_factor;
     for (int it = 1; it <= d->max_iter; ++it)
         al[it] = ms_scaling_factor == 0.0 ? 1.0 - std::pow(2.0, -1.0 * it / 1.0) : ms_scaling_factor;
+    for (int it = 1; it <= std::min(d->max_iter, 1100); ++it)
+        if (ms_scaling_factor == 0.0 && al[it] != 1.0 - std::ldexp(1.0, -it)) return fail(QD_ECUDA, "alpha schedule mismatch");
     if (precision == QD_PREC_F64) {
         if ((rc = upload(d->d_prior, pr))) return rc;
         if ((rc = upload(d->d_alpha, al))) return rc;
@@ -532,6 +589,32 @@ extern "C" int qd_bp_create(qd_graph *g, const double *h_channel_probs, int32_t 
         std::vector<float> prf(pr.begin(), pr.end()), alf(al.begin(), al.end());
         if ((rc = upload(d->d_prior, prf))) return rc;
         if ((rc = upload(d->d_alpha, alf))) return rc;
+    }
+    {   // per-column message positions, padded to the column tile, ~0 = no edge
+        const size_t cnt = (size_t)gd.n * d->vmax;
+        if (d->idx_bytes == 2) {
+            std::vector<uint16_t> v(cnt, (uint16_t)0xFFFF);
+            for (int j = 0; j < gd.n; ++j)
+                for (int t = g->col_ptr[j]; t < g->col_ptr[j + 1]; ++t)
+                    v[(size_t)j * d->vmax + (t - g->col_ptr[j])] = (uint16_t)g->csc_pos[t];
+            if ((rc = upload(d->d_vidx, v))) return rc;
+        } else {
+            std::vector<uint32_t> v(cnt, 0xFFFFFFFFu);
+            for (int j = 0; j < gd.n; ++j)
+                for (int t = g->col_ptr[j]; t < g->col_ptr[j + 1]; ++t)
+                    v[(size_t)j * d->vmax + (t - g->col_ptr[j])] = g->csc_pos[t];
+            if ((rc = upload(d->d_vidx, v))) return rc;
+        }
+    }
+    {   // common degree of each 32-column chunk (0 = mixed): lets a warp run an unpredicated column update
+        std::vector<uint8_t> cd((gd.n + 31) / 32, 0);
+        for (int c0 = 0; c0 < gd.n; c0 += 32) {
+            const int d0 = g->col_ptr[c0 + 1] - g->col_ptr[c0];
+            bool same = d0 >= 3 && d0 <= 6 && d0 <= d->vmax;
+            for (int j = c0; j < std::min(gd.n, c0 + 32) && same; ++j) same = (g->col_ptr[j + 1] - g->col_ptr[j]) == d0;
+            cd[c0 / 32] = same ? (uint8_t)d0 : 0;
+        }
+        if ((rc = upload(d->d_chunk_deg, cd))) return rc;
     }
     if ((rc = d->d_next.alloc(sizeof(unsigned long long) * 2))) return rc;
     if ((rc = bp_default_config(d.get()))) return rc;
@@ -551,9 +634,11 @@ extern "C" int qd_bp_configure(qd_bp *d, int32_t threads, int32_t slots, int32_t
     int t = threads > 0 ? threads : d->threads, s = slots > 0 ? slots : d->slots, c = ctas_per_sm > 0 ? ctas_per_sm : d->ctas_per_sm;
     if (t % 32 || t > 1024 || s > 64) return fail(QD_EINVAL, "threads must be a multiple of 32 <= 1024, slots <= 64");
     if (s > t) return fail(QD_EINVAL, "slots must not exceed threads");
-    const size_t smem = bp_smem(d, s);
+    int stage = 1;
+    size_t smem = bp_smem(d, s, true);
+    if (smem > (size_t)d->g->smem_optin) { stage = 0; smem = bp_smem(d, s, false); }
     if (smem > (size_t)d->g->smem_optin) return fail(QD_EUNSUP, "configuration does not fit shared memory");
-    d->threads = t; d->slots = s; d->ctas_per_sm = c; d->smem = smem;
+    d->threads = t; d->slots = s; d->ctas_per_sm = c; d->smem = smem; d->stage_idx = stage;
     return 0;
 }
 
@@ -585,8 +670,9 @@ static int bp_launch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int6
     cudaStream_t st = (cudaStream_t)stream;
     BpParams p{};
     p.g = g;
-    p.prior = d->d_prior.p; p.alpha = d->d_alpha.p;
-    p.max_iter = d->max_iter; p.slots = d->slots;
+    p.prior = d->d_prior.p; p.alpha = d->d_alpha.p; p.vidx = d->d_vidx.p;
+    p.chunk_deg = d->d_chunk_deg.as<uint8_t>();
+    p.max_iter = d->max_iter; p.slots = d->slots; p.stage_idx = d->stage_idx;
     p.synd = d_synd; p.synd_stride = synd_stride; p.shots = shots;
     p.corr = d_corr; p.corr_stride = corr_stride;
     p.conv = d_converged; p.iters = d_iters; p.llr = d_llr;
