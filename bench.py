@@ -133,6 +133,7 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--slots", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--teams", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -202,8 +203,8 @@ def main():
     logicals = Logicals(code.logicals.z, device=local_rank)
     sampler = Sampler(q, n, device=local_rank)
     dec = bp_decoder(graph, error_rate=prior, precision=args.precision, **opts)
-    if args.threads or args.slots or args.ctas:
-        dec.configure(args.threads, args.slots, args.ctas)
+    if args.threads or args.slots or args.ctas or args.teams:
+        dec.configure(args.threads, args.slots, args.ctas, args.teams)
     cfg = dec.config()
     config["launch"] = cfg
 

@@ -27,6 +27,8 @@
 //     bit-reproducible.
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace qd {
@@ -55,7 +57,8 @@ struct BpParams {
     const void *vidx;             // IT[n][VMAX]: message positions of each column, ~0 = none
     const uint8_t *chunk_deg;     // [ceil(n/32)] common degree of the 32 columns of a chunk, 0 = mixed
     int max_iter;
-    int slots;
+    int slots;                    // shots in flight per CTA (all teams)
+    int groups;                   // warp teams per CTA; slots % groups == 0, blockDim % (32 * groups) == 0
     int stage_idx;                // copy vidx + prior into shared memory
     const uint32_t *synd; int synd_stride;
     long long shots;
@@ -151,15 +154,20 @@ template <> __device__ __forceinline__ double pow2_neg<double>(int it) { return 
 template <> __device__ __forceinline__ float pow2_neg<float>(int it) { return it < 127 ? __int_as_float((127 - it) << 23) : 0.0f; }
 
 
-// ---- bit-node update of one column with a compile-time edge count D (no predication).
-// qa[t] = shared address of the t-th edge's message (rows ascending).  Returns the hard decision.
-template <typename real, int METHOD, int D>
-__device__ __forceinline__ unsigned bit_update(const uint32_t (&qa)[D], real pj, real &soft)
+// ---- bit-node update of one column with a compile-time edge count D (no predication), split into
+// load / compute / store so that two slots can be interleaved by the instruction scheduler.
+template <typename real, int D>
+__device__ __forceinline__ void bit_load(const uint32_t (&qa)[D], real (&cv)[D])
 {
-    using A = Ar<real>;
-    real cv[D], pre[D];
 #pragma unroll
     for (int t = 0; t < D; ++t) cv[t] = lds_real(qa[t], real());
+}
+// cv: check->bit messages in; bit->check messages out.  Returns the hard decision.
+template <typename real, int METHOD, int D>
+__device__ __forceinline__ unsigned bit_compute(real (&cv)[D], real pj, real &soft)
+{
+    using A = Ar<real>;
+    real pre[D];
     real temp = pj;
     unsigned dbit;
     if (METHOD == QD_BP_MIN_SUM_K) {
@@ -169,7 +177,7 @@ __device__ __forceinline__ unsigned bit_update(const uint32_t (&qa)[D], real pj,
         soft = temp;
         real suf = (real)0;
 #pragma unroll
-        for (int t = D - 1; t >= 0; --t) { sts_real(qa[t], A::add(pre[t], suf)); suf = A::add(suf, cv[t]); }
+        for (int t = D - 1; t >= 0; --t) { const real c = cv[t]; cv[t] = A::add(pre[t], suf); suf = A::add(suf, c); }
     } else {
 #pragma unroll
         for (int t = 0; t < D; ++t) {
@@ -181,11 +189,18 @@ __device__ __forceinline__ unsigned bit_update(const uint32_t (&qa)[D], real pj,
         real suf = (real)1;
 #pragma unroll
         for (int t = D - 1; t >= 0; --t) {
-            sts_real(qa[t], A::mul(pre[t], suf)); suf = A::mul(suf, cv[t]);
+            const real c = cv[t];
+            cv[t] = A::mul(pre[t], suf); suf = A::mul(suf, c);
             if (suf != suf) suf = (real)1;
         }
     }
     return dbit;
+}
+template <typename real, int D>
+__device__ __forceinline__ void bit_store(const uint32_t (&qa)[D], const real (&cv)[D])
+{
+#pragma unroll
+    for (int t = 0; t < D; ++t) sts_real(qa[t], cv[t]);
 }
 
 // |x| and sign bit through the integer pipe (keeps the fp64 pipe for compares)
@@ -196,6 +211,41 @@ __device__ __forceinline__ unsigned hi_bits(float v) { return (unsigned)__float_
 __device__ __forceinline__ double xor_hi(double v, unsigned m) { return __hiloint2double(__double2hiint(v) ^ (int)m, __double2loint(v)); }
 __device__ __forceinline__ float xor_hi(float v, unsigned m) { return __int_as_float(__float_as_int(v) ^ (int)m); }
 
+
+// ---- min-sum check-node update of a row of compile-time degree RD, register resident.
+// v: bit->check messages in, check->bit messages out.  sign0 = syndrome bit << 31.
+// Sign handling uses the sign BIT instead of (v <= 0): the two differ only for v = +0.0, and then
+// min1 = 0, so every message whose sign would change is a zero, whose sign no later comparison,
+// sum or output can observe.
+template <typename real, int RD>
+__device__ __forceinline__ void check_ms_compute(real (&v)[RD], unsigned sign0, real al)
+{
+    using A = Ar<real>;
+    unsigned sx = sign0;
+    unsigned hk[RD];
+#pragma unroll
+    for (int k = 0; k < RD; ++k) { hk[k] = hi_bits(v[k]); sx ^= hk[k]; v[k] = abs_bits(v[k]); }
+    real m1, m2;
+    if (RD >= 2) {
+        const bool lt = v[1] < v[0];
+        m1 = lt ? v[1] : v[0];
+        m2 = lt ? v[0] : v[1];
+    } else { m1 = v[0]; m2 = A::big(); }
+#pragma unroll
+    for (int k = 2; k < RD; ++k) {
+        const real a = v[k];
+        const bool lt1 = a < m1, lt2 = a < m2;
+        m2 = lt1 ? m1 : (lt2 ? a : m2);
+        m1 = lt1 ? a : m1;
+    }
+    const real m1a = A::mul(m1, al), m2a = A::mul(m2, al);
+#pragma unroll
+    for (int k = 0; k < RD; ++k) {
+        const real out = v[k] == m1 ? m2a : m1a;
+        v[k] = xor_hi(out, (sx ^ hk[k]) & 0x80000000u);
+    }
+}
+
 template <typename real, int METHOD, int RD, int VMAX, typename IT, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) bp_kernel(const BpParams p)
 {
@@ -205,27 +255,51 @@ __global__ void __launch_bounds__(MAXT, 1) bp_kernel(const BpParams p)
     constexpr int RB = (int)sizeof(real);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GraphDev &g = p.g;
-    const int S = p.slots;
-    const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31;
+    const int S_all = p.slots;
+    const int lane = threadIdx.x & 31;
     const int P = RD > 0 ? (RD | 1) : g.pitch;
     const int FB = g.fb;
 
-    const BpSmemLayout L = bp_smem_layout(g.npos, g.m, g.n, FB, g.nwn, g.nwm, S, RB, VMAX * (int)sizeof(IT),
+    const BpSmemLayout L = bp_smem_layout(g.npos, g.m, g.n, FB, g.nwn, g.nwm, S_all, RB, VMAX * (int)sizeof(IT),
                                           p.stage_idx != 0);
-    real *msg = reinterpret_cast<real *>(smem_raw + L.msg);
-    unsigned char *flags = smem_raw + L.flags;                          // [S][m][FB]
-    uint32_t *dec = reinterpret_cast<uint32_t *>(smem_raw + L.bits);     // [S][nwn]
-    uint32_t *syn = dec + (size_t)S * g.nwn;                            // [S][nwm] original syndrome
-    uint32_t *res = syn + (size_t)S * g.nwm;                            // [S][nwm] s ^ H e_hat
-    BpCtl *ctl = reinterpret_cast<BpCtl *>(smem_raw + L.ctl);
-
     const real *prior = static_cast<const real *>(p.prior);
     const IT *vidx = static_cast<const IT *>(p.vidx);
-    if (p.stage_idx) {
+    if (p.stage_idx) {                                       // whole CTA: stage the static tables once
         IT *sv = reinterpret_cast<IT *>(smem_raw + L.vidx);
         real *sp = reinterpret_cast<real *>(smem_raw + L.prior);
-        for (int i = tid; i < g.n * VMAX; i += NT) sv[i] = vidx[i];
-        for (int i = tid; i < g.n; i += NT) sp[i] = prior[i];
+        for (int i = threadIdx.x; i < g.n * VMAX; i += blockDim.x) sv[i] = vidx[i];
+        for (int i = threadIdx.x; i < g.n; i += blockDim.x) sp[i] = prior[i];
+    }
+    __syncthreads();                                         // the only CTA-wide barrier
+
+    // ---- warp groups: the CTA's warps are split into `groups` teams, each owning S_all/groups slots
+    // and synchronising on its own named barrier.  Teams drift out of phase, so one team's
+    // shared-memory bursts overlap another team's arithmetic.
+    const int G = p.groups;
+    const int NT = (int)blockDim.x / G;                      // threads of a team (multiple of 32)
+    const int gid = (int)threadIdx.x / NT;
+    const int tid = (int)threadIdx.x - gid * NT;
+    const int S = S_all / G;                                 // slots of a team
+    const int s_lo = gid * S;
+    auto gsync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(NT) : "memory"); };
+    auto gsync_or = [&](int f) -> int {
+        int r;
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.s32 %0, 1, 0, p;\n\t}"
+                     : "=r"(r) : "r"(f), "r"(gid + 1), "r"(NT) : "memory");
+        return r;
+    };
+    // team-local views of the per-slot arrays
+    real *msg = reinterpret_cast<real *>(smem_raw + L.msg) + (size_t)s_lo * g.npos;
+    unsigned char *flags = smem_raw + L.flags + (size_t)s_lo * g.m * FB;      // [S][m][FB]
+    uint32_t *dec_all = reinterpret_cast<uint32_t *>(smem_raw + L.bits);        // [S_all][nwn]
+    uint32_t *syn_all = dec_all + (size_t)S_all * g.nwn;                       // [S_all][nwm] original syndrome
+    uint32_t *res_all = syn_all + (size_t)S_all * g.nwm;                       // [S_all][nwm] s ^ H e_hat
+    uint32_t *dec = dec_all + (size_t)s_lo * g.nwn, *syn = syn_all + (size_t)s_lo * g.nwm,
+             *res = res_all + (size_t)s_lo * g.nwm;
+    BpCtl *ctl = reinterpret_cast<BpCtl *>(smem_raw + L.ctl) + s_lo;
+    if (p.stage_idx) {
+        vidx = reinterpret_cast<const IT *>(smem_raw + L.vidx);
+        prior = reinterpret_cast<const real *>(smem_raw + L.prior);
     }
     // 32-bit shared addresses of the hot arrays
     const uint32_t a_msg = smem_u32(msg), a_flags = smem_u32(flags), a_dec = smem_u32(dec), a_syn = smem_u32(syn),
@@ -238,7 +312,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_kernel(const BpParams p)
     const int m32 = (g.m + 31) & ~31, n32 = (g.n + 31) & ~31;
     const int flag_words = (int)(((size_t)g.m * FB) >> 3);              // 8-byte flag words per slot
 
-    long long c_fail = 0, c_shots = 0, c_nc = 0, c_it = 0;   // meaningful on thread 0 only
+    long long c_fail = 0, c_shots = 0, c_nc = 0, c_it = 0;   // meaningful on thread 0 of a team only
 
     if (tid < S) {
         const unsigned long long id = atomicAdd(p.next_shot, 1ULL);
@@ -246,7 +320,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_kernel(const BpParams p)
         ctl[tid].unsat[0] = ctl[tid].unsat[1] = 0;
         ctl[tid].born = id < (unsigned long long)p.shots ? -1 : BP_IDLE;   // -1: part of iteration 0 in full
     }
-    __syncthreads();
+    gsync();
 
     // ---- (re)load every slot born in `stamp`: syndrome, cleared decisions/flags, bit->check messages = priors
     auto load_slots = [&](int stamp) {
@@ -273,7 +347,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_kernel(const BpParams p)
         }
     };
     load_slots(-1);
-    __syncthreads();
+    gsync();
     bool any_shot = false;
     for (int s = 0; s < S; ++s) any_shot |= ctl[s].born != BP_IDLE;
 
@@ -288,6 +362,71 @@ __global__ void __launch_bounds__(MAXT, 1) bp_kernel(const BpParams p)
                   if (RD > 0) { pos0 = c * P; deg = RD; }
                   else { const uint32_t d = g.row_desc[c]; pos0 = d & 0xFFFFFF; deg = d >> 24; }
               }
+              if (METHOD == QD_BP_MIN_SUM_K && RD > 0 && RD <= 8) {
+                constexpr int RDN = RD > 0 ? RD : 1;
+                // fast path: two slots at a time, loads / arithmetic / stores of both in one basic block
+                const bool valid = c < g.m;
+                const uint32_t rowoff = (uint32_t)(valid ? pos0 : 0) * RB, floff = (uint32_t)(valid ? c : 0) * FB;
+                const uint32_t woff = (uint32_t)(c >> 5) * 4u;
+                auto alpha_of = [&](int born) -> real {
+                    return alpha_fixed != (real)0 ? alpha_fixed : A::sub((real)1, pow2_neg<real>(T - born));
+                };
+                auto finish = [&](int s, uint32_t wofs, uint32_t resw, unsigned newbit) {
+                    const uint32_t neww = __ballot_sync(0xffffffffu, valid ? newbit : 0u);
+                    if (lane == 0) {
+                        if (neww != resw) sts_u32(a_res + wofs, neww);
+                        if (neww) atomicAdd(&ctl[s].unsat[ub], __popc(neww));
+                    }
+                };
+                for (int s = 0; s < S; s += 2) {
+                    const int born0 = (int)lds_u32(a_born + s * (uint32_t)sizeof(BpCtl));
+                    const int born1 = s + 1 < S ? (int)lds_u32(a_born + (s + 1) * (uint32_t)sizeof(BpCtl)) : BP_IDLE;
+                    const bool act0 = born0 != BP_IDLE, act1 = born1 != BP_IDLE;      // warp-uniform
+                    const uint32_t row0 = a_msg + s * msg_stride + rowoff, row1 = row0 + msg_stride;
+                    const uint32_t fa0 = a_flags + s * flag_stride + floff, fa1 = fa0 + flag_stride;
+                    const uint32_t w0 = (uint32_t)(s * g.nwm) * 4u + woff, w1 = w0 + (uint32_t)g.nwm * 4u;
+                    if (act0 && act1) {
+                        real v0[RDN], v1[RDN];
+                        const uint32_t resw0 = lds_u32(a_res + w0), resw1 = lds_u32(a_res + w1);
+                        const uint32_t synw0 = lds_u32(a_syn + w0), synw1 = lds_u32(a_syn + w1);
+                        const unsigned long long f0 = lds_u64(fa0), f1 = lds_u64(fa1);
+#pragma unroll
+                        for (int k = 0; k < RDN; ++k) v0[k] = lds_real(row0 + k * RB, real());
+#pragma unroll
+                        for (int k = 0; k < RDN; ++k) v1[k] = lds_real(row1 + k * RB, real());
+                        const unsigned nb0 = ((resw0 >> lane) ^ (unsigned)__popcll(f0)) & 1u;
+                        const unsigned nb1 = ((resw1 >> lane) ^ (unsigned)__popcll(f1)) & 1u;
+                        check_ms_compute<real, RDN>(v0, ((synw0 >> lane) & 1u) << 31, alpha_of(born0));
+                        check_ms_compute<real, RDN>(v1, ((synw1 >> lane) & 1u) << 31, alpha_of(born1));
+                        if (valid) {
+#pragma unroll
+                            for (int k = 0; k < RDN; ++k) sts_real(row0 + k * RB, v0[k]);
+#pragma unroll
+                            for (int k = 0; k < RDN; ++k) sts_real(row1 + k * RB, v1[k]);
+                            if (f0) sts_u64(fa0, 0ULL);
+                            if (f1) sts_u64(fa1, 0ULL);
+                        }
+                        finish(s, w0, resw0, nb0);
+                        finish(s + 1, w1, resw1, nb1);
+                    } else if (act0 || act1) {
+                        const int sa = act0 ? s : s + 1;
+                        const uint32_t row = act0 ? row0 : row1, fa = act0 ? fa0 : fa1, w = act0 ? w0 : w1;
+                        real v[RDN];
+                        const uint32_t resw = lds_u32(a_res + w), synw = lds_u32(a_syn + w);
+                        const unsigned long long f = lds_u64(fa);
+#pragma unroll
+                        for (int k = 0; k < RDN; ++k) v[k] = lds_real(row + k * RB, real());
+                        const unsigned nb = ((resw >> lane) ^ (unsigned)__popcll(f)) & 1u;
+                        check_ms_compute<real, RDN>(v, ((synw >> lane) & 1u) << 31, alpha_of(act0 ? born0 : born1));
+                        if (valid) {
+#pragma unroll
+                            for (int k = 0; k < RDN; ++k) sts_real(row + k * RB, v[k]);
+                            if (f) sts_u64(fa, 0ULL);
+                        }
+                        finish(sa, w, resw, nb);
+                    }
+                }
+              } else
               for (int s = 0; s < S; ++s) {
                 const int born = (int)lds_u32(a_born + s * (uint32_t)sizeof(BpCtl));
                 if (born != BP_IDLE) {                                       // warp-uniform
@@ -316,35 +455,12 @@ __global__ void __launch_bounds__(MAXT, 1) bp_kernel(const BpParams p)
                             const real al = alpha_fixed != (real)0 ? alpha_fixed
                                                                    : A::sub((real)1, pow2_neg<real>(T - born));
                             if (RD > 0) {
-                                // Sign handling uses the sign BIT instead of (v <= 0): the two differ only
-                                // for v = +0.0, and then min1 = 0, so every message whose sign would change
-                                // is a zero, whose sign no later comparison can observe.
                                 real v[DMAX];
 #pragma unroll
                                 for (int k = 0; k < RD; ++k) v[k] = lds_real(row + k * RB, real());
-                                unsigned sx = sbit << 31;                    // parity of syndrome bit and all signs
-                                unsigned hk[DMAX];
+                                check_ms_compute<real, DMAX>(v, sbit << 31, al);
 #pragma unroll
-                                for (int k = 0; k < RD; ++k) { hk[k] = hi_bits(v[k]); sx ^= hk[k]; v[k] = abs_bits(v[k]); }
-                                real m1, m2;
-                                if (RD >= 2) {
-                                    const bool lt = v[1] < v[0];
-                                    m1 = lt ? v[1] : v[0];
-                                    m2 = lt ? v[0] : v[1];
-                                } else { m1 = v[0]; m2 = A::big(); }
-#pragma unroll
-                                for (int k = 2; k < RD; ++k) {
-                                    const real a = v[k];
-                                    const bool lt1 = a < m1, lt2 = a < m2;
-                                    m2 = lt1 ? m1 : (lt2 ? a : m2);
-                                    m1 = lt1 ? a : m1;
-                                }
-                                const real m1a = A::mul(m1, al), m2a = A::mul(m2, al);
-#pragma unroll
-                                for (int k = 0; k < RD; ++k) {
-                                    const real out = v[k] == m1 ? m2a : m1a;
-                                    sts_real(row + k * RB, xor_hi(out, (sx ^ hk[k]) & 0x80000000u));
-                                }
+                                for (int k = 0; k < RD; ++k) sts_real(row + k * RB, v[k]);
                             } else {
                                 real m1 = A::big(), m2 = A::big();
                                 unsigned par = sbit;
@@ -396,7 +512,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_kernel(const BpParams p)
               }
             }
         }
-        __syncthreads();
+        gsync();
 
         // ================================================================== retire / refill
         bool any_done = false;
@@ -417,15 +533,15 @@ __global__ void __launch_bounds__(MAXT, 1) bp_kernel(const BpParams p)
                 int f = 0;
                 if (p.err) {
                     const uint32_t *e = p.err + shot * (long long)p.err_stride;
-                    __syncthreads();
+                    gsync();
                     for (int w = tid; w < g.nwn; w += NT) D[w] ^= e[w];
-                    __syncthreads();
+                    gsync();
                     for (int i = tid; i < p.k; i += NT) {
                         uint32_t acc = 0u;
                         for (int w = 0; w < g.nwn; ++w) acc ^= p.lzT[(size_t)w * p.k + i] & D[w];
                         f |= __popc(acc) & 1;
                     }
-                    f = __syncthreads_or(f);
+                    f = gsync_or(f);
                 }
                 if (tid == 0) {
                     if (p.conv) p.conv[shot] = (uint8_t)conv;
@@ -434,7 +550,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_kernel(const BpParams p)
                     c_fail += f; c_shots += 1; c_nc += !conv; c_it += it;
                 }
             }
-            __syncthreads();
+            gsync();
             if (tid < S) {
                 const int born = ctl[tid].born, it = T - born - 1;
                 const bool done = born != BP_IDLE && it >= 1 && (ctl[tid].unsat[ub] == 0 || it >= p.max_iter);
@@ -446,7 +562,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_kernel(const BpParams p)
                     ctl[tid].born = more ? T : BP_IDLE;
                 }
             }
-            __syncthreads();
+            gsync();
             bool any_active = false;
             for (int s = 0; s < S; ++s) any_active |= ctl[s].born != BP_IDLE;
             if (!any_active) break;
@@ -484,97 +600,136 @@ __global__ void __launch_bounds__(MAXT, 1) bp_kernel(const BpParams p)
               }
 #pragma unroll
               for (int t = 0; t < VMAX; ++t) qo[t] = (uint32_t)pos[t] * RB;
+              // ---- decision word of the warp + flip flags for one slot
+              auto publish = [&](int s, uint32_t mbase, unsigned dbit, int deg) {
+                  const uint32_t neww = __ballot_sync(0xffffffffu, dbit);
+                  const uint32_t da = a_dec + (uint32_t)(s * g.nwn + (j >> 5)) * 4u;
+                  const uint32_t flips = lds_u32(da) ^ neww;
+                  if (flips) {                                                // warp-uniform
+                      if ((flips >> lane) & 1u) {
+                          const uint32_t fbase = a_flags + s * flag_stride;
+#pragma unroll
+                          for (int t = 0; t < VMAX; ++t)
+                              if (t < deg) {
+                                  const uint32_t q = (uint32_t)pos[t];           // message position
+                                  uint32_t fp;
+                                  if (RD > 0) {                                // row * FB + k  =  q + (FB - P) * row
+                                      constexpr int Pc = RD | 1, FBc = RD <= 8 ? 8 : 16;
+                                      fp = q + (uint32_t)(FBc - Pc) * (q / (uint32_t)Pc);
+                                  } else fp = g.fpos_of_pos[q];
+                                  sts_u8(fbase + fp, 1u);
+                              }
+                      }
+                      __syncwarp();
+                      if (lane == 0) sts_u32(da, neww);
+                  }
+              };
+              auto soft_out = [&](int s, real soft) {
+                  if (p.llr && j < g.n)
+                      p.llr[ctl[s].shot * (long long)g.n + j] =
+                          METHOD == QD_BP_MIN_SUM_K ? (double)soft : (double)A::lg(A::div((real)1, soft));
+              };
+              // ---- uniform-degree chunk: unpredicated update, two slots interleaved
+              auto run_uniform = [&](auto dtag) {
+                  constexpr int D = decltype(dtag)::value;
+                  const bool valid = j < g.n;
+                  uint32_t qb[D];
+#pragma unroll
+                  for (int t = 0; t < D; ++t) qb[t] = valid ? qo[t < VMAX ? t : 0] : 0u;
+                  for (int s = 0; s < S; s += 2) {
+                      const int born0 = (int)lds_u32(a_born + s * (uint32_t)sizeof(BpCtl));
+                      const int born1 = s + 1 < S ? (int)lds_u32(a_born + (s + 1) * (uint32_t)sizeof(BpCtl)) : BP_IDLE;
+                      const bool act0 = born0 != BP_IDLE && born0 != T, act1 = born1 != BP_IDLE && born1 != T;
+                      const uint32_t mb0 = a_msg + s * msg_stride, mb1 = mb0 + msg_stride;
+                      if (act0 && act1) {
+                          uint32_t q0[D], q1[D];
+#pragma unroll
+                          for (int t = 0; t < D; ++t) { q0[t] = mb0 + qb[t]; q1[t] = mb1 + qb[t]; }
+                          real c0[D], c1[D], soft0, soft1;
+                          bit_load<real, D>(q0, c0);
+                          bit_load<real, D>(q1, c1);
+                          const unsigned d0 = bit_compute<real, METHOD, D>(c0, pj, soft0);
+                          const unsigned d1 = bit_compute<real, METHOD, D>(c1, pj, soft1);
+                          if (valid) { bit_store<real, D>(q0, c0); bit_store<real, D>(q1, c1); }
+                          soft_out(s, soft0);
+                          soft_out(s + 1, soft1);
+                          publish(s, mb0, valid ? d0 : 0u, D);
+                          publish(s + 1, mb1, valid ? d1 : 0u, D);
+                      } else if (act0 || act1) {
+                          const int sa = act0 ? s : s + 1;
+                          const uint32_t mb = act0 ? mb0 : mb1;
+                          uint32_t q[D];
+#pragma unroll
+                          for (int t = 0; t < D; ++t) q[t] = mb + qb[t];
+                          real c[D], soft;
+                          bit_load<real, D>(q, c);
+                          const unsigned d = bit_compute<real, METHOD, D>(c, pj, soft);
+                          if (valid) bit_store<real, D>(q, c);
+                          soft_out(sa, soft);
+                          publish(sa, mb, valid ? d : 0u, D);
+                      }
+                  }
+              };
+              // cd: common degree of the 32 columns of this chunk (0 = mixed); warp-uniform
+              const int cdw = __shfl_sync(0xffffffffu, cd, 0);
+              if (cdw == 3 && VMAX >= 3) run_uniform(std::integral_constant<int, 3>());
+              else if (cdw == 4 && VMAX >= 4) run_uniform(std::integral_constant<int, 4>());
+              else if (cdw == 5 && VMAX >= 5) run_uniform(std::integral_constant<int, 5>());
+              else if (cdw == 6 && VMAX >= 6) run_uniform(std::integral_constant<int, 6>());
+              else
               for (int s = 0; s < S; ++s) {
                 const int born = (int)lds_u32(a_born + s * (uint32_t)sizeof(BpCtl));
                 if (born != BP_IDLE && born != T) {                          // warp-uniform
                     const uint32_t mbase = a_msg + s * msg_stride;
                     unsigned dbit = 0u;
-                    uint32_t qa[VMAX];                                       // shared addresses of the column's messages
                     int deg = 0;
+                    real soft = (real)0;
                     if (j < g.n) {
+                        // mixed-degree chunk: predicated sweep over the column tile
+                        uint32_t qa[VMAX];
 #pragma unroll
                         for (int t = 0; t < VMAX; ++t) qa[t] = mbase + qo[t];
-                        // cd: every column of this 32-column chunk has the same degree (0 = mixed): warp-uniform
-                        real soft = (real)0;
-                        if (cd == 3 && VMAX >= 3) {
-                            const uint32_t q3[3] = {qa[0], qa[1], qa[2]};
-                            dbit = bit_update<real, METHOD, 3>(q3, pj, soft); deg = 3;
-                        } else if (cd == 4 && VMAX >= 4) {
-                            const uint32_t q4[4] = {qa[0], qa[1], qa[2], qa[3]};
-                            dbit = bit_update<real, METHOD, 4>(q4, pj, soft); deg = 4;
-                        } else if (cd == 5 && VMAX >= 5) {
-                            const uint32_t q5[5] = {qa[0], qa[1], qa[2], qa[3], qa[4 % VMAX]};
-                            dbit = bit_update<real, METHOD, 5>(q5, pj, soft); deg = 5;
-                        } else if (cd == 6 && VMAX >= 6) {
-                            const uint32_t q6[6] = {qa[0], qa[1], qa[2], qa[3], qa[4 % VMAX], qa[5 % VMAX]};
-                            dbit = bit_update<real, METHOD, 6>(q6, pj, soft); deg = 6;
-                        } else {
-                            // mixed-degree chunk: predicated sweep over the column tile
-                            real cv[VMAX], pre[VMAX];
-                            real temp = pj;
+                        real cv[VMAX], pre[VMAX];
+                        real temp = pj;
 #pragma unroll
-                            for (int t = 0; t < VMAX; ++t) {
-                                if (pos[t] != NONE) { cv[t] = lds_real(qa[t], real()); deg = t + 1; }
-                            }
-                            if (METHOD == QD_BP_MIN_SUM_K) {
-#pragma unroll
-                                for (int t = 0; t < VMAX; ++t)
-                                    if (t < deg) { pre[t] = temp; temp = A::add(temp, cv[t]); }
-                                dbit = temp <= (real)0 ? 1u : 0u;
-                                real suf = (real)0;
-#pragma unroll
-                                for (int t = VMAX - 1; t >= 0; --t)
-                                    if (t < deg) { sts_real(qa[t], A::add(pre[t], suf)); suf = A::add(suf, cv[t]); }
-                            } else {
-#pragma unroll
-                                for (int t = 0; t < VMAX; ++t)
-                                    if (t < deg) {
-                                        pre[t] = temp; temp = A::mul(temp, cv[t]);
-                                        if (temp != temp) temp = (real)1;
-                                    }
-                                dbit = temp >= (real)1 ? 1u : 0u;
-                                real suf = (real)1;
-#pragma unroll
-                                for (int t = VMAX - 1; t >= 0; --t)
-                                    if (t < deg) {
-                                        sts_real(qa[t], A::mul(pre[t], suf)); suf = A::mul(suf, cv[t]);
-                                        if (suf != suf) suf = (real)1;
-                                    }
-                            }
-                            soft = temp;
+                        for (int t = 0; t < VMAX; ++t) {
+                            if (pos[t] != NONE) { cv[t] = lds_real(qa[t], real()); deg = t + 1; }
                         }
-                        if (p.llr)
-                            p.llr[ctl[s].shot * (long long)g.n + j] =
-                                METHOD == QD_BP_MIN_SUM_K ? (double)soft : (double)A::lg(A::div((real)1, soft));
-                    }
-                    // one decision word per warp (j is warp-aligned); a flipped bit flags its edges
-                    const uint32_t neww = __ballot_sync(0xffffffffu, dbit);
-                    const uint32_t da = a_dec + (uint32_t)(s * g.nwn + (j >> 5)) * 4u;
-                    const uint32_t flips = lds_u32(da) ^ neww;
-                    if (flips) {                                              // warp-uniform
-                        if ((flips >> lane) & 1u) {
-                            const uint32_t fbase = a_flags + s * flag_stride;
+                        if (METHOD == QD_BP_MIN_SUM_K) {
+#pragma unroll
+                            for (int t = 0; t < VMAX; ++t)
+                                if (t < deg) { pre[t] = temp; temp = A::add(temp, cv[t]); }
+                            dbit = temp <= (real)0 ? 1u : 0u;
+                            real suf = (real)0;
+#pragma unroll
+                            for (int t = VMAX - 1; t >= 0; --t)
+                                if (t < deg) { sts_real(qa[t], A::add(pre[t], suf)); suf = A::add(suf, cv[t]); }
+                        } else {
 #pragma unroll
                             for (int t = 0; t < VMAX; ++t)
                                 if (t < deg) {
-                                    const uint32_t q = (qa[t] - mbase) / RB;     // message position
-                                    uint32_t fp;
-                                    if (RD > 0) {                                // row * FB + k  =  q + (FB - P) * row
-                                        constexpr int Pc = RD | 1, FBc = RD <= 8 ? 8 : 16;
-                                        fp = q + (uint32_t)(FBc - Pc) * (q / (uint32_t)Pc);
-                                    } else fp = g.fpos_of_pos[q];
-                                    sts_u8(fbase + fp, 1u);
+                                    pre[t] = temp; temp = A::mul(temp, cv[t]);
+                                    if (temp != temp) temp = (real)1;
+                                }
+                            dbit = temp >= (real)1 ? 1u : 0u;
+                            real suf = (real)1;
+#pragma unroll
+                            for (int t = VMAX - 1; t >= 0; --t)
+                                if (t < deg) {
+                                    sts_real(qa[t], A::mul(pre[t], suf)); suf = A::mul(suf, cv[t]);
+                                    if (suf != suf) suf = (real)1;
                                 }
                         }
-                        __syncwarp();
-                        if (lane == 0) sts_u32(da, neww);
+                        soft = temp;
                     }
+                    soft_out(s, soft);
+                    publish(s, mbase, dbit, deg);
                 }
               }
             }
         }
         if (tid < S) ctl[tid].unsat[ub ^ 1] = 0;          // buffer of the next check pass; nobody reads it now
-        __syncthreads();
+        gsync();
     }
 
     if (tid == 0 && p.counters && c_shots) {

@@ -193,7 +193,7 @@ struct qd_bp {
     int rd = 0;            // compile-time row degree of the selected kernel (0 = generic rows)
     int idx_bytes = 2;     // bytes per message position in vidx
     int stage_idx = 0;     // vidx + priors staged in shared memory
-    int threads = 0, slots = 0, ctas_per_sm = 0;
+    int threads = 0, slots = 0, ctas_per_sm = 0, groups = 1;
     size_t smem = 0;
     DevBuf d_prior, d_alpha, d_next, d_vidx, d_chunk_deg;
     // host-buffer pipeline state
@@ -488,18 +488,21 @@ static bp_kernel_fn pick_bp_rd(int rd, int vmax)
 template <typename real, int METHOD>
 static bp_kernel_fn pick_bp(int rd, int vmax, int threads)
 {
+    // register budget follows the number of resident threads per SM (threads x CTAs/SM)
     if (threads <= 512) return pick_bp_rd<real, METHOD, 512>(rd, vmax);
+    if (threads <= 640) return pick_bp_rd<real, METHOD, 640>(rd, vmax);
     if (threads <= 768) return pick_bp_rd<real, METHOD, 768>(rd, vmax);
+    if (threads <= 896) return pick_bp_rd<real, METHOD, 896>(rd, vmax);
     return pick_bp_rd<real, METHOD, 1024>(rd, vmax);
 }
 
 static bp_kernel_fn bp_kernel_for(const qd_bp *d)
 {
     if (d->precision == QD_PREC_F64)
-        return d->method == QD_BP_MIN_SUM ? pick_bp<double, QD_BP_MIN_SUM>(d->rd, d->vmax, d->threads)
-                                          : pick_bp<double, QD_BP_PRODUCT_SUM>(d->rd, d->vmax, d->threads);
-    return d->method == QD_BP_MIN_SUM ? pick_bp<float, QD_BP_MIN_SUM>(d->rd, d->vmax, d->threads)
-                                      : pick_bp<float, QD_BP_PRODUCT_SUM>(d->rd, d->vmax, d->threads);
+        return d->method == QD_BP_MIN_SUM ? pick_bp<double, QD_BP_MIN_SUM>(d->rd, d->vmax, d->threads * d->ctas_per_sm)
+                                          : pick_bp<double, QD_BP_PRODUCT_SUM>(d->rd, d->vmax, d->threads * d->ctas_per_sm);
+    return d->method == QD_BP_MIN_SUM ? pick_bp<float, QD_BP_MIN_SUM>(d->rd, d->vmax, d->threads * d->ctas_per_sm)
+                                      : pick_bp<float, QD_BP_PRODUCT_SUM>(d->rd, d->vmax, d->threads * d->ctas_per_sm);
 }
 
 static size_t bp_smem(const qd_bp *d, int slots, bool stage)
@@ -527,7 +530,7 @@ static int bp_default_config(qd_bp *d)
     const long long work = (long long)slots * std::max(g.n, g.m);
     int threads = ctas > 1 ? 512 : 1024;
     while (threads > 128 && (long long)threads * 2 > work) threads /= 2;
-    d->threads = threads; d->slots = slots; d->ctas_per_sm = ctas;
+    d->threads = threads; d->slots = slots; d->ctas_per_sm = ctas; d->groups = 1;
     d->smem = bp_smem(d, slots, d->stage_idx);
     return 0;
 }
@@ -628,23 +631,26 @@ extern "C" int qd_bp_destroy(qd_bp *d)
     return 0;
 }
 
-extern "C" int qd_bp_configure(qd_bp *d, int32_t threads, int32_t slots, int32_t ctas_per_sm)
+extern "C" int qd_bp_configure(qd_bp *d, int32_t threads, int32_t slots, int32_t ctas_per_sm, int32_t teams)
 {
     if (!d) return fail(QD_EINVAL, "NULL handle");
     int t = threads > 0 ? threads : d->threads, s = slots > 0 ? slots : d->slots, c = ctas_per_sm > 0 ? ctas_per_sm : d->ctas_per_sm;
+    int gr = teams > 0 ? teams : (slots > 0 || threads > 0 ? 1 : d->groups);
     if (t % 32 || t > 1024 || s > 64) return fail(QD_EINVAL, "threads must be a multiple of 32 <= 1024, slots <= 64");
-    if (s > t) return fail(QD_EINVAL, "slots must not exceed threads");
+    if (gr > 15 || s % gr || t % (32 * gr)) return fail(QD_EINVAL, "teams must divide slots and threads/32 (and be <= 15)");
+    if (s / gr > t / gr) return fail(QD_EINVAL, "slots per team must not exceed threads per team");
     int stage = 1;
     size_t smem = bp_smem(d, s, true);
     if (smem > (size_t)d->g->smem_optin) { stage = 0; smem = bp_smem(d, s, false); }
     if (smem > (size_t)d->g->smem_optin) return fail(QD_EUNSUP, "configuration does not fit shared memory");
-    d->threads = t; d->slots = s; d->ctas_per_sm = c; d->smem = smem; d->stage_idx = stage;
+    d->threads = t; d->slots = s; d->ctas_per_sm = c; d->groups = gr; d->smem = smem; d->stage_idx = stage;
     return 0;
 }
 
-extern "C" int qd_bp_get_config(qd_bp *d, int32_t *threads, int32_t *slots, int32_t *ctas_per_sm, int32_t *smem_bytes,
-                                int32_t *grid)
+extern "C" int qd_bp_get_config(qd_bp *d, int32_t *threads, int32_t *slots, int32_t *ctas_per_sm, int32_t *teams,
+                                int32_t *smem_bytes, int32_t *grid)
 {
+    if (d && teams) *teams = d->groups;
     if (!d) return fail(QD_EINVAL, "NULL handle");
     if (threads) *threads = d->threads;
     if (slots) *slots = d->slots;
@@ -672,7 +678,7 @@ static int bp_launch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int6
     p.g = g;
     p.prior = d->d_prior.p; p.alpha = d->d_alpha.p; p.vidx = d->d_vidx.p;
     p.chunk_deg = d->d_chunk_deg.as<uint8_t>();
-    p.max_iter = d->max_iter; p.slots = d->slots; p.stage_idx = d->stage_idx;
+    p.max_iter = d->max_iter; p.slots = d->slots; p.groups = d->groups; p.stage_idx = d->stage_idx;
     p.synd = d_synd; p.synd_stride = synd_stride; p.shots = shots;
     p.corr = d_corr; p.corr_stride = corr_stride;
     p.conv = d_converged; p.iters = d_iters; p.llr = d_llr;

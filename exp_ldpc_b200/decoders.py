@@ -225,14 +225,14 @@ class bp_decoder:
         return self._h
 
     # ---- launch geometry (tuning)
-    def configure(self, threads=0, slots=0, ctas_per_sm=0):
-        _lib.check(_lib.lib().qd_bp_configure(self._h, threads, slots, ctas_per_sm))
+    def configure(self, threads=0, slots=0, ctas_per_sm=0, teams=0):
+        _lib.check(_lib.lib().qd_bp_configure(self._h, threads, slots, ctas_per_sm, teams))
         return self.config()
 
     def config(self) -> dict:
-        v = [C.c_int32() for _ in range(5)]
+        v = [C.c_int32() for _ in range(6)]
         _lib.check(_lib.lib().qd_bp_get_config(self._h, *[C.byref(x) for x in v]))
-        return dict(zip(("threads", "slots", "ctas_per_sm", "smem_bytes", "grid"), (x.value for x in v)))
+        return dict(zip(("threads", "slots", "ctas_per_sm", "teams", "smem_bytes", "grid"), (x.value for x in v)))
 
     # ---- the ldpc call
     def decode(self, input_vector) -> np.ndarray:

@@ -100,11 +100,13 @@ int qd_logical_fail_batch(qd_logicals *l, const uint32_t *d_a, const uint32_t *d
 int qd_bp_create(qd_graph *g, const double *h_channel_probs, int32_t max_iter, int32_t method,
                  double ms_scaling_factor, int32_t precision, qd_bp **out);
 int qd_bp_destroy(qd_bp *d);
-/* launch geometry override for tuning (threads per CTA, shots in flight per CTA, CTAs per SM);
- * 0 keeps the heuristic value.  Fails if the configuration does not fit shared memory. */
-int qd_bp_configure(qd_bp *d, int32_t threads, int32_t slots, int32_t ctas_per_sm);
+/* launch geometry override for tuning (threads per CTA, shots in flight per CTA, CTAs per SM,
+ * warp teams per CTA: the CTA's warps are split into `teams` groups with their own barrier and
+ * their own share of the slots); 0 keeps the current value.  Fails if the configuration does
+ * not fit shared memory. */
+int qd_bp_configure(qd_bp *d, int32_t threads, int32_t slots, int32_t ctas_per_sm, int32_t teams);
 int qd_bp_get_config(qd_bp *d, int32_t *threads, int32_t *slots, int32_t *ctas_per_sm,
-                     int32_t *smem_bytes, int32_t *grid);
+                     int32_t *teams, int32_t *smem_bytes, int32_t *grid);
 
 /* Decode `shots` packed syndromes.  Required: d_synd, d_corr.  Optional (NULL to skip):
  *   d_converged[shots], d_iters[shots], d_llr[shots*n] (posterior log-ratio of the last

@@ -25,6 +25,7 @@ ap.add_argument("--max-iter", type=int, default=None)
 ap.add_argument("--threads", default="256,512,768,1024")
 ap.add_argument("--slots", default="1,2,3,4,5,6,8")
 ap.add_argument("--ctas", default="1,2,3,4")
+ap.add_argument("--teams", default="1")
 ap.add_argument("--reps", type=int, default=2)
 a = ap.parse_args()
 
@@ -53,14 +54,15 @@ sampler.run_device(0, 0, 0, shots, d_err, es)
 graph.syndrome_batch_device(d_err, es, shots, d_syn, ss)
 print("default config", dec.config(), flush=True)
 results = []
-combos = [dec.config()] + [dict(threads=t, slots=s, ctas_per_sm=c) for t, s, c in itertools.product(
-    [int(x) for x in a.threads.split(",")], [int(x) for x in a.slots.split(",")], [int(x) for x in a.ctas.split(",")])]
+combos = [dec.config()] + [dict(threads=t, slots=s, ctas_per_sm=c, teams=g) for t, s, c, g in itertools.product(
+    [int(x) for x in a.threads.split(",")], [int(x) for x in a.slots.split(",")], [int(x) for x in a.ctas.split(",")],
+    [int(x) for x in a.teams.split(",")])]
 for cfg in combos:
-    t, s, c = cfg["threads"], cfg["slots"], cfg["ctas_per_sm"]
+    t, s, c, g = cfg["threads"], cfg["slots"], cfg["ctas_per_sm"], cfg["teams"]
     if t * c > 2048:
         continue
     try:
-        got = dec.configure(t, s, c)
+        got = dec.configure(t, s, c, g)
     except Exception:
         continue
     if got["smem_bytes"] * c > 232448 - 1024 * c:
@@ -77,7 +79,7 @@ for cfg in combos:
             best = min(best, e0.elapsed_time(e1))
     cnt = d_cnt.tolist()
     rate = shots / (best * 1e-3)
-    results.append((rate, t, s, c, got["smem_bytes"]))
-    print(f"threads={t:5d} slots={s:2d} ctas={c} smem={got['smem_bytes']:7d}  {rate / 1e6:8.3f} Mshots/s  mean_iters={cnt[3] / max(1, cnt[1]):.2f}", flush=True)
+    results.append((rate, t, s, c, g, got["smem_bytes"]))
+    print(f"threads={t:5d} slots={s:2d} ctas={c} teams={g} smem={got['smem_bytes']:7d}  {rate / 1e6:8.3f} Mshots/s  mean_iters={cnt[3] / max(1, cnt[1]):.2f}", flush=True)
 results.sort(reverse=True)
 print("BEST", results[:5])

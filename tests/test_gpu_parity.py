@@ -114,7 +114,9 @@ def test_decoders_match_committed_golden_vectors(gpu, codes, name):
 
 @pytest.mark.parametrize("name", ["ms_sched_225", "ps_225", "ms_sched_1600"])
 @pytest.mark.parametrize("config", [dict(threads=32, slots=1, ctas_per_sm=1), dict(threads=96, slots=3, ctas_per_sm=2),
-                                    dict(threads=1024, slots=1, ctas_per_sm=1), dict(threads=256, slots=3, ctas_per_sm=1)])
+                                    dict(threads=1024, slots=1, ctas_per_sm=1), dict(threads=256, slots=3, ctas_per_sm=1),
+                                    dict(threads=512, slots=4, ctas_per_sm=1, teams=2), dict(threads=384, slots=3, ctas_per_sm=1, teams=3),
+                                    dict(threads=1024, slots=4, ctas_per_sm=1, teams=4)])
 def test_bp_result_independent_of_launch_geometry(gpu, codes, name, config):
     g = np.load(os.path.join(GOLDEN, "decoder_vectors.npz"))
     out = _run_gpu_case(name, codes, config=config)
