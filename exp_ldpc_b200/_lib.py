@@ -41,6 +41,8 @@ SIGNATURES = {
     "qd_bp_destroy": (C.c_int, [vp]),
     "qd_bp_configure": (C.c_int, [vp, i32, i32, i32, i32]),
     "qd_bp_get_config": (C.c_int, [vp, P(i32), P(i32), P(i32), P(i32), P(i32), P(i32)]),
+    "qd_bp_select_kernel": (C.c_int, [vp, i32]),
+    "qd_bp_get_kernel": (C.c_int, [vp, P(i32), P(i32), P(i32)]),
     "qd_bp_decode_batch": (C.c_int, [vp, vp, i32, i64, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp]),
     "qd_bp_decode_batch_host": (C.c_int, [vp, vp, i32, i64, vp, i32, vp, vp]),
     "qd_bp_decode_one": (C.c_int, [vp, vp, vp, P(i32), P(i32), vp]),

@@ -1,0 +1,472 @@
+// bp7_kernel.cuh — flooding BP for row-regular Tanner graphs, "thread-owned state" variant.
+//
+// Same computation as bp_kernel.cuh (syndrome BP of ldpc.bp_decoder as the reference calls it at
+// python/qldpc/misc/_experiment.py:110-117,137-149; CPU restatement: oracle/qldpc_oracle.c), same
+// persistent-CTA / slot-refill scheme, but laid out so that the hot loops are almost pure
+// load-compute-store:
+//
+//   * S (compile time) shots per CTA share one message array, slot-minor:
+//         element(row, k, s) = row * RP + k * S + s,      RP = (RD * S) | 1   (odd => a warp that
+//     owns 32 consecutive rows reads/writes 32 different banks), so every shared-memory access of
+//     the check pass is [row base register + immediate] and every access of the bit pass is
+//     [edge base register + immediate]: no address arithmetic per slot;
+//   * a thread owns the same rows and the same column records in every iteration, so the per-row
+//     and per-column bits of state live in REGISTERS: syndrome bit, running residual-syndrome bit
+//     (one bit per owned row x slot) and the previous hard decision (one bit per owned column x
+//     slot).  No ballots, no decision words and no syndrome words in shared memory on the hot path;
+//   * a column whose decision flipped raises one flag byte per incident edge (addresses come
+//     precomputed with the column record); the owning row thread folds the 8 flag bytes of its
+//     (row, slot) into the residual bit with one 64-bit load + popcount.  Unsatisfied slots are
+//     OR-reduced per warp (one REDUX + at most one shared atomic per warp and pass);
+//   * column records are sorted by degree and every degree class is padded to a multiple of 32
+//     with records that point at a scratch row, so a warp always runs an unpredicated,
+//     compile-time-degree column update; rows beyond m use the same scratch row;
+//   * min-sum check update = exclusive prefix/suffix minima, exactly the two sweeps of the serial
+//     decoder (3(RD-2) minima per row instead of min/second-min bookkeeping);
+//   * fp64: every operation is an explicitly rounded intrinsic issued in the serial order, so
+//     decisions, iteration counts and soft outputs are bit-identical to the CPU restatement.
+#pragma once
+
+#include "bp_kernel.cuh"
+
+namespace qd {
+
+constexpr int BP7_SMAX = 8;
+
+struct Bp7Params {
+    int m, n, nwm, nwn;
+    int m32;                    // rows rounded up to a multiple of 32
+    int nrec;                   // column records (degree classes padded to multiples of 32)
+    int max_iter;
+    int staged;                 // record table copied to shared memory
+    int uniform_prior;
+    double prior0;              // the common prior (decoder domain) when uniform_prior
+    double alpha_fixed;         // 0 => alpha_it = 1 - 2^-it
+    const uint4 *table;         // VMAX/4 uint4 per record, see bp7_pack_record()
+    const uint8_t *chunk_deg;   // [nrec / 32]
+    const void *prior_rec;      // real[nrec], decoder domain
+    const uint16_t *col_id;     // [nrec]; 0xFFFF = padding record
+    const uint32_t *const_bits; // [nwn] decisions of columns without edges
+    const uint32_t *synd; int synd_stride;
+    long long shots;
+    uint32_t *corr; int corr_stride;
+    uint8_t *conv; int32_t *iters; double *llr;
+    const uint32_t *err; int err_stride;
+    const uint32_t *lzT; int k;
+    uint8_t *fail;
+    long long *counters;        // {failures, shots, non_converged, iterations}
+    unsigned long long *next_shot;
+};
+
+struct Bp7Ctl {
+    long long shot[BP7_SMAX];
+    int born[BP7_SMAX];         // see BpCtl::born
+    unsigned unsat[2];          // bit s: slot s has an unsatisfied check (buffer T & 1)
+    int pad[2];
+};
+
+struct Bp7SmemLayout {
+    size_t msg, flags, table, out, ctl, total;
+    int msg_elems;              // elements of the message array (incl. scratch row)
+};
+
+__host__ __device__ inline int bp7_row_pitch(int rd, int s) { return (rd * s) | 1; }
+
+__host__ __device__ inline Bp7SmemLayout bp7_smem_layout(int m, int nrec, int nwn, int rd, int vmax, int s,
+                                                         int real_bytes, bool staged)
+{
+    Bp7SmemLayout L;
+    const int rp = bp7_row_pitch(rd, s);
+    L.msg_elems = (m + 1) * rp + 8 * s + 8;     // scratch row m, long enough for 8 scratch edges
+    size_t o = 0;
+    L.msg = o;   o += ((size_t)L.msg_elems * real_bytes + 15) & ~(size_t)15;
+    L.flags = o; o += (size_t)(m + 1) * s * 8;
+    o = (o + 15) & ~(size_t)15;
+    L.table = o; o += staged ? (size_t)nrec * vmax * 4 : 0;
+    L.out = o;   o += ((size_t)s * nwn * 4 + 15) & ~(size_t)15;
+    L.ctl = o;   o += sizeof(Bp7Ctl);
+    L.total = o;
+    return L;
+}
+
+// ---- [register + immediate] shared-memory accesses
+template <int OFF> __device__ __forceinline__ double lds_off(uint32_t a, double)
+{ double v; asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF)); return v; }
+template <int OFF> __device__ __forceinline__ float lds_off(uint32_t a, float)
+{ float v; asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF)); return v; }
+template <int OFF> __device__ __forceinline__ void sts_off(uint32_t a, double v)
+{ asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "d"(v) : "memory"); }
+template <int OFF> __device__ __forceinline__ void sts_off(uint32_t a, float v)
+{ asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(a), "n"(OFF), "f"(v) : "memory"); }
+template <int OFF> __device__ __forceinline__ unsigned long long lds_u64_off(uint32_t a)
+{ unsigned long long v; asm volatile("ld.shared.u64 %0, [%1+%2];" : "=l"(v) : "r"(a), "n"(OFF)); return v; }
+template <int OFF> __device__ __forceinline__ void sts_u64_off(uint32_t a, unsigned long long v)
+{ asm volatile("st.shared.u64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "l"(v) : "memory"); }
+template <int OFF> __device__ __forceinline__ void sts_u8_off(uint32_t a, uint32_t v)
+{ asm volatile("st.shared.u8 [%0+%1], %2;" ::"r"(a), "n"(OFF), "r"(v) : "memory"); }
+
+// ---- min-sum check update, exclusive prefix / suffix minima (the two sweeps of the serial decoder)
+// v: bit->check messages in, check->bit messages out.  sign0 = syndrome bit << 31.  Signs travel
+// as sign BITS (see check_ms_compute in bp_kernel.cuh for why that equals the serial `<= 0` rule).
+template <typename real, int RD>
+__device__ __forceinline__ void check_ms7(real (&v)[RD], unsigned sign0, real al)
+{
+    using A = Ar<real>;
+    unsigned hk[RD];
+    unsigned sx = sign0;
+#pragma unroll
+    for (int k = 0; k < RD; ++k) { hk[k] = hi_bits(v[k]); sx ^= hk[k]; v[k] = abs_bits(v[k]); }
+    real pm[RD];                                   // pm[k] = min(|v[0..k-1]|), k >= 1
+    pm[0] = A::big();
+    if (RD > 1) pm[1] = v[0];
+#pragma unroll
+    for (int k = 2; k < RD; ++k) pm[k] = A::mn(pm[k - 1], v[k - 1]);
+    real sm = A::big();                            // min(|v[k+1..]|)
+#pragma unroll
+    for (int k = RD - 1; k >= 0; --k) {
+        const real mag = k == RD - 1 ? pm[k] : (k == 0 ? sm : A::mn(pm[k], sm));
+        sm = k == RD - 1 ? v[k] : A::mn(sm, v[k]);
+        v[k] = xor_hi(A::mul(mag, al), (sx ^ hk[k]) & 0x80000000u);
+    }
+}
+
+// ---- product-sum check update in the probability-ratio domain, register resident
+template <typename real, int RD>
+__device__ __forceinline__ void check_ps7(real (&v)[RD], unsigned sbit)
+{
+    using A = Ar<real>;
+    real t[RD], pre[RD];
+    real temp = sbit ? (real)-1 : (real)1;
+#pragma unroll
+    for (int k = 0; k < RD; ++k) {
+        t[k] = A::sub(A::div((real)2, A::add((real)1, v[k])), (real)1);
+        pre[k] = temp;
+        temp = A::mul(temp, t[k]);
+    }
+    temp = (real)1;
+#pragma unroll
+    for (int k = RD - 1; k >= 0; --k) {
+        const real x = A::mul(pre[k], temp);
+        v[k] = A::div(A::sub((real)1, x), A::add((real)1, x));
+        temp = A::mul(temp, t[k]);
+    }
+}
+
+template <typename real, int METHOD, int RD, int VMAX, int S, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
+{
+    using A = Ar<real>;
+    static_assert(VMAX == 4 || VMAX == 8, "column tile");
+    static_assert(S >= 1 && S <= BP7_SMAX, "slots");
+    constexpr int RB = (int)sizeof(real);
+    constexpr int RP = (RD * S) | 1;
+    constexpr unsigned SMASK = (1u << S) - 1u;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = (int)threadIdx.x, NT = (int)blockDim.x, lane = tid & 31;
+
+    const Bp7SmemLayout L = bp7_smem_layout(p.m, p.nrec, p.nwn, RD, VMAX, S, RB, p.staged != 0);
+    const uint32_t a_msg = smem_u32(smem_raw + L.msg), a_flags = smem_u32(smem_raw + L.flags),
+                   a_tab = smem_u32(smem_raw + L.table);
+    uint32_t *outbits = reinterpret_cast<uint32_t *>(smem_raw + L.out);          // [S][nwn]
+    Bp7Ctl *ctl = reinterpret_cast<Bp7Ctl *>(smem_raw + L.ctl);
+    const real *prior_rec = static_cast<const real *>(p.prior_rec);
+    const real alpha_fixed = (real)p.alpha_fixed;
+    const bool staged = p.staged != 0;
+
+    if (staged) {
+        uint4 *st = reinterpret_cast<uint4 *>(smem_raw + L.table);
+        for (int i = tid; i < p.nrec * (VMAX / 4); i += NT) st[i] = p.table[i];
+    }
+    if (tid < S) {
+        const unsigned long long id = atomicAdd(p.next_shot, 1ULL);
+        const bool more = id < (unsigned long long)p.shots;
+        ctl->shot[tid] = more ? (long long)id : -1;
+        ctl->born[tid] = more ? -1 : BP_IDLE;          // -1: takes part in iteration 0 in full
+    }
+    if (tid == 0) ctl->unsat[0] = ctl->unsat[1] = 0u;
+    __syncthreads();
+
+    // ---- thread-owned state, bit (i * S + s): i-th owned row / column record, slot s
+    unsigned synbits = 0u, resbits = 0u, decbits = 0u;
+    long long c_fail = 0, c_shots = 0, c_nc = 0, c_it = 0;      // thread 0 only
+
+    // record -> shared addresses of its edges (slot 0) and of their flip-flag bytes (slot 0)
+    auto load_record = [&](int r, uint32_t (&ea)[VMAX], uint32_t (&fa)[VMAX]) {
+        uint32_t w[VMAX];                                        // VMAX/2 words of mq, then VMAX/2 of fq
+#pragma unroll
+        for (int q = 0; q < VMAX / 4; ++q) {
+            const uint4 x = staged ? lds_v4(a_tab + (uint32_t)(r * (VMAX / 4) + q) * 16u)
+                                   : __ldg(p.table + (size_t)r * (VMAX / 4) + q);
+            w[4 * q + 0] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
+        }
+#pragma unroll
+        for (int t = 0; t < VMAX; ++t) {
+            const uint32_t mw = w[t >> 1], fw = w[VMAX / 2 + (t >> 1)];
+            ea[t] = a_msg + ((t & 1) ? (mw >> 16) : (mw & 0xffffu)) * RB;
+            fa[t] = a_flags + ((t & 1) ? (fw >> 16) : (fw & 0xffffu));
+        }
+    };
+    auto prior_of = [&](int r) -> real { return p.uniform_prior ? (real)p.prior0 : prior_rec[r]; };
+
+    // ---- (re)load every slot born in `stamp`
+    auto load_slots = [&](int stamp) {
+        unsigned fresh = 0u;
+#pragma unroll
+        for (int s = 0; s < S; ++s) fresh |= (ctl->born[s] == stamp ? 1u : 0u) << s;
+        if (!fresh) return;
+        int i = 0;
+        for (int c = tid; c < p.m32; c += NT, ++i) {
+            const bool valid = c < p.m;
+            const uint32_t fb = a_flags + (uint32_t)(valid ? c : p.m) * (S * 8);
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                if ((fresh >> s) & 1u) {
+                    const int bi = i * S + s;
+                    unsigned b = 0u;
+                    if (valid) b = (p.synd[ctl->shot[s] * (long long)p.synd_stride + (c >> 5)] >> (c & 31)) & 1u;
+                    synbits = (synbits & ~(1u << bi)) | (b << bi);
+                    resbits = (resbits & ~(1u << bi)) | (b << bi);
+                    sts_u64(fb + s * 8, 0ULL);
+                }
+        }
+        i = 0;
+        for (int r = tid; r < p.nrec; r += NT, ++i) {
+            uint32_t ea[VMAX], fa[VMAX];
+            load_record(r, ea, fa);
+            const int deg = p.chunk_deg[r >> 5];
+            const real pj = prior_of(r);
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+                if ((fresh >> s) & 1u) {
+                    decbits &= ~(1u << (i * S + s));
+#pragma unroll
+                    for (int t = 0; t < VMAX; ++t)
+                        if (t < deg) sts_real(ea[t] + s * RB, pj);
+                }
+        }
+    };
+    load_slots(-1);
+    __syncthreads();
+    bool any_shot = false;
+#pragma unroll
+    for (int s = 0; s < S; ++s) any_shot |= ctl->born[s] != BP_IDLE;
+
+    for (int T = 0; any_shot; ++T) {
+        const int ub = T & 1;
+        // ================================================================== check pass
+        {
+            int born[S];
+            unsigned act = 0u;
+#pragma unroll
+            for (int s = 0; s < S; ++s) { born[s] = ctl->born[s]; act |= (born[s] != BP_IDLE ? 1u : 0u) << s; }
+            unsigned un = 0u;
+            int i = 0;
+            for (int c = tid; c < p.m32; c += NT, ++i) {
+                const bool valid = c < p.m;
+                const uint32_t row = (uint32_t)(valid ? c : p.m);
+                const uint32_t rb = a_msg + row * (uint32_t)(RP * RB);
+                const uint32_t fb = a_flags + row * (uint32_t)(S * 8);
+                auto body = [&](auto stag) {
+                    constexpr int s = decltype(stag)::value;
+                    const int bi = i * S + s;
+                    const unsigned long long f = lds_u64_off<s * 8>(fb);
+                    real v[RD];
+#pragma unroll
+                    for (int k = 0; k < RD; ++k) v[k] = lds_real(rb + (uint32_t)((k * S + s) * RB), real());
+                    resbits ^= ((unsigned)__popcll(f) & 1u) << bi;
+                    if (f) sts_u64_off<s * 8>(fb, 0ULL);
+                    un |= (valid ? (resbits >> bi) & 1u : 0u) << s;
+                    const unsigned sbit = (synbits >> bi) & 1u;
+                    if (METHOD == QD_BP_MIN_SUM_K) {
+                        const real al = alpha_fixed != (real)0 ? alpha_fixed : A::sub((real)1, pow2_neg<real>(T - born[s]));
+                        check_ms7<real, RD>(v, sbit << 31, al);
+                    } else {
+                        check_ps7<real, RD>(v, sbit);
+                    }
+#pragma unroll
+                    for (int k = 0; k < RD; ++k) sts_real(rb + (uint32_t)((k * S + s) * RB), v[k]);
+                };
+                if (act == SMASK) {                             // steady state: straight-line over the slots
+                    if (S > 0) body(std::integral_constant<int, 0>());
+                    if (S > 1) body(std::integral_constant<int, 1 % S>());
+                    if (S > 2) body(std::integral_constant<int, 2 % S>());
+                    if (S > 3) body(std::integral_constant<int, 3 % S>());
+                    if (S > 4) body(std::integral_constant<int, 4 % S>());
+                    if (S > 5) body(std::integral_constant<int, 5 % S>());
+                    if (S > 6) body(std::integral_constant<int, 6 % S>());
+                    if (S > 7) body(std::integral_constant<int, 7 % S>());
+                } else {
+                    if (S > 0 && (act & 1u)) body(std::integral_constant<int, 0>());
+                    if (S > 1 && (act & 2u)) body(std::integral_constant<int, 1 % S>());
+                    if (S > 2 && (act & 4u)) body(std::integral_constant<int, 2 % S>());
+                    if (S > 3 && (act & 8u)) body(std::integral_constant<int, 3 % S>());
+                    if (S > 4 && (act & 16u)) body(std::integral_constant<int, 4 % S>());
+                    if (S > 5 && (act & 32u)) body(std::integral_constant<int, 5 % S>());
+                    if (S > 6 && (act & 64u)) body(std::integral_constant<int, 6 % S>());
+                    if (S > 7 && (act & 128u)) body(std::integral_constant<int, 7 % S>());
+                }
+            }
+            un = __reduce_or_sync(0xffffffffu, un);
+            if (lane == 0 && un) atomicOr(&ctl->unsat[ub], un);
+        }
+        __syncthreads();
+
+        // ================================================================== retire / refill
+        {
+            const unsigned unsat = ctl->unsat[ub];
+            unsigned done = 0u;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const int b = ctl->born[s], it = T - b - 1;
+                done |= (b != BP_IDLE && it >= 1 && (!((unsat >> s) & 1u) || it >= p.max_iter) ? 1u : 0u) << s;
+            }
+            if (done) {
+                // hard decisions of the finished slots, back in column order
+                for (int w = tid; w < S * p.nwn; w += NT) outbits[w] = p.const_bits[w % p.nwn];
+                __syncthreads();
+                {
+                    int i = 0;
+                    for (int r = tid; r < p.nrec; r += NT, ++i) {
+                        const unsigned bits = (decbits >> (i * S)) & done;
+                        if (bits) {
+                            const unsigned col = p.col_id[r];
+                            if (col != 0xFFFFu) {
+#pragma unroll
+                                for (int s = 0; s < S; ++s)
+                                    if ((bits >> s) & 1u) atomicOr(&outbits[s * p.nwn + (col >> 5)], 1u << (col & 31));
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                for (int s = 0; s < S; ++s) {
+                    if (!((done >> s) & 1u)) continue;
+                    const int it = T - ctl->born[s] - 1;
+                    const int conv = !((unsat >> s) & 1u);
+                    const long long shot = ctl->shot[s];
+                    uint32_t *D = outbits + s * p.nwn;
+                    uint32_t *dst = p.corr + shot * (long long)p.corr_stride;
+                    for (int w = tid; w < p.corr_stride; w += NT) dst[w] = w < p.nwn ? D[w] : 0u;
+                    int f = 0;
+                    if (p.err) {
+                        const uint32_t *e = p.err + shot * (long long)p.err_stride;
+                        __syncthreads();
+                        for (int w = tid; w < p.nwn; w += NT) D[w] ^= e[w];
+                        __syncthreads();
+                        for (int i = tid; i < p.k; i += NT) {
+                            uint32_t acc = 0u;
+                            for (int w = 0; w < p.nwn; ++w) acc ^= p.lzT[(size_t)w * p.k + i] & D[w];
+                            f |= __popc(acc) & 1;
+                        }
+                        f = __syncthreads_or(f);
+                    }
+                    if (tid == 0) {
+                        if (p.conv) p.conv[shot] = (uint8_t)conv;
+                        if (p.iters) p.iters[shot] = it;
+                        if (p.fail) p.fail[shot] = (uint8_t)f;
+                        c_fail += f; c_shots += 1; c_nc += !conv; c_it += it;
+                    }
+                }
+                __syncthreads();
+                if (tid < S && ((done >> tid) & 1u)) {
+                    const unsigned long long id = atomicAdd(p.next_shot, 1ULL);
+                    const bool more = id < (unsigned long long)p.shots;
+                    ctl->shot[tid] = more ? (long long)id : -1;
+                    ctl->born[tid] = more ? T : BP_IDLE;
+                }
+                __syncthreads();
+                bool any_active = false;
+#pragma unroll
+                for (int s = 0; s < S; ++s) any_active |= ctl->born[s] != BP_IDLE;
+                if (!any_active) break;
+                load_slots(T);
+                // no barrier: the bit pass below skips slots born in T and ends with a barrier
+            }
+        }
+
+        // ================================================================== bit pass
+        {
+            unsigned run = 0u;
+            long long shot_of[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const int b = ctl->born[s];
+                run |= (b != BP_IDLE && b != T ? 1u : 0u) << s;
+                shot_of[s] = p.llr ? ctl->shot[s] : 0;
+            }
+            int i = 0;
+            for (int r = tid; r < p.nrec; r += NT, ++i) {
+                uint32_t ea[VMAX], fa[VMAX];
+                load_record(r, ea, fa);
+                const real pj = prior_of(r);
+                const int deg = __shfl_sync(0xffffffffu, (int)__ldg(p.chunk_deg + (r >> 5)), 0);
+                auto run_deg = [&](auto dtag) {
+                    constexpr int D = decltype(dtag)::value;
+                    auto body = [&](auto stag) {
+                        constexpr int s = decltype(stag)::value;
+                        const int bi = i * S + s;
+                        real cv[D], soft;
+#pragma unroll
+                        for (int t = 0; t < D; ++t) cv[t] = lds_off<s * RB>(ea[t], real());
+                        const unsigned dbit = bit_compute<real, METHOD, D>(cv, pj, soft);
+#pragma unroll
+                        for (int t = 0; t < D; ++t) sts_off<s * RB>(ea[t], cv[t]);
+                        const unsigned flip = ((decbits >> bi) & 1u) ^ dbit;
+                        if (flip) {
+#pragma unroll
+                            for (int t = 0; t < D; ++t) sts_u8_off<s * 8>(fa[t], 1u);
+                        }
+                        decbits ^= flip << bi;
+                        if (p.llr) {
+                            const unsigned col = p.col_id[r];
+                            if (col != 0xFFFFu)
+                                p.llr[shot_of[s] * (long long)p.n + col] =
+                                    METHOD == QD_BP_MIN_SUM_K ? (double)soft : (double)A::lg(A::div((real)1, soft));
+                        }
+                    };
+                    if (run == SMASK) {
+                        if (S > 0) body(std::integral_constant<int, 0>());
+                        if (S > 1) body(std::integral_constant<int, 1 % S>());
+                        if (S > 2) body(std::integral_constant<int, 2 % S>());
+                        if (S > 3) body(std::integral_constant<int, 3 % S>());
+                        if (S > 4) body(std::integral_constant<int, 4 % S>());
+                        if (S > 5) body(std::integral_constant<int, 5 % S>());
+                        if (S > 6) body(std::integral_constant<int, 6 % S>());
+                        if (S > 7) body(std::integral_constant<int, 7 % S>());
+                    } else {
+                        if (S > 0 && (run & 1u)) body(std::integral_constant<int, 0>());
+                        if (S > 1 && (run & 2u)) body(std::integral_constant<int, 1 % S>());
+                        if (S > 2 && (run & 4u)) body(std::integral_constant<int, 2 % S>());
+                        if (S > 3 && (run & 8u)) body(std::integral_constant<int, 3 % S>());
+                        if (S > 4 && (run & 16u)) body(std::integral_constant<int, 4 % S>());
+                        if (S > 5 && (run & 32u)) body(std::integral_constant<int, 5 % S>());
+                        if (S > 6 && (run & 64u)) body(std::integral_constant<int, 6 % S>());
+                        if (S > 7 && (run & 128u)) body(std::integral_constant<int, 7 % S>());
+                    }
+                };
+                switch (deg) {
+                case 1: run_deg(std::integral_constant<int, 1>()); break;
+                case 2: run_deg(std::integral_constant<int, 2>()); break;
+                case 3: run_deg(std::integral_constant<int, 3>()); break;
+                case 4: run_deg(std::integral_constant<int, 4>()); break;
+                case 5: if (VMAX > 4) run_deg(std::integral_constant<int, (VMAX > 4 ? 5 : 1)>()); break;
+                case 6: if (VMAX > 4) run_deg(std::integral_constant<int, (VMAX > 4 ? 6 : 1)>()); break;
+                case 7: if (VMAX > 4) run_deg(std::integral_constant<int, (VMAX > 4 ? 7 : 1)>()); break;
+                case 8: if (VMAX > 4) run_deg(std::integral_constant<int, (VMAX > 4 ? 8 : 1)>()); break;
+                default: break;
+                }
+            }
+        }
+        if (tid == 0) ctl->unsat[ub ^ 1] = 0u;              // buffer of the next check pass
+        __syncthreads();
+    }
+
+    if (tid == 0 && p.counters && c_shots) {
+        atomicAdd((unsigned long long *)&p.counters[0], (unsigned long long)c_fail);
+        atomicAdd((unsigned long long *)&p.counters[1], (unsigned long long)c_shots);
+        atomicAdd((unsigned long long *)&p.counters[2], (unsigned long long)c_nc);
+        atomicAdd((unsigned long long *)&p.counters[3], (unsigned long long)c_it);
+    }
+}
+
+}  // namespace qd

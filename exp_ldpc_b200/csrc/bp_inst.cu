@@ -1,0 +1,58 @@
+// bp_inst.cu — explicit instantiations of the BP kernels, one translation unit per
+// (precision, method): compiled several times with -DQD_INST_REAL / -DQD_INST_METHOD /
+// -DQD_INST_TAG so that the objects build in parallel.  Each object exports two pickers.
+#include "bp7_kernel.cuh"
+#include "bp_pick.h"
+
+#ifndef QD_INST_REAL
+#error "compile with -DQD_INST_REAL=double|float -DQD_INST_METHOD=0|3 -DQD_INST_TAG=f64_ms|..."
+#endif
+
+namespace qd {
+
+#define QD_CAT_(a, b) a##b
+#define QD_CAT(a, b) QD_CAT_(a, b)
+
+// ---- generic kernel (any row degrees): column tile 8 or 16, 32-bit message positions ----------
+bp_kernel_fn QD_CAT(pick_bp6_, QD_INST_TAG)(int vmax, int threads)
+{
+    typedef QD_INST_REAL real;
+    constexpr int M = QD_INST_METHOD;
+    if (threads <= 512)
+        return vmax <= 8 ? bp_kernel<real, M, 0, 8, uint32_t, 512> : bp_kernel<real, M, 0, 16, uint32_t, 512>;
+    return vmax <= 8 ? bp_kernel<real, M, 0, 8, uint32_t, 1024> : bp_kernel<real, M, 0, 16, uint32_t, 1024>;
+}
+
+// ---- row-regular kernel: (row degree, column tile) x slots -------------------------------------
+template <typename real, int M, int RD, int VMAX>
+static bp7_kernel_fn pick7_s(int slots)
+{
+    switch (slots) {
+    case 1: return bp7_kernel<real, M, RD, VMAX, 1, BP7_MAXT, 1>;
+    case 2: return bp7_kernel<real, M, RD, VMAX, 2, BP7_MAXT, 1>;
+#ifndef QD_FAST_BUILD
+    case 3: return bp7_kernel<real, M, RD, VMAX, 3, BP7_MAXT, 1>;
+    case 6: return bp7_kernel<real, M, RD, VMAX, 6, BP7_MAXT, 1>;
+#endif
+    case 4: return bp7_kernel<real, M, RD, VMAX, 4, BP7_MAXT, 1>;
+    case 8: return bp7_kernel<real, M, RD, VMAX, 8, BP7_MAXT, 1>;
+    default: return nullptr;
+    }
+}
+
+bp7_kernel_fn QD_CAT(pick_bp7_, QD_INST_TAG)(int rd, int vmax, int slots)
+{
+    typedef QD_INST_REAL real;
+    constexpr int M = QD_INST_METHOD;
+    switch (rd * 100 + vmax) {
+    case 704: return pick7_s<real, M, 7, 4>(slots);
+#ifndef QD_FAST_BUILD
+    case 604: return pick7_s<real, M, 6, 4>(slots);
+    case 808: return pick7_s<real, M, 8, 8>(slots);
+    case 908: return pick7_s<real, M, 9, 8>(slots);
+#endif
+    default: return nullptr;
+    }
+}
+
+}  // namespace qd

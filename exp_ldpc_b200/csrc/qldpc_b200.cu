@@ -12,7 +12,8 @@
 #include <string>
 #include <vector>
 
-#include "bp_kernel.cuh"
+#include "bp7_kernel.cuh"
+#include "bp_pick.h"
 #include "ssf_kernel.cuh"
 
 namespace qd {
@@ -168,6 +169,7 @@ struct qd_graph {
     GraphDev dev{};
     std::vector<int32_t> row_ptr, col_idx, col_ptr;
     std::vector<uint32_t> row_desc, col_desc, csc_pos, csc_row, fpos_of_pos;
+    std::vector<uint8_t> csc_k;      // index of the edge within its row
     DevBuf d_row_desc, d_col_desc, d_csc_pos, d_csc_row, d_row_ptr, d_col_idx, d_fpos;
     int sm_count = 0, smem_optin = 0;
 };
@@ -184,10 +186,9 @@ struct qd_sampler {
     DevBuf d_thr;
 };
 
-typedef void (*bp_kernel_fn)(const BpParams);
-
 struct qd_bp {
     qd_graph *g = nullptr;
+    int device = 0;        // copy: the graph handle may be destroyed before the decoder
     int max_iter = 0, method = 0, precision = 64;
     int vmax = 4;          // register tile of a column
     int rd = 0;            // compile-time row degree of the selected kernel (0 = generic rows)
@@ -196,6 +197,11 @@ struct qd_bp {
     int threads = 0, slots = 0, ctas_per_sm = 0, groups = 1;
     size_t smem = 0;
     DevBuf d_prior, d_alpha, d_next, d_vidx, d_chunk_deg;
+    // row-regular kernel (bp7_kernel.cuh): record table for the configured slot count
+    int v7 = 0, v7_nrec = 0, v7_uniform = 0, v7_staged = 0;
+    double v7_prior0 = 0.0, alpha_fixed = 0.0;
+    std::vector<double> prior_dom;   // priors in the decoder's domain, per column
+    DevBuf d7_table, d7_chunk_deg, d7_prior_rec, d7_col_id, d7_const_bits;
     // host-buffer pipeline state
     cudaStream_t streams[2] = {nullptr, nullptr};
     cudaEvent_t done[2] = {nullptr, nullptr};
@@ -212,6 +218,7 @@ struct qd_bp {
 
 struct qd_ssf {
     qd_graph *g = nullptr;
+    int device = 0;
     SsfDev dev{};
     int max_rounds = 0;
     int threads = 128;
@@ -317,6 +324,7 @@ extern "C" int qd_graph_create(int32_t m, int32_t n, int64_t nnz, const int32_t 
     if (max_col > 255) return fail(QD_EUNSUP, "column degree > 255");
     g->csc_pos.resize(std::max<int64_t>(nnz, 1));
     g->csc_row.resize(std::max<int64_t>(nnz, 1));
+    g->csc_k.resize(std::max<int64_t>(nnz, 1));
     g->col_desc.resize(n);
     {
         std::vector<int> fill(g->col_ptr.begin(), g->col_ptr.end() - 1);
@@ -325,6 +333,7 @@ extern "C" int qd_graph_create(int32_t m, int32_t n, int64_t nnz, const int32_t 
                 const int t = fill[h_col_idx[e]]++;
                 g->csc_pos[t] = (uint32_t)pos_of_edge[e];
                 g->csc_row[t] = (uint32_t)i;
+                g->csc_k[t] = (uint8_t)(e - h_row_ptr[i]);
             }
         for (int j = 0; j < n; ++j)
             g->col_desc[j] = (uint32_t)g->col_ptr[j] | ((uint32_t)(g->col_ptr[j + 1] - g->col_ptr[j]) << 24);
@@ -460,49 +469,20 @@ extern "C" int qd_logical_fail_batch(qd_logicals *l, const uint32_t *d_a, const 
 // =============================================================================================
 // BP
 // =============================================================================================
-// ---- kernel instantiation table ---------------------------------------------------------------
-// specialised: regular row degree RD in {6,7,8,9}, column tile 4 or 8, 16-bit message positions;
-// generic:     any row degree (<= 255; <= 16 for product-sum), column tile 8 or 16, 32-bit positions.
-template <typename real, int METHOD, int MAXT>
-static bp_kernel_fn pick_bp_rd(int rd, int vmax)
-{
-#ifdef QD_FAST_BUILD
-    if (rd == 7 && vmax == 4) return bp_kernel<real, METHOD, 7, 4, uint16_t, MAXT>;
-    return vmax <= 8 ? bp_kernel<real, METHOD, 0, 8, uint32_t, MAXT> : bp_kernel<real, METHOD, 0, 16, uint32_t, MAXT>;
-#else
-    switch (rd * 100 + vmax) {
-    case 604: return bp_kernel<real, METHOD, 6, 4, uint16_t, MAXT>;
-    case 608: return bp_kernel<real, METHOD, 6, 8, uint16_t, MAXT>;
-    case 704: return bp_kernel<real, METHOD, 7, 4, uint16_t, MAXT>;
-    case 708: return bp_kernel<real, METHOD, 7, 8, uint16_t, MAXT>;
-    case 804: return bp_kernel<real, METHOD, 8, 4, uint16_t, MAXT>;
-    case 808: return bp_kernel<real, METHOD, 8, 8, uint16_t, MAXT>;
-    case 904: return bp_kernel<real, METHOD, 9, 4, uint16_t, MAXT>;
-    case 908: return bp_kernel<real, METHOD, 9, 8, uint16_t, MAXT>;
-    case 8:   return bp_kernel<real, METHOD, 0, 8, uint32_t, MAXT>;
-    default:  return bp_kernel<real, METHOD, 0, 16, uint32_t, MAXT>;
-    }
-#endif
-}
-
-template <typename real, int METHOD>
-static bp_kernel_fn pick_bp(int rd, int vmax, int threads)
-{
-    // register budget follows the number of resident threads per SM (threads x CTAs/SM)
-    if (threads <= 512) return pick_bp_rd<real, METHOD, 512>(rd, vmax);
-    if (threads <= 640) return pick_bp_rd<real, METHOD, 640>(rd, vmax);
-    if (threads <= 768) return pick_bp_rd<real, METHOD, 768>(rd, vmax);
-    if (threads <= 896) return pick_bp_rd<real, METHOD, 896>(rd, vmax);
-    return pick_bp_rd<real, METHOD, 1024>(rd, vmax);
-}
-
+// ---- kernel pickers (instantiations live in bp_inst.cu, one object per precision x method) ----
 static bp_kernel_fn bp_kernel_for(const qd_bp *d)
 {
+    const int t = d->threads * d->ctas_per_sm;
     if (d->precision == QD_PREC_F64)
-        return d->method == QD_BP_MIN_SUM ? pick_bp<double, QD_BP_MIN_SUM>(d->rd, d->vmax, d->threads * d->ctas_per_sm)
-                                          : pick_bp<double, QD_BP_PRODUCT_SUM>(d->rd, d->vmax, d->threads * d->ctas_per_sm);
-    return d->method == QD_BP_MIN_SUM ? pick_bp<float, QD_BP_MIN_SUM>(d->rd, d->vmax, d->threads * d->ctas_per_sm)
-                                      : pick_bp<float, QD_BP_PRODUCT_SUM>(d->rd, d->vmax, d->threads * d->ctas_per_sm);
+        return d->method == QD_BP_MIN_SUM ? pick_bp6_f64_ms(d->vmax, t) : pick_bp6_f64_ps(d->vmax, t);
+    return d->method == QD_BP_MIN_SUM ? pick_bp6_f32_ms(d->vmax, t) : pick_bp6_f32_ps(d->vmax, t);
+}
+
+static bp7_kernel_fn bp7_kernel_for(const qd_bp *d, int slots)
+{
+    if (d->precision == QD_PREC_F64)
+        return d->method == QD_BP_MIN_SUM ? pick_bp7_f64_ms(d->rd, d->vmax, slots) : pick_bp7_f64_ps(d->rd, d->vmax, slots);
+    return d->method == QD_BP_MIN_SUM ? pick_bp7_f32_ms(d->rd, d->vmax, slots) : pick_bp7_f32_ps(d->rd, d->vmax, slots);
 }
 
 static size_t bp_smem(const qd_bp *d, int slots, bool stage)
@@ -535,64 +515,12 @@ static int bp_default_config(qd_bp *d)
     return 0;
 }
 
-extern "C" int qd_bp_create(qd_graph *g, const double *h_channel_probs, int32_t max_iter, int32_t method,
-                            double ms_scaling_factor, int32_t precision, qd_bp **out)
+// tables of the generic kernel: per-column message positions and per-chunk common degree
+static int bp6_prepare(qd_bp *d)
 {
-    if (!out) return fail(QD_EINVAL, "out is NULL");
-    *out = nullptr;
-    if (!g || !h_channel_probs) return fail(QD_EINVAL, "graph or channel_probs is NULL");
-    if (method != QD_BP_PRODUCT_SUM && method != QD_BP_MIN_SUM) return fail(QD_EINVAL, "unknown bp method");
-    if (precision != QD_PREC_F64 && precision != QD_PREC_F32) return fail(QD_EINVAL, "precision must be 64 or 32");
-    if (max_iter < 0) return fail(QD_EINVAL, "max_iter < 0");
-    int rc = use_device(g->device);
-    if (rc) return rc;
+    qd_graph *g = d->g;
     const GraphDev &gd = g->dev;
-    std::unique_ptr<qd_bp> d(new qd_bp);
-    d->g = g;
-    d->max_iter = max_iter > 0 ? max_iter : gd.n;   // ldpc convention: 0 -> n
-    d->method = method;
-    d->precision = precision;
-    if (gd.max_col_deg > 16) return fail(QD_EUNSUP, "column degree > 16 not supported by the shared-memory BP kernel");
-    const bool special = gd.regular_deg >= 6 && gd.regular_deg <= 9 && gd.max_col_deg <= 8 && gd.npos < 65535 &&
-                         gd.pitch == (gd.regular_deg | 1);
-#ifdef QD_FAST_BUILD
-    const bool have_special = special && gd.regular_deg == 7 && gd.max_col_deg <= 4;
-#else
-    const bool have_special = special;
-#endif
-    if (have_special) {
-        d->rd = gd.regular_deg;
-        d->vmax = gd.max_col_deg <= 4 ? 4 : 8;
-        d->idx_bytes = 2;
-    } else {
-        d->rd = 0;
-        d->vmax = gd.max_col_deg <= 8 ? 8 : 16;
-        d->idx_bytes = 4;
-        if (method == QD_BP_PRODUCT_SUM && gd.max_row_deg > 16)
-            return fail(QD_EUNSUP, "product-sum: row degree > 16 not supported by the shared-memory BP kernel");
-    }
-    // priors in the decoder's domain, computed in double with the host libm (same as the oracle)
-    std::vector<double> pr(gd.n), al(d->max_iter + 1, 0.0);
-    for (int j = 0; j < gd.n; ++j) {
-        const double p = h_channel_probs[j];
-        if (!(p > 0.0) || !(p < 1.0)) return fail(QD_EINVAL, "channel probabilities must lie in (0, 1)");
-        pr[j] = method == QD_BP_MIN_SUM ? std::log((1.0 - p) / p) : p / (1.0 - p);
-    }
-    // al[0] = the fixed scaling factor (0 selects the 1 - 2^-it schedule, formed exactly on the device);
-    // al[1..] = the schedule as the host computes it (reference values, checked against the device formula)
-    al[0] = ms_scaling_factor;
-    for (int it = 1; it <= d->max_iter; ++it)
-        al[it] = ms_scaling_factor == 0.0 ? 1.0 - std::pow(2.0, -1.0 * it / 1.0) : ms_scaling_factor;
-    for (int it = 1; it <= std::min(d->max_iter, 1100); ++it)
-        if (ms_scaling_factor == 0.0 && al[it] != 1.0 - std::ldexp(1.0, -it)) return fail(QD_ECUDA, "alpha schedule mismatch");
-    if (precision == QD_PREC_F64) {
-        if ((rc = upload(d->d_prior, pr))) return rc;
-        if ((rc = upload(d->d_alpha, al))) return rc;
-    } else {
-        std::vector<float> prf(pr.begin(), pr.end()), alf(al.begin(), al.end());
-        if ((rc = upload(d->d_prior, prf))) return rc;
-        if ((rc = upload(d->d_alpha, alf))) return rc;
-    }
+    int rc;
     {   // per-column message positions, padded to the column tile, ~0 = no edge
         const size_t cnt = (size_t)gd.n * d->vmax;
         if (d->idx_bytes == 2) {
@@ -619,21 +547,278 @@ extern "C" int qd_bp_create(qd_graph *g, const double *h_channel_probs, int32_t 
         }
         if ((rc = upload(d->d_chunk_deg, cd))) return rc;
     }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// row-regular kernel (bp7_kernel.cuh): record table, launch geometry
+// ---------------------------------------------------------------------------------------------
+static const int kBp7Slots[] = {8, 6, 4, 3, 2, 1};
+
+static size_t bp7_smem(const qd_bp *d, int slots, bool staged, int nrec)
+{
+    const GraphDev &g = d->g->dev;
+    return bp7_smem_layout(g.m, nrec, g.nwn, d->rd, d->vmax, slots, d->precision == QD_PREC_F64 ? 8 : 4, staged).total;
+}
+
+static int bp7_nrec(const qd_bp *d)
+{
+    const qd_graph *g = d->g;
+    std::vector<int> cnt(d->vmax + 1, 0);
+    for (int j = 0; j < g->dev.n; ++j) cnt[g->col_ptr[j + 1] - g->col_ptr[j]]++;
+    int nrec = 0;
+    for (int dg = 1; dg <= d->vmax; ++dg) nrec += (cnt[dg] + 31) / 32 * 32;
+    return nrec;
+}
+
+// can a (slots, threads) geometry be represented?  per-thread state is one bit per owned
+// (row | record, slot) in a 32-bit register; positions are 16-bit
+static bool bp7_geometry_ok(const qd_bp *d, int slots, int threads, int nrec)
+{
+    const GraphDev &g = d->g->dev;
+    const int m32 = (g.m + 31) / 32 * 32;
+    const Bp7SmemLayout L = bp7_smem_layout(g.m, nrec, g.nwn, d->rd, d->vmax, slots, 8, false);
+    if (L.msg_elems > 65535 || (g.m + 1) * slots * 8 > 65535 || g.n >= 65535) return false;
+    if (threads < 32 || threads > BP7_MAXT || threads % 32) return false;
+    if (((m32 + threads - 1) / threads) * slots > 32) return false;
+    if (((nrec + threads - 1) / threads) * slots > 32) return false;
+    return bp7_kernel_for(d, slots) != nullptr;
+}
+
+// build and upload the record table for `slots` shots per CTA
+static int bp7_prepare(qd_bp *d, int slots)
+{
+    qd_graph *g = d->g;
+    const GraphDev &gd = g->dev;
+    const int V = d->vmax, S = slots, RD = d->rd, RP = bp7_row_pitch(RD, S);
+    std::vector<std::vector<int>> cls(V + 1);
+    std::vector<uint32_t> const_bits(std::max(gd.nwn, 1), 0u);
+    for (int j = 0; j < gd.n; ++j) {
+        const int dg = g->col_ptr[j + 1] - g->col_ptr[j];
+        if (dg == 0) {   // no edges: the decision never changes (serial rule: llr <= 0, resp. ratio >= 1)
+            const double pr = d->prior_dom[j];
+            if (d->method == QD_BP_MIN_SUM ? pr <= 0.0 : pr >= 1.0) const_bits[j >> 5] |= 1u << (j & 31);
+        } else cls[dg].push_back(j);
+    }
+    std::vector<uint16_t> table, col_id;
+    std::vector<uint8_t> chunk_deg;
+    std::vector<double> prior_rec;
+    for (int dg = 1; dg <= V; ++dg) {
+        const int cnt = (int)cls[dg].size(), padded = (cnt + 31) / 32 * 32;
+        for (int r = 0; r < padded; ++r) {
+            uint16_t mq[8] = {0}, fq[8] = {0};
+            const int j = r < cnt ? cls[dg][r] : -1;
+            for (int t = 0; t < V; ++t) {
+                if (t < dg && j >= 0) {
+                    const int e = g->col_ptr[j] + t;
+                    const int row = (int)g->csc_row[e], k = g->csc_k[e];
+                    mq[t] = (uint16_t)(row * RP + k * S);
+                    fq[t] = (uint16_t)(row * S * 8 + k);
+                } else {             // scratch row
+                    mq[t] = (uint16_t)(gd.m * RP + t * S);
+                    fq[t] = (uint16_t)(gd.m * S * 8 + t);
+                }
+            }
+            for (int t = 0; t < V; ++t) table.push_back(mq[t]);
+            for (int t = 0; t < V; ++t) table.push_back(fq[t]);
+            col_id.push_back(j >= 0 ? (uint16_t)j : (uint16_t)0xFFFF);
+            prior_rec.push_back(j >= 0 ? d->prior_dom[j] : d->prior_dom[0]);
+            if ((r & 31) == 0) chunk_deg.push_back((uint8_t)dg);
+        }
+    }
+    d->v7_nrec = (int)col_id.size();
+    if (table.empty()) { table.assign(2 * V, 0); col_id.assign(1, 0xFFFF); prior_rec.assign(1, 1.0); chunk_deg.assign(1, 0); }
+    int rc;
+    if ((rc = upload(d->d7_table, table))) return rc;
+    if ((rc = upload(d->d7_col_id, col_id))) return rc;
+    if ((rc = upload(d->d7_chunk_deg, chunk_deg))) return rc;
+    if ((rc = upload(d->d7_const_bits, const_bits))) return rc;
+    if (d->precision == QD_PREC_F64) {
+        if ((rc = upload(d->d7_prior_rec, prior_rec))) return rc;
+    } else {
+        std::vector<float> pf(prior_rec.begin(), prior_rec.end());
+        if ((rc = upload(d->d7_prior_rec, pf))) return rc;
+    }
+    return 0;
+}
+
+// set (threads, slots, ctas) for the row-regular kernel; 0 = choose
+static int bp7_configure(qd_bp *d, int threads, int slots, int ctas)
+{
+    const GraphDev &g = d->g->dev;
+    const size_t budget = (size_t)d->g->smem_optin;
+    const int nrec = bp7_nrec(d);
+    const int m32 = (g.m + 31) / 32 * 32;
+    auto pick_threads = [&](int S) -> int {
+        // fewest passes over the owned rows / records, then the fewest idle lanes
+        int best = 0; long best_cost = -1;
+        for (int t = 32; t <= BP7_MAXT; t += 32) {
+            if (!bp7_geometry_ok(d, S, t, nrec)) continue;
+            const long cost = (long)((m32 + t - 1) / t) * 4 * d->rd + (long)((nrec + t - 1) / t) * 9;
+            const long score = cost * 4096 + t;                  // equal passes: fewer threads
+            if (best_cost < 0 || score < best_cost) { best_cost = score; best = t; }
+        }
+        return best;
+    };
+    int S = slots, T = threads, staged = 1;
+    if (S <= 0) {
+        // as many shots per SM as shared memory holds: big graphs take one CTA per SM, small ones several
+        S = 0;
+        for (int cand : kBp7Slots) {
+            if (!bp7_kernel_for(d, cand)) continue;
+            const bool fits_staged = bp7_smem(d, cand, true, nrec) <= budget;
+            if (!fits_staged && bp7_smem(d, cand, false, nrec) > budget) continue;
+            if (!pick_threads(cand)) continue;
+            // small graphs: prefer more CTAs over more slots once a CTA holds >= 4 shots
+            if (cand > 4 && bp7_smem(d, 4, true, nrec) * 2 <= budget && bp7_kernel_for(d, 4) && pick_threads(4)) continue;
+            S = cand;
+            break;
+        }
+        if (!S) return fail(QD_EUNSUP, "row-regular BP kernel: graph does not fit shared memory");
+    }
+    if (!bp7_kernel_for(d, S)) return fail(QD_EINVAL, "slots must be one of the compiled slot counts (1,2,3,4,6,8)");
+    if (T <= 0) T = pick_threads(S);
+    if (!T || !bp7_geometry_ok(d, S, T, nrec))
+        return fail(QD_EINVAL, "threads/slots: owned rows x slots and owned columns x slots must be <= 32, threads <= 800");
+    size_t smem = bp7_smem(d, S, true, nrec);
+    if (smem > budget) { staged = 0; smem = bp7_smem(d, S, false, nrec); }
+    if (smem > budget) return fail(QD_EUNSUP, "configuration does not fit shared memory");
+    int C = ctas;
+    if (C <= 0) {
+        const size_t per_sm = 228u * 1024u;                       // B200: 228 KB per SM, 1 KB reserved per CTA
+        C = (int)std::max<size_t>(1, per_sm / (smem + 1024));
+        C = std::min(C, std::max(1, BP7_MAXT / T));               // 80 registers x 800 threads fill the register file
+        C = std::min(C, 8);
+    }
+    int rc;
+    if (S != d->slots || !d->d7_table.p) { if ((rc = bp7_prepare(d, S))) return rc; }
+    d->threads = T; d->slots = S; d->ctas_per_sm = C; d->groups = 1; d->smem = smem; d->v7_staged = staged;
+    return 0;
+}
+
+
+// pick the kernel family and its default launch geometry.  Row-regular graphs with a compiled
+// (row degree, column tile) pair take the thread-owned-state kernel (bp7_kernel.cuh) when they fit;
+// everything else the generic kernel (bp_kernel.cuh).
+static int bp_choose_kernel(qd_bp *d, bool allow_regular)
+{
+    const GraphDev &gd = d->g->dev;
+    int rc;
+    d->v7 = 0;
+    if (allow_regular && gd.regular_deg >= 2 && gd.max_col_deg >= 1 && gd.max_col_deg <= 8) {
+        d->rd = gd.regular_deg;
+        d->vmax = gd.max_col_deg <= 4 ? 4 : 8;
+        if (!bp7_kernel_for(d, 1) && d->vmax == 4) d->vmax = 8;
+        if (bp7_kernel_for(d, 1)) {
+            d->v7 = 1;
+            d->slots = 0;
+            d->d7_table.alloc(0);
+            if (bp7_configure(d, 0, 0, 0) != 0) d->v7 = 0;     // does not fit: generic kernel
+        }
+    }
+    if (!d->v7) {
+        d->rd = 0;
+        d->vmax = gd.max_col_deg <= 8 ? 8 : 16;
+        d->idx_bytes = 4;
+        if ((rc = bp6_prepare(d))) return rc;
+        if ((rc = bp_default_config(d))) return rc;
+    }
+    return 0;
+}
+
+extern "C" int qd_bp_select_kernel(qd_bp *d, int32_t family)
+{
+    if (!d) return fail(QD_EINVAL, "NULL handle");
+    if (family != 0 && family != 6 && family != 7) return fail(QD_EINVAL, "kernel family must be 0 (automatic), 6 (generic) or 7 (row-regular)");
+    int rc = use_device(d->g->device);
+    if (rc) return rc;
+    if ((rc = bp_choose_kernel(d, family != 6))) return rc;
+    if (family == 7 && !d->v7) return fail(QD_EUNSUP, "the row-regular BP kernel does not support this graph");
+    return 0;
+}
+
+extern "C" int qd_bp_get_kernel(qd_bp *d, int32_t *family, int32_t *row_degree, int32_t *column_tile)
+{
+    if (!d) return fail(QD_EINVAL, "NULL handle");
+    if (family) *family = d->v7 ? 7 : 6;
+    if (row_degree) *row_degree = d->rd;
+    if (column_tile) *column_tile = d->vmax;
+    return 0;
+}
+
+extern "C" int qd_bp_create(qd_graph *g, const double *h_channel_probs, int32_t max_iter, int32_t method,
+                            double ms_scaling_factor, int32_t precision, qd_bp **out)
+{
+    if (!out) return fail(QD_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!g || !h_channel_probs) return fail(QD_EINVAL, "graph or channel_probs is NULL");
+    if (method != QD_BP_PRODUCT_SUM && method != QD_BP_MIN_SUM) return fail(QD_EINVAL, "unknown bp method");
+    if (precision != QD_PREC_F64 && precision != QD_PREC_F32) return fail(QD_EINVAL, "precision must be 64 or 32");
+    if (max_iter < 0) return fail(QD_EINVAL, "max_iter < 0");
+    int rc = use_device(g->device);
+    if (rc) return rc;
+    const GraphDev &gd = g->dev;
+    std::unique_ptr<qd_bp> d(new qd_bp);
+    d->g = g;
+    d->device = g->device;
+    d->max_iter = max_iter > 0 ? max_iter : gd.n;   // ldpc convention: 0 -> n
+    d->method = method;
+    d->precision = precision;
+    if (gd.max_col_deg > 16) return fail(QD_EUNSUP, "column degree > 16 not supported by the shared-memory BP kernel");
+    d->alpha_fixed = ms_scaling_factor;
+    d->rd = 0;
+    d->vmax = gd.max_col_deg <= 8 ? 8 : 16;
+    d->idx_bytes = 4;
+    if (method == QD_BP_PRODUCT_SUM && gd.max_row_deg > 16)
+        return fail(QD_EUNSUP, "product-sum: row degree > 16 not supported by the shared-memory BP kernel");
+    // priors in the decoder's domain, computed in double with the host libm (same as the oracle)
+    std::vector<double> pr(gd.n), al(d->max_iter + 1, 0.0);
+    for (int j = 0; j < gd.n; ++j) {
+        const double p = h_channel_probs[j];
+        if (!(p > 0.0) || !(p < 1.0)) return fail(QD_EINVAL, "channel probabilities must lie in (0, 1)");
+        pr[j] = method == QD_BP_MIN_SUM ? std::log((1.0 - p) / p) : p / (1.0 - p);
+    }
+    d->prior_dom = pr;
+    d->v7_uniform = 1;
+    for (int j = 1; j < gd.n; ++j) if (pr[j] != pr[0]) { d->v7_uniform = 0; break; }
+    d->v7_prior0 = pr[0];
+    // al[0] = the fixed scaling factor (0 selects the 1 - 2^-it schedule, formed exactly on the device);
+    // al[1..] = the schedule as the host computes it (reference values, checked against the device formula)
+    al[0] = ms_scaling_factor;
+    for (int it = 1; it <= d->max_iter; ++it)
+        al[it] = ms_scaling_factor == 0.0 ? 1.0 - std::pow(2.0, -1.0 * it / 1.0) : ms_scaling_factor;
+    for (int it = 1; it <= std::min(d->max_iter, 1100); ++it)
+        if (ms_scaling_factor == 0.0 && al[it] != 1.0 - std::ldexp(1.0, -it)) return fail(QD_ECUDA, "alpha schedule mismatch");
+    if (precision == QD_PREC_F64) {
+        if ((rc = upload(d->d_prior, pr))) return rc;
+        if ((rc = upload(d->d_alpha, al))) return rc;
+    } else {
+        std::vector<float> prf(pr.begin(), pr.end()), alf(al.begin(), al.end());
+        if ((rc = upload(d->d_prior, prf))) return rc;
+        if ((rc = upload(d->d_alpha, alf))) return rc;
+    }
     if ((rc = d->d_next.alloc(sizeof(unsigned long long) * 2))) return rc;
-    if ((rc = bp_default_config(d.get()))) return rc;
+    if ((rc = bp_choose_kernel(d.get(), true))) return rc;
     *out = d.release();
     return 0;
 }
 
 extern "C" int qd_bp_destroy(qd_bp *d)
 {
-    if (d) { cudaSetDevice(d->g->device); delete d; }
+    if (d) { cudaSetDevice(d->device); delete d; }
     return 0;
 }
 
 extern "C" int qd_bp_configure(qd_bp *d, int32_t threads, int32_t slots, int32_t ctas_per_sm, int32_t teams)
 {
     if (!d) return fail(QD_EINVAL, "NULL handle");
+    if (d->v7) {
+        if (teams > 1) return fail(QD_EINVAL, "the row-regular BP kernel runs one team per CTA");
+        int rc = use_device(d->g->device);
+        if (rc) return rc;
+        return bp7_configure(d, threads > 0 ? threads : (slots > 0 ? 0 : d->threads), slots > 0 ? slots : d->slots,
+                             ctas_per_sm > 0 ? ctas_per_sm : (slots > 0 || threads > 0 ? 0 : d->ctas_per_sm));
+    }
     int t = threads > 0 ? threads : d->threads, s = slots > 0 ? slots : d->slots, c = ctas_per_sm > 0 ? ctas_per_sm : d->ctas_per_sm;
     int gr = teams > 0 ? teams : (slots > 0 || threads > 0 ? 1 : d->groups);
     if (t % 32 || t > 1024 || s > 64) return fail(QD_EINVAL, "threads must be a multiple of 32 <= 1024, slots <= 64");
@@ -674,6 +859,40 @@ static int bp_launch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int6
     int rc = use_device(d->g->device);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (d->v7) {
+        Bp7Params q{};
+        q.m = g.m; q.n = g.n; q.nwm = g.nwm; q.nwn = g.nwn;
+        q.m32 = (g.m + 31) / 32 * 32;
+        q.nrec = d->v7_nrec;
+        q.max_iter = d->max_iter;
+        q.staged = d->v7_staged;
+        q.uniform_prior = d->v7_uniform;
+        q.prior0 = d->v7_prior0;
+        q.alpha_fixed = d->alpha_fixed;
+        q.table = d->d7_table.as<uint4>();
+        q.chunk_deg = d->d7_chunk_deg.as<uint8_t>();
+        q.prior_rec = d->d7_prior_rec.p;
+        q.col_id = d->d7_col_id.as<uint16_t>();
+        q.const_bits = d->d7_const_bits.as<uint32_t>();
+        q.synd = d_synd; q.synd_stride = synd_stride; q.shots = shots;
+        q.corr = d_corr; q.corr_stride = corr_stride;
+        q.conv = d_converged; q.iters = d_iters; q.llr = d_llr;
+        q.err = d_err; q.err_stride = err_stride;
+        q.lzT = d_err ? logicals->d_lzT.as<uint32_t>() : nullptr;
+        q.k = d_err ? logicals->k : 0;
+        q.fail = d_fail;
+        q.counters = (long long *)d_counters;
+        q.next_shot = d->d_next.as<unsigned long long>() + queue;
+        bp7_kernel_fn fn7 = bp7_kernel_for(d, d->slots);
+        if (!fn7) return fail(QD_EUNSUP, "no row-regular BP kernel compiled for this geometry");
+        QD_CUDA(cudaFuncSetAttribute(fn7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem));
+        QD_CUDA(cudaMemsetAsync(q.next_shot, 0, sizeof(unsigned long long), st));
+        const long long want7 = (shots + d->slots - 1) / d->slots;
+        const unsigned grid7 = (unsigned)std::min<long long>((long long)d->g->sm_count * d->ctas_per_sm, want7);
+        fn7<<<grid7, d->threads, d->smem, st>>>(q);
+        QD_CUDA(cudaGetLastError());
+        return 0;
+    }
     BpParams p{};
     p.g = g;
     p.prior = d->d_prior.p; p.alpha = d->d_alpha.p; p.vidx = d->d_vidx.p;
@@ -869,6 +1088,7 @@ extern "C" int qd_ssf_create(qd_graph *hz, int32_t num_generators, const int32_t
     }
     std::unique_ptr<qd_ssf> d(new qd_ssf);
     d->g = hz;
+    d->device = hz->device;
     d->max_rounds = max_rounds;
     if ((rc = upload(d->d_gen_ptr, gen_ptr))) return rc;
     if ((rc = upload(d->d_gen_idx, gen_idx))) return rc;
@@ -889,7 +1109,7 @@ extern "C" int qd_ssf_create(qd_graph *hz, int32_t num_generators, const int32_t
 
 extern "C" int qd_ssf_destroy(qd_ssf *d)
 {
-    if (d) { cudaSetDevice(d->g->device); delete d; }
+    if (d) { cudaSetDevice(d->device); delete d; }
     return 0;
 }
 

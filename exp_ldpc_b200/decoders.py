@@ -169,11 +169,12 @@ class bp_decoder:
     does (the reference passes OSD options to ``bp_decoder`` too, ``_experiment.py:110-113``).
 
     Extra keywords: ``precision`` ('f64' reproduces the reference's double-precision operation
-    order bit for bit; 'f32' is faster, not reproducible), ``device``.
+    order bit for bit; 'f32' is faster, not reproducible), ``device``, ``kernel`` ('auto' |
+    'generic' | 'regular': which CUDA kernel family decodes; the results are identical).
     """
 
     def __init__(self, parity_check_matrix, error_rate=None, max_iter=0, bp_method=0, ms_scaling_factor=1.0,
-                 channel_probs=(None,), precision="f64", device=0, **_ignored):
+                 channel_probs=(None,), precision="f64", device=0, kernel="auto", **_ignored):
         self.graph = parity_check_matrix if isinstance(parity_check_matrix, TannerGraph) else TannerGraph(
             parity_check_matrix, device)
         self.m, self.n = self.graph.m, self.graph.n
@@ -203,6 +204,8 @@ class bp_decoder:
         self._h = C.c_void_p()
         _lib.check(_lib.lib().qd_bp_create(self.graph.handle, _lib.ptr(self.channel_probs), int(max_iter), self.bp_method,
                                            self.ms_scaling_factor, self.precision, C.byref(self._h)))
+        if kernel != "auto":
+            _lib.check(_lib.lib().qd_bp_select_kernel(self._h, {"generic": 6, "regular": 7}[kernel]))
         self.converge = 0
         self.iter = 0
         self.bp_decoding = np.zeros(self.n, dtype=np.int64)
@@ -232,7 +235,11 @@ class bp_decoder:
     def config(self) -> dict:
         v = [C.c_int32() for _ in range(6)]
         _lib.check(_lib.lib().qd_bp_get_config(self._h, *[C.byref(x) for x in v]))
-        return dict(zip(("threads", "slots", "ctas_per_sm", "teams", "smem_bytes", "grid"), (x.value for x in v)))
+        out = dict(zip(("threads", "slots", "ctas_per_sm", "teams", "smem_bytes", "grid"), (x.value for x in v)))
+        k = [C.c_int32() for _ in range(3)]
+        _lib.check(_lib.lib().qd_bp_get_kernel(self._h, *[C.byref(x) for x in k]))
+        out["kernel"] = {6: "generic", 7: "regular"}[k[0].value]
+        return out
 
     # ---- the ldpc call
     def decode(self, input_vector) -> np.ndarray:

@@ -78,7 +78,7 @@ class CodeCapacityExperiment:
     """Device pipeline for one (code, p, decoder) point: owns the graph, sampler, logicals, decoder."""
 
     def __init__(self, code: QuantumCode, flip_probability: float, prior: float, decoder_mode: str = "bp",
-                 bp_options: Optional[Dict] = None, device: int = 0, precision: str = "f64"):
+                 bp_options: Optional[Dict] = None, device: int = 0, precision: str = "f64", kernel: str = "auto"):
         self.code = code
         self.device = int(device)
         self.n = code.num_qubits
@@ -91,7 +91,8 @@ class CodeCapacityExperiment:
         if decoder_mode == "bp":
             self.decoder = bp_decoder(self.graph, error_rate=prior, max_iter=opts.get("max_iter", 0),
                                       bp_method=opts.get("bp_method", "ps"),
-                                      ms_scaling_factor=opts.get("ms_scaling_factor", 0.0), precision=precision)
+                                      ms_scaling_factor=opts.get("ms_scaling_factor", 0.0), precision=precision,
+                                      kernel=kernel)
             self._bp, self._ssf = self.decoder.handle, None
         elif decoder_mode == "ssf":
             self.decoder = ssf_decoder(self.graph, code.checks.x, max_rounds=opts.get("max_rounds", 0))

@@ -108,6 +108,12 @@ int qd_bp_configure(qd_bp *d, int32_t threads, int32_t slots, int32_t ctas_per_s
 int qd_bp_get_config(qd_bp *d, int32_t *threads, int32_t *slots, int32_t *ctas_per_sm,
                      int32_t *teams, int32_t *smem_bytes, int32_t *grid);
 
+/* Kernel family (testing / tuning).  qd_bp_create picks automatically: 7 = row-regular kernel
+ * (all rows of H have the same degree and a kernel is compiled for it), 6 = generic kernel (any
+ * row degrees).  select: 0 = automatic, 6 / 7 = force; resets the launch geometry. */
+int qd_bp_select_kernel(qd_bp *d, int32_t family);
+int qd_bp_get_kernel(qd_bp *d, int32_t *family, int32_t *row_degree, int32_t *column_tile);
+
 /* Decode `shots` packed syndromes.  Required: d_synd, d_corr.  Optional (NULL to skip):
  *   d_converged[shots], d_iters[shots], d_llr[shots*n] (posterior log-ratio of the last
  *   iteration), and the fused failure epilogue: d_err (the sampled error / readout the syndrome

@@ -84,20 +84,51 @@ def test_syndrome_and_logical_flag_bit_exact(gpu, codes, which):
     assert torch.equal(d_s3, torch.bitwise_xor(d_s, d_s2))
 
 
-def _run_gpu_case(name, codes, precision="f64", config=None):
+def _run_gpu_case(name, codes, precision="f64", config=None, kernel="auto"):
     from exp_ldpc_b200.experiment import CodeCapacityExperiment
     from tests_golden_cases import CASES, case_probabilities
     key, decoder, opts, p, shots, seed = CASES[name]
     q, prior = case_probabilities(p)
-    exp = CodeCapacityExperiment(codes[key], q, prior, decoder, opts, precision=precision)
+    exp = CodeCapacityExperiment(codes[key], q, prior, decoder, opts, precision=precision, kernel=kernel)
+    if decoder == "bp" and kernel != "auto":
+        assert exp.decoder.config()["kernel"] == kernel
     if config and decoder == "bp":
-        exp.decoder.configure(**config)
+        try:
+            exp.decoder.configure(**config)
+        except ValueError as e:          # geometry not representable for this graph
+            pytest.skip(str(e))
     return exp.run(shots, seed=seed, per_shot=True)
 
 
 def _all_case_names():
     from tests_golden_cases import CASES
     return list(CASES)
+
+
+def _bp_case_names():
+    from tests_golden_cases import CASES
+    return [k for k, v in CASES.items() if v[1] == "bp"]
+
+
+@pytest.mark.parametrize("name", _bp_case_names())
+def test_generic_bp_kernel_matches_committed_golden_vectors(gpu, codes, name):
+    """The HGP codes are row-regular and take the row-regular kernel by default; the generic kernel
+    (irregular graphs) must give the same bits."""
+    g = np.load(os.path.join(GOLDEN, "decoder_vectors.npz"))
+    out = _run_gpu_case(name, codes, kernel="generic")
+    assert np.array_equal(np.packbits(out["decodings"], axis=1), g[name + "_dec"])
+    assert np.array_equal(out["iters"], g[name + "_iters"])
+    assert np.array_equal(out["fail"], g[name + "_fail"])
+    assert np.array_equal(out["converged"], g[name + "_conv"])
+
+
+def test_hgp_codes_take_the_row_regular_kernel(gpu, codes):
+    from exp_ldpc_b200.decoders import bp_decoder
+    for key in ("hgp225", "hgp1600"):
+        for prec in ("f64", "f32"):
+            for method in ("ms", "ps"):
+                cfg = bp_decoder(codes[key].checks.z, error_rate=0.02, max_iter=8, bp_method=method, precision=prec).config()
+                assert cfg["kernel"] == "regular", (key, prec, method, cfg)
 
 
 @pytest.mark.parametrize("name", _all_case_names())
@@ -119,9 +150,21 @@ def test_decoders_match_committed_golden_vectors(gpu, codes, name):
                                     dict(threads=1024, slots=4, ctas_per_sm=1, teams=4)])
 def test_bp_result_independent_of_launch_geometry(gpu, codes, name, config):
     g = np.load(os.path.join(GOLDEN, "decoder_vectors.npz"))
-    out = _run_gpu_case(name, codes, config=config)
+    out = _run_gpu_case(name, codes, config=config, kernel="generic")
     assert np.array_equal(np.packbits(out["decodings"], axis=1), g[name + "_dec"])
     assert np.array_equal(out["iters"], g[name + "_iters"])
+
+
+@pytest.mark.parametrize("name", ["ms_sched_225", "ps_225", "ms_sched_1600"])
+@pytest.mark.parametrize("config", [dict(threads=32, slots=1, ctas_per_sm=1), dict(threads=64, slots=4, ctas_per_sm=2),
+                                    dict(threads=128, slots=8, ctas_per_sm=1), dict(threads=800, slots=2, ctas_per_sm=1),
+                                    dict(threads=256, slots=4, ctas_per_sm=1), dict(threads=288, slots=1, ctas_per_sm=2)])
+def test_regular_bp_kernel_independent_of_launch_geometry(gpu, codes, name, config):
+    g = np.load(os.path.join(GOLDEN, "decoder_vectors.npz"))
+    out = _run_gpu_case(name, codes, config=config, kernel="regular")
+    assert np.array_equal(np.packbits(out["decodings"], axis=1), g[name + "_dec"])
+    assert np.array_equal(out["iters"], g[name + "_iters"])
+    assert np.array_equal(out["fail"], g[name + "_fail"])
 
 
 @pytest.mark.parametrize("method,alpha,p", [("ms", 0.0, 0.01), ("ms", 0.0, 0.04), ("ms", 0.8, 0.02), ("ps", 0.0, 0.03)])
