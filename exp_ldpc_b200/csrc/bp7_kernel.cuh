@@ -5,11 +5,12 @@
 // persistent-CTA / slot-refill scheme, but laid out so that the hot loops are almost pure
 // load-compute-store:
 //
-//   * S (compile time) shots per CTA share one message array, slot-minor:
-//         element(row, k, s) = row * RP + k * S + s,      RP = (RD * S) | 1   (odd => a warp that
-//     owns 32 consecutive rows reads/writes 32 different banks), so every shared-memory access of
-//     the check pass is [row base register + immediate] and every access of the bit pass is
-//     [edge base register + immediate]: no address arithmetic per slot;
+//   * S (compile time) shots per CTA share one message array organised in 128-byte lines (one
+//     line = one sweep over all shared-memory banks): message e of slot s lives in line
+//     index(e) * S + s at bank colour(e).  The (colour, index) placement comes from a Koenig edge
+//     colouring computed on the host (bp7_layout.h) and makes EVERY access of BOTH passes bank-
+//     conflict free for any Tanner graph; the slot only adds the immediate s * 128 to an address,
+//     so every shared-memory access is [edge base register + immediate];
 //   * a thread owns the same rows and the same column records in every iteration, so the per-row
 //     and per-column bits of state live in REGISTERS: syndrome bit, running residual-syndrome bit
 //     (one bit per owned row x slot) and the previous hard decision (one bit per owned column x
@@ -36,13 +37,15 @@ constexpr int BP7_SMAX = 8;
 struct Bp7Params {
     int m, n, nwm, nwn;
     int m32;                    // rows rounded up to a multiple of 32
+    int lines;                  // 128-byte message lines per slot
     int nrec;                   // column records (degree classes padded to multiples of 32)
     int max_iter;
     int staged;                 // record table copied to shared memory
     int uniform_prior;
     double prior0;              // the common prior (decoder domain) when uniform_prior
     double alpha_fixed;         // 0 => alpha_it = 1 - 2^-it
-    const uint4 *table;         // VMAX/4 uint4 per record, see bp7_pack_record()
+    const uint4 *table;         // VMAX/4 uint4 per record: u16 message element indices, then u16 flag offsets
+    const uint4 *row_table;     // (RD+3)/4 uint4 per row (m32 rows): byte offsets of the row's messages (slot 0)
     const uint8_t *chunk_deg;   // [nrec / 32]
     const void *prior_rec;      // real[nrec], decoder domain
     const uint16_t *col_id;     // [nrec]; 0xFFFF = padding record
@@ -70,17 +73,18 @@ struct Bp7SmemLayout {
     int msg_elems;              // elements of the message array (incl. scratch row)
 };
 
-__host__ __device__ inline int bp7_row_pitch(int rd, int s) { return (rd * s) | 1; }
+// flag bytes of a row: S records of 8 bytes; the odd pitch keeps the check pass conflict free
+__host__ __device__ inline int bp7_flag_pitch(int s) { return (s | 1) * 8; }
 
-__host__ __device__ inline Bp7SmemLayout bp7_smem_layout(int m, int nrec, int nwn, int rd, int vmax, int s,
+// lines: 128-byte lines per slot (from the layout); one more line group is scratch for padding lanes
+__host__ __device__ inline Bp7SmemLayout bp7_smem_layout(int m, int nrec, int nwn, int lines, int vmax, int s,
                                                          int real_bytes, bool staged)
 {
     Bp7SmemLayout L;
-    const int rp = bp7_row_pitch(rd, s);
-    L.msg_elems = (m + 1) * rp + 8 * s + 8;     // scratch row m, long enough for 8 scratch edges
+    L.msg_elems = (lines + 1) * s * (128 / real_bytes);
     size_t o = 0;
-    L.msg = o;   o += ((size_t)L.msg_elems * real_bytes + 15) & ~(size_t)15;
-    L.flags = o; o += (size_t)(m + 1) * s * 8;
+    L.msg = o;   o += (size_t)(lines + 1) * s * 128;
+    L.flags = o; o += (size_t)(m + 1) * bp7_flag_pitch(s);
     o = (o + 15) & ~(size_t)15;
     L.table = o; o += staged ? (size_t)nrec * vmax * 4 : 0;
     L.out = o;   o += ((size_t)s * nwn * 4 + 15) & ~(size_t)15;
@@ -159,12 +163,14 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
     static_assert(VMAX == 4 || VMAX == 8, "column tile");
     static_assert(S >= 1 && S <= BP7_SMAX, "slots");
     constexpr int RB = (int)sizeof(real);
-    constexpr int RP = (RD * S) | 1;
+    constexpr int LINE = 128;                            // bytes between the slots of one message
+    constexpr int FP = (S | 1) * 8;                      // flag bytes per row (bp7_flag_pitch)
+    constexpr int RQ = (RD + 3) / 4;                     // uint4 per row-table entry
     constexpr unsigned SMASK = (1u << S) - 1u;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = (int)threadIdx.x, NT = (int)blockDim.x, lane = tid & 31;
 
-    const Bp7SmemLayout L = bp7_smem_layout(p.m, p.nrec, p.nwn, RD, VMAX, S, RB, p.staged != 0);
+    const Bp7SmemLayout L = bp7_smem_layout(p.m, p.nrec, p.nwn, p.lines, VMAX, S, RB, p.staged != 0);
     const uint32_t a_msg = smem_u32(smem_raw + L.msg), a_flags = smem_u32(smem_raw + L.flags),
                    a_tab = smem_u32(smem_raw + L.table);
     uint32_t *outbits = reinterpret_cast<uint32_t *>(smem_raw + L.out);          // [S][nwn]
@@ -206,6 +212,17 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
             fa[t] = a_flags + ((t & 1) ? (fw >> 16) : (fw & 0xffffu));
         }
     };
+    // row -> shared addresses of its messages (slot 0), in column order
+    auto load_row = [&](int c, uint32_t (&ra)[RD]) {
+        uint32_t w[4 * RQ];
+#pragma unroll
+        for (int q = 0; q < RQ; ++q) {
+            const uint4 x = __ldg(p.row_table + (size_t)c * RQ + q);
+            w[4 * q + 0] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
+        }
+#pragma unroll
+        for (int k = 0; k < RD; ++k) ra[k] = a_msg + w[k];
+    };
     auto prior_of = [&](int r) -> real { return p.uniform_prior ? (real)p.prior0 : prior_rec[r]; };
 
     // ---- (re)load every slot born in `stamp`
@@ -217,7 +234,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
         int i = 0;
         for (int c = tid; c < p.m32; c += NT, ++i) {
             const bool valid = c < p.m;
-            const uint32_t fb = a_flags + (uint32_t)(valid ? c : p.m) * (S * 8);
+            const uint32_t fb = a_flags + (uint32_t)(valid ? c : p.m) * FP;
 #pragma unroll
             for (int s = 0; s < S; ++s)
                 if ((fresh >> s) & 1u) {
@@ -241,7 +258,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                     decbits &= ~(1u << (i * S + s));
 #pragma unroll
                     for (int t = 0; t < VMAX; ++t)
-                        if (t < deg) sts_real(ea[t] + s * RB, pj);
+                        if (t < deg) sts_real(ea[t] + s * LINE, pj);
                 }
         }
     };
@@ -263,16 +280,16 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
             int i = 0;
             for (int c = tid; c < p.m32; c += NT, ++i) {
                 const bool valid = c < p.m;
-                const uint32_t row = (uint32_t)(valid ? c : p.m);
-                const uint32_t rb = a_msg + row * (uint32_t)(RP * RB);
-                const uint32_t fb = a_flags + row * (uint32_t)(S * 8);
+                const uint32_t fb = a_flags + (uint32_t)(valid ? c : p.m) * FP;
+                uint32_t ra[RD];
+                load_row(c, ra);
                 auto body = [&](auto stag) {
                     constexpr int s = decltype(stag)::value;
                     const int bi = i * S + s;
                     const unsigned long long f = lds_u64_off<s * 8>(fb);
                     real v[RD];
 #pragma unroll
-                    for (int k = 0; k < RD; ++k) v[k] = lds_real(rb + (uint32_t)((k * S + s) * RB), real());
+                    for (int k = 0; k < RD; ++k) v[k] = lds_off<s * LINE>(ra[k], real());
                     resbits ^= ((unsigned)__popcll(f) & 1u) << bi;
                     if (f) sts_u64_off<s * 8>(fb, 0ULL);
                     un |= (valid ? (resbits >> bi) & 1u : 0u) << s;
@@ -284,7 +301,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                         check_ps7<real, RD>(v, sbit);
                     }
 #pragma unroll
-                    for (int k = 0; k < RD; ++k) sts_real(rb + (uint32_t)((k * S + s) * RB), v[k]);
+                    for (int k = 0; k < RD; ++k) sts_off<s * LINE>(ra[k], v[k]);
                 };
                 if (act == SMASK) {                             // steady state: straight-line over the slots
                     if (S > 0) body(std::integral_constant<int, 0>());
@@ -407,10 +424,10 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                         const int bi = i * S + s;
                         real cv[D], soft;
 #pragma unroll
-                        for (int t = 0; t < D; ++t) cv[t] = lds_off<s * RB>(ea[t], real());
+                        for (int t = 0; t < D; ++t) cv[t] = lds_off<s * LINE>(ea[t], real());
                         const unsigned dbit = bit_compute<real, METHOD, D>(cv, pj, soft);
 #pragma unroll
-                        for (int t = 0; t < D; ++t) sts_off<s * RB>(ea[t], cv[t]);
+                        for (int t = 0; t < D; ++t) sts_off<s * LINE>(ea[t], cv[t]);
                         const unsigned flip = ((decbits >> bi) & 1u) ^ dbit;
                         if (flip) {
 #pragma unroll

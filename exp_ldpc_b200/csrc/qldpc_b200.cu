@@ -8,11 +8,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <list>
 #include <memory>
 #include <string>
 #include <vector>
 
 #include "bp7_kernel.cuh"
+#include "bp7_layout.h"
 #include "bp_pick.h"
 #include "ssf_kernel.cuh"
 
@@ -170,6 +172,8 @@ struct qd_graph {
     std::vector<int32_t> row_ptr, col_idx, col_ptr;
     std::vector<uint32_t> row_desc, col_desc, csc_pos, csc_row, fpos_of_pos;
     std::vector<uint8_t> csc_k;      // index of the edge within its row
+    // message placements of the thread-owned-state BP kernel, keyed by (banks, column tile)
+    std::list<std::pair<int, Bp7Layout>> bp7_layouts;   // list: references stay valid
     DevBuf d_row_desc, d_col_desc, d_csc_pos, d_csc_row, d_row_ptr, d_col_idx, d_fpos;
     int sm_count = 0, smem_optin = 0;
 };
@@ -201,7 +205,8 @@ struct qd_bp {
     int v7 = 0, v7_nrec = 0, v7_uniform = 0, v7_staged = 0;
     double v7_prior0 = 0.0, alpha_fixed = 0.0;
     std::vector<double> prior_dom;   // priors in the decoder's domain, per column
-    DevBuf d7_table, d7_chunk_deg, d7_prior_rec, d7_col_id, d7_const_bits;
+    int v7_lines = 0;
+    DevBuf d7_table, d7_row_table, d7_chunk_deg, d7_prior_rec, d7_col_id, d7_const_bits;
     // host-buffer pipeline state
     cudaStream_t streams[2] = {nullptr, nullptr};
     cudaEvent_t done[2] = {nullptr, nullptr};
@@ -555,81 +560,98 @@ static int bp6_prepare(qd_bp *d)
 // ---------------------------------------------------------------------------------------------
 static const int kBp7Slots[] = {8, 6, 4, 3, 2, 1};
 
-static size_t bp7_smem(const qd_bp *d, int slots, bool staged, int nrec)
+static const Bp7Layout &bp7_layout_of(qd_bp *d)
 {
-    const GraphDev &g = d->g->dev;
-    return bp7_smem_layout(g.m, nrec, g.nwn, d->rd, d->vmax, slots, d->precision == QD_PREC_F64 ? 8 : 4, staged).total;
+    qd_graph *g = d->g;
+    const int nb = d->precision == QD_PREC_F64 ? 16 : 32;
+    const int key = nb * 100 + d->vmax;
+    for (auto &kv : g->bp7_layouts) if (kv.first == key) return kv.second;
+    Bp7LayoutProblem P;
+    P.m = g->dev.m; P.n = g->dev.n;
+    P.row_ptr = g->row_ptr.data(); P.col_idx = g->col_idx.data(); P.col_ptr = g->col_ptr.data();
+    P.vmax = d->vmax; P.nb = nb;
+    g->bp7_layouts.emplace_back(key, bp7_colour_layout(P));
+    return g->bp7_layouts.back().second;
 }
 
-static int bp7_nrec(const qd_bp *d)
+static size_t bp7_smem(qd_bp *d, int slots, bool staged)
 {
-    const qd_graph *g = d->g;
-    std::vector<int> cnt(d->vmax + 1, 0);
-    for (int j = 0; j < g->dev.n; ++j) cnt[g->col_ptr[j + 1] - g->col_ptr[j]]++;
-    int nrec = 0;
-    for (int dg = 1; dg <= d->vmax; ++dg) nrec += (cnt[dg] + 31) / 32 * 32;
-    return nrec;
+    const GraphDev &g = d->g->dev;
+    const Bp7Layout &L = bp7_layout_of(d);
+    return bp7_smem_layout(g.m, L.nrec, g.nwn, L.lines, d->vmax, slots, d->precision == QD_PREC_F64 ? 8 : 4, staged).total;
 }
 
 // can a (slots, threads) geometry be represented?  per-thread state is one bit per owned
-// (row | record, slot) in a 32-bit register; positions are 16-bit
-static bool bp7_geometry_ok(const qd_bp *d, int slots, int threads, int nrec)
+// (row | record, slot) in a 32-bit register; message positions are 16-bit element indices
+static bool bp7_geometry_ok(qd_bp *d, int slots, int threads)
 {
     const GraphDev &g = d->g->dev;
+    const Bp7Layout &L = bp7_layout_of(d);
     const int m32 = (g.m + 31) / 32 * 32;
-    const Bp7SmemLayout L = bp7_smem_layout(g.m, nrec, g.nwn, d->rd, d->vmax, slots, 8, false);
-    if (L.msg_elems > 65535 || (g.m + 1) * slots * 8 > 65535 || g.n >= 65535) return false;
+    const Bp7SmemLayout SL = bp7_smem_layout(g.m, L.nrec, g.nwn, L.lines, d->vmax, slots, d->precision == QD_PREC_F64 ? 8 : 4, false);
+    if (SL.msg_elems > 65535 || (g.m + 1) * bp7_flag_pitch(slots) > 65535 || g.n >= 65535) return false;
     if (threads < 32 || threads > BP7_MAXT || threads % 32) return false;
     if (((m32 + threads - 1) / threads) * slots > 32) return false;
-    if (((nrec + threads - 1) / threads) * slots > 32) return false;
+    if (((L.nrec + threads - 1) / threads) * slots > 32) return false;
     return bp7_kernel_for(d, slots) != nullptr;
 }
 
-// build and upload the record table for `slots` shots per CTA
+// build and upload the tables for `slots` shots per CTA
 static int bp7_prepare(qd_bp *d, int slots)
 {
     qd_graph *g = d->g;
     const GraphDev &gd = g->dev;
-    const int V = d->vmax, S = slots, RD = d->rd, RP = bp7_row_pitch(RD, S);
-    std::vector<std::vector<int>> cls(V + 1);
+    const Bp7Layout &L = bp7_layout_of(d);
+    const int V = d->vmax, S = slots, RD = d->rd, NB = L.nb, RB = 128 / NB, FP = bp7_flag_pitch(S);
+    const int m32 = (gd.m + 31) / 32 * 32, RQ = (RD + 3) / 4;
+    // element index (slot 0) of a CSR edge; scratch elements live in the extra line group
+    auto elem = [&](int e) { return L.index[e] * NB * S + L.colour[e]; };
+    auto scratch = [&](int lane) { return L.lines * NB * S + (lane % NB); };
     std::vector<uint32_t> const_bits(std::max(gd.nwn, 1), 0u);
-    for (int j = 0; j < gd.n; ++j) {
-        const int dg = g->col_ptr[j + 1] - g->col_ptr[j];
-        if (dg == 0) {   // no edges: the decision never changes (serial rule: llr <= 0, resp. ratio >= 1)
+    for (int j = 0; j < gd.n; ++j)
+        if (g->col_ptr[j + 1] == g->col_ptr[j]) {   // no edges: the decision never changes (llr <= 0, resp. ratio >= 1)
             const double pr = d->prior_dom[j];
             if (d->method == QD_BP_MIN_SUM ? pr <= 0.0 : pr >= 1.0) const_bits[j >> 5] |= 1u << (j & 31);
-        } else cls[dg].push_back(j);
-    }
-    std::vector<uint16_t> table, col_id;
-    std::vector<uint8_t> chunk_deg;
-    std::vector<double> prior_rec;
+        }
+    // CSR edge of the t-th edge of a column
+    std::vector<int> csr_edge(std::max(gd.nnz, 1));
+    for (int j = 0; j < gd.n; ++j)
+        for (int t = g->col_ptr[j]; t < g->col_ptr[j + 1]; ++t)
+            csr_edge[t] = g->row_ptr[g->csc_row[t]] + g->csc_k[t];
+    std::vector<uint16_t> table((size_t)std::max(L.nrec, 1) * 2 * V, 0), col_id(std::max(L.nrec, 1), 0xFFFF);
+    std::vector<uint8_t> chunk_deg(std::max(L.nrec / 32, 1), 0);
+    std::vector<double> prior_rec(std::max(L.nrec, 1), d->prior_dom[0]);
+    int r0 = 0;
     for (int dg = 1; dg <= V; ++dg) {
-        const int cnt = (int)cls[dg].size(), padded = (cnt + 31) / 32 * 32;
-        for (int r = 0; r < padded; ++r) {
-            uint16_t mq[8] = {0}, fq[8] = {0};
-            const int j = r < cnt ? cls[dg][r] : -1;
+        const int cnt = (int)L.cls[dg].size(), padded = (cnt + 31) / 32 * 32;
+        for (int i = 0; i < padded; ++i) {
+            const int r = r0 + i, j = i < cnt ? L.cls[dg][i] : -1;
+            uint16_t *mq = &table[(size_t)r * 2 * V], *fq = mq + V;
             for (int t = 0; t < V; ++t) {
-                if (t < dg && j >= 0) {
-                    const int e = g->col_ptr[j] + t;
-                    const int row = (int)g->csc_row[e], k = g->csc_k[e];
-                    mq[t] = (uint16_t)(row * RP + k * S);
-                    fq[t] = (uint16_t)(row * S * 8 + k);
-                } else {             // scratch row
-                    mq[t] = (uint16_t)(gd.m * RP + t * S);
-                    fq[t] = (uint16_t)(gd.m * S * 8 + t);
+                if (j >= 0 && t < dg) {
+                    const int ce = g->col_ptr[j] + t;
+                    mq[t] = (uint16_t)elem(csr_edge[ce]);
+                    fq[t] = (uint16_t)((int)g->csc_row[ce] * FP + g->csc_k[ce]);
+                } else {
+                    mq[t] = (uint16_t)scratch(r);
+                    fq[t] = (uint16_t)(gd.m * FP + (t & 7));
                 }
             }
-            for (int t = 0; t < V; ++t) table.push_back(mq[t]);
-            for (int t = 0; t < V; ++t) table.push_back(fq[t]);
-            col_id.push_back(j >= 0 ? (uint16_t)j : (uint16_t)0xFFFF);
-            prior_rec.push_back(j >= 0 ? d->prior_dom[j] : d->prior_dom[0]);
-            if ((r & 31) == 0) chunk_deg.push_back((uint8_t)dg);
+            if (j >= 0) { col_id[r] = (uint16_t)j; prior_rec[r] = d->prior_dom[j]; }
+            chunk_deg[r >> 5] = (uint8_t)dg;
         }
+        r0 += padded;
     }
-    d->v7_nrec = (int)col_id.size();
-    if (table.empty()) { table.assign(2 * V, 0); col_id.assign(1, 0xFFFF); prior_rec.assign(1, 1.0); chunk_deg.assign(1, 0); }
+    std::vector<uint32_t> row_table((size_t)m32 * RQ * 4, 0u);
+    for (int c = 0; c < m32; ++c)
+        for (int k = 0; k < RQ * 4; ++k)
+            row_table[(size_t)c * RQ * 4 + k] =
+                (uint32_t)((c < gd.m && k < RD ? elem(g->row_ptr[c] + k) : scratch(c)) * RB);
+    d->v7_nrec = L.nrec;
+    d->v7_lines = L.lines;
     int rc;
     if ((rc = upload(d->d7_table, table))) return rc;
+    if ((rc = upload(d->d7_row_table, row_table))) return rc;
     if ((rc = upload(d->d7_col_id, col_id))) return rc;
     if ((rc = upload(d->d7_chunk_deg, chunk_deg))) return rc;
     if ((rc = upload(d->d7_const_bits, const_bits))) return rc;
@@ -647,13 +669,13 @@ static int bp7_configure(qd_bp *d, int threads, int slots, int ctas)
 {
     const GraphDev &g = d->g->dev;
     const size_t budget = (size_t)d->g->smem_optin;
-    const int nrec = bp7_nrec(d);
+    const int nrec = bp7_layout_of(d).nrec;
     const int m32 = (g.m + 31) / 32 * 32;
     auto pick_threads = [&](int S) -> int {
         // fewest passes over the owned rows / records, then the fewest idle lanes
         int best = 0; long best_cost = -1;
         for (int t = 32; t <= BP7_MAXT; t += 32) {
-            if (!bp7_geometry_ok(d, S, t, nrec)) continue;
+            if (!bp7_geometry_ok(d, S, t)) continue;
             const long cost = (long)((m32 + t - 1) / t) * 4 * d->rd + (long)((nrec + t - 1) / t) * 9;
             const long score = cost * 4096 + t;                  // equal passes: fewer threads
             if (best_cost < 0 || score < best_cost) { best_cost = score; best = t; }
@@ -666,11 +688,11 @@ static int bp7_configure(qd_bp *d, int threads, int slots, int ctas)
         S = 0;
         for (int cand : kBp7Slots) {
             if (!bp7_kernel_for(d, cand)) continue;
-            const bool fits_staged = bp7_smem(d, cand, true, nrec) <= budget;
-            if (!fits_staged && bp7_smem(d, cand, false, nrec) > budget) continue;
+            const bool fits_staged = bp7_smem(d, cand, true) <= budget;
+            if (!fits_staged && bp7_smem(d, cand, false) > budget) continue;
             if (!pick_threads(cand)) continue;
             // small graphs: prefer more CTAs over more slots once a CTA holds >= 4 shots
-            if (cand > 4 && bp7_smem(d, 4, true, nrec) * 2 <= budget && bp7_kernel_for(d, 4) && pick_threads(4)) continue;
+            if (cand > 4 && bp7_smem(d, 4, true) * 2 <= budget && bp7_kernel_for(d, 4) && pick_threads(4)) continue;
             S = cand;
             break;
         }
@@ -678,10 +700,10 @@ static int bp7_configure(qd_bp *d, int threads, int slots, int ctas)
     }
     if (!bp7_kernel_for(d, S)) return fail(QD_EINVAL, "slots must be one of the compiled slot counts (1,2,3,4,6,8)");
     if (T <= 0) T = pick_threads(S);
-    if (!T || !bp7_geometry_ok(d, S, T, nrec))
+    if (!T || !bp7_geometry_ok(d, S, T))
         return fail(QD_EINVAL, "threads/slots: owned rows x slots and owned columns x slots must be <= 32, threads <= 800");
-    size_t smem = bp7_smem(d, S, true, nrec);
-    if (smem > budget) { staged = 0; smem = bp7_smem(d, S, false, nrec); }
+    size_t smem = bp7_smem(d, S, true);
+    if (smem > budget) { staged = 0; smem = bp7_smem(d, S, false); }
     if (smem > budget) return fail(QD_EUNSUP, "configuration does not fit shared memory");
     int C = ctas;
     if (C <= 0) {
@@ -864,6 +886,8 @@ static int bp_launch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int6
         q.m = g.m; q.n = g.n; q.nwm = g.nwm; q.nwn = g.nwn;
         q.m32 = (g.m + 31) / 32 * 32;
         q.nrec = d->v7_nrec;
+        q.lines = d->v7_lines;
+        q.row_table = d->d7_row_table.as<uint4>();
         q.max_iter = d->max_iter;
         q.staged = d->v7_staged;
         q.uniform_prior = d->v7_uniform;
