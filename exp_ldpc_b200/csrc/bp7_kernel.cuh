@@ -112,25 +112,30 @@ template <int OFF> __device__ __forceinline__ void sts_u8_off(uint32_t a, uint32
 // ---- min-sum check update, exclusive prefix / suffix minima (the two sweeps of the serial decoder)
 // v: bit->check messages in, check->bit messages out.  sign0 = syndrome bit << 31.  Signs travel
 // as sign BITS (see check_ms_compute in bp_kernel.cuh for why that equals the serial `<= 0` rule).
+// value of smaller magnitude (ties keep a): the compare and the final multiply take |x| through
+// operand modifiers, so no instruction is spent on absolute values
+__device__ __forceinline__ double mn_abs(double a, double b) { return fabs(b) < fabs(a) ? b : a; }
+__device__ __forceinline__ float mn_abs(float a, float b) { return fabsf(b) < fabsf(a) ? b : a; }
+
 template <typename real, int RD>
 __device__ __forceinline__ void check_ms7(real (&v)[RD], unsigned sign0, real al)
 {
     using A = Ar<real>;
-    unsigned hk[RD];
     unsigned sx = sign0;
 #pragma unroll
-    for (int k = 0; k < RD; ++k) { hk[k] = hi_bits(v[k]); sx ^= hk[k]; v[k] = abs_bits(v[k]); }
-    real pm[RD];                                   // pm[k] = min(|v[0..k-1]|), k >= 1
+    for (int k = 0; k < RD; ++k) sx ^= hi_bits(v[k]);
+    real pm[RD];                                   // pm[k]: smallest-magnitude value among v[0..k-1], k >= 1
     pm[0] = A::big();
     if (RD > 1) pm[1] = v[0];
 #pragma unroll
-    for (int k = 2; k < RD; ++k) pm[k] = A::mn(pm[k - 1], v[k - 1]);
-    real sm = A::big();                            // min(|v[k+1..]|)
+    for (int k = 2; k < RD; ++k) pm[k] = mn_abs(pm[k - 1], v[k - 1]);
+    real sm = A::big();                            // same among v[k+1..]
 #pragma unroll
     for (int k = RD - 1; k >= 0; --k) {
-        const real mag = k == RD - 1 ? pm[k] : (k == 0 ? sm : A::mn(pm[k], sm));
-        sm = k == RD - 1 ? v[k] : A::mn(sm, v[k]);
-        v[k] = xor_hi(A::mul(mag, al), (sx ^ hk[k]) & 0x80000000u);
+        const real pick = k == RD - 1 ? pm[k] : (k == 0 ? sm : mn_abs(pm[k], sm));
+        sm = k == RD - 1 ? v[k] : mn_abs(sm, v[k]);
+        const real mag = A::mul(fabs(pick), al);
+        v[k] = xor_hi(mag, (sx ^ hi_bits(v[k])) & 0x80000000u);
     }
 }
 
