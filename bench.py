@@ -313,8 +313,19 @@ def main():
     sm_mhz = clk.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
     smem_peak = sm_count * 128 * sm_mhz * 1e6 / 1e9
     smem_achieved = smem_bytes_per_shot * shots / (kernel_ms * 1e-3) / 1e9
+    kernel_name = "bp7_kernel" if cfg.get("kernel") == "regular" else "bp_kernel"
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full`
+    # capture of this workload (per launch of the captured shot count, scaled to this launch)
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:{args.precision}")
+        if tr and tr.get("kernel") == kernel_name:
+            traffic = tr["dram_bytes_per_shot"] * shots
+    except (OSError, ValueError):
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": "bp_kernel", "kernel_ms": kernel_ms,
+                "traffic": traffic, "kernel": kernel_name, "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_launch": bytes_per_shot * shots,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_shot": bytes_per_shot,
                 "note": "HBM is touched for I/O only; the kernel is bound by shared memory / issue, see roofline_smem"}

@@ -161,6 +161,105 @@ __device__ __forceinline__ void check_ps7(real (&v)[RD], unsigned sbit)
     }
 }
 
+// ---- one slot of one row: load, and compute + store.  The shared-memory accesses are volatile asm
+// and keep their program order, so the callers issue the loads of the next slots by hand before the
+// arithmetic of the current one (software pipeline over the slots).
+template <typename real, int RD, int s>
+__device__ __forceinline__ void row_ld(const uint32_t (&ra)[RD], uint32_t fb, real (&v)[RD], unsigned long long &f)
+{
+    f = lds_u64_off<s * 8>(fb);
+#pragma unroll
+    for (int k = 0; k < RD; ++k) v[k] = lds_off<s * 128>(ra[k], real());
+}
+
+template <typename real, int METHOD, int RD, int S, int s>
+__device__ __forceinline__ void row_cs(const uint32_t (&ra)[RD], uint32_t fb, real (&v)[RD], unsigned long long f, int i,
+                                       bool valid, unsigned synbits, unsigned &resbits, unsigned &un, real al)
+{
+    const int bi = i * S + s;
+    resbits ^= ((unsigned)__popcll(f) & 1u) << bi;
+    if (f) sts_u64_off<s * 8>(fb, 0ULL);
+    un |= (valid ? (resbits >> bi) & 1u : 0u) << s;
+    const unsigned sbit = (synbits >> bi) & 1u;
+    if (METHOD == QD_BP_MIN_SUM_K) check_ms7<real, RD>(v, sbit << 31, al);
+    else check_ps7<real, RD>(v, sbit);
+#pragma unroll
+    for (int k = 0; k < RD; ++k) sts_off<s * 128>(ra[k], v[k]);
+}
+
+template <typename real, int D, int VMAX, int s>
+__device__ __forceinline__ void col_ld(const uint32_t (&ea)[VMAX], real (&cv)[D])
+{
+#pragma unroll
+    for (int t = 0; t < D; ++t) cv[t] = lds_off<s * 128>(ea[t], real());
+}
+
+struct Bp7LlrOut { double *llr; const uint16_t *col_id; int n; };
+
+template <typename real, int METHOD, int D, int VMAX, int S, int s>
+__device__ __forceinline__ void col_cs(const uint32_t (&ea)[VMAX], const uint32_t (&fa)[VMAX], real (&cv)[D], real pj, int i,
+                                       unsigned &decbits, const Bp7LlrOut &lo, int r, long long shot)
+{
+    using A = Ar<real>;
+    const int bi = i * S + s;
+    real soft;
+    const unsigned dbit = bit_compute<real, METHOD, D>(cv, pj, soft);
+#pragma unroll
+    for (int t = 0; t < D; ++t) sts_off<s * 128>(ea[t], cv[t]);
+    const unsigned flip = ((decbits >> bi) & 1u) ^ dbit;
+    if (flip) {
+#pragma unroll
+        for (int t = 0; t < D; ++t) sts_u8_off<s * 8>(fa[t], 1u);
+    }
+    decbits ^= flip << bi;
+    if (lo.llr) {
+        const unsigned col = lo.col_id[r];
+        if (col != 0xFFFFu)
+            lo.llr[shot * (long long)lo.n + col] =
+                METHOD == QD_BP_MIN_SUM_K ? (double)soft : (double)A::lg(A::div((real)1, soft));
+    }
+}
+
+// all slots of one column record of compile-time degree D
+template <typename real, int METHOD, int D, int VMAX, int S>
+__device__ __forceinline__ void col_update(const uint32_t (&ea)[VMAX], const uint32_t (&fa)[VMAX], real pj, int i, unsigned run,
+                                           unsigned &decbits, const Bp7LlrOut &lo, int r, const long long (&shot_of)[S])
+{
+    constexpr unsigned SMASK = (1u << S) - 1u;
+    real ca[D], cb[D], cc[D];
+#define QD_LD(n, buf) col_ld<real, D, VMAX, (n) % S>(ea, buf)
+#define QD_CS(n, buf) col_cs<real, METHOD, D, VMAX, S, (n) % S>(ea, fa, buf, pj, i, decbits, lo, r, shot_of[(n) % S])
+    if (run == SMASK) {                                  // three buffers: two slots of loads in flight
+        QD_LD(0, ca);
+        if (S > 1) QD_LD(1, cb);
+        if (S > 2) QD_LD(2, cc);
+        QD_CS(0, ca);
+        if (S > 3) QD_LD(3, ca);
+        if (S > 1) QD_CS(1, cb);
+        if (S > 4) QD_LD(4, cb);
+        if (S > 2) QD_CS(2, cc);
+        if (S > 5) QD_LD(5, cc);
+        if (S > 3) QD_CS(3, ca);
+        if (S > 6) QD_LD(6, ca);
+        if (S > 4) QD_CS(4, cb);
+        if (S > 7) QD_LD(7, cb);
+        if (S > 5) QD_CS(5, cc);
+        if (S > 6) QD_CS(6, ca);
+        if (S > 7) QD_CS(7, cb);
+    } else {
+        if (S > 0 && (run & 1u)) { QD_LD(0, ca); QD_CS(0, ca); }
+        if (S > 1 && (run & 2u)) { QD_LD(1, ca); QD_CS(1, ca); }
+        if (S > 2 && (run & 4u)) { QD_LD(2, ca); QD_CS(2, ca); }
+        if (S > 3 && (run & 8u)) { QD_LD(3, ca); QD_CS(3, ca); }
+        if (S > 4 && (run & 16u)) { QD_LD(4, ca); QD_CS(4, ca); }
+        if (S > 5 && (run & 32u)) { QD_LD(5, ca); QD_CS(5, ca); }
+        if (S > 6 && (run & 64u)) { QD_LD(6, ca); QD_CS(6, ca); }
+        if (S > 7 && (run & 128u)) { QD_LD(7, ca); QD_CS(7, ca); }
+    }
+#undef QD_LD
+#undef QD_CS
+}
+
 template <typename real, int METHOD, int RD, int VMAX, int S, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
 {
@@ -288,45 +387,42 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                 const uint32_t fb = a_flags + (uint32_t)(valid ? c : p.m) * FP;
                 uint32_t ra[RD];
                 load_row(c, ra);
-                auto body = [&](auto stag) {
-                    constexpr int s = decltype(stag)::value;
-                    const int bi = i * S + s;
-                    const unsigned long long f = lds_u64_off<s * 8>(fb);
-                    real v[RD];
-#pragma unroll
-                    for (int k = 0; k < RD; ++k) v[k] = lds_off<s * LINE>(ra[k], real());
-                    resbits ^= ((unsigned)__popcll(f) & 1u) << bi;
-                    if (f) sts_u64_off<s * 8>(fb, 0ULL);
-                    un |= (valid ? (resbits >> bi) & 1u : 0u) << s;
-                    const unsigned sbit = (synbits >> bi) & 1u;
-                    if (METHOD == QD_BP_MIN_SUM_K) {
-                        const real al = alpha_fixed != (real)0 ? alpha_fixed : A::sub((real)1, pow2_neg<real>(T - born[s]));
-                        check_ms7<real, RD>(v, sbit << 31, al);
-                    } else {
-                        check_ps7<real, RD>(v, sbit);
-                    }
-#pragma unroll
-                    for (int k = 0; k < RD; ++k) sts_off<s * LINE>(ra[k], v[k]);
+                real va[RD], vb[RD];
+                unsigned long long fa = 0ULL, fbb = 0ULL;
+                auto alpha_of = [&](int s) -> real {
+                    return alpha_fixed != (real)0 ? alpha_fixed : A::sub((real)1, pow2_neg<real>(T - born[s]));
                 };
-                if (act == SMASK) {                             // steady state: straight-line over the slots
-                    if (S > 0) body(std::integral_constant<int, 0>());
-                    if (S > 1) body(std::integral_constant<int, 1 % S>());
-                    if (S > 2) body(std::integral_constant<int, 2 % S>());
-                    if (S > 3) body(std::integral_constant<int, 3 % S>());
-                    if (S > 4) body(std::integral_constant<int, 4 % S>());
-                    if (S > 5) body(std::integral_constant<int, 5 % S>());
-                    if (S > 6) body(std::integral_constant<int, 6 % S>());
-                    if (S > 7) body(std::integral_constant<int, 7 % S>());
+#define QD_LD(n, buf, f) row_ld<real, RD, (n) % S>(ra, fb, buf, f)
+#define QD_CS(n, buf, f) row_cs<real, METHOD, RD, S, (n) % S>(ra, fb, buf, f, i, valid, synbits, resbits, un, alpha_of((n) % S))
+                if (act == SMASK) {                             // steady state: straight line, two buffers
+                    QD_LD(0, va, fa);
+                    if (S > 1) QD_LD(1, vb, fbb);
+                    QD_CS(0, va, fa);
+                    if (S > 2) QD_LD(2, va, fa);
+                    if (S > 1) QD_CS(1, vb, fbb);
+                    if (S > 3) QD_LD(3, vb, fbb);
+                    if (S > 2) QD_CS(2, va, fa);
+                    if (S > 4) QD_LD(4, va, fa);
+                    if (S > 3) QD_CS(3, vb, fbb);
+                    if (S > 5) QD_LD(5, vb, fbb);
+                    if (S > 4) QD_CS(4, va, fa);
+                    if (S > 6) QD_LD(6, va, fa);
+                    if (S > 5) QD_CS(5, vb, fbb);
+                    if (S > 7) QD_LD(7, vb, fbb);
+                    if (S > 6) QD_CS(6, va, fa);
+                    if (S > 7) QD_CS(7, vb, fbb);
                 } else {
-                    if (S > 0 && (act & 1u)) body(std::integral_constant<int, 0>());
-                    if (S > 1 && (act & 2u)) body(std::integral_constant<int, 1 % S>());
-                    if (S > 2 && (act & 4u)) body(std::integral_constant<int, 2 % S>());
-                    if (S > 3 && (act & 8u)) body(std::integral_constant<int, 3 % S>());
-                    if (S > 4 && (act & 16u)) body(std::integral_constant<int, 4 % S>());
-                    if (S > 5 && (act & 32u)) body(std::integral_constant<int, 5 % S>());
-                    if (S > 6 && (act & 64u)) body(std::integral_constant<int, 6 % S>());
-                    if (S > 7 && (act & 128u)) body(std::integral_constant<int, 7 % S>());
+                    if (S > 0 && (act & 1u)) { QD_LD(0, va, fa); QD_CS(0, va, fa); }
+                    if (S > 1 && (act & 2u)) { QD_LD(1, va, fa); QD_CS(1, va, fa); }
+                    if (S > 2 && (act & 4u)) { QD_LD(2, va, fa); QD_CS(2, va, fa); }
+                    if (S > 3 && (act & 8u)) { QD_LD(3, va, fa); QD_CS(3, va, fa); }
+                    if (S > 4 && (act & 16u)) { QD_LD(4, va, fa); QD_CS(4, va, fa); }
+                    if (S > 5 && (act & 32u)) { QD_LD(5, va, fa); QD_CS(5, va, fa); }
+                    if (S > 6 && (act & 64u)) { QD_LD(6, va, fa); QD_CS(6, va, fa); }
+                    if (S > 7 && (act & 128u)) { QD_LD(7, va, fa); QD_CS(7, va, fa); }
                 }
+#undef QD_LD
+#undef QD_CS
             }
             un = __reduce_or_sync(0xffffffffu, un);
             if (lane == 0 && un) atomicOr(&ctl->unsat[ub], un);
@@ -422,61 +518,20 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                 load_record(r, ea, fa);
                 const real pj = prior_of(r);
                 const int deg = __shfl_sync(0xffffffffu, (int)__ldg(p.chunk_deg + (r >> 5)), 0);
-                auto run_deg = [&](auto dtag) {
-                    constexpr int D = decltype(dtag)::value;
-                    auto body = [&](auto stag) {
-                        constexpr int s = decltype(stag)::value;
-                        const int bi = i * S + s;
-                        real cv[D], soft;
-#pragma unroll
-                        for (int t = 0; t < D; ++t) cv[t] = lds_off<s * LINE>(ea[t], real());
-                        const unsigned dbit = bit_compute<real, METHOD, D>(cv, pj, soft);
-#pragma unroll
-                        for (int t = 0; t < D; ++t) sts_off<s * LINE>(ea[t], cv[t]);
-                        const unsigned flip = ((decbits >> bi) & 1u) ^ dbit;
-                        if (flip) {
-#pragma unroll
-                            for (int t = 0; t < D; ++t) sts_u8_off<s * 8>(fa[t], 1u);
-                        }
-                        decbits ^= flip << bi;
-                        if (p.llr) {
-                            const unsigned col = p.col_id[r];
-                            if (col != 0xFFFFu)
-                                p.llr[shot_of[s] * (long long)p.n + col] =
-                                    METHOD == QD_BP_MIN_SUM_K ? (double)soft : (double)A::lg(A::div((real)1, soft));
-                        }
-                    };
-                    if (run == SMASK) {
-                        if (S > 0) body(std::integral_constant<int, 0>());
-                        if (S > 1) body(std::integral_constant<int, 1 % S>());
-                        if (S > 2) body(std::integral_constant<int, 2 % S>());
-                        if (S > 3) body(std::integral_constant<int, 3 % S>());
-                        if (S > 4) body(std::integral_constant<int, 4 % S>());
-                        if (S > 5) body(std::integral_constant<int, 5 % S>());
-                        if (S > 6) body(std::integral_constant<int, 6 % S>());
-                        if (S > 7) body(std::integral_constant<int, 7 % S>());
-                    } else {
-                        if (S > 0 && (run & 1u)) body(std::integral_constant<int, 0>());
-                        if (S > 1 && (run & 2u)) body(std::integral_constant<int, 1 % S>());
-                        if (S > 2 && (run & 4u)) body(std::integral_constant<int, 2 % S>());
-                        if (S > 3 && (run & 8u)) body(std::integral_constant<int, 3 % S>());
-                        if (S > 4 && (run & 16u)) body(std::integral_constant<int, 4 % S>());
-                        if (S > 5 && (run & 32u)) body(std::integral_constant<int, 5 % S>());
-                        if (S > 6 && (run & 64u)) body(std::integral_constant<int, 6 % S>());
-                        if (S > 7 && (run & 128u)) body(std::integral_constant<int, 7 % S>());
-                    }
-                };
+                const Bp7LlrOut lo{p.llr, p.col_id, p.n};
+#define QD_COL(D_) col_update<real, METHOD, (D_), VMAX, S>(ea, fa, pj, i, run, decbits, lo, r, shot_of)
                 switch (deg) {
-                case 1: run_deg(std::integral_constant<int, 1>()); break;
-                case 2: run_deg(std::integral_constant<int, 2>()); break;
-                case 3: run_deg(std::integral_constant<int, 3>()); break;
-                case 4: run_deg(std::integral_constant<int, 4>()); break;
-                case 5: if (VMAX > 4) run_deg(std::integral_constant<int, (VMAX > 4 ? 5 : 1)>()); break;
-                case 6: if (VMAX > 4) run_deg(std::integral_constant<int, (VMAX > 4 ? 6 : 1)>()); break;
-                case 7: if (VMAX > 4) run_deg(std::integral_constant<int, (VMAX > 4 ? 7 : 1)>()); break;
-                case 8: if (VMAX > 4) run_deg(std::integral_constant<int, (VMAX > 4 ? 8 : 1)>()); break;
+                case 1: QD_COL(1); break;
+                case 2: QD_COL(2); break;
+                case 3: QD_COL(3); break;
+                case 4: QD_COL(4); break;
+                case 5: if (VMAX > 4) QD_COL(VMAX > 4 ? 5 : 1); break;
+                case 6: if (VMAX > 4) QD_COL(VMAX > 4 ? 6 : 1); break;
+                case 7: if (VMAX > 4) QD_COL(VMAX > 4 ? 7 : 1); break;
+                case 8: if (VMAX > 4) QD_COL(VMAX > 4 ? 8 : 1); break;
                 default: break;
                 }
+#undef QD_COL
             }
         }
         if (tid == 0) ctl->unsat[ub ^ 1] = 0u;              // buffer of the next check pass

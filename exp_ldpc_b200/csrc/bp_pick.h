@@ -8,7 +8,10 @@ struct Bp7Params;
 typedef void (*bp_kernel_fn)(const BpParams);
 typedef void (*bp7_kernel_fn)(const Bp7Params);
 
-constexpr int BP7_MAXT = 800;   // launch bound of the row-regular kernel (80 registers / thread)
+#ifndef QD_BP7_MAXT
+#define QD_BP7_MAXT 800
+#endif
+constexpr int BP7_MAXT = QD_BP7_MAXT;   // launch bound of the row-regular kernel (sets the register budget)
 
 #define QD_DECL_PICK(tag)                                        \
     bp_kernel_fn pick_bp6_##tag(int vmax, int threads);          \

@@ -141,11 +141,16 @@ def run_simulation(samples, code, meas_prior, data_prior, noise_model, noise_mod
 
 
 def p_sweep(samples, p_values, noise_model, noise_model_args, meas_prior, data_prior, *, code, rounds, decoder_mode,
-            bp_osd_options, seed: int = 0, device: Optional[int] = None, precision: str = "f64", group=None):
+            bp_osd_options, seed: int = 0, device: Optional[int] = None, precision: str = "f64", group=None,
+            shard_runner: Optional[Callable] = None):
     """``p_sweep`` of ``misc/p_sweep.py:17-40``: one row per p with the reference's columns
     (``p_ph, failures, samples, walltime, rounds, decoder_mode`` + the BP options), plus
     ``non_converged`` / ``iters_total`` / ``n_gpus``.  Under ``torch.distributed`` every rank
-    decodes its own shot range and the four counters are combined by one all-reduce per p."""
+    decodes its own shot range and the four counters are combined by one all-reduce per p.
+
+    ``shard_runner(p_ph, flip_probability, prior, lo, hi) -> dict(failures, shots, non_converged,
+    iters_total)`` replaces the GPU pipeline for one shard; the multi-rank CPU tests inject the
+    oracle there (the product default is the CUDA pipeline and nothing else)."""
     import pandas as pd
     import torch
 
@@ -160,11 +165,15 @@ def p_sweep(samples, p_values, noise_model, noise_model_args, meas_prior, data_p
     for p_ph in p_values:
         t0 = time.time()
         nm = noise_model(**noise_model_args(p_ph))
-        exp = CodeCapacityExperiment(code, nm.code_capacity_flip_probability(), data_prior(p_ph, 0, 0), decoder_mode,
-                                     bp_osd_options, device=device, precision=precision)
-        res = exp.run(hi - lo, seed=seed, shot0=lo)
+        if shard_runner is None:
+            exp = CodeCapacityExperiment(code, nm.code_capacity_flip_probability(), data_prior(p_ph, 0, 0), decoder_mode,
+                                         bp_osd_options, device=device, precision=precision)
+            res = exp.run(hi - lo, seed=seed, shot0=lo)
+        else:
+            res = shard_runner(p_ph, nm.code_capacity_flip_probability(), data_prior(p_ph, 0, 0), lo, hi)
+        on_gpu = torch.cuda.is_available() and (not dist.is_initialized() or dist.get_backend(group) == "nccl")
         counters = torch.tensor([res["failures"], res["shots"], res["non_converged"], res["iters_total"]],
-                                dtype=torch.int64, device=f"cuda:{device}" if torch.cuda.is_available() else "cpu")
+                                dtype=torch.int64, device=f"cuda:{device}" if on_gpu else "cpu")
         if world > 1:
             dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=group)
         f, s, nc, it = (int(v) for v in counters.tolist())

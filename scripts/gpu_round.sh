@@ -22,6 +22,6 @@ python bench.py --workload $WL $EXTRA --steps 2 --warmup 3 --shots 131072 --no-c
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches_${WL}.csv \
     python bench.py --workload $WL $EXTRA --steps 2 --warmup 3 --shots 131072 --no-cpu-baseline > $OUT/${TAG}_ncu_launches_${WL}.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:bp_ -s 3 -c 1 -f -o $OUT/${TAG}_bp_${WL} \
+ncu --set full --clock-control none --import-source on -k regex:bp -s 3 -c 1 -f -o $OUT/${TAG}_bp_${WL} \
     python bench.py --workload $WL $EXTRA --steps 2 --warmup 3 --shots 131072 --no-cpu-baseline --no-e2e > $OUT/${TAG}_ncu_full_${WL}.log 2>&1
 echo "ncu full rc=$?"
