@@ -73,18 +73,20 @@ struct Bp7SmemLayout {
     int msg_elems;              // elements of the message array (incl. scratch row)
 };
 
-// flag bytes of a row: S records of 8 bytes; the odd pitch keeps the check pass conflict free
-__host__ __device__ inline int bp7_flag_pitch(int s) { return (s | 1) * 8; }
+// flag bytes of a row: S records of 8 (row degree <= 8) or 16 bytes; the pitch is an odd number of
+// 8-byte words, which keeps the check pass conflict free
+__host__ __device__ inline int bp7_flag_record(int rd) { return rd <= 8 ? 8 : 16; }
+__host__ __device__ inline int bp7_flag_pitch(int s, int rd) { return ((s * bp7_flag_record(rd) / 8) | 1) * 8; }
 
 // lines: 128-byte lines per slot (from the layout); one more line group is scratch for padding lanes
-__host__ __device__ inline Bp7SmemLayout bp7_smem_layout(int m, int nrec, int nwn, int lines, int vmax, int s,
+__host__ __device__ inline Bp7SmemLayout bp7_smem_layout(int m, int nrec, int nwn, int lines, int rd, int vmax, int s,
                                                          int real_bytes, bool staged)
 {
     Bp7SmemLayout L;
     L.msg_elems = (lines + 1) * s * (128 / real_bytes);
     size_t o = 0;
     L.msg = o;   o += (size_t)(lines + 1) * s * 128;
-    L.flags = o; o += (size_t)(m + 1) * bp7_flag_pitch(s);
+    L.flags = o; o += (size_t)(m + 1) * bp7_flag_pitch(s, rd);
     o = (o + 15) & ~(size_t)15;
     L.table = o; o += staged ? (size_t)nrec * vmax * 4 : 0;
     L.out = o;   o += ((size_t)s * nwn * 4 + 15) & ~(size_t)15;
@@ -167,7 +169,12 @@ __device__ __forceinline__ void check_ps7(real (&v)[RD], unsigned sbit)
 template <typename real, int RD, int s>
 __device__ __forceinline__ void row_ld(const uint32_t (&ra)[RD], uint32_t fb, real (&v)[RD], unsigned long long &f)
 {
-    f = lds_u64_off<s * 8>(fb);
+    constexpr int FB = RD <= 8 ? 8 : 16;
+    f = lds_u64_off<s * FB>(fb);
+    if (RD > 8) {                       // second flag word: fold it in, keep "any flag set" in bit 63
+        const unsigned long long g = lds_u64_off<s * FB + (RD > 8 ? 8 : 0)>(fb);
+        f = ((unsigned long long)((__popcll(f) + __popcll(g)) & 1)) | ((f | g) ? 0x8000000000000002ULL : 0ULL);
+    }
 #pragma unroll
     for (int k = 0; k < RD; ++k) v[k] = lds_off<s * 128>(ra[k], real());
 }
@@ -176,9 +183,13 @@ template <typename real, int METHOD, int RD, int S, int s>
 __device__ __forceinline__ void row_cs(const uint32_t (&ra)[RD], uint32_t fb, real (&v)[RD], unsigned long long f, int i,
                                        bool valid, unsigned synbits, unsigned &resbits, unsigned &un, real al)
 {
+    constexpr int FB = RD <= 8 ? 8 : 16;
     const int bi = i * S + s;
-    resbits ^= ((unsigned)__popcll(f) & 1u) << bi;
-    if (f) sts_u64_off<s * 8>(fb, 0ULL);
+    resbits ^= ((unsigned)__popcll(f) & 1u) << bi;      // RD > 8: f was folded by row_ld (even popcount pad)
+    if (f) {
+        sts_u64_off<s * FB>(fb, 0ULL);
+        if (RD > 8) sts_u64_off<s * FB + (RD > 8 ? 8 : 0)>(fb, 0ULL);
+    }
     un |= (valid ? (resbits >> bi) & 1u : 0u) << s;
     const unsigned sbit = (synbits >> bi) & 1u;
     if (METHOD == QD_BP_MIN_SUM_K) check_ms7<real, RD>(v, sbit << 31, al);
@@ -196,7 +207,7 @@ __device__ __forceinline__ void col_ld(const uint32_t (&ea)[VMAX], real (&cv)[D]
 
 struct Bp7LlrOut { double *llr; const uint16_t *col_id; int n; };
 
-template <typename real, int METHOD, int D, int VMAX, int S, int s>
+template <typename real, int METHOD, int D, int VMAX, int S, int FB, int s>
 __device__ __forceinline__ void col_cs(const uint32_t (&ea)[VMAX], const uint32_t (&fa)[VMAX], real (&cv)[D], real pj, int i,
                                        unsigned &decbits, const Bp7LlrOut &lo, int r, long long shot)
 {
@@ -209,7 +220,7 @@ __device__ __forceinline__ void col_cs(const uint32_t (&ea)[VMAX], const uint32_
     const unsigned flip = ((decbits >> bi) & 1u) ^ dbit;
     if (flip) {
 #pragma unroll
-        for (int t = 0; t < D; ++t) sts_u8_off<s * 8>(fa[t], 1u);
+        for (int t = 0; t < D; ++t) sts_u8_off<s * FB>(fa[t], 1u);
     }
     decbits ^= flip << bi;
     if (lo.llr) {
@@ -221,14 +232,14 @@ __device__ __forceinline__ void col_cs(const uint32_t (&ea)[VMAX], const uint32_
 }
 
 // all slots of one column record of compile-time degree D
-template <typename real, int METHOD, int D, int VMAX, int S>
+template <typename real, int METHOD, int D, int VMAX, int S, int FB>
 __device__ __forceinline__ void col_update(const uint32_t (&ea)[VMAX], const uint32_t (&fa)[VMAX], real pj, int i, unsigned run,
                                            unsigned &decbits, const Bp7LlrOut &lo, int r, const long long (&shot_of)[S])
 {
     constexpr unsigned SMASK = (1u << S) - 1u;
     real ca[D], cb[D], cc[D];
 #define QD_LD(n, buf) col_ld<real, D, VMAX, (n) % S>(ea, buf)
-#define QD_CS(n, buf) col_cs<real, METHOD, D, VMAX, S, (n) % S>(ea, fa, buf, pj, i, decbits, lo, r, shot_of[(n) % S])
+#define QD_CS(n, buf) col_cs<real, METHOD, D, VMAX, S, FB, (n) % S>(ea, fa, buf, pj, i, decbits, lo, r, shot_of[(n) % S])
     if (run == SMASK) {                                  // three buffers: two slots of loads in flight
         QD_LD(0, ca);
         if (S > 1) QD_LD(1, cb);
@@ -268,13 +279,14 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
     static_assert(S >= 1 && S <= BP7_SMAX, "slots");
     constexpr int RB = (int)sizeof(real);
     constexpr int LINE = 128;                            // bytes between the slots of one message
-    constexpr int FP = (S | 1) * 8;                      // flag bytes per row (bp7_flag_pitch)
+    constexpr int FB = RD <= 8 ? 8 : 16;                 // flag bytes per (row, slot)
+    constexpr int FP = ((S * FB / 8) | 1) * 8;           // flag bytes per row (bp7_flag_pitch)
     constexpr int RQ = (RD + 3) / 4;                     // uint4 per row-table entry
     constexpr unsigned SMASK = (1u << S) - 1u;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = (int)threadIdx.x, NT = (int)blockDim.x, lane = tid & 31;
 
-    const Bp7SmemLayout L = bp7_smem_layout(p.m, p.nrec, p.nwn, p.lines, VMAX, S, RB, p.staged != 0);
+    const Bp7SmemLayout L = bp7_smem_layout(p.m, p.nrec, p.nwn, p.lines, RD, VMAX, S, RB, p.staged != 0);
     const uint32_t a_msg = smem_u32(smem_raw + L.msg), a_flags = smem_u32(smem_raw + L.flags),
                    a_tab = smem_u32(smem_raw + L.table);
     uint32_t *outbits = reinterpret_cast<uint32_t *>(smem_raw + L.out);          // [S][nwn]
@@ -347,7 +359,8 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                     if (valid) b = (p.synd[ctl->shot[s] * (long long)p.synd_stride + (c >> 5)] >> (c & 31)) & 1u;
                     synbits = (synbits & ~(1u << bi)) | (b << bi);
                     resbits = (resbits & ~(1u << bi)) | (b << bi);
-                    sts_u64(fb + s * 8, 0ULL);
+                    sts_u64(fb + s * FB, 0ULL);
+                    if (FB > 8) sts_u64(fb + s * FB + 8, 0ULL);
                 }
         }
         i = 0;
@@ -519,7 +532,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                 const real pj = prior_of(r);
                 const int deg = __shfl_sync(0xffffffffu, (int)__ldg(p.chunk_deg + (r >> 5)), 0);
                 const Bp7LlrOut lo{p.llr, p.col_id, p.n};
-#define QD_COL(D_) col_update<real, METHOD, (D_), VMAX, S>(ea, fa, pj, i, run, decbits, lo, r, shot_of)
+#define QD_COL(D_) col_update<real, METHOD, (D_), VMAX, S, FB>(ea, fa, pj, i, run, decbits, lo, r, shot_of)
                 switch (deg) {
                 case 1: QD_COL(1); break;
                 case 2: QD_COL(2); break;

@@ -578,7 +578,7 @@ static size_t bp7_smem(qd_bp *d, int slots, bool staged)
 {
     const GraphDev &g = d->g->dev;
     const Bp7Layout &L = bp7_layout_of(d);
-    return bp7_smem_layout(g.m, L.nrec, g.nwn, L.lines, d->vmax, slots, d->precision == QD_PREC_F64 ? 8 : 4, staged).total;
+    return bp7_smem_layout(g.m, L.nrec, g.nwn, L.lines, d->rd, d->vmax, slots, d->precision == QD_PREC_F64 ? 8 : 4, staged).total;
 }
 
 // can a (slots, threads) geometry be represented?  per-thread state is one bit per owned
@@ -588,8 +588,8 @@ static bool bp7_geometry_ok(qd_bp *d, int slots, int threads)
     const GraphDev &g = d->g->dev;
     const Bp7Layout &L = bp7_layout_of(d);
     const int m32 = (g.m + 31) / 32 * 32;
-    const Bp7SmemLayout SL = bp7_smem_layout(g.m, L.nrec, g.nwn, L.lines, d->vmax, slots, d->precision == QD_PREC_F64 ? 8 : 4, false);
-    if (SL.msg_elems > 65535 || (g.m + 1) * bp7_flag_pitch(slots) > 65535 || g.n >= 65535) return false;
+    const Bp7SmemLayout SL = bp7_smem_layout(g.m, L.nrec, g.nwn, L.lines, d->rd, d->vmax, slots, d->precision == QD_PREC_F64 ? 8 : 4, false);
+    if (SL.msg_elems > 65535 || (g.m + 1) * bp7_flag_pitch(slots, d->rd) > 65535 || g.n >= 65535) return false;
     if (threads < 32 || threads > BP7_MAXT || threads % 32) return false;
     if (((m32 + threads - 1) / threads) * slots > 32) return false;
     if (((L.nrec + threads - 1) / threads) * slots > 32) return false;
@@ -602,7 +602,7 @@ static int bp7_prepare(qd_bp *d, int slots)
     qd_graph *g = d->g;
     const GraphDev &gd = g->dev;
     const Bp7Layout &L = bp7_layout_of(d);
-    const int V = d->vmax, S = slots, RD = d->rd, NB = L.nb, RB = 128 / NB, FP = bp7_flag_pitch(S);
+    const int V = d->vmax, S = slots, RD = d->rd, NB = L.nb, RB = 128 / NB, FP = bp7_flag_pitch(S, RD), FB = bp7_flag_record(RD);
     const int m32 = (gd.m + 31) / 32 * 32, RQ = (RD + 3) / 4;
     // element index (slot 0) of a CSR edge; scratch elements live in the extra line group
     auto elem = [&](int e) { return L.index[e] * NB * S + L.colour[e]; };
@@ -634,7 +634,7 @@ static int bp7_prepare(qd_bp *d, int slots)
                     fq[t] = (uint16_t)((int)g->csc_row[ce] * FP + g->csc_k[ce]);
                 } else {
                     mq[t] = (uint16_t)scratch(r);
-                    fq[t] = (uint16_t)(gd.m * FP + (t & 7));
+                    fq[t] = (uint16_t)(gd.m * FP + (t % FB));
                 }
             }
             if (j >= 0) { col_id[r] = (uint16_t)j; prior_rec[r] = d->prior_dom[j]; }

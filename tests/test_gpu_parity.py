@@ -291,3 +291,67 @@ def test_full_size_properties_n6400(gpu, code6400):
     ref = po.run_code_capacity(hz, code6400.logicals.z, q, prior, decoder="bp", max_iter=32, bp_method="ms", seed=1,
                                shots=48, per_shot=True)
     assert np.array_equal(ref["decodings"], a["decodings"][:48]) and np.array_equal(ref["iters"], a["iters"][:48])
+
+
+# ---------------------------------------------------------------------------------------------
+# the other code families of BASELINE.json (configs 3-4): row degrees 6 / 8 / 9, column tile 4 / 8
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def family_codes():
+    from exp_ldpc_b200 import code_builders as cb
+    return {name: getattr(cb, name)() for name in ("pk19_b1_882", "pk20_qc_1054", "pk19_b3_1270", "a5_lift_2700")}
+
+
+@pytest.mark.parametrize("name", ["pk19_b1_882", "pk20_qc_1054", "pk19_b3_1270", "a5_lift_2700"])
+@pytest.mark.parametrize("method,alpha,p", [("ms", 0.0, 0.03), ("ms", 0.75, 0.06), ("ps", 0.0, 0.04)])
+def test_bp_code_families_against_live_oracle(gpu, family_codes, name, method, alpha, p):
+    from exp_ldpc_b200.experiment import CodeCapacityExperiment
+    from oracle import pyoracle as po
+    code = family_codes[name]
+    q, prior = 2 * p / 3 + p - 4 / 3 * p * p, 2 * p / 3
+    shots = 384
+    opts = dict(max_iter=24, bp_method=method, ms_scaling_factor=alpha)
+    ref = po.run_code_capacity(code.checks.z, code.logicals.z, q, prior, decoder="bp", max_iter=24, bp_method=method,
+                               ms_scaling_factor=alpha, seed=11, shots=shots, per_shot=True)
+    for kernel in ("regular", "generic"):
+        exp = CodeCapacityExperiment(code, q, prior, "bp", opts, kernel=kernel)
+        assert exp.decoder.config()["kernel"] == kernel
+        got = exp.run(shots, seed=11, per_shot=True)
+        assert (got["decodings"] == ref["decodings"]).all(), (kernel, "hard decisions differ")
+        assert np.array_equal(got["iters"], ref["iters"]) and np.array_equal(got["fail"], ref["fail"])
+        assert np.array_equal(got["converged"], ref["converged"])
+
+
+@pytest.mark.parametrize("name,p", [("pk19_b1_882", 0.01), ("pk20_qc_1054", 0.01), ("a5_lift_2700", 0.006)])
+def test_ssf_code_families_against_live_oracle(gpu, family_codes, name, p):
+    from exp_ldpc_b200.experiment import CodeCapacityExperiment
+    from oracle import pyoracle as po
+    code = family_codes[name]
+    q = prior = 2 * p / 3
+    shots = 192
+    got = CodeCapacityExperiment(code, q, prior, "ssf", {}).run(shots, seed=3, per_shot=True)
+    ref = po.run_code_capacity(code.checks.z, code.logicals.z, q, prior, decoder="ssf", hx=code.checks.x, seed=3,
+                               shots=shots, per_shot=True)
+    assert (got["decodings"] == ref["decodings"]).all()
+    assert np.array_equal(got["iters"], ref["iters"]) and np.array_equal(got["fail"], ref["fail"])
+    assert np.array_equal(got["converged"], ref["converged"])
+
+
+def test_bp_per_bit_priors_match_oracle(gpu, code225):
+    """channel_probs vector (the hybrid decoder's data / measurement priors, _experiment.py:106-113)."""
+    from exp_ldpc_b200.decoders import bp_decoder
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(1)
+    hz = code225.checks.z
+    probs = rng.uniform(0.005, 0.2, hz.shape[1])
+    err = (rng.random((200, hz.shape[1])) < probs).astype(np.uint8)
+    synd = (err @ hz.T.toarray()) % 2
+    for method in ("ms", "ps"):
+        ref = po.OracleBP(hz, channel_probs=probs, max_iter=30, bp_method=method, ms_scaling_factor=0.0)
+        for kernel in ("regular", "generic"):
+            dec = bp_decoder(hz, channel_probs=probs, max_iter=30, bp_method=method, ms_scaling_factor=0.0, kernel=kernel)
+            corr, conv, its = dec.decode_batch(synd)
+            for s in range(synd.shape[0]):
+                want = ref.decode(synd[s])
+                assert np.array_equal(corr[s], want), (method, kernel, s)
+                assert its[s] == ref.iter and conv[s] == ref.converge
