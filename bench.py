@@ -35,12 +35,26 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+_BP = dict(max_iter=32, bp_method="ms", ms_scaling_factor=0.0)
 WORKLOADS = {
-    # name: (qecc file, p, bp options)
-    "hgp_34_n1600": ("hgp_34_n1600.qecc", 0.05, dict(max_iter=32, bp_method="ms", ms_scaling_factor=0.0)),
-    "hgp_34_n6400": ("hgp_34_n6400.qecc", 0.05, dict(max_iter=32, bp_method="ms", ms_scaling_factor=0.0)),
-    "hgp_34_n225": ("hgp_34_n225.qecc", 0.05, dict(max_iter=32, bp_method="ms", ms_scaling_factor=0.0)),
+    # name: (qecc file | code_builders function, p, bp options, description)
+    "hgp_34_n1600": ("hgp_34_n1600.qecc", 0.05, _BP, "(3,4) HGP"),                       # BASELINE configs[1]
+    "hgp_34_n6400": ("hgp_34_n6400.qecc", 0.05, _BP, "(3,4) HGP"),                       # BASELINE configs[1]
+    "hgp_34_n225": ("hgp_34_n225.qecc", 0.05, _BP, "(3,4) HGP"),                         # BASELINE configs[0]
+    "lp_882": ("builder:pk19_b1_882", 0.05, _BP, "QC lifted product [[882,24]]"),        # BASELINE configs[2]
+    "qclp_1054": ("builder:pk20_qc_1054", 0.05, _BP, "QC lifted product [[1054,140]]"),
+    "a5lp_2700": ("builder:a5_lift_2700", 0.05, _BP, "PSL(2,5) lifted product n=2700"),  # BASELINE configs[3]
 }
+SSF_DEFAULT_P = 0.01
+
+
+def load_workload(name):
+    src = WORKLOADS[name][0]
+    if src.startswith("builder:"):
+        from exp_ldpc_b200 import code_builders
+        return getattr(code_builders, src.split(":", 1)[1])()
+    from exp_ldpc_b200.codes import load_code
+    return load_code(os.path.join(ROOT, "codes", src))
 
 
 def probabilities(p):
@@ -99,13 +113,13 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_port_throughput(code, p, opts, target_seconds=12.0, threads=0):
+def cpu_port_throughput(code, p, opts, target_seconds=12.0, threads=0, decoder="bp"):
     """Time the CPU oracle (the port of the reference's decoder) on a bounded sample of the same
     workload; returns (shots/s, cores, sample description, mean iterations)."""
     from oracle import pyoracle as po
     q, prior = probabilities(p)
     cores = po.num_threads() if threads <= 0 else threads
-    kw = dict(decoder="bp", max_iter=opts["max_iter"], bp_method=opts["bp_method"],
+    kw = dict(decoder=decoder, hx=code.checks.x, max_iter=opts["max_iter"], bp_method=opts["bp_method"],
               ms_scaling_factor=opts["ms_scaling_factor"], seed=0, threads=cores)
     probe = 64 * cores
     t0 = time.perf_counter()
@@ -127,6 +141,7 @@ def main():
     ap.add_argument("--workload", default="hgp_34_n1600", choices=sorted(WORKLOADS))
     ap.add_argument("--shots", type=int, default=1 << 20, help="shots per GPU per step")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--decoder", default="bp", choices=["bp", "ssf"])
     ap.add_argument("--p", type=float, default=None)
     ap.add_argument("--max-iter", type=int, default=None)
     ap.add_argument("--bp-method", default=None)
@@ -144,24 +159,30 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    from exp_ldpc_b200.codes import load_code
-    fname, p, opts = WORKLOADS[args.workload]
+    _, p, opts, family = WORKLOADS[args.workload]
     opts = dict(opts)
+    ssf = args.decoder == "ssf"
+    if ssf:
+        p = SSF_DEFAULT_P
     if args.p is not None:
         p = args.p
     if args.max_iter is not None:
         opts["max_iter"] = args.max_iter
     if args.bp_method is not None:
         opts["bp_method"] = args.bp_method
-    code = load_code(os.path.join(ROOT, "codes", fname))
+    code = load_workload(args.workload)
     m, n = code.checks.z.shape
     nnz = int(code.checks.z.nnz)
     q, prior = probabilities(p)
-    config = {"workload": f"{args.workload}: (3,4) HGP n={n} m={m} nnz={nnz} k={code.num_logicals}, code capacity, "
-                          f"BP {opts['bp_method']} alpha={'1-2^-it' if opts['ms_scaling_factor'] == 0 else opts['ms_scaling_factor']} "
-                          f"max_iter={opts['max_iter']} early-exit, p={p} (flip q={q:.5f}, prior 2p/3)",
-              "shots_per_step_per_gpu": args.shots, "p": p, "max_iter": opts["max_iter"], "bp_method": opts["bp_method"],
-              "precision": args.precision, "parallelism": f"shots sharded over {world} rank(s), one all-reduce of int64[4] per step",
+    how = ("small-set-flip (candidate sets = subsets of the X-generator supports)" if ssf else
+           f"BP {opts['bp_method']} alpha={'1-2^-it' if opts['ms_scaling_factor'] == 0 else opts['ms_scaling_factor']} "
+           f"max_iter={opts['max_iter']} early-exit")
+    metric = "decoded shots/sec (SSF, fixed p)" if ssf else "decoded shots/sec (BP, fixed p and iteration cap)"
+    dtype = "u32" if ssf else args.precision
+    config = {"workload": f"{args.workload}: {family} n={n} m={m} nnz={nnz} k={code.num_logicals}, code capacity, "
+                          f"{how}, p={p} (flip q={q:.5f}, prior 2p/3)",
+              "shots_per_step_per_gpu": args.shots, "p": p, "decoder": args.decoder, "max_iter": opts["max_iter"],
+              "bp_method": opts["bp_method"], "precision": dtype, "parallelism": f"shots sharded over {world} rank(s), one all-reduce of int64[4] per step",
               "l2": "inputs larger than L2 (no flush needed)"}
 
     # ------------------------------------------------------------------ reference arm (CPU port)
@@ -173,13 +194,15 @@ def main():
         sample = ""
         per_step = max(2.0, min(20.0, 120.0 / (args.steps + args.warmup)))
         for i in range(args.warmup + args.steps):
-            r, cores, sample, _ = cpu_port_throughput(code, p, opts, target_seconds=per_step if i >= args.warmup else 1.0)
+            r, cores, sample, _ = cpu_port_throughput(code, p, opts, target_seconds=per_step if i >= args.warmup else 1.0,
+                                                      decoder=args.decoder)
             if i >= args.warmup:
                 rates.append(r)
         v = statistics.mean(rates)
-        line = {"metric": "decoded shots/sec (BP, fixed p and iteration cap)", "value": v, "unit": "shots/s",
+        line = {"metric": metric, "value": v, "unit": "shots/s",
                 "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32" if ssf else "f64",
                 "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "shots/s", "cores": cores, "kind": "port",
                                  "sample": sample + " per step (oracle/qldpc_oracle.c; the reference's own decoder `ldpc` is not installable here)"},
@@ -198,15 +221,25 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from exp_ldpc_b200.decoders import Logicals, Sampler, TannerGraph, bp_decoder, row_words
+    from exp_ldpc_b200.decoders import Logicals, Sampler, TannerGraph, bp_decoder, row_words, ssf_decoder
     graph = TannerGraph(code.checks.z, device=local_rank)
     logicals = Logicals(code.logicals.z, device=local_rank)
     sampler = Sampler(q, n, device=local_rank)
-    dec = bp_decoder(graph, error_rate=prior, precision=args.precision, **opts)
-    if args.threads or args.slots or args.ctas or args.teams:
-        dec.configure(args.threads, args.slots, args.ctas, args.teams)
-    cfg = dec.config()
+    if ssf:
+        dec = ssf_decoder(graph, code.checks.x)
+        cfg = {"kernel": "ssf"}
+    else:
+        dec = bp_decoder(graph, error_rate=prior, precision=args.precision, **opts)
+        if args.threads or args.slots or args.ctas or args.teams:
+            dec.configure(args.threads, args.slots, args.ctas, args.teams)
+        cfg = dec.config()
     config["launch"] = cfg
+
+    def launch(cnt_row):
+        if ssf:
+            dec.decode_batch_device(d_syn, ss, shots, d_cor, es, d_conv, d_it, d_err, es, logicals, d_fail, cnt_row, stream)
+        else:
+            dec.decode_batch_device(d_syn, ss, shots, d_cor, es, d_conv, d_it, None, d_err, es, logicals, d_fail, cnt_row, stream)
 
     shots = args.shots
     es, ss = row_words(n), row_words(m)
@@ -226,7 +259,7 @@ def main():
 
     def decode_step(row):
         cnt_row = d_cnt[row]
-        dec.decode_batch_device(d_syn, ss, shots, d_cor, es, d_conv, d_it, None, d_err, es, logicals, d_fail, cnt_row, stream)
+        launch(cnt_row)
         if world > 1:
             dist.all_reduce(cnt_row)   # the one collective of the path: sum of the 4 counters
 
@@ -251,7 +284,7 @@ def main():
     for i in range(args.steps):
         cnt_row = d_cnt[i]
         k_ev[i][0].record()
-        dec.decode_batch_device(d_syn, ss, shots, d_cor, es, d_conv, d_it, None, d_err, es, logicals, d_fail, cnt_row, stream)
+        launch(cnt_row)
         k_ev[i][1].record()
         if world > 1:
             dist.all_reduce(cnt_row)
@@ -277,8 +310,8 @@ def main():
         h_syn.copy_(d_syn)
         torch.cuda.synchronize()
         h_np = h_syn.numpy().view(np.uint32)
-        for _ in range(2):
-            dec.decode_batch(h_np[: max(1, shots // 8)], packed=True, return_packed=True)
+        for _ in range(2):          # full-size warm-up: the pinned staging buffers of the library are sized here
+            dec.decode_batch(h_np, packed=True, return_packed=True)
         barrier()
         t0 = time.perf_counter()
         e2e_steps = max(1, min(args.steps, 3))
@@ -291,7 +324,8 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": shots * world * e2e_steps / float(tt.item()), "unit": "shots/s",
                "h2d_bytes_per_step": int(shots * ss * 4), "d2h_bytes_per_step": int(shots * (es * 4 + 1 + 4)),
-               "api": "bp_decoder.decode_batch(packed host syndromes) -> qd_bp_decode_batch_host", "steps": e2e_steps}
+               "api": f"{'ssf' if ssf else 'bp'}_decoder.decode_batch(packed host syndromes) -> "
+                      f"qd_{'ssf' if ssf else 'bp'}_decode_batch_host", "steps": e2e_steps}
 
     if rank != 0:
         if world > 1:
@@ -313,12 +347,12 @@ def main():
     sm_mhz = clk.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
     smem_peak = sm_count * 128 * sm_mhz * 1e6 / 1e9
     smem_achieved = smem_bytes_per_shot * shots / (kernel_ms * 1e-3) / 1e9
-    kernel_name = "bp7_kernel" if cfg.get("kernel") == "regular" else "bp_kernel"
+    kernel_name = {"regular": "bp7_kernel", "ssf": "ssf_kernel"}.get(cfg.get("kernel"), "bp_kernel")
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full`
     # capture of this workload (per launch of the captured shot count, scaled to this launch)
     traffic = None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:{args.precision}")
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{args.workload}:{dtype}")
         if tr and tr.get("kernel") == kernel_name:
             traffic = tr["dram_bytes_per_shot"] * shots
     except (OSError, ValueError):
@@ -328,7 +362,8 @@ def main():
                 "algorithmic_bytes_per_launch": bytes_per_shot * shots,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_shot": bytes_per_shot,
-                "note": "HBM is touched for I/O only; the kernel is bound by shared memory / issue, see roofline_smem"}
+                "note": ("HBM is touched for I/O only; the kernel is bound by integer issue rate" if ssf else
+                         "HBM is touched for I/O only; the kernel is bound by shared memory / issue, see roofline_smem")}
     roofline_smem = {"bound": "shared-memory", "achieved": smem_achieved, "peak": smem_peak, "unit": "GB/s",
                      "frac": smem_achieved / smem_peak, "algorithmic_bytes_per_shot": smem_bytes_per_shot,
                      "mean_iterations": mean_iters, "edge_updates_per_s": 2.0 * nnz * mean_iters * shots / (kernel_ms * 1e-3),
@@ -336,13 +371,15 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        v, cores, sample, cpu_iters = cpu_port_throughput(code, p, opts, target_seconds=12.0)
+        v, cores, sample, cpu_iters = cpu_port_throughput(code, p, opts, target_seconds=12.0, decoder=args.decoder)
         cpu = {"value": v, "unit": "shots/s", "cores": cores, "kind": "port", "sample": sample,
                "mean_iterations": cpu_iters}
 
-    line = {"metric": "decoded shots/sec (BP, fixed p and iteration cap)", "value": value, "unit": "shots/s",
+    if ssf:
+        roofline_smem = None
+    line = {"metric": metric, "value": value, "unit": "shots/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": config, "e2e": e2e, "gpu_launches": args.steps, "clocks": clk, "roofline": roofline,
             "roofline_smem": roofline_smem, "cpu_baseline": cpu,
             "counters": {"failures": int(cnt[0]), "shots": int(cnt[1]), "non_converged": int(cnt[2]),

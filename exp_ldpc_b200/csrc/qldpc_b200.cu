@@ -228,7 +228,7 @@ struct qd_ssf {
     int max_rounds = 0;
     int threads = 128;
     size_t smem = 0;
-    DevBuf d_gen_ptr, d_gen_idx, d_win_ptr, d_win_chk, d_qmask, d_next;
+    DevBuf d_gen_ptr, d_gen_idx, d_win_ptr, d_win_chk, d_qmask, d_chk_ptr, d_chk_gen, d_next;
     cudaStream_t streams[2] = {nullptr, nullptr};
     cudaEvent_t done[2] = {nullptr, nullptr};
     DevBuf d_in[2], d_out[2], d_conv[2], d_it[2];
@@ -984,10 +984,14 @@ static int host_pipeline(H *d, int device, int nwm, int nwn, const uint32_t *h_s
         QD_CUDA(cudaEventSynchronize(d->done[b]));
         const int64_t s0 = c * chunk, ns = std::min(chunk, shots - s0);
         const uint32_t *src = d->h_out[b].template as<uint32_t>();
-        for (int64_t s = 0; s < ns; ++s) {
-            uint32_t *dst = h_corr + (s0 + s) * corr_stride;
-            std::memcpy(dst, src + s * os, (size_t)nwn * 4);
-            for (int w = nwn; w < corr_stride; ++w) dst[w] = 0u;
+        if (corr_stride == os) {                                  // rows already have the caller's stride
+            std::memcpy(h_corr + s0 * corr_stride, src, (size_t)ns * os * 4);
+        } else {
+            for (int64_t s = 0; s < ns; ++s) {
+                uint32_t *dst = h_corr + (s0 + s) * corr_stride;
+                std::memcpy(dst, src + s * os, (size_t)nwn * 4);
+                for (int w = nwn; w < corr_stride; ++w) dst[w] = 0u;
+            }
         }
         if (h_conv) std::memcpy(h_conv + s0, d->h_conv[b].p, (size_t)ns);
         if (h_it) std::memcpy(h_it + s0, d->h_it[b].p, (size_t)ns * 4);
@@ -998,9 +1002,13 @@ static int host_pipeline(H *d, int device, int nwm, int nwn, const uint32_t *h_s
         if (c >= 2 && (rc = drain(c - 2))) return rc;
         const int64_t s0 = c * chunk, ns = std::min(chunk, shots - s0);
         uint32_t *stage = d->h_in[b].template as<uint32_t>();
-        for (int64_t s = 0; s < ns; ++s) {
-            std::memcpy(stage + s * is, h_synd + (s0 + s) * synd_stride, (size_t)nwm * 4);
-            for (int w = nwm; w < is; ++w) stage[s * is + w] = 0u;
+        if (synd_stride == is) {                                  // caller already uses the device stride
+            std::memcpy(stage, h_synd + s0 * synd_stride, (size_t)ns * is * 4);
+        } else {
+            for (int64_t s = 0; s < ns; ++s) {
+                std::memcpy(stage + s * is, h_synd + (s0 + s) * synd_stride, (size_t)nwm * 4);
+                for (int w = nwm; w < is; ++w) stage[s * is + w] = 0u;
+            }
         }
         cudaStream_t st = d->streams[b];
         QD_CUDA(cudaMemcpyAsync(d->d_in[b].p, stage, (size_t)ns * is * 4, cudaMemcpyHostToDevice, st));
@@ -1110,6 +1118,15 @@ extern "C" int qd_ssf_create(qd_graph *hz, int32_t num_generators, const int32_t
         win_chk.insert(win_chk.end(), win.begin(), win.end());
         win_ptr[gi + 1] = (int)win_chk.size();
     }
+    // check -> generators whose window contains it (what a flip invalidates)
+    std::vector<int32_t> chk_ptr(g.m + 1, 0), chk_gen(win_chk.size());
+    for (int32_t c : win_chk) chk_ptr[c + 1]++;
+    for (int c = 0; c < g.m; ++c) chk_ptr[c + 1] += chk_ptr[c];
+    {
+        std::vector<int32_t> fill(chk_ptr.begin(), chk_ptr.end() - 1);
+        for (int gi = 0; gi < mg; ++gi)
+            for (int z = win_ptr[gi]; z < win_ptr[gi + 1]; ++z) chk_gen[fill[win_chk[z]]++] = gi;
+    }
     std::unique_ptr<qd_ssf> d(new qd_ssf);
     d->g = hz;
     d->device = hz->device;
@@ -1119,14 +1136,17 @@ extern "C" int qd_ssf_create(qd_graph *hz, int32_t num_generators, const int32_t
     if ((rc = upload(d->d_win_ptr, win_ptr))) return rc;
     if ((rc = upload(d->d_win_chk, win_chk))) return rc;
     if ((rc = upload(d->d_qmask, qmask))) return rc;
+    if ((rc = upload(d->d_chk_ptr, chk_ptr))) return rc;
+    if ((rc = upload(d->d_chk_gen, chk_gen))) return rc;
     if ((rc = d->d_next.alloc(sizeof(unsigned long long) * 2))) return rc;
     SsfDev &s = d->dev;
     s.m = g.m; s.n = g.n; s.nwm = g.nwm; s.nwn = g.nwn; s.mg = mg; s.max_w = max_w;
     s.gen_ptr = d->d_gen_ptr.as<int32_t>(); s.gen_idx = d->d_gen_idx.as<int32_t>();
     s.win_ptr = d->d_win_ptr.as<int32_t>(); s.win_chk = d->d_win_chk.as<int32_t>();
     s.qmask = d->d_qmask.as<unsigned long long>();
+    s.chk_ptr = d->d_chk_ptr.as<int32_t>(); s.chk_gen = d->d_chk_gen.as<int32_t>();
     d->threads = 128;
-    d->smem = ssf_smem_bytes(g.nwn, g.nwm, d->threads);
+    d->smem = ssf_smem_bytes(g.nwn, g.nwm, mg, d->threads);
     *out = d.release();
     return 0;
 }

@@ -2,9 +2,12 @@
 // CPU restatement: oracle/qldpc_oracle.c orc_ssf_decode; the reference itself has no SSF).
 //
 // One CTA per shot in flight (persistent, shots pulled from a global atomic queue).  Per round:
-//   * every thread scans its generators: the syndrome restricted to the generator's check window
-//     is gathered into one 64-bit word; the 2^w - 1 candidate subsets are walked in Gray-code
-//     order, one XOR + two popcounts each:  delta = 2 popc(local & T) - popc(T);
+//   * the best candidate of every generator is CACHED in shared memory; a flip only invalidates the
+//     generators whose check window contains a check that changed (host-built check -> generators
+//     lists), so after the first round a thread rescans a handful of generators instead of all;
+//   * scanning a generator: the syndrome restricted to the generator's check window is gathered
+//     into one 64-bit word; the 2^w - 1 candidate subsets are walked in Gray-code order, one XOR +
+//     two popcounts each:  delta = 2 popc(local & T) - popc(T);
 //   * candidates are ranked by an exact integer key  (delta * 27720 / |F|, lowest generator,
 //     lowest subset mask)  — 27720 = lcm(1..12) makes the ratio an integer, so the arg-max is a
 //     plain 64-bit max and ties break exactly like the serial oracle;
@@ -23,6 +26,7 @@ struct SsfDev {
     const int32_t *gen_ptr, *gen_idx;        // generator supports (rows of Hx)
     const int32_t *win_ptr, *win_chk;        // per generator: its window of adjacent checks (<= 64)
     const unsigned long long *qmask;         // per support entry: toggle mask in window coordinates
+    const int32_t *chk_ptr, *chk_gen;        // per check: the generators whose window contains it
 };
 
 struct SsfParams {
@@ -39,9 +43,9 @@ struct SsfParams {
     unsigned long long *next_shot;
 };
 
-__host__ __device__ inline size_t ssf_smem_bytes(int nwn, int nwm, int threads)
+__host__ __device__ inline size_t ssf_smem_bytes(int nwn, int nwm, int mg, int threads)
 {
-    return (size_t)4 * (nwn + nwm) + 8 * (size_t)(threads / 32 + 2) + 32;
+    return (size_t)8 * (threads / 32 + 2) + (size_t)8 * mg + (size_t)4 * (nwn + nwm) + (size_t)((mg + 15) & ~15) + 32;
 }
 
 // 27720 / size for size in 1..12
@@ -63,8 +67,10 @@ __global__ void __launch_bounds__(256) ssf_kernel(const SsfParams p)
     const SsfDev &s = p.s;
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
     unsigned long long *red = reinterpret_cast<unsigned long long *>(smem_raw);   // [nwarps + 2]
-    uint32_t *sigma = reinterpret_cast<uint32_t *>(red + nwarps + 2);              // [nwm]
+    unsigned long long *gkeys = red + nwarps + 2;                                  // [mg] cached best key per generator
+    uint32_t *sigma = reinterpret_cast<uint32_t *>(gkeys + s.mg);                  // [nwm]
     uint32_t *dec = sigma + s.nwm;                                                // [nwn]
+    uint8_t *dirty = reinterpret_cast<uint8_t *>(dec + s.nwn);                    // [mg] cached key is stale
     __shared__ long long sh_shot;
     __shared__ int sh_weight;
 
@@ -87,6 +93,7 @@ __global__ void __launch_bounds__(256) ssf_kernel(const SsfParams p)
             w8 = warp_sum(w8);
             if (lane == 0 && w8) atomicAdd(&sh_weight, w8);
             for (int w = tid; w < s.nwn; w += NT) dec[w] = 0u;
+            for (int g = tid; g < s.mg; g += NT) dirty[g] = 1;
         }
         __syncthreads();
         int weight = sh_weight;
@@ -94,6 +101,9 @@ __global__ void __launch_bounds__(256) ssf_kernel(const SsfParams p)
         while (weight > 0 && (p.max_rounds == 0 || rounds < p.max_rounds)) {
             unsigned long long best = 0ULL;
             for (int g = tid; g < s.mg; g += NT) {
+                if (!dirty[g]) { const unsigned long long k = gkeys[g]; best = k > best ? k : best; continue; }
+                dirty[g] = 0;
+                unsigned long long gbest = 0ULL;
                 const int lo = s.gen_ptr[g], w = s.gen_ptr[g + 1] - lo;
                 const int wlo = s.win_ptr[g], nw = s.win_ptr[g + 1] - wlo;
                 unsigned long long local = 0ULL;
@@ -101,7 +111,7 @@ __global__ void __launch_bounds__(256) ssf_kernel(const SsfParams p)
                     const int c = s.win_chk[wlo + z];
                     local |= (unsigned long long)((sigma[c >> 5] >> (c & 31)) & 1u) << z;
                 }
-                if (!local) continue;
+                if (!local) { gkeys[g] = 0ULL; continue; }
                 unsigned long long qm[SSF_MAX_W];
 #pragma unroll
                 for (int t = 0; t < SSF_MAX_W; ++t) qm[t] = t < w ? s.qmask[lo + t] : 0ULL;
@@ -120,9 +130,11 @@ __global__ void __launch_bounds__(256) ssf_kernel(const SsfParams p)
                         const unsigned long long key =
                             ((unsigned long long)((unsigned)delta * inv_size[__popc(gray)]) << 40) | gkey |
                             (unsigned long long)(0xFFFFu - gray);
-                        best = key > best ? key : best;
+                        gbest = key > gbest ? key : gbest;
                     }
                 }
+                gkeys[g] = gbest;
+                best = gbest > best ? gbest : best;
             }
             best = warp_max_u64(best);
             if (lane == 0) red[warp] = best;
@@ -150,6 +162,7 @@ __global__ void __launch_bounds__(256) ssf_kernel(const SsfParams p)
             if (tid >= 32 && tid - 32 < nw && ((T >> (tid - 32)) & 1ULL)) {
                 const int c = s.win_chk[wlo + tid - 32];
                 atomicXor(&sigma[c >> 5], 1u << (c & 31));
+                for (int z = s.chk_ptr[c]; z < s.chk_ptr[c + 1]; ++z) dirty[s.chk_gen[z]] = 1;
             }
             weight -= delta;
             ++rounds;

@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-from bench import WORKLOADS, probabilities  # noqa: E402
+from bench import WORKLOADS, load_workload, probabilities  # noqa: E402
 from exp_ldpc_b200.codes import load_code  # noqa: E402
 from exp_ldpc_b200.decoders import Logicals, Sampler, TannerGraph, bp_decoder, row_words  # noqa: E402
 
@@ -29,7 +29,7 @@ ap.add_argument("--teams", default="1")
 ap.add_argument("--reps", type=int, default=2)
 a = ap.parse_args()
 
-fname, p, opts = WORKLOADS[a.workload]
+_, p, opts, _family = WORKLOADS[a.workload]
 opts = dict(opts)
 if a.p is not None:
     p = a.p
@@ -37,7 +37,7 @@ if a.bp_method:
     opts["bp_method"] = a.bp_method
 if a.max_iter is not None:
     opts["max_iter"] = a.max_iter
-code = load_code(os.path.join(ROOT, "codes", fname))
+code = load_workload(a.workload)
 m, n = code.checks.z.shape
 q, prior = probabilities(p)
 dev = torch.device("cuda:0")
