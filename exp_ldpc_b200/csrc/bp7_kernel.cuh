@@ -166,8 +166,9 @@ __device__ __forceinline__ void check_ps7(real (&v)[RD], unsigned sbit)
 // ---- one slot of one row: load, and compute + store.  The shared-memory accesses are volatile asm
 // and keep their program order, so the callers issue the loads of the next slots by hand before the
 // arithmetic of the current one (software pipeline over the slots).
-template <typename real, int RD, int s>
-__device__ __forceinline__ void row_ld(const uint32_t (&ra)[RD], uint32_t fb, real (&v)[RD], unsigned long long &f)
+template <typename real, int METHOD, int RD, int s>
+__device__ __forceinline__ void row_ld(const uint32_t (&ra)[RD], uint32_t fb, real (&v)[RD], unsigned long long &f,
+                                       unsigned dummy)
 {
     constexpr int FB = RD <= 8 ? 8 : 16;
     f = lds_u64_off<s * FB>(fb);
@@ -177,6 +178,11 @@ __device__ __forceinline__ void row_ld(const uint32_t (&ra)[RD], uint32_t fb, re
     }
 #pragma unroll
     for (int k = 0; k < RD; ++k) v[k] = lds_off<s * 128>(ra[k], real());
+    if (dummy) {                        // rows shorter than RD: the missing edges read as the neutral message
+#pragma unroll
+        for (int k = 0; k < RD; ++k)
+            if ((dummy >> k) & 1u) v[k] = METHOD == QD_BP_MIN_SUM_K ? Ar<real>::big() : (real)0;
+    }
 }
 
 template <typename real, int METHOD, int RD, int S, int s>
@@ -271,7 +277,7 @@ __device__ __forceinline__ void col_update(const uint32_t (&ea)[VMAX], const uin
 #undef QD_CS
 }
 
-template <typename real, int METHOD, int RD, int VMAX, int S, int MAXT, int MINB>
+template <typename real, int METHOD, int RD, int VMAX, int S, bool IRREG, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
 {
     using A = Ar<real>;
@@ -329,15 +335,19 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
         }
     };
     // row -> shared addresses of its messages (slot 0), in column order
-    auto load_row = [&](int c, uint32_t (&ra)[RD]) {
+    auto load_row = [&](int c, uint32_t (&ra)[RD], unsigned &dummy) {
         uint32_t w[4 * RQ];
 #pragma unroll
         for (int q = 0; q < RQ; ++q) {
             const uint4 x = __ldg(p.row_table + (size_t)c * RQ + q);
             w[4 * q + 0] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
         }
+        dummy = 0u;
 #pragma unroll
-        for (int k = 0; k < RD; ++k) ra[k] = a_msg + w[k];
+        for (int k = 0; k < RD; ++k) {
+            ra[k] = a_msg + (IRREG ? (w[k] & 0x7fffffffu) : w[k]);
+            if (IRREG) dummy |= (w[k] >> 31) << k;          // bit 31 of an entry: no such edge in this row
+        }
     };
     auto prior_of = [&](int r) -> real { return p.uniform_prior ? (real)p.prior0 : prior_rec[r]; };
 
@@ -399,13 +409,14 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                 const bool valid = c < p.m;
                 const uint32_t fb = a_flags + (uint32_t)(valid ? c : p.m) * FP;
                 uint32_t ra[RD];
-                load_row(c, ra);
+                unsigned dummy;
+                load_row(c, ra, dummy);
                 real va[RD], vb[RD];
                 unsigned long long fa = 0ULL, fbb = 0ULL;
                 auto alpha_of = [&](int s) -> real {
                     return alpha_fixed != (real)0 ? alpha_fixed : A::sub((real)1, pow2_neg<real>(T - born[s]));
                 };
-#define QD_LD(n, buf, f) row_ld<real, RD, (n) % S>(ra, fb, buf, f)
+#define QD_LD(n, buf, f) row_ld<real, METHOD, RD, (n) % S>(ra, fb, buf, f, dummy)
 #define QD_CS(n, buf, f) row_cs<real, METHOD, RD, S, (n) % S>(ra, fb, buf, f, i, valid, synbits, resbits, un, alpha_of((n) % S))
                 if (act == SMASK) {                             // steady state: straight line, two buffers
                     QD_LD(0, va, fa);

@@ -23,33 +23,35 @@ bp_kernel_fn QD_CAT(pick_bp6_, QD_INST_TAG)(int vmax, int threads)
     return vmax <= 8 ? bp_kernel<real, M, 0, 8, uint32_t, 1024> : bp_kernel<real, M, 0, 16, uint32_t, 1024>;
 }
 
-// ---- row-regular kernel: (row degree, column tile) x slots -------------------------------------
-template <typename real, int M, int RD, int VMAX>
+// ---- thread-owned-state kernel: (max row degree, column tile) x slots; IRREG = rows may be shorter
+template <typename real, int M, int RD, int VMAX, bool IRREG>
 static bp7_kernel_fn pick7_s(int slots)
 {
     switch (slots) {
-    case 1: return bp7_kernel<real, M, RD, VMAX, 1, BP7_MAXT, 1>;
-    case 2: return bp7_kernel<real, M, RD, VMAX, 2, BP7_MAXT, 1>;
+    case 1: return bp7_kernel<real, M, RD, VMAX, 1, IRREG, BP7_MAXT, 1>;
+    case 2: return bp7_kernel<real, M, RD, VMAX, 2, IRREG, BP7_MAXT, 1>;
 #ifndef QD_FAST_BUILD
-    case 3: return bp7_kernel<real, M, RD, VMAX, 3, BP7_MAXT, 1>;
-    case 6: return bp7_kernel<real, M, RD, VMAX, 6, BP7_MAXT, 1>;
+    case 3: return bp7_kernel<real, M, RD, VMAX, 3, IRREG, BP7_MAXT, 1>;
+    case 6: return bp7_kernel<real, M, RD, VMAX, 6, IRREG, BP7_MAXT, 1>;
 #endif
-    case 4: return bp7_kernel<real, M, RD, VMAX, 4, BP7_MAXT, 1>;
-    case 8: return bp7_kernel<real, M, RD, VMAX, 8, BP7_MAXT, 1>;
+    case 4: return bp7_kernel<real, M, RD, VMAX, 4, IRREG, BP7_MAXT, 1>;
+    case 8: return bp7_kernel<real, M, RD, VMAX, 8, IRREG, BP7_MAXT, 1>;
     default: return nullptr;
     }
 }
 
-bp7_kernel_fn QD_CAT(pick_bp7_, QD_INST_TAG)(int rd, int vmax, int slots)
+bp7_kernel_fn QD_CAT(pick_bp7_, QD_INST_TAG)(int rd, int vmax, int slots, int irregular)
 {
     typedef QD_INST_REAL real;
     constexpr int M = QD_INST_METHOD;
-    switch (rd * 100 + vmax) {
-    case 704: return pick7_s<real, M, 7, 4>(slots);
+    switch ((irregular ? 10000 : 0) + rd * 100 + vmax) {
+    case 704: return pick7_s<real, M, 7, 4, false>(slots);
+    case 10904: return pick7_s<real, M, 9, 4, true>(slots);      // spacetime matrices of (3,4) HGP codes
 #ifndef QD_FAST_BUILD
-    case 604: return pick7_s<real, M, 6, 4>(slots);
-    case 808: return pick7_s<real, M, 8, 8>(slots);
-    case 908: return pick7_s<real, M, 9, 8>(slots);
+    case 604: return pick7_s<real, M, 6, 4, false>(slots);
+    case 808: return pick7_s<real, M, 8, 8, false>(slots);
+    case 908: return pick7_s<real, M, 9, 8, false>(slots);
+    case 10804: return pick7_s<real, M, 8, 4, true>(slots);      // single-shot [H | I], spacetime of weight-6 rows
 #endif
     default: return nullptr;
     }

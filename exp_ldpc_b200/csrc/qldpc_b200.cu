@@ -202,7 +202,7 @@ struct qd_bp {
     size_t smem = 0;
     DevBuf d_prior, d_alpha, d_next, d_vidx, d_chunk_deg;
     // row-regular kernel (bp7_kernel.cuh): record table for the configured slot count
-    int v7 = 0, v7_nrec = 0, v7_uniform = 0, v7_staged = 0;
+    int v7 = 0, v7_nrec = 0, v7_uniform = 0, v7_staged = 0, v7_irreg = 0;
     double v7_prior0 = 0.0, alpha_fixed = 0.0;
     std::vector<double> prior_dom;   // priors in the decoder's domain, per column
     int v7_lines = 0;
@@ -486,8 +486,10 @@ static bp_kernel_fn bp_kernel_for(const qd_bp *d)
 static bp7_kernel_fn bp7_kernel_for(const qd_bp *d, int slots)
 {
     if (d->precision == QD_PREC_F64)
-        return d->method == QD_BP_MIN_SUM ? pick_bp7_f64_ms(d->rd, d->vmax, slots) : pick_bp7_f64_ps(d->rd, d->vmax, slots);
-    return d->method == QD_BP_MIN_SUM ? pick_bp7_f32_ms(d->rd, d->vmax, slots) : pick_bp7_f32_ps(d->rd, d->vmax, slots);
+        return d->method == QD_BP_MIN_SUM ? pick_bp7_f64_ms(d->rd, d->vmax, slots, d->v7_irreg)
+                                          : pick_bp7_f64_ps(d->rd, d->vmax, slots, d->v7_irreg);
+    return d->method == QD_BP_MIN_SUM ? pick_bp7_f32_ms(d->rd, d->vmax, slots, d->v7_irreg)
+                                      : pick_bp7_f32_ps(d->rd, d->vmax, slots, d->v7_irreg);
 }
 
 static size_t bp_smem(const qd_bp *d, int slots, bool stage)
@@ -643,10 +645,14 @@ static int bp7_prepare(qd_bp *d, int slots)
         r0 += padded;
     }
     std::vector<uint32_t> row_table((size_t)m32 * RQ * 4, 0u);
-    for (int c = 0; c < m32; ++c)
-        for (int k = 0; k < RQ * 4; ++k)
-            row_table[(size_t)c * RQ * 4 + k] =
-                (uint32_t)((c < gd.m && k < RD ? elem(g->row_ptr[c] + k) : scratch(c)) * RB);
+    for (int c = 0; c < m32; ++c) {
+        const int deg = c < gd.m ? g->row_ptr[c + 1] - g->row_ptr[c] : 0;
+        for (int k = 0; k < RQ * 4; ++k) {
+            uint32_t v = (uint32_t)((k < deg ? elem(g->row_ptr[c] + k) : scratch(c)) * RB);
+            if (d->v7_irreg && c < gd.m && k >= deg) v |= 0x80000000u;     // no such edge: reads as the neutral message
+            row_table[(size_t)c * RQ * 4 + k] = v;
+        }
+    }
     d->v7_nrec = L.nrec;
     d->v7_lines = L.lines;
     int rc;
@@ -727,11 +733,21 @@ static int bp_choose_kernel(qd_bp *d, bool allow_regular)
     const GraphDev &gd = d->g->dev;
     int rc;
     d->v7 = 0;
-    if (allow_regular && gd.regular_deg >= 2 && gd.max_col_deg >= 1 && gd.max_col_deg <= 8) {
-        d->rd = gd.regular_deg;
-        d->vmax = gd.max_col_deg <= 4 ? 4 : 8;
-        if (!bp7_kernel_for(d, 1) && d->vmax == 4) d->vmax = 8;
-        if (bp7_kernel_for(d, 1)) {
+    if (allow_regular && gd.max_row_deg >= 2 && gd.max_col_deg >= 1 && gd.max_col_deg <= 8) {
+        // candidates: exact (row degree, column tile) for row-regular graphs, else the padded variants
+        const int vm0 = gd.max_col_deg <= 4 ? 4 : 8;
+        bool found = false;
+        if (gd.regular_deg > 0)
+            for (int vm = vm0; vm <= 8 && !found; vm += 4) {
+                d->rd = gd.regular_deg; d->vmax = vm; d->v7_irreg = 0;
+                found = bp7_kernel_for(d, 1) != nullptr;
+            }
+        for (int rd = gd.max_row_deg; rd <= 9 && !found; ++rd)
+            for (int vm = vm0; vm <= 8 && !found; vm += 4) {
+                d->rd = rd; d->vmax = vm; d->v7_irreg = 1;
+                found = bp7_kernel_for(d, 1) != nullptr;
+            }
+        if (found) {
             d->v7 = 1;
             d->slots = 0;
             d->d7_table.alloc(0);
@@ -740,6 +756,7 @@ static int bp_choose_kernel(qd_bp *d, bool allow_regular)
     }
     if (!d->v7) {
         d->rd = 0;
+        d->v7_irreg = 0;
         d->vmax = gd.max_col_deg <= 8 ? 8 : 16;
         d->idx_bytes = 4;
         if ((rc = bp6_prepare(d))) return rc;

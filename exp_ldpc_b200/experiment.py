@@ -30,7 +30,7 @@ from . import _lib
 from .codes import QuantumCode
 from .decoders import Logicals, Sampler, TannerGraph, bp_decoder, row_words, ssf_decoder, unpack_bits
 
-__all__ = ["depolarizing_noise", "NoiseModel", "CodeCapacityExperiment", "run_simulation", "p_sweep",
+__all__ = ["depolarizing_noise", "NoiseModel", "CodeCapacityExperiment", "SpacetimeExperiment", "run_simulation", "p_sweep",
            "shard_range", "binomial_ci"]
 
 
@@ -75,26 +75,32 @@ def binomial_ci(failures: int, shots: int, z: float = 1.959963984540054):
 
 
 class CodeCapacityExperiment:
-    """Device pipeline for one (code, p, decoder) point: owns the graph, sampler, logicals, decoder."""
+    """Device pipeline for one (check matrix, noise, decoder) point: owns the graph, sampler, logicals,
+    decoder.  ``flip_probability`` and ``prior`` may be scalars or per-column vectors."""
 
-    def __init__(self, code: QuantumCode, flip_probability: float, prior: float, decoder_mode: str = "bp",
-                 bp_options: Optional[Dict] = None, device: int = 0, precision: str = "f64", kernel: str = "auto"):
+    def __init__(self, code: QuantumCode, flip_probability, prior, decoder_mode: str = "bp",
+                 bp_options: Optional[Dict] = None, device: int = 0, precision: str = "f64", kernel: str = "auto",
+                 check_matrix=None, logicals=None):
         self.code = code
         self.device = int(device)
-        self.n = code.num_qubits
-        hz = code.checks.z
+        hz = code.checks.z if check_matrix is None else check_matrix
+        lz = code.logicals.z if logicals is None else logicals
+        self.n = int(hz.shape[1])
         self.graph = TannerGraph(hz, device)
-        self.logicals = Logicals(code.logicals.z, device)
+        self.logicals = Logicals(lz, device)
         self.sampler = Sampler(flip_probability, self.n, device)
         self.decoder_mode = decoder_mode
         opts = dict(bp_options or {})
         if decoder_mode == "bp":
-            self.decoder = bp_decoder(self.graph, error_rate=prior, max_iter=opts.get("max_iter", 0),
+            pr = np.broadcast_to(np.asarray(prior, dtype=np.float64), (self.n,))
+            self.decoder = bp_decoder(self.graph, channel_probs=pr, max_iter=opts.get("max_iter", 0),
                                       bp_method=opts.get("bp_method", "ps"),
                                       ms_scaling_factor=opts.get("ms_scaling_factor", 0.0), precision=precision,
                                       kernel=kernel)
             self._bp, self._ssf = self.decoder.handle, None
         elif decoder_mode == "ssf":
+            if check_matrix is not None:
+                raise NotImplementedError("small-set-flip decodes the code's own check matrix only")
             self.decoder = ssf_decoder(self.graph, code.checks.x, max_rounds=opts.get("max_rounds", 0))
             self._bp, self._ssf = None, self.decoder.handle
         elif decoder_mode in ("bposd", "bposd_single_shot", "bposd_hybrid", "bpd_detector"):
@@ -120,6 +126,42 @@ class CodeCapacityExperiment:
         if per_shot:
             out.update(decodings=unpack_bits(corr, self.n), fail=fail, converged=conv, iters=its)
         return out
+
+
+class SpacetimeExperiment(CodeCapacityExperiment):
+    """Phenomenological multi-round decoding on the device (BASELINE.json configs[4] with the fault
+    model of the decoder's own priors; Stim circuit-level sampling is SURVEY.md §8 f2).
+
+    The decoding problem is the reference's ``SpacetimeCode(Hz, rounds)`` matrix
+    (``spacetime_code.py:46-75``): columns = data faults of rounds 0..T, then T*m measurement
+    faults.  A shot draws every column j with probability ``prior_j`` (``data_prior`` on data
+    columns, ``meas_prior`` on measurement columns — explicit per column, not through the
+    reference's mis-sized ``data_bits`` view), forms ``s = H_st f``, decodes, and
+    fails iff ``Lz . fold(f ^ f_hat) != 0`` with ``fold`` = ``final_correction``
+    (``spacetime_code.py:81-84``).  The fold is linear, so it is absorbed into the logical operators:
+    ``L_st = [Lz | Lz | ... | Lz | 0]`` and the fused epilogue of the decode kernel does the rest."""
+
+    def __init__(self, code: QuantumCode, rounds: int, data_prior: float, meas_prior: float,
+                 bp_options: Optional[Dict] = None, device: int = 0, precision: str = "f64", kernel: str = "auto"):
+        from .spacetime import SpacetimeCode
+        st = SpacetimeCode(code.checks.z, rounds)
+        h_st = st.spacetime_check_matrix
+        m, n = code.checks.z.shape
+        T = int(rounds)
+        prior = np.concatenate([np.full((T + 1) * n, float(data_prior)), np.full(T * m, float(meas_prior))])
+        lz = np.asarray(code.logicals.z) & 1
+        l_st = np.concatenate([lz] * (T + 1) + [np.zeros((lz.shape[0], T * m), dtype=lz.dtype)], axis=1)
+        self.spacetime = st
+        self.rounds = T
+        self.prior = prior
+        super().__init__(code, prior, prior, "bp", bp_options, device=device, precision=precision, kernel=kernel,
+                         check_matrix=h_st, logicals=l_st)
+
+    def final_corrections(self, spacetime_decodings: np.ndarray) -> np.ndarray:
+        """``SpacetimeCode.final_correction`` for a batch of decoded fault vectors (rows)."""
+        n = self.code.num_qubits
+        x = np.asarray(spacetime_decodings)[:, :(self.rounds + 1) * n].reshape(-1, self.rounds + 1, n)
+        return (x.sum(axis=1) % 2).astype(np.uint8)
 
 
 def run_simulation(samples, code, meas_prior, data_prior, noise_model, noise_model_args, bp_osd_options, rounds,
@@ -181,3 +223,92 @@ def p_sweep(samples, p_values, noise_model, noise_model_args, meas_prior, data_p
                "decoder_mode": decoder_mode, **bp_osd_options, "non_converged": nc, "iters_total": it, "n_gpus": world}
         rows.append(row)
     return pd.DataFrame.from_records(rows)
+
+
+# ---------------------------------------------------------------------------------------------
+# command line: mirror of p_sweep_main (python/qldpc/misc/p_sweep.py:43-78) and of the option helpers
+# add_bposd_args / unpack_bposd_args / load_code (python/qldpc/misc/_experiment.py:213-235)
+# ---------------------------------------------------------------------------------------------
+_SWEEP_SPEC = None
+
+
+def parse_sweep_spec(x: str):
+    """``(a, b, c)`` with floats a <= b and an int c > 0 (``p_sweep.py:43-55``)."""
+    import re
+    global _SWEEP_SPEC
+    if _SWEEP_SPEC is None:
+        _SWEEP_SPEC = re.compile(r'^\s*[(](.+),(.+),(.+)[)]\s*$')
+    result = _SWEEP_SPEC.match(x)
+    if result is None:
+        raise RuntimeError('Unable to parse sweep specification, expecting (a, b, c) where a,b : float, c : int, '
+                           'a<=b, and c > 0. Ex: (0.3, 1e3, 10)')
+    lower, upper, points = float(result.group(1)), float(result.group(2)), int(result.group(3))
+    if points <= 0 or lower > upper:
+        raise RuntimeError('Number of points non-positive or lower bound exceeded upper bound')
+    return lower, upper, points
+
+
+def add_bposd_args(parser):
+    """Same flags as ``_experiment.py:213-219``."""
+    parser.add_argument('--bposd_max_iter', type=lambda x: int(x) if x is not None else None, default=None,
+                        help='Maximum number of iterations for BP. Default is the number of qubits in the code')
+    parser.add_argument('--bposd_bp_method', choices=['ps', 'ms', 'msl'], default='ps',
+                        help='BP method (product-sum, min-sum, min-sum log)')
+    parser.add_argument('--bposd_ms_scaling_factor', type=float, default=0,
+                        help='Min sum scaling factor. Use variable scaling factor method if 0')
+    parser.add_argument('--bposd_osd_method', choices=['osd_e', 'osd_cs', 'osd0'], default='osd_cs', help='OSD method')
+    parser.add_argument('--bposd_osd_order', type=int, default=7, help='OSD search depth')
+
+
+def unpack_bposd_args(parsed_args, code) -> dict:
+    """``_experiment.py:221-229``."""
+    return {
+        'max_iter': parsed_args.bposd_max_iter if parsed_args.bposd_max_iter is not None else code.num_qubits,
+        'bp_method': parsed_args.bposd_bp_method,
+        'ms_scaling_factor': parsed_args.bposd_ms_scaling_factor,
+        'osd_method': parsed_args.bposd_osd_method,
+        'osd_order': parsed_args.bposd_osd_order,
+    }
+
+
+def p_sweep_main(noise_model_args, noise_model, meas_prior, data_prior, argv=None):
+    """Same command line as the reference's ``p_sweep_main``; prints the result CSV on rank 0.
+    ``--decoder_mode`` additionally accepts ``bp`` and ``ssf`` (the modes this engine decodes);
+    ``--rounds`` defaults to 0 (code capacity), the case the engine covers."""
+    import sys
+    from argparse import ArgumentParser
+    from pathlib import Path
+
+    import torch
+
+    from .codes import load_code
+    parser = ArgumentParser(description='Sweep the physical error rate for the given quantum code on the GPU(s)')
+    parser.add_argument('code', type=Path)
+    parser.add_argument('--samples', type=int, help='Number of samples to take', required=True)
+    parser.add_argument('--p_sweep', type=parse_sweep_spec, required=True,
+                        help='lower and upper bounds of the sweep + number of points in the form (lower, upper, points)')
+    parser.add_argument('--rounds', type=int, help='Number of rounds of syndrome extraction', default=0)
+    parser.add_argument('--decoder_mode', default='bp',
+                        choices=['bp', 'ssf', 'bposd', 'bposd_single_shot', 'bposd_hybrid', 'bpd_detector'])
+    parser.add_argument('--linspace', type=bool, default=False,
+                        help='linearly spaced points (default: uniform spacing in log space)')
+    parser.add_argument('--precision', default='f64', choices=['f64', 'f32'])
+    parser.add_argument('--seed', type=int, default=0)
+    add_bposd_args(parser)
+    args = parser.parse_args(sys.argv[1:] if argv is None else argv)
+    code = load_code(args.code)
+    bp_osd_options = unpack_bposd_args(args, code)
+    sweep = np.linspace(*args.p_sweep) if args.linspace else np.geomspace(*args.p_sweep)
+    dist = torch.distributed
+    import os
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not dist.is_initialized():
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
+    result = p_sweep(samples=args.samples, code=code, rounds=args.rounds, noise_model=noise_model,
+                     noise_model_args=noise_model_args, meas_prior=meas_prior, data_prior=data_prior, p_values=sweep,
+                     decoder_mode=args.decoder_mode, bp_osd_options=bp_osd_options, seed=args.seed, precision=args.precision)
+    if not dist.is_initialized() or dist.get_rank() == 0:
+        result.to_csv(sys.stdout)
+    if dist.is_initialized():
+        dist.destroy_process_group()
+    return result

@@ -122,3 +122,23 @@ def test_noise_model_flip_probability():
     nm = depolarizing_noise(0.03, 0.03)
     assert abs(nm.code_capacity_flip_probability() - (0.02 + 0.03 - 2 * 0.02 * 0.03)) < 1e-15
     assert abs(depolarizing_noise(0.03, 0.0).code_capacity_flip_probability() - 0.02) < 1e-15
+
+
+def test_p_sweep_cli_options_match_reference():
+    """Flag names / defaults of python/qldpc/misc/_experiment.py:213-229 and p_sweep.py:43-67."""
+    from argparse import ArgumentParser
+    from exp_ldpc_b200.experiment import add_bposd_args, parse_sweep_spec, unpack_bposd_args
+    ap = ArgumentParser()
+    add_bposd_args(ap)
+    a = ap.parse_args([])
+
+    class _Code:
+        num_qubits = 225
+    o = unpack_bposd_args(a, _Code)
+    assert o == {'max_iter': 225, 'bp_method': 'ps', 'ms_scaling_factor': 0, 'osd_method': 'osd_cs', 'osd_order': 7}
+    a = ap.parse_args(['--bposd_max_iter', '32', '--bposd_bp_method', 'ms', '--bposd_ms_scaling_factor', '0.625'])
+    assert unpack_bposd_args(a, _Code)['max_iter'] == 32
+    assert parse_sweep_spec("(0.01, 1e-1, 10)") == (0.01, 0.1, 10)
+    for bad in ("0.1,0.2,3", "(0.2,0.1,3)", "(0.1,0.2,0)"):
+        with pytest.raises(RuntimeError):
+            parse_sweep_spec(bad)

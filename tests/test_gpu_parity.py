@@ -355,3 +355,56 @@ def test_bp_per_bit_priors_match_oracle(gpu, code225):
                 want = ref.decode(synd[s])
                 assert np.array_equal(corr[s], want), (method, kernel, s)
                 assert its[s] == ref.iter and conv[s] == ref.converge
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-round (spacetime) decoding, phenomenological faults: irregular check matrices
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rounds", [0, 1, 3])
+@pytest.mark.parametrize("method", ["ms", "ps"])
+def test_spacetime_experiment_against_live_oracle(gpu, code225, rounds, method):
+    """H_st = SpacetimeCode(Hz, T) (spacetime_code.py:46-75); faults drawn from the per-column priors;
+    failure = Lz . final_correction(f ^ f_hat) (spacetime_code.py:81-84, _experiment.py:208-209)."""
+    from exp_ldpc_b200.experiment import SpacetimeExperiment
+    from oracle import pyoracle as po
+    opts = dict(max_iter=30, bp_method=method, ms_scaling_factor=0.0)
+    shots = 256
+    data_prior, meas_prior = 0.012, 0.02
+    for kernel in ("auto", "generic"):
+        exp = SpacetimeExperiment(code225, rounds, data_prior, meas_prior, opts, kernel=kernel)
+        if kernel == "auto":
+            assert exp.decoder.config()["kernel"] == "regular"      # padded-row variant for T = 3
+        got = exp.run(shots, seed=21, per_shot=True)
+        h_st = exp.spacetime.spacetime_check_matrix
+        n, m = code225.num_qubits, code225.checks.z.shape[0]
+        assert h_st.shape == ((rounds + 1) * m, (rounds + 1) * n + rounds * m)
+        lz = np.asarray(code225.logicals.z) & 1
+        l_st = np.concatenate([lz] * (rounds + 1) + [np.zeros((lz.shape[0], rounds * m), dtype=lz.dtype)], axis=1)
+        ref = po.run_code_capacity(h_st, l_st, exp.prior, exp.prior, decoder="bp", seed=21, shots=shots, per_shot=True, **opts)
+        assert (got["decodings"] == ref["decodings"]).all(), (kernel, rounds, method)
+        assert np.array_equal(got["iters"], ref["iters"]) and np.array_equal(got["converged"], ref["converged"])
+        assert np.array_equal(got["fail"], ref["fail"])
+        # the fused failure flag equals the reference recipe: fold both fault vectors, then Lz
+        err = po.sample_bits(21, 0, 0, shots, po.thresholds(exp.prior))
+        folded = exp.final_corrections(err ^ got["decodings"])
+        want = ((folded.astype(np.int64) @ lz.T.astype(np.int64)) % 2).any(axis=1)
+        assert np.array_equal(want.astype(np.uint8), got["fail"])
+
+
+def test_single_shot_matrix_decodes_like_oracle(gpu, code225):
+    """[H | I] of SpacetimeCodeSingleShot (spacetime_code.py:20-25): rows of weight 8, columns 1/3/4."""
+    from exp_ldpc_b200.decoders import bp_decoder
+    from exp_ldpc_b200.spacetime import SpacetimeCodeSingleShot
+    from oracle import pyoracle as po
+    h = SpacetimeCodeSingleShot(code225.checks.z).spacetime_check_matrix
+    rng = np.random.default_rng(3)
+    probs = np.concatenate([np.full(code225.num_qubits, 0.02), np.full(h.shape[0], 0.03)])
+    err = (rng.random((128, h.shape[1])) < probs).astype(np.uint8)
+    synd = (err @ h.T.toarray()) % 2
+    ref = po.OracleBP(h, channel_probs=probs, max_iter=20, bp_method="ms", ms_scaling_factor=0.0)
+    for kernel in ("auto", "generic"):
+        dec = bp_decoder(h, channel_probs=probs, max_iter=20, bp_method="ms", ms_scaling_factor=0.0, kernel=kernel)
+        corr, conv, its = dec.decode_batch(synd)
+        for s in range(synd.shape[0]):
+            assert np.array_equal(corr[s], ref.decode(synd[s])), (kernel, s)
+            assert its[s] == ref.iter and conv[s] == ref.converge
