@@ -44,12 +44,36 @@ WORKLOADS = {
     "lp_882": ("builder:pk19_b1_882", 0.05, _BP, "QC lifted product [[882,24]]"),        # BASELINE configs[2]
     "qclp_1054": ("builder:pk20_qc_1054", 0.05, _BP, "QC lifted product [[1054,140]]"),
     "a5lp_2700": ("builder:a5_lift_2700", 0.05, _BP, "PSL(2,5) lifted product n=2700"),  # BASELINE configs[3]
+    # BASELINE configs[4]: spacetime matrix of the [[225,9]] code, T rounds, phenomenological faults drawn from
+    # the decoder's priors (data and measurement 2p/3); Stim circuit-level sampling is a "next" row
+    "st_hgp225_T3": ("spacetime:hgp_34_n225.qecc:3", 0.02, _BP, "spacetime (T=3) of the (3,4) HGP [[225,9]] code"),
+    "st_hgp1600_T3": ("spacetime:hgp_34_n1600.qecc:3", 0.02, _BP, "spacetime (T=3) of the (3,4) HGP n=1600 code"),
 }
 SSF_DEFAULT_P = 0.01
 
 
+def decoding_problem(name, code, p):
+    """(check matrix, logical operators, per-column flip probability, per-column prior) the decoder sees."""
+    src = WORKLOADS[name][0]
+    q, prior = probabilities(p)
+    if src.startswith("spacetime:"):
+        from exp_ldpc_b200.spacetime import SpacetimeCode
+        T = int(src.split(":")[2])
+        m, n = code.checks.z.shape
+        h_st = SpacetimeCode(code.checks.z, T).spacetime_check_matrix
+        lz = np.asarray(code.logicals.z) & 1
+        l_st = np.concatenate([lz] * (T + 1) + [np.zeros((lz.shape[0], T * m), dtype=lz.dtype)], axis=1)
+        pr = np.full(h_st.shape[1], prior)
+        return h_st, l_st, pr, pr
+    n = code.checks.z.shape[1]
+    return code.checks.z, np.asarray(code.logicals.z) & 1, np.full(n, q), np.full(n, prior)
+
+
 def load_workload(name):
     src = WORKLOADS[name][0]
+    if src.startswith("spacetime:"):
+        from exp_ldpc_b200.codes import load_code
+        return load_code(os.path.join(ROOT, "codes", src.split(":")[1]))
     if src.startswith("builder:"):
         from exp_ldpc_b200 import code_builders
         return getattr(code_builders, src.split(":", 1)[1])()
@@ -113,21 +137,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_port_throughput(code, p, opts, target_seconds=12.0, threads=0, decoder="bp"):
+def cpu_port_throughput(code, p, opts, target_seconds=12.0, threads=0, decoder="bp", problem=None):
     """Time the CPU oracle (the port of the reference's decoder) on a bounded sample of the same
     workload; returns (shots/s, cores, sample description, mean iterations)."""
     from oracle import pyoracle as po
-    q, prior = probabilities(p)
+    hz, lz, q, prior = problem
     cores = po.num_threads() if threads <= 0 else threads
     kw = dict(decoder=decoder, hx=code.checks.x, max_iter=opts["max_iter"], bp_method=opts["bp_method"],
               ms_scaling_factor=opts["ms_scaling_factor"], seed=0, threads=cores)
     probe = 64 * cores
     t0 = time.perf_counter()
-    po.run_code_capacity(code.checks.z, code.logicals.z, q, prior, shots=probe, **kw)
+    po.run_code_capacity(hz, lz, q, prior, shots=probe, **kw)
     dt = max(time.perf_counter() - t0, 1e-4)
     shots = int(max(probe, min(5_000_000, probe * target_seconds / dt)))
     t0 = time.perf_counter()
-    r = po.run_code_capacity(code.checks.z, code.logicals.z, q, prior, shots=shots, shot0=probe, **kw)
+    r = po.run_code_capacity(hz, lz, q, prior, shots=shots, shot0=probe, **kw)
     dt = time.perf_counter() - t0
     return shots / dt, cores, f"{shots} shots of the same workload, {dt:.1f} s wall on {cores} threads", r["iters_total"] / shots
 
@@ -171,15 +195,18 @@ def main():
     if args.bp_method is not None:
         opts["bp_method"] = args.bp_method
     code = load_workload(args.workload)
-    m, n = code.checks.z.shape
-    nnz = int(code.checks.z.nnz)
-    q, prior = probabilities(p)
+    problem = decoding_problem(args.workload, code, p)
+    hz_dec, lz_dec, q_vec, prior_vec = problem
+    m, n = hz_dec.shape
+    nnz = int(hz_dec.nnz)
+    q, prior = float(q_vec[0]), float(prior_vec[0])
     how = ("small-set-flip (candidate sets = subsets of the X-generator supports)" if ssf else
            f"BP {opts['bp_method']} alpha={'1-2^-it' if opts['ms_scaling_factor'] == 0 else opts['ms_scaling_factor']} "
            f"max_iter={opts['max_iter']} early-exit")
     metric = "decoded shots/sec (SSF, fixed p)" if ssf else "decoded shots/sec (BP, fixed p and iteration cap)"
     dtype = "u32" if ssf else args.precision
-    config = {"workload": f"{args.workload}: {family} n={n} m={m} nnz={nnz} k={code.num_logicals}, code capacity, "
+    config = {"workload": f"{args.workload}: {family} n={n} m={m} nnz={nnz} k={code.num_logicals}, "
+                          f"{'phenomenological faults' if WORKLOADS[args.workload][0].startswith('spacetime:') else 'code capacity'}, "
                           f"{how}, p={p} (flip q={q:.5f}, prior 2p/3)",
               "shots_per_step_per_gpu": args.shots, "p": p, "decoder": args.decoder, "max_iter": opts["max_iter"],
               "bp_method": opts["bp_method"], "precision": dtype, "parallelism": f"shots sharded over {world} rank(s), one all-reduce of int64[4] per step",
@@ -195,7 +222,7 @@ def main():
         per_step = max(2.0, min(20.0, 120.0 / (args.steps + args.warmup)))
         for i in range(args.warmup + args.steps):
             r, cores, sample, _ = cpu_port_throughput(code, p, opts, target_seconds=per_step if i >= args.warmup else 1.0,
-                                                      decoder=args.decoder)
+                                                      decoder=args.decoder, problem=problem)
             if i >= args.warmup:
                 rates.append(r)
         v = statistics.mean(rates)
@@ -222,14 +249,14 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from exp_ldpc_b200.decoders import Logicals, Sampler, TannerGraph, bp_decoder, row_words, ssf_decoder
-    graph = TannerGraph(code.checks.z, device=local_rank)
-    logicals = Logicals(code.logicals.z, device=local_rank)
-    sampler = Sampler(q, n, device=local_rank)
+    graph = TannerGraph(hz_dec, device=local_rank)
+    logicals = Logicals(lz_dec, device=local_rank)
+    sampler = Sampler(q_vec, n, device=local_rank)
     if ssf:
         dec = ssf_decoder(graph, code.checks.x)
         cfg = {"kernel": "ssf"}
     else:
-        dec = bp_decoder(graph, error_rate=prior, precision=args.precision, **opts)
+        dec = bp_decoder(graph, channel_probs=prior_vec, precision=args.precision, **opts)
         if args.threads or args.slots or args.ctas or args.teams:
             dec.configure(args.threads, args.slots, args.ctas, args.teams)
         cfg = dec.config()
@@ -371,7 +398,8 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        v, cores, sample, cpu_iters = cpu_port_throughput(code, p, opts, target_seconds=12.0, decoder=args.decoder)
+        v, cores, sample, cpu_iters = cpu_port_throughput(code, p, opts, target_seconds=12.0, decoder=args.decoder,
+                                                          problem=problem)
         cpu = {"value": v, "unit": "shots/s", "cores": cores, "kind": "port", "sample": sample,
                "mean_iterations": cpu_iters}
 

@@ -712,8 +712,12 @@ static int bp7_configure(qd_bp *d, int threads, int slots, int ctas)
     if (smem > budget) { staged = 0; smem = bp7_smem(d, S, false); }
     if (smem > budget) return fail(QD_EUNSUP, "configuration does not fit shared memory");
     int C = ctas;
+    const size_t per_sm = 228u * 1024u;                           // B200: 228 KB per SM, 1 KB reserved per CTA
+    if (C > 1 && staged && (smem + 1024) * C > per_sm) {           // requested CTAs/SM only fit without the staged table
+        const size_t un = bp7_smem(d, S, false);
+        if ((un + 1024) * C <= per_sm) { staged = 0; smem = un; }
+    }
     if (C <= 0) {
-        const size_t per_sm = 228u * 1024u;                       // B200: 228 KB per SM, 1 KB reserved per CTA
         C = (int)std::max<size_t>(1, per_sm / (smem + 1024));
         C = std::min(C, std::max(1, BP7_MAXT / T));               // 80 registers x 800 threads fill the register file
         C = std::min(C, 8);
