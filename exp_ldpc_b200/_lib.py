@@ -46,11 +46,16 @@ SIGNATURES = {
     "qd_bp_decode_batch": (C.c_int, [vp, vp, i32, i64, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp]),
     "qd_bp_decode_batch_host": (C.c_int, [vp, vp, i32, i64, vp, i32, vp, vp]),
     "qd_bp_decode_one": (C.c_int, [vp, vp, vp, P(i32), P(i32), vp]),
+    "qd_osd_create": (C.c_int, [vp, P(vp)]),
+    "qd_osd_destroy": (C.c_int, [vp]),
+    "qd_osd_rank": (C.c_int, [vp]),
+    "qd_bposd_decode_batch": (C.c_int, [vp, vp, vp, i32, i64, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]),
+    "qd_bposd_decode_batch_host": (C.c_int, [vp, vp, vp, i32, i64, vp, i32, vp, vp]),
     "qd_ssf_create": (C.c_int, [vp, i32, vp, vp, i32, P(vp)]),
     "qd_ssf_destroy": (C.c_int, [vp]),
     "qd_ssf_decode_batch": (C.c_int, [vp, vp, i32, i64, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]),
     "qd_ssf_decode_batch_host": (C.c_int, [vp, vp, i32, i64, vp, i32, vp, vp]),
-    "qd_code_capacity_run": (C.c_int, [vp, vp, vp, vp, vp, u64, i64, i64, vp, vp, i32, vp, vp, vp]),
+    "qd_code_capacity_run": (C.c_int, [vp, vp, vp, vp, vp, vp, u64, i64, i64, vp, vp, i32, vp, vp, vp]),
 }
 
 _lib = None
@@ -76,7 +81,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.qd_abi_version() != 1:
+        if L.qd_abi_version() != 2:
             raise RuntimeError("libqldpc_b200.so ABI version mismatch; rebuild the extension")
         _lib = L
     return _lib

@@ -42,6 +42,8 @@ struct Bp7Params {
     int max_iter;
     int staged;                 // record table copied to shared memory
     int uniform_prior;
+    int llr_mode;               // 0: posterior log-ratio after every iteration; 1: raw soft output (total LLR for
+                                // min-sum, posterior ratio for product-sum) of the LAST allowed iteration only
     double prior0;              // the common prior (decoder domain) when uniform_prior
     double alpha_fixed;         // 0 => alpha_it = 1 - 2^-it
     const uint4 *table;         // VMAX/4 uint4 per record: u16 message element indices, then u16 flag offsets
@@ -211,7 +213,7 @@ __device__ __forceinline__ void col_ld(const uint32_t (&ea)[VMAX], real (&cv)[D]
     for (int t = 0; t < D; ++t) cv[t] = lds_off<s * 128>(ea[t], real());
 }
 
-struct Bp7LlrOut { double *llr; const uint16_t *col_id; int n; };
+struct Bp7LlrOut { double *llr; const uint16_t *col_id; int n; int raw; };
 
 template <typename real, int METHOD, int D, int VMAX, int S, int FB, int s>
 __device__ __forceinline__ void col_cs(const uint32_t (&ea)[VMAX], const uint32_t (&fa)[VMAX], real (&cv)[D], real pj, int i,
@@ -229,11 +231,11 @@ __device__ __forceinline__ void col_cs(const uint32_t (&ea)[VMAX], const uint32_
         for (int t = 0; t < D; ++t) sts_u8_off<s * FB>(fa[t], 1u);
     }
     decbits ^= flip << bi;
-    if (lo.llr) {
+    if (lo.llr && shot >= 0) {
         const unsigned col = lo.col_id[r];
         if (col != 0xFFFFu)
             lo.llr[shot * (long long)lo.n + col] =
-                METHOD == QD_BP_MIN_SUM_K ? (double)soft : (double)A::lg(A::div((real)1, soft));
+                (METHOD == QD_BP_MIN_SUM_K || lo.raw) ? (double)soft : (double)A::lg(A::div((real)1, soft));
     }
 }
 
@@ -534,7 +536,8 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
             for (int s = 0; s < S; ++s) {
                 const int b = ctl->born[s];
                 run |= (b != BP_IDLE && b != T ? 1u : 0u) << s;
-                shot_of[s] = p.llr ? ctl->shot[s] : 0;
+                // soft output of this slot wanted in this pass?  (mode 1: only the iteration that hits the cap)
+                shot_of[s] = p.llr && b != BP_IDLE && (p.llr_mode == 0 || T - b == p.max_iter) ? ctl->shot[s] : -1;
             }
             int i = 0;
             for (int r = tid; r < p.nrec; r += NT, ++i) {
@@ -542,7 +545,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                 load_record(r, ea, fa);
                 const real pj = prior_of(r);
                 const int deg = __shfl_sync(0xffffffffu, (int)__ldg(p.chunk_deg + (r >> 5)), 0);
-                const Bp7LlrOut lo{p.llr, p.col_id, p.n};
+                const Bp7LlrOut lo{p.llr, p.col_id, p.n, p.llr_mode};
 #define QD_COL(D_) col_update<real, METHOD, (D_), VMAX, S, FB>(ea, fa, pj, i, run, decbits, lo, r, shot_of)
                 switch (deg) {
                 case 1: QD_COL(1); break;

@@ -64,6 +64,7 @@ struct BpParams {
     long long shots;
     uint32_t *corr; int corr_stride;
     uint8_t *conv; int32_t *iters; double *llr;
+    int llr_mode;                 // 0: log-ratio after every iteration; 1: raw soft output of the last allowed iteration
     const uint32_t *err; int err_stride;
     const uint32_t *lzT; int k;   // logical operators, packed and transposed: [nwn][k]
     uint8_t *fail;
@@ -625,9 +626,9 @@ __global__ void __launch_bounds__(MAXT, 1) bp_kernel(const BpParams p)
                   }
               };
               auto soft_out = [&](int s, real soft) {
-                  if (p.llr && j < g.n)
+                  if (p.llr && j < g.n && (p.llr_mode == 0 || T - ctl[s].born == p.max_iter))
                       p.llr[ctl[s].shot * (long long)g.n + j] =
-                          METHOD == QD_BP_MIN_SUM_K ? (double)soft : (double)A::lg(A::div((real)1, soft));
+                          (METHOD == QD_BP_MIN_SUM_K || p.llr_mode) ? (double)soft : (double)A::lg(A::div((real)1, soft));
               };
               // ---- uniform-degree chunk: unpredicated update, two slots interleaved
               auto run_uniform = [&](auto dtag) {

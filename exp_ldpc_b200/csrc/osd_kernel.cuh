@@ -1,0 +1,220 @@
+// osd_kernel.cuh — ordered-statistics post-processing, order 0 (OSD-0), for the shots belief
+// propagation did not converge on.
+//
+// Stands in for the OSD stage of ldpc.bposd_decoder(osd_method="osd0") as the reference calls it at
+// python/qldpc/misc/_experiment.py:23-27,51,59,77,82,96-100,125; CPU restatement:
+// oracle/qldpc_oracle.c orc_osd0 (parity unpinned, see oracle/qldpc_oracle.h).
+//
+// Definition: rank the columns most-likely-in-error first by the soft output of the last BP
+// iteration (ascending total LLR for min-sum, descending posterior ratio for product-sum, ties by
+// column index); the first rank(H) linearly independent columns in that order are the information
+// set S; the decoding is the unique solution of H_S x_S = s, zero elsewhere.  The answer does not
+// depend on how the elimination is carried out, only on the ranking, so the kernel is free to
+// pick its own pivots:
+//   * one CTA per shot; the augmented matrix [H | s] lives bit-packed in shared memory (m rows of
+//     ceil((n+1)/64) 64-bit words);
+//   * ranking = bitonic sort of (order-preserving 64-bit image of the key, column index);
+//   * per ranked column: one ballot pass collects the rows that hold the column's bit, warp 0
+//     picks the first such row that is not a pivot yet, then the warps XOR the pivot row into the
+//     other marked rows (Gauss-Jordan), one row per warp at a time, one 64-bit word per lane;
+//   * stops after rank(H) pivots (computed once on the host).
+// Integer only => bit-identical to the oracle.
+#pragma once
+
+#include "common.cuh"
+
+namespace qd {
+
+struct OsdParams {
+    int m, n, nwm, nwn;
+    int W;                      // 64-bit words per row of [H | s]
+    int P;                      // sort size: power of two >= n
+    int rank;                   // rank of H
+    int negate_key;             // product-sum: rank by descending ratio
+    const int32_t *row_ptr, *col_idx;
+    const uint32_t *synd; int synd_stride;
+    const double *soft;         // [shots][n] raw soft output of the last BP iteration
+    const uint8_t *conv;        // BP convergence flags (1: shot is skipped)
+    long long shots;
+    uint32_t *corr; int corr_stride;
+    const uint32_t *err; int err_stride;
+    const uint32_t *lzT; int k;
+    uint8_t *fail;              // in: flag of the BP decoding; out: flag of the OSD decoding
+    long long *counters;        // counters[0] (failures) is corrected by the change of the flag
+    unsigned long long *next_shot;
+};
+
+struct OsdSmemLayout { size_t rows, keys, idx, rowmask, used, pcol, dec, total; };
+
+__host__ __device__ inline OsdSmemLayout osd_smem_layout(int m, int W, int P, int nwm, int nwn)
+{
+    OsdSmemLayout L;
+    size_t o = 0;
+    L.rows = o;    o += (size_t)m * W * 8;
+    L.keys = o;    o += (size_t)P * 8;
+    L.idx = o;     o += ((size_t)P * 2 + 7) & ~(size_t)7;
+    L.rowmask = o; o += ((size_t)nwm * 4 + 7) & ~(size_t)7;
+    L.used = o;    o += ((size_t)nwm * 4 + 7) & ~(size_t)7;
+    L.pcol = o;    o += ((size_t)m * 2 + 7) & ~(size_t)7;
+    L.dec = o;     o += ((size_t)nwn * 4 + 7) & ~(size_t)7;
+    L.total = o;
+    return L;
+}
+
+__global__ void __launch_bounds__(512, 1) osd0_kernel(const OsdParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = (int)threadIdx.x, NT = (int)blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+    const OsdSmemLayout L = osd_smem_layout(p.m, p.W, p.P, p.nwm, p.nwn);
+    unsigned long long *R = reinterpret_cast<unsigned long long *>(smem_raw + L.rows);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw + L.keys);
+    uint16_t *idx = reinterpret_cast<uint16_t *>(smem_raw + L.idx);
+    uint32_t *rowmask = reinterpret_cast<uint32_t *>(smem_raw + L.rowmask);
+    uint32_t *used = reinterpret_cast<uint32_t *>(smem_raw + L.used);
+    uint16_t *pcol = reinterpret_cast<uint16_t *>(smem_raw + L.pcol);
+    uint32_t *dec = reinterpret_cast<uint32_t *>(smem_raw + L.dec);
+    __shared__ long long sh_shot;
+    __shared__ int sh_piv;
+    const int W = p.W, m = p.m, n = p.n;
+    long long c_delta = 0;                                    // thread 0: change of the failure count
+
+    for (;;) {
+        if (tid == 0) {
+            long long pick = -1;
+            for (;;) {
+                const unsigned long long id = atomicAdd(p.next_shot, 1ULL);
+                if (id >= (unsigned long long)p.shots) break;
+                if (!p.conv[id]) { pick = (long long)id; break; }
+            }
+            sh_shot = pick;
+        }
+        __syncthreads();
+        const long long shot = sh_shot;
+        if (shot < 0) break;
+
+        // ---- 1. ranking
+        for (int i = tid; i < p.P; i += NT) {
+            unsigned long long key = ~0ULL;
+            if (i < n) {
+                double d = p.soft[shot * (long long)n + i];
+                if (p.negate_key) d = -d;
+                if (d == 0.0) d = 0.0;                              // -0.0 ranks like +0.0 (the oracle compares values)
+                const unsigned long long b = (unsigned long long)__double_as_longlong(d);
+                key = b ^ ((b >> 63) ? ~0ULL : 0x8000000000000000ULL);
+            }
+            keys[i] = key;
+            idx[i] = (uint16_t)i;
+        }
+        __syncthreads();
+        for (int k2 = 2; k2 <= p.P; k2 <<= 1)
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < p.P; i += NT) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const unsigned long long ka = keys[i], kb = keys[l];
+                        const uint16_t ia = idx[i], ib = idx[l];
+                        const bool a_gt_b = ka > kb || (ka == kb && ia > ib);
+                        const bool up = (i & k2) == 0;
+                        if (a_gt_b == up) { keys[i] = kb; keys[l] = ka; idx[i] = ib; idx[l] = ia; }
+                    }
+                }
+                __syncthreads();
+            }
+
+        // ---- 2. [H | s]
+        for (int i = tid; i < m * W; i += NT) R[i] = 0ULL;
+        for (int i = tid; i < p.nwm; i += NT) used[i] = 0u;
+        for (int i = tid; i < m; i += NT) pcol[i] = (uint16_t)0xFFFF;
+        __syncthreads();
+        {
+            const uint32_t *s = p.synd + shot * (long long)p.synd_stride;
+            for (int r = tid; r < m; r += NT) {
+                unsigned long long *row = R + (size_t)r * W;
+                for (int e = p.row_ptr[r]; e < p.row_ptr[r + 1]; ++e) {
+                    const int c = p.col_idx[e];
+                    row[c >> 6] |= 1ULL << (c & 63);
+                }
+                if ((s[r >> 5] >> (r & 31)) & 1u) row[n >> 6] |= 1ULL << (n & 63);
+            }
+        }
+        __syncthreads();
+
+        // ---- 3. Gauss-Jordan over the ranked columns
+        const int m32 = (m + 31) & ~31;
+        int rank = 0;
+        for (int t = 0; t < n && rank < p.rank; ++t) {
+            const int c = idx[t];
+            const int cw = c >> 6, cb = c & 63;
+            for (int r0 = warp * 32; r0 < m32; r0 += nwarps * 32) {
+                const int r = r0 + lane;
+                const unsigned bit = r < m ? (unsigned)((R[(size_t)r * W + cw] >> cb) & 1ULL) : 0u;
+                const unsigned mask = __ballot_sync(0xffffffffu, bit);
+                if (lane == 0) rowmask[r0 >> 5] = mask;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                int best = 0x7fffffff;
+                for (int w = lane; w < p.nwm; w += 32) {
+                    const uint32_t cand = rowmask[w] & ~used[w];
+                    if (cand) { best = min(best, w * 32 + __ffs(cand) - 1); break; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+                if (lane == 0) {
+                    sh_piv = best == 0x7fffffff ? -1 : best;
+                    if (best != 0x7fffffff) { used[best >> 5] |= 1u << (best & 31); pcol[best] = (uint16_t)c; }
+                }
+            }
+            __syncthreads();
+            const int piv = sh_piv;
+            if (piv < 0) continue;                               // dependent on the columns ranked before it
+            ++rank;
+            const unsigned long long *prow = R + (size_t)piv * W;
+            for (int w = warp; w < p.nwm; w += nwarps) {
+                uint32_t mask = rowmask[w];
+                if ((piv >> 5) == w) mask &= ~(1u << (piv & 31));
+                while (mask) {
+                    const int r = w * 32 + __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    unsigned long long *row = R + (size_t)r * W;
+                    for (int j = lane; j < W; j += 32) row[j] ^= prow[j];
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- 4. solution on the information set
+        for (int w = tid; w < p.nwn; w += NT) dec[w] = 0u;
+        __syncthreads();
+        for (int r = tid; r < m; r += NT) {
+            const unsigned pc = pcol[r];
+            if (pc != 0xFFFFu && ((R[(size_t)r * W + (n >> 6)] >> (n & 63)) & 1ULL)) atomicOr(&dec[pc >> 5], 1u << (pc & 31));
+        }
+        __syncthreads();
+        uint32_t *dst = p.corr + shot * (long long)p.corr_stride;
+        for (int w = tid; w < p.corr_stride; w += NT) dst[w] = w < p.nwn ? dec[w] : 0u;
+        if (p.err) {
+            const uint32_t *e = p.err + shot * (long long)p.err_stride;
+            __syncthreads();
+            for (int w = tid; w < p.nwn; w += NT) dec[w] ^= e[w];
+            __syncthreads();
+            int f = 0;
+            for (int i = tid; i < p.k; i += NT) {
+                uint32_t acc = 0u;
+                for (int w = 0; w < p.nwn; ++w) acc ^= p.lzT[(size_t)w * p.k + i] & dec[w];
+                f |= __popc(acc) & 1;
+            }
+            f = __syncthreads_or(f);
+            if (tid == 0) {
+                const int old = p.fail ? p.fail[shot] : 0;
+                if (p.fail) p.fail[shot] = (uint8_t)f;
+                c_delta += f - old;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && p.counters && c_delta)
+        atomicAdd((unsigned long long *)&p.counters[0], (unsigned long long)c_delta);   // two's complement: may be negative
+}
+
+}  // namespace qd

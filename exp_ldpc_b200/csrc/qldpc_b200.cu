@@ -16,6 +16,7 @@
 #include "bp7_kernel.cuh"
 #include "bp7_layout.h"
 #include "bp_pick.h"
+#include "osd_kernel.cuh"
 #include "ssf_kernel.cuh"
 
 namespace qd {
@@ -206,6 +207,7 @@ struct qd_bp {
     double v7_prior0 = 0.0, alpha_fixed = 0.0;
     std::vector<double> prior_dom;   // priors in the decoder's domain, per column
     int v7_lines = 0;
+    int llr_mode = 0;      // what d_llr receives (0: log-ratio every iteration, 1: raw soft output of the last iteration)
     DevBuf d7_table, d7_row_table, d7_chunk_deg, d7_prior_rec, d7_col_id, d7_const_bits;
     // host-buffer pipeline state
     cudaStream_t streams[2] = {nullptr, nullptr};
@@ -219,6 +221,14 @@ struct qd_bp {
             if (done[i]) cudaEventDestroy(done[i]);
         }
     }
+};
+
+struct qd_osd {
+    qd_graph *g = nullptr;
+    int device = 0;
+    int rank = 0, W = 0, P = 0;
+    size_t smem = 0;
+    DevBuf d_next, d_soft, d_conv;
 };
 
 struct qd_ssf {
@@ -914,6 +924,7 @@ static int bp_launch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int6
         q.uniform_prior = d->v7_uniform;
         q.prior0 = d->v7_prior0;
         q.alpha_fixed = d->alpha_fixed;
+        q.llr_mode = d->llr_mode;
         q.table = d->d7_table.as<uint4>();
         q.chunk_deg = d->d7_chunk_deg.as<uint8_t>();
         q.prior_rec = d->d7_prior_rec.p;
@@ -946,6 +957,7 @@ static int bp_launch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int6
     p.synd = d_synd; p.synd_stride = synd_stride; p.shots = shots;
     p.corr = d_corr; p.corr_stride = corr_stride;
     p.conv = d_converged; p.iters = d_iters; p.llr = d_llr;
+    p.llr_mode = d->llr_mode;
     p.err = d_err; p.err_stride = err_stride;
     p.lzT = d_err ? logicals->d_lzT.as<uint32_t>() : nullptr;
     p.k = d_err ? logicals->k : 0;
@@ -1098,6 +1110,160 @@ extern "C" int qd_bp_decode_one(qd_bp *d, const uint8_t *h_syndrome, uint8_t *h_
 }
 
 // =============================================================================================
+// OSD-0 post-processing (BP + OSD)
+// =============================================================================================
+static int gf2_rank_of_csr(int m, int n, const std::vector<int32_t> &row_ptr, const std::vector<int32_t> &col_idx)
+{
+    const int W = (n + 63) / 64;
+    std::vector<uint64_t> a((size_t)std::max(m, 1) * W, 0);
+    for (int i = 0; i < m; ++i)
+        for (int e = row_ptr[i]; e < row_ptr[i + 1]; ++e) a[(size_t)i * W + (col_idx[e] >> 6)] |= 1ULL << (col_idx[e] & 63);
+    int rank = 0;
+    for (int c = 0; c < n && rank < m; ++c) {
+        int piv = -1;
+        for (int i = rank; i < m; ++i)
+            if ((a[(size_t)i * W + (c >> 6)] >> (c & 63)) & 1ULL) { piv = i; break; }
+        if (piv < 0) continue;
+        if (piv != rank)
+            for (int w = 0; w < W; ++w) std::swap(a[(size_t)piv * W + w], a[(size_t)rank * W + w]);
+        for (int i = rank + 1; i < m; ++i)
+            if ((a[(size_t)i * W + (c >> 6)] >> (c & 63)) & 1ULL)
+                for (int w = c >> 6; w < W; ++w) a[(size_t)i * W + w] ^= a[(size_t)rank * W + w];
+        ++rank;
+    }
+    return rank;
+}
+
+extern "C" int qd_osd_create(qd_graph *g, qd_osd **out)
+{
+    if (!out) return fail(QD_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!g) return fail(QD_EINVAL, "graph is NULL");
+    int rc = use_device(g->device);
+    if (rc) return rc;
+    const GraphDev &gd = g->dev;
+    if (gd.n >= 65535) return fail(QD_EUNSUP, "OSD: more than 65534 columns");
+    std::unique_ptr<qd_osd> o(new qd_osd);
+    o->g = g; o->device = g->device;
+    o->W = ((gd.n + 1 + 63) / 64) | 1;      // odd row pitch (in 64-bit words): column reads are bank-conflict free
+    o->P = 1;
+    while (o->P < gd.n) o->P <<= 1;
+    o->smem = osd_smem_layout(gd.m, o->W, o->P, gd.nwm, gd.nwn).total;
+    if (o->smem > (size_t)g->smem_optin)
+        return fail(QD_EUNSUP, "OSD: [H | s] (" + std::to_string(o->smem) + " B bit-packed) does not fit shared memory");
+    o->rank = gf2_rank_of_csr(gd.m, gd.n, g->row_ptr, g->col_idx);
+    if ((rc = o->d_next.alloc(sizeof(unsigned long long) * 2))) return rc;
+    *out = o.release();
+    return 0;
+}
+
+extern "C" int qd_osd_destroy(qd_osd *o)
+{
+    if (o) { cudaSetDevice(o->device); delete o; }
+    return 0;
+}
+
+extern "C" int qd_osd_rank(qd_osd *o)
+{
+    return o ? o->rank : fail(QD_EINVAL, "NULL handle");
+}
+
+static int osd_launch(qd_osd *o, int negate_key, const uint32_t *d_synd, int32_t synd_stride, int64_t shots,
+                      const double *d_soft, const uint8_t *d_conv, uint32_t *d_corr, int32_t corr_stride,
+                      const uint32_t *d_err, int32_t err_stride, qd_logicals *logicals, uint8_t *d_fail,
+                      int64_t *d_counters, cudaStream_t st, int queue)
+{
+    const GraphDev &g = o->g->dev;
+    OsdParams p{};
+    p.m = g.m; p.n = g.n; p.nwm = g.nwm; p.nwn = g.nwn;
+    p.W = o->W; p.P = o->P; p.rank = o->rank; p.negate_key = negate_key;
+    p.row_ptr = g.row_ptr; p.col_idx = g.col_idx;
+    p.synd = d_synd; p.synd_stride = synd_stride;
+    p.soft = d_soft; p.conv = d_conv; p.shots = shots;
+    p.corr = d_corr; p.corr_stride = corr_stride;
+    p.err = d_err; p.err_stride = err_stride;
+    p.lzT = d_err ? logicals->d_lzT.as<uint32_t>() : nullptr;
+    p.k = d_err ? logicals->k : 0;
+    p.fail = d_fail;
+    p.counters = (long long *)d_counters;
+    p.next_shot = o->d_next.as<unsigned long long>() + queue;
+    QD_CUDA(cudaFuncSetAttribute(osd0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->smem));
+    QD_CUDA(cudaMemsetAsync(p.next_shot, 0, sizeof(unsigned long long), st));
+    int per_sm = 0;
+    const int threads = g.m >= 256 ? 512 : 256;
+    QD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, osd0_kernel, threads, o->smem));
+    per_sm = std::max(1, per_sm);
+    const unsigned grid = (unsigned)std::min<long long>((long long)o->g->sm_count * per_sm, shots);
+    osd0_kernel<<<grid, threads, o->smem, st>>>(p);
+    QD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// BP on the whole batch (soft output of the last iteration captured), then OSD-0 on the shots BP left unconverged
+static int bposd_launch(qd_bp *d, qd_osd *o, const uint32_t *d_synd, int32_t synd_stride, int64_t shots, uint32_t *d_corr,
+                        int32_t corr_stride, uint8_t *d_converged, int32_t *d_iters, const uint32_t *d_err,
+                        int32_t err_stride, qd_logicals *logicals, uint8_t *d_fail, int64_t *d_counters, void *stream,
+                        int queue)
+{
+    if (!d || !o) return fail(QD_EINVAL, "NULL handle");
+    if (o->g != d->g) return fail(QD_EINVAL, "OSD handle was built on a different graph");
+    if (shots <= 0) return shots < 0 ? fail(QD_EINVAL, "shots < 0") : 0;
+    int rc = use_device(d->device);
+    if (rc) return rc;
+    const GraphDev &g = d->g->dev;
+    // the soft outputs take 8n bytes per shot: decode in slices of at most 1 GiB of them
+    const int64_t slice = std::max<int64_t>(1, std::min<int64_t>(shots, (1LL << 30) / (8LL * g.n)));
+    if ((rc = o->d_soft.ensure((size_t)slice * g.n * 8))) return rc;
+    if (!d_converged && (rc = o->d_conv.ensure((size_t)slice))) return rc;
+    const int saved = d->llr_mode;
+    d->llr_mode = 1;
+    for (int64_t s0 = 0; s0 < shots && !rc; s0 += slice) {
+        const int64_t ns = std::min(slice, shots - s0);
+        uint8_t *conv = d_converged ? d_converged + s0 : o->d_conv.as<uint8_t>();
+        rc = bp_launch(d, d_synd + s0 * synd_stride, synd_stride, ns, d_corr + s0 * corr_stride, corr_stride, conv,
+                       d_iters ? d_iters + s0 : nullptr, o->d_soft.as<double>(), d_err ? d_err + s0 * err_stride : nullptr,
+                       err_stride, logicals, d_fail ? d_fail + s0 : nullptr, d_counters, stream, queue);
+        if (!rc)
+            rc = osd_launch(o, d->method == QD_BP_PRODUCT_SUM, d_synd + s0 * synd_stride, synd_stride, ns,
+                            o->d_soft.as<double>(), conv, d_corr + s0 * corr_stride, corr_stride,
+                            d_err ? d_err + s0 * err_stride : nullptr, err_stride, logicals, d_fail ? d_fail + s0 : nullptr,
+                            d_counters, (cudaStream_t)stream, queue);
+    }
+    d->llr_mode = saved;
+    return rc;
+}
+
+extern "C" int qd_bposd_decode_batch(qd_bp *d, qd_osd *o, const uint32_t *d_synd, int32_t synd_stride, int64_t shots,
+                                     uint32_t *d_corr, int32_t corr_stride, uint8_t *d_converged, int32_t *d_iters,
+                                     const uint32_t *d_err, int32_t err_stride, qd_logicals *logicals, uint8_t *d_fail,
+                                     int64_t *d_counters, void *stream)
+{
+    if (!d_synd || !d_corr) return fail(QD_EINVAL, "bad bposd_decode_batch arguments");
+    if (d && (synd_stride < d->g->dev.nwm || corr_stride < d->g->dev.nwn)) return fail(QD_EINVAL, "stride too small");
+    if (d_err && (!logicals || (d && err_stride < d->g->dev.nwn))) return fail(QD_EINVAL, "fused epilogue needs logicals and err_stride >= ceil(n/32)");
+    if (d_fail && !d_err) return fail(QD_EINVAL, "d_fail needs d_err");
+    return bposd_launch(d, o, d_synd, synd_stride, shots, d_corr, corr_stride, d_converged, d_iters, d_err, err_stride,
+                        logicals, d_fail, d_counters, stream, 0);
+}
+
+extern "C" int qd_bposd_decode_batch_host(qd_bp *d, qd_osd *o, const uint32_t *h_synd, int32_t synd_stride, int64_t shots,
+                                          uint32_t *h_corr, int32_t corr_stride, uint8_t *h_converged, int32_t *h_iters)
+{
+    if (!d || !o || !h_synd || !h_corr || shots < 0) return fail(QD_EINVAL, "bad bposd_decode_batch_host arguments");
+    const GraphDev &g = d->g->dev;
+    if (synd_stride < g.nwm || corr_stride < g.nwn) return fail(QD_EINVAL, "stride too small");
+    if (shots == 0) return 0;
+    auto launch = [&](const uint32_t *in, int is, int64_t ns, uint32_t *out, int os, uint8_t *conv, int32_t *it,
+                      cudaStream_t st) -> int {
+        // the OSD scratch (soft outputs) is per handle: run the slices on one stream at a time
+        QD_CUDA(cudaDeviceSynchronize());
+        return bposd_launch(d, o, in, is, ns, out, os, conv, it, nullptr, 0, nullptr, nullptr, nullptr, st, 0);
+    };
+    return host_pipeline(d, d->device, g.nwm, g.nwn, h_synd, synd_stride, shots, h_corr, corr_stride, h_converged,
+                         h_iters, launch);
+}
+
+// =============================================================================================
 // SSF
 // =============================================================================================
 extern "C" int qd_ssf_create(qd_graph *hz, int32_t num_generators, const int32_t *h_gen_row_ptr,
@@ -1245,7 +1411,7 @@ extern "C" int qd_ssf_decode_batch_host(qd_ssf *d, const uint32_t *h_synd, int32
 // =============================================================================================
 // code-capacity experiment
 // =============================================================================================
-extern "C" int qd_code_capacity_run(qd_graph *hz, qd_bp *bp, qd_ssf *ssf, qd_sampler *sampler, qd_logicals *logicals,
+extern "C" int qd_code_capacity_run(qd_graph *hz, qd_bp *bp, qd_ssf *ssf, qd_osd *osd, qd_sampler *sampler, qd_logicals *logicals,
                                     uint64_t seed, int64_t shot0, int64_t shots, int64_t *h_counters, uint32_t *h_corr,
                                     int32_t corr_stride, uint8_t *h_fail, uint8_t *h_converged, int32_t *h_iters)
 {
@@ -1253,7 +1419,8 @@ extern "C" int qd_code_capacity_run(qd_graph *hz, qd_bp *bp, qd_ssf *ssf, qd_sam
     if ((bp == nullptr) == (ssf == nullptr)) return fail(QD_EINVAL, "exactly one of bp / ssf must be given");
     const GraphDev &g = hz->dev;
     if (sampler->nbits != g.n || logicals->n != g.n) return fail(QD_EINVAL, "sampler / logicals size mismatch");
-    if ((bp && bp->g != hz) || (ssf && ssf->g != hz)) return fail(QD_EINVAL, "decoder was built on a different graph");
+    if ((bp && bp->g != hz) || (ssf && ssf->g != hz) || (osd && osd->g != hz)) return fail(QD_EINVAL, "decoder was built on a different graph");
+    if (osd && !bp) return fail(QD_EINVAL, "OSD post-processing needs a BP decoder");
     if (h_corr && corr_stride < g.nwn) return fail(QD_EINVAL, "corr_stride too small");
     int rc = use_device(hz->device);
     if (rc) return rc;
@@ -1274,7 +1441,11 @@ extern "C" int qd_code_capacity_run(qd_graph *hz, qd_bp *bp, qd_ssf *ssf, qd_sam
         const int64_t ns = std::min(chunk, shots - s0);
         if ((rc = qd_sampler_run(sampler, seed, 0u, shot0 + s0, ns, d_err.as<uint32_t>(), es, nullptr))) return rc;
         if ((rc = qd_syndrome_batch(hz, d_err.as<uint32_t>(), es, ns, d_syn.as<uint32_t>(), ss, nullptr))) return rc;
-        if (bp)
+        if (bp && osd)
+            rc = qd_bposd_decode_batch(bp, osd, d_syn.as<uint32_t>(), ss, ns, d_cor.as<uint32_t>(), es, d_conv.as<uint8_t>(),
+                                       d_it.as<int32_t>(), d_err.as<uint32_t>(), es, logicals, d_fail.as<uint8_t>(),
+                                       d_cnt.as<int64_t>(), nullptr);
+        else if (bp)
             rc = qd_bp_decode_batch(bp, d_syn.as<uint32_t>(), ss, ns, d_cor.as<uint32_t>(), es, d_conv.as<uint8_t>(),
                                     d_it.as<int32_t>(), nullptr, d_err.as<uint32_t>(), es, logicals, d_fail.as<uint8_t>(),
                                     d_cnt.as<int64_t>(), nullptr);

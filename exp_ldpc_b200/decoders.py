@@ -25,7 +25,7 @@ from . import _lib
 from .codes import canonical_csr
 
 __all__ = [
-    "pack_bits", "unpack_bits", "row_words", "TannerGraph", "Logicals", "Sampler", "bp_decoder", "ssf_decoder",
+    "pack_bits", "unpack_bits", "row_words", "TannerGraph", "Logicals", "Sampler", "bp_decoder", "bposd_decoder", "ssf_decoder",
     "bernoulli_thresholds",
 ]
 
@@ -281,6 +281,85 @@ class bp_decoder:
             self._h, _lib.ptr(d_synd), synd_stride, shots, _lib.ptr(d_corr), corr_stride, _lib.ptr(d_converged),
             _lib.ptr(d_iters), _lib.ptr(d_llr), _lib.ptr(d_err), err_stride,
             logicals.handle if logicals is not None else None, _lib.ptr(d_fail), _lib.ptr(d_counters), stream))
+
+
+class bposd_decoder(bp_decoder):
+    """Drop-in for ``ldpc.bposd_decoder`` (``_experiment.py:23-27,96-100``): belief propagation, then
+    ordered-statistics post-processing on the shots BP did not converge on.
+
+    ``osd_method`` 'osd0' / 'osd_0' (information set = the first rank(H) independent columns in the
+    order of the BP soft output, no higher-order search) is implemented; the reference's default
+    'osd_cs' (order 7) and 'osd_e' are not and raise ``NotImplementedError``.
+    Side outputs as upstream: ``bp_decoding`` (BP's own hard decision), ``osdw_decoding`` = the returned
+    vector, ``converge`` / ``iter`` describe the BP stage."""
+
+    def __init__(self, parity_check_matrix, error_rate=None, max_iter=0, bp_method=0, ms_scaling_factor=1.0,
+                 channel_probs=(None,), osd_order=-1, osd_method="osd0", precision="f64", device=0, kernel="auto",
+                 **_ignored):
+        key = str(osd_method).lower()
+        if key in ("osd_e", "osde", "exhaustive", "e", "osd_cs", "1", "cs", "combination_sweep"):
+            if int(osd_order) > 0:
+                raise NotImplementedError(f"osd_method '{osd_method}' with osd_order > 0 is not implemented (only OSD-0)")
+        elif key not in ("osd0", "osd_0", "0", "zero"):
+            raise ValueError(f"ERROR: OSD method '{osd_method}' invalid. Please choose from the following methods: "
+                             "'OSD_0', 'OSD_E' or 'OSD_CS'.")
+        super().__init__(parity_check_matrix, error_rate=error_rate, max_iter=max_iter, bp_method=bp_method,
+                         ms_scaling_factor=ms_scaling_factor, channel_probs=channel_probs, precision=precision,
+                         device=device, kernel=kernel)
+        self.osd_method = "osd0"
+        self.osd_order = 0
+        self._osd = C.c_void_p()
+        _lib.check(_lib.lib().qd_osd_create(self.graph.handle, C.byref(self._osd)))
+        self.osd0_decoding = np.zeros(self.n, dtype=np.int64)
+        self.osdw_decoding = np.zeros(self.n, dtype=np.int64)
+
+    def close(self):
+        if getattr(self, "_osd", None) and self._osd.value:
+            _lib.lib().qd_osd_destroy(self._osd)
+            self._osd = C.c_void_p()
+        super().close()
+
+    @property
+    def osd_handle(self):
+        return self._osd
+
+    @property
+    def rank(self) -> int:
+        return int(_lib.lib().qd_osd_rank(self._osd))
+
+    def decode_batch(self, syndromes, packed: bool = False, return_packed: bool = False):
+        nwm = (self.m + 31) // 32
+        s = _as_syndrome_batch(syndromes, self.m, packed, nwm)
+        shots = s.shape[0]
+        cstride = row_words(self.n)
+        corr = np.zeros((shots, cstride), dtype=np.uint32)
+        conv = np.zeros(shots, dtype=np.uint8)
+        its = np.zeros(shots, dtype=np.int32)
+        _lib.check(_lib.lib().qd_bposd_decode_batch_host(self._h, self._osd, _lib.ptr(s), s.shape[1], shots, _lib.ptr(corr),
+                                                         cstride, _lib.ptr(conv), _lib.ptr(its)))
+        if return_packed:
+            return corr, conv, its
+        return unpack_bits(corr, self.n), conv, its
+
+    def decode(self, input_vector) -> np.ndarray:
+        s = np.asarray(input_vector)
+        if s.shape != (self.m,):
+            raise ValueError(f"The input to the ldpc.bp_decoder.decode must be a syndrome (of length={self.m}). "
+                             f"The inputted vector has length={s.shape[0] if s.ndim else 0}. Valid formats are `np.ndarray`.")
+        corr, conv, its = self.decode_batch(s[None, :])
+        self.converge, self.iter = int(conv[0]), int(its[0])
+        self.osd0_decoding = self.osdw_decoding = corr[0].astype(np.int64)
+        return self.osdw_decoding
+
+    def decode_batch_device(self, d_synd, synd_stride, shots, d_corr, corr_stride, d_converged=None, d_iters=None,
+                            d_llr=None, d_err=None, err_stride=0, logicals: Optional[Logicals] = None, d_fail=None,
+                            d_counters=None, stream=None):
+        if d_llr is not None:
+            raise ValueError("bposd_decoder.decode_batch_device does not export soft outputs")
+        _lib.check(_lib.lib().qd_bposd_decode_batch(
+            self._h, self._osd, _lib.ptr(d_synd), synd_stride, shots, _lib.ptr(d_corr), corr_stride, _lib.ptr(d_converged),
+            _lib.ptr(d_iters), _lib.ptr(d_err), err_stride, logicals.handle if logicals is not None else None,
+            _lib.ptr(d_fail), _lib.ptr(d_counters), stream))
 
 
 class ssf_decoder:

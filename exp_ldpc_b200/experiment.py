@@ -28,7 +28,7 @@ import numpy as np
 
 from . import _lib
 from .codes import QuantumCode
-from .decoders import Logicals, Sampler, TannerGraph, bp_decoder, row_words, ssf_decoder, unpack_bits
+from .decoders import Logicals, Sampler, TannerGraph, bp_decoder, bposd_decoder, row_words, ssf_decoder, unpack_bits
 
 __all__ = ["depolarizing_noise", "NoiseModel", "CodeCapacityExperiment", "SpacetimeExperiment", "run_simulation", "p_sweep",
            "shard_range", "binomial_ci"]
@@ -91,21 +91,28 @@ class CodeCapacityExperiment:
         self.sampler = Sampler(flip_probability, self.n, device)
         self.decoder_mode = decoder_mode
         opts = dict(bp_options or {})
-        if decoder_mode == "bp":
+        self._osd = None
+        if decoder_mode in ("bp", "bposd"):
+            # "bposd": the reference's default mode for rounds = 0 — BP + OSD on the code's check matrix
+            # (BPOSDCorrect, _experiment.py:62-83); only osd_method "osd0" exists here
             pr = np.broadcast_to(np.asarray(prior, dtype=np.float64), (self.n,))
-            self.decoder = bp_decoder(self.graph, channel_probs=pr, max_iter=opts.get("max_iter", 0),
-                                      bp_method=opts.get("bp_method", "ps"),
-                                      ms_scaling_factor=opts.get("ms_scaling_factor", 0.0), precision=precision,
-                                      kernel=kernel)
+            kw = dict(channel_probs=pr, max_iter=opts.get("max_iter", 0), bp_method=opts.get("bp_method", "ps"),
+                      ms_scaling_factor=opts.get("ms_scaling_factor", 0.0), precision=precision, kernel=kernel)
+            if decoder_mode == "bposd":
+                self.decoder = bposd_decoder(self.graph, osd_method=opts.get("osd_method", "osd0"),
+                                             osd_order=opts.get("osd_order", 0), **kw)
+                self._osd = self.decoder.osd_handle
+            else:
+                self.decoder = bp_decoder(self.graph, **kw)
             self._bp, self._ssf = self.decoder.handle, None
         elif decoder_mode == "ssf":
             if check_matrix is not None:
                 raise NotImplementedError("small-set-flip decodes the code's own check matrix only")
             self.decoder = ssf_decoder(self.graph, code.checks.x, max_rounds=opts.get("max_rounds", 0))
             self._bp, self._ssf = None, self.decoder.handle
-        elif decoder_mode in ("bposd", "bposd_single_shot", "bposd_hybrid", "bpd_detector"):
+        elif decoder_mode in ("bposd_single_shot", "bposd_hybrid", "bpd_detector"):
             raise NotImplementedError(
-                f"decoder_mode '{decoder_mode}' needs the OSD post-processor / Stim DEM (SURVEY.md §8 f1-f2)")
+                f"decoder_mode '{decoder_mode}' needs the multi-round circuit sampler / Stim DEM (SURVEY.md §8 f2)")
         else:
             raise RuntimeError("Unknown decoder operation mode")   # _experiment.py:189
 
@@ -119,7 +126,7 @@ class CodeCapacityExperiment:
             conv = np.zeros(shots, dtype=np.uint8)
             its = np.zeros(shots, dtype=np.int32)
         _lib.check(_lib.lib().qd_code_capacity_run(
-            self.graph.handle, self._bp, self._ssf, self.sampler.handle, self.logicals.handle, int(seed), int(shot0),
+            self.graph.handle, self._bp, self._ssf, self._osd, self.sampler.handle, self.logicals.handle, int(seed), int(shot0),
             int(shots), _lib.ptr(counters), _lib.ptr(corr), cs, _lib.ptr(fail), _lib.ptr(conv), _lib.ptr(its)))
         out = dict(failures=int(counters[0]), shots=int(counters[1]), non_converged=int(counters[2]),
                    iters_total=int(counters[3]))

@@ -20,6 +20,9 @@
  *   qd_code_capacity_run  <- run_simulation(samples, ...) for rounds = 0, returning the counts that
  *                            p_sweep sums                    python/qldpc/misc/_experiment.py:154-210
  *                                                            python/qldpc/misc/p_sweep.py:28-32
+ *   qd_osd_*, qd_bposd_*  <- ldpc.bposd_decoder(..., osd_method="osd0").decode(syndrome): BP, then
+ *                            OSD-0 on the shots BP left unconverged
+ *                                                            python/qldpc/misc/_experiment.py:23-27,51,59,82,96-100,125
  *   qd_ssf_*              <- (absent from the reference; SURVEY.md Appendix C is the specification)
  *
  * Conventions
@@ -43,7 +46,7 @@
 extern "C" {
 #endif
 
-#define QD_ABI_VERSION 1
+#define QD_ABI_VERSION 2
 
 #define QD_EINVAL   (-1)   /* bad argument                       */
 #define QD_ENODEV   (-2)   /* no usable CUDA device              */
@@ -62,6 +65,7 @@ typedef struct qd_logicals qd_logicals;
 typedef struct qd_sampler  qd_sampler;
 typedef struct qd_bp       qd_bp;
 typedef struct qd_ssf      qd_ssf;
+typedef struct qd_osd      qd_osd;
 
 int         qd_abi_version(void);
 const char *qd_last_error(void);
@@ -131,6 +135,23 @@ int qd_bp_decode_batch_host(qd_bp *d, const uint32_t *h_synd, int32_t synd_strid
 int qd_bp_decode_one(qd_bp *d, const uint8_t *h_syndrome, uint8_t *h_decoding, int32_t *converged,
                      int32_t *iters, double *h_llr);
 
+/* ---- BP + OSD-0 ----------------------------------------------------------------------------- */
+/* OSD-0: rank the columns by the soft output of the last BP iteration (most likely in error
+ * first, ties by index), take the first rank(H) independent ones as information set, solve.
+ * Needs [H | s] bit-packed in shared memory (m * ceil((n+1)/64) * 8 bytes): QD_EUNSUP otherwise. */
+int qd_osd_create(qd_graph *g, qd_osd **out);
+int qd_osd_destroy(qd_osd *o);
+int qd_osd_rank(qd_osd *o);                       /* rank of H over GF(2) */
+/* As qd_bp_decode_batch; shots with converged == 0 get the OSD-0 decoding (d_converged keeps the
+ * BP flag; d_fail / d_counters[0] describe the final decoding). */
+int qd_bposd_decode_batch(qd_bp *d, qd_osd *o, const uint32_t *d_synd, int32_t synd_stride,
+                          int64_t shots, uint32_t *d_corr, int32_t corr_stride, uint8_t *d_converged,
+                          int32_t *d_iters, const uint32_t *d_err, int32_t err_stride,
+                          qd_logicals *logicals, uint8_t *d_fail, int64_t *d_counters, void *stream);
+int qd_bposd_decode_batch_host(qd_bp *d, qd_osd *o, const uint32_t *h_synd, int32_t synd_stride,
+                               int64_t shots, uint32_t *h_corr, int32_t corr_stride,
+                               uint8_t *h_converged, int32_t *h_iters);
+
 /* ---- small-set-flip ------------------------------------------------------------------------ */
 /* hz: graph of the checks whose syndrome is decoded; generators: rows of Hx (host CSR).        */
 int qd_ssf_create(qd_graph *hz, int32_t num_generators, const int32_t *h_gen_row_ptr,
@@ -145,11 +166,12 @@ int qd_ssf_decode_batch_host(qd_ssf *d, const uint32_t *h_synd, int32_t synd_str
                              int32_t *h_rounds);
 
 /* ---- code-capacity experiment: sample -> syndrome -> decode -> residual -> logical flag ---- */
-/* Exactly one of bp / ssf is non-NULL.  Decodes global shots [shot0, shot0+shots) drawn from
+/* Exactly one of bp / ssf is non-NULL; osd (nullable, with bp) adds OSD-0 post-processing.
+ * Decodes global shots [shot0, shot0+shots) drawn from
  * `sampler` with key `seed`; h_counters[4] = {failures, shots, non_converged, iterations}.
  * Optional per-shot host outputs (NULL to skip): h_corr (packed, stride words), h_fail,
  * h_converged, h_iters. */
-int qd_code_capacity_run(qd_graph *hz, qd_bp *bp, qd_ssf *ssf, qd_sampler *sampler,
+int qd_code_capacity_run(qd_graph *hz, qd_bp *bp, qd_ssf *ssf, qd_osd *osd, qd_sampler *sampler,
                          qd_logicals *logicals, uint64_t seed, int64_t shot0, int64_t shots,
                          int64_t *h_counters, uint32_t *h_corr, int32_t corr_stride,
                          uint8_t *h_fail, uint8_t *h_converged, int32_t *h_iters);

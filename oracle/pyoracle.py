@@ -53,6 +53,12 @@ def lib():
         L.orc_bp_destroy.argtypes = [C.c_void_p]
         L.orc_bp_decode.argtypes = [C.c_void_p, u8p, u8p, f64p, C.POINTER(C.c_int)]
         L.orc_bp_decode.restype = C.c_int
+        L.orc_bp_soft.argtypes = [C.c_void_p]
+        L.orc_bp_soft.restype = f64p
+        L.orc_osd0.argtypes = [C.c_int, C.c_int, i32p, i32p, u8p, f64p, u8p]
+        L.orc_osd0.restype = C.c_int
+        L.orc_bposd0_decode.argtypes = [C.c_void_p, u8p, u8p, C.POINTER(C.c_int)]
+        L.orc_bposd0_decode.restype = C.c_int
         L.orc_ssf_create.argtypes = [C.c_int, C.c_int, i32p, i32p, C.c_int, i32p, i32p]
         L.orc_ssf_create.restype = C.c_void_p
         L.orc_ssf_destroy.argtypes = [C.c_void_p]
@@ -145,6 +151,32 @@ class OracleBP:
         return dec.astype(np.int64)
 
 
+class OracleBPOSD0(OracleBP):
+    """``ldpc.bposd_decoder(..., osd_method='osd0')`` restatement: BP, then OSD-0 if BP did not converge."""
+
+    def decode(self, synd) -> np.ndarray:
+        s = np.ascontiguousarray(np.asarray(synd).astype(np.int64) & 1, dtype=np.uint8)
+        assert s.shape == (self.m,)
+        dec = np.zeros(self.n, dtype=np.uint8)
+        it = C.c_int(0)
+        self.converge = lib().orc_bposd0_decode(self._h, _p(s, C.c_uint8), _p(dec, C.c_uint8), C.byref(it))
+        self.iter = it.value
+        self.soft = np.ctypeslib.as_array(lib().orc_bp_soft(self._h), shape=(self.n,)).copy()
+        return dec.astype(np.int64)
+
+
+def osd0(h, synd, key_ascending) -> np.ndarray:
+    """OSD-0 solution for an explicit ranking key (ascending = most likely in error first)."""
+    m, n, ptr, idx = _csr(h)
+    s = np.ascontiguousarray(np.asarray(synd).astype(np.int64) & 1, dtype=np.uint8)
+    key = np.ascontiguousarray(key_ascending, dtype=np.float64)
+    dec = np.zeros(n, dtype=np.uint8)
+    ok = lib().orc_osd0(m, n, _p(ptr, C.c_int32), _p(idx, C.c_int32), _p(s, C.c_uint8), _p(key, C.c_double), _p(dec, C.c_uint8))
+    if not ok:
+        raise ValueError("syndrome is not in the column space of H")
+    return dec
+
+
 class OracleSSF:
     def __init__(self, hz, hx):
         self.m, self.n, self._zp, self._zi = _csr(hz)
@@ -208,7 +240,7 @@ def run_code_capacity(hz, lz, q_sample, prior, *, decoder="bp", hx=None, max_ite
         fail = np.zeros(shots, dtype=np.uint8)
     null8, null32 = C.POINTER(C.c_uint8)(), C.POINTER(C.c_int32)()
     rc = lib().orc_run_code_capacity(
-        C.byref(x), 1 if decoder == "ssf" else 0, int(seed), int(shot0), int(shots), int(threads),
+        C.byref(x), {"bp": 0, "ssf": 1, "bposd0": 2}[decoder], int(seed), int(shot0), int(shots), int(threads),
         _p(counters, C.c_int64),
         _p(dec, C.c_uint8) if per_shot else null8, _p(conv, C.c_uint8) if per_shot else null8,
         _p(its, C.c_int32) if per_shot else null32, _p(fail, C.c_uint8) if per_shot else null8)

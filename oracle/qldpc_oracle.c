@@ -96,6 +96,7 @@ struct orc_bp {
     double *b2c, *c2b;     /* per-edge messages, CSR order */
     int *esgn;             /* per-edge sign counter of the min-sum pass */
     uint8_t *dec_synd;
+    double *soft;          /* raw soft output of the last iteration: total LLR (min-sum), ratio R (product-sum) */
     int max_iter, method;
     double alpha;
 };
@@ -125,6 +126,7 @@ orc_bp *orc_bp_create(int m, int n, const int32_t *row_ptr, const int32_t *col_i
     d->c2b = (double *)malloc(sizeof(double) * (nnz ? nnz : 1));
     d->esgn = (int *)malloc(sizeof(int) * (nnz ? nnz : 1));
     d->dec_synd = (uint8_t *)malloc(m ? m : 1);
+    d->soft = (double *)calloc(n ? n : 1, sizeof(double));
     d->max_iter = max_iter > 0 ? max_iter : n;   /* ldpc: max_iter == 0 -> n */
     d->method = method;
     d->alpha = alpha;
@@ -135,7 +137,7 @@ void orc_bp_destroy(orc_bp *d)
 {
     if (!d) return;
     free(d->row_ptr); free(d->col_idx); free(d->col_ptr); free(d->csc_edge); free(d->probs);
-    free(d->b2c); free(d->c2b); free(d->esgn); free(d->dec_synd); free(d);
+    free(d->b2c); free(d->c2b); free(d->esgn); free(d->dec_synd); free(d->soft); free(d);
 }
 
 static int bp_converged(const orc_bp *d, const uint8_t *synd, const uint8_t *decoding)
@@ -180,6 +182,7 @@ static int bp_prob_ratios(orc_bp *d, const uint8_t *synd, uint8_t *decoding, dou
                 if (isnan(temp)) temp = 1.0;
             }
             if (llr) llr[j] = log(1.0 / temp);
+            d->soft[j] = temp;
             decoding[j] = (uint8_t)(temp >= 1.0);
             temp = 1.0;
             for (int32_t t = hi - 1; t >= lo; --t) {
@@ -237,6 +240,7 @@ static int bp_min_sum_log(orc_bp *d, const uint8_t *synd, uint8_t *decoding, dou
                 temp += c2b[e];
             }
             if (llr) llr[j] = temp;
+            d->soft[j] = temp;
             decoding[j] = (uint8_t)(temp <= 0);
             temp = 0.0;
             for (int32_t t = hi - 1; t >= lo; --t) {
@@ -259,6 +263,76 @@ int orc_bp_decode(orc_bp *d, const uint8_t *synd, uint8_t *decoding, double *llr
     if (iters) *iters = it;
     return conv;
 }
+
+/* ============================================================================================
+ * OSD-0 — restatement of ldpc.bposd_decoder with osd_method "osd0" (reference call sites
+ * python/qldpc/misc/_experiment.py:23-27,51,59,77,82,96-100,125).  PARITY UNPINNED (see header).
+ * Columns are ranked most-likely-in-error first by the BP soft output of the last iteration:
+ * ascending total LLR for min-sum; for product-sum descending posterior ratio R (the order of
+ * ascending log(1/R) without a trip through libm); ties by column index.  The first rank(H)
+ * linearly independent columns in that order are the information set S; the decoding is the
+ * unique solution of H_S x_S = s, zero elsewhere.  Plain Gauss-Jordan on the dense matrix.
+ * ========================================================================================== */
+typedef struct { double key; int idx; } orc_rank_t;
+static int orc_rank_cmp(const void *a, const void *b)
+{
+    const orc_rank_t *x = (const orc_rank_t *)a, *y = (const orc_rank_t *)b;
+    if (x->key < y->key) return -1;
+    if (x->key > y->key) return 1;
+    return x->idx - y->idx;
+}
+
+int orc_osd0(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, const uint8_t *synd,
+             const double *key_ascending, uint8_t *decoding)
+{
+    const int W = (n + 1 + 63) / 64;
+    uint64_t *R = (uint64_t *)calloc((size_t)(m ? m : 1) * W, sizeof(uint64_t));
+    orc_rank_t *ord = (orc_rank_t *)malloc(sizeof(orc_rank_t) * (n ? n : 1));
+    int *pcol = (int *)malloc(sizeof(int) * (m ? m : 1));
+    for (int i = 0; i < m; ++i) {
+        for (int32_t e = row_ptr[i]; e < row_ptr[i + 1]; ++e) R[(size_t)i * W + (col_idx[e] >> 6)] |= (uint64_t)1 << (col_idx[e] & 63);
+        if (synd[i]) R[(size_t)i * W + (n >> 6)] |= (uint64_t)1 << (n & 63);
+        pcol[i] = -1;
+    }
+    for (int j = 0; j < n; ++j) { ord[j].key = key_ascending[j]; ord[j].idx = j; }
+    qsort(ord, (size_t)n, sizeof(orc_rank_t), orc_rank_cmp);
+    int rank = 0;
+    for (int t = 0; t < n && rank < m; ++t) {
+        const int c = ord[t].idx;
+        int piv = -1;
+        for (int i = 0; i < m; ++i)
+            if (pcol[i] < 0 && ((R[(size_t)i * W + (c >> 6)] >> (c & 63)) & 1)) { piv = i; break; }
+        if (piv < 0) continue;
+        pcol[piv] = c;
+        ++rank;
+        for (int i = 0; i < m; ++i)
+            if (i != piv && ((R[(size_t)i * W + (c >> 6)] >> (c & 63)) & 1))
+                for (int w = 0; w < W; ++w) R[(size_t)i * W + w] ^= R[(size_t)piv * W + w];
+    }
+    memset(decoding, 0, (size_t)n);
+    int consistent = 1;
+    for (int i = 0; i < m; ++i) {
+        const int sbit = (int)((R[(size_t)i * W + (n >> 6)] >> (n & 63)) & 1);
+        if (pcol[i] >= 0) decoding[pcol[i]] = (uint8_t)sbit;
+        else if (sbit) consistent = 0;      /* syndrome outside the column space: cannot happen for s = H e */
+    }
+    free(R); free(ord); free(pcol);
+    return consistent;
+}
+
+/* BP, then OSD-0 on the shots BP did not converge on.  Returns the BP convergence flag. */
+int orc_bposd0_decode(orc_bp *d, const uint8_t *synd, uint8_t *decoding, int *iters)
+{
+    const int conv = orc_bp_decode(d, synd, decoding, NULL, iters);
+    if (conv) return 1;
+    double *key = (double *)malloc(sizeof(double) * (d->n ? d->n : 1));
+    for (int j = 0; j < d->n; ++j) key[j] = d->method == 0 ? -d->soft[j] : d->soft[j];
+    orc_osd0(d->m, d->n, d->row_ptr, d->col_idx, synd, key, decoding);
+    free(key);
+    return 0;
+}
+
+const double *orc_bp_soft(const orc_bp *d) { return d->soft; }
 
 /* ============================================================================================
  * Small-set-flip.  Candidate sets: non-empty subsets F of the support of
@@ -417,7 +491,7 @@ static void *orc_worker_main(void *arg)
     const orc_experiment *x = w->x;
     orc_bp *bp = NULL;
     orc_ssf *ssf = NULL;
-    if (w->decoder == 0)
+    if (w->decoder == 0 || w->decoder == 2)
         bp = orc_bp_create(x->m, x->n, x->row_ptr, x->col_idx, x->probs, x->max_iter, x->method, x->alpha);
     else
         ssf = orc_ssf_create(x->m, x->n, x->row_ptr, x->col_idx, x->mg, x->hx_row_ptr, x->hx_col_idx);
@@ -432,7 +506,8 @@ static void *orc_worker_main(void *arg)
             int it = 0, conv;
             orc_sample_bits(w->seed, 0u, w->shot0 + s, 1, x->n, x->thr, err);
             orc_syndrome(x->m, x->row_ptr, x->col_idx, err, syn);
-            if (bp) conv = orc_bp_decode(bp, syn, dec, NULL, &it);
+            if (bp && w->decoder == 2) conv = orc_bposd0_decode(bp, syn, dec, &it);
+            else if (bp) conv = orc_bp_decode(bp, syn, dec, NULL, &it);
             else conv = orc_ssf_decode(ssf, syn, x->max_iter, dec, &it, NULL);
             if (w->decodings) memcpy(w->decodings + s * (int64_t)x->n, dec, (size_t)x->n);
             for (int j = 0; j < x->n; ++j) err[j] ^= dec[j];

@@ -26,7 +26,7 @@ def test_header_symbols_all_exported(built):
     for name in declared:
         assert hasattr(L, name), f"{name} declared in include/qldpc_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == declared, "ctypes signature table out of sync with the header"
-    assert L.qd_abi_version() == 1
+    assert L.qd_abi_version() == 2
 
 
 def test_exports_are_plain_c(built):

@@ -408,3 +408,50 @@ def test_single_shot_matrix_decodes_like_oracle(gpu, code225):
         for s in range(synd.shape[0]):
             assert np.array_equal(corr[s], ref.decode(synd[s])), (kernel, s)
             assert its[s] == ref.iter and conv[s] == ref.converge
+
+
+# ---------------------------------------------------------------------------------------------
+# BP + OSD-0 (ldpc.bposd_decoder with osd_method "osd0"; _experiment.py:23-27,77,82,96-100,125)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("which,method,p,kernel", [("hgp225", "ms", 0.04, "auto"), ("hgp225", "ps", 0.03, "auto"),
+                                                  ("hgp225", "ms", 0.05, "generic"), ("hgp1600", "ms", 0.025, "auto")])
+def test_bposd0_experiment_against_live_oracle(gpu, codes, which, method, p, kernel):
+    from exp_ldpc_b200.experiment import CodeCapacityExperiment
+    from oracle import pyoracle as po
+    code = codes[which]
+    q, prior = 2 * p / 3 + p - 4 / 3 * p * p, 2 * p / 3
+    shots = 400 if which == "hgp225" else 96
+    opts = dict(max_iter=16, bp_method=method, ms_scaling_factor=0.0, osd_method="osd0")
+    got = CodeCapacityExperiment(code, q, prior, "bposd", opts, kernel=kernel).run(shots, seed=17, per_shot=True)
+    ref = po.run_code_capacity(code.checks.z, code.logicals.z, q, prior, decoder="bposd0", max_iter=16, bp_method=method,
+                               ms_scaling_factor=0.0, seed=17, shots=shots, per_shot=True)
+    assert 0 < ref["non_converged"] < shots                        # both branches exercised
+    assert (got["decodings"] == ref["decodings"]).all()
+    assert np.array_equal(got["converged"], ref["converged"]) and np.array_equal(got["iters"], ref["iters"])
+    assert np.array_equal(got["fail"], ref["fail"])
+    assert got["failures"] == ref["failures"] == int(ref["fail"].sum())
+    assert got["non_converged"] == ref["non_converged"]
+    # BP + OSD always returns a correction with the right syndrome
+    hz = code.checks.z
+    err = po.sample_bits(17, 0, 0, shots, po.thresholds(q, hz.shape[1]))
+    assert not (((err ^ got["decodings"]) @ hz.T.toarray()) % 2).any()
+
+
+def test_bposd_decoder_duck_type(gpu, code225):
+    """ldpc.bposd_decoder call shape of _experiment.py:96-100,125."""
+    from exp_ldpc_b200.decoders import bposd_decoder
+    from oracle import pyoracle as po
+    hz = code225.checks.z
+    dec = bposd_decoder(hz, error_rate=0.03, max_iter=10, bp_method="ms", ms_scaling_factor=0, osd_method="osd0", osd_order=0)
+    ref = po.OracleBPOSD0(hz, error_rate=0.03, max_iter=10, bp_method="ms", ms_scaling_factor=0.0)
+    assert dec.rank == 108
+    rng = np.random.default_rng(2)
+    for _ in range(20):
+        e = (rng.random(hz.shape[1]) < 0.06).astype(np.uint8)
+        s = ((hz @ e) % 2).astype(float)                            # the reference hands in float64 0/1
+        assert np.array_equal(dec.decode(s), ref.decode(s))
+        assert (dec.converge, dec.iter) == (ref.converge, ref.iter)
+    with pytest.raises(NotImplementedError):
+        bposd_decoder(hz, error_rate=0.03, osd_method="osd_cs", osd_order=7)
+    corr, conv, its = dec.decode_batch(np.zeros((3, hz.shape[0])))
+    assert not corr.any() and conv.all()

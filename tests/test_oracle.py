@@ -248,3 +248,66 @@ def test_committed_decoder_vectors(code225, code1600):
         out = run_case(name, {"hgp225": code225, "hgp1600": code1600})
         assert np.array_equal(np.packbits(out["decodings"], axis=1), g[name + "_dec"]), name
         assert np.array_equal(out["iters"], g[name + "_iters"]) and np.array_equal(out["fail"], g[name + "_fail"])
+
+
+# ---------------------------------------------------------------------------------------------
+# OSD-0 (ldpc.bposd_decoder, osd_method "osd0"): the oracle against an independent numpy elimination
+# ---------------------------------------------------------------------------------------------
+def _numpy_osd0(h, synd, key):
+    order = np.lexsort((np.arange(h.shape[1]), key))           # ascending key, ties by column index
+    a = (h.toarray()[:, order] % 2).astype(np.uint8)
+    b = np.asarray(synd, dtype=np.uint8).copy()
+    m = a.shape[0]
+    used = np.zeros(m, bool)
+    pcol = -np.ones(m, int)
+    for c in range(a.shape[1]):
+        rows = np.where((a[:, c] == 1) & ~used)[0]
+        if len(rows) == 0:
+            continue
+        r = rows[0]
+        used[r], pcol[r] = True, c
+        for i in np.where(a[:, c] == 1)[0]:
+            if i != r:
+                a[i] ^= a[r]
+                b[i] ^= b[r]
+    x = np.zeros(h.shape[1], np.uint8)
+    for r in range(m):
+        if pcol[r] >= 0:
+            x[order[pcol[r]]] = b[r]
+    return x
+
+
+def test_osd0_matches_numpy_elimination(code225):
+    from oracle import pyoracle as po
+    hz = code225.checks.z
+    rng = np.random.default_rng(0)
+    for trial in range(12):
+        e = (rng.random(hz.shape[1]) < 0.06).astype(np.uint8)
+        s = (hz @ e) % 2
+        key = rng.normal(size=hz.shape[1]) if trial % 3 else np.round(rng.normal(size=hz.shape[1]), 0)   # with ties
+        x = po.osd0(hz, s, key)
+        assert np.array_equal((hz @ x) % 2, s)
+        assert np.array_equal(x, _numpy_osd0(hz, s, key))
+    # zero syndrome -> zero; information set prefers the low keys
+    assert not po.osd0(hz, np.zeros(hz.shape[0], np.uint8), rng.normal(size=hz.shape[1])).any()
+
+
+def test_bposd0_keeps_converged_bp_and_fixes_the_rest(code225):
+    from oracle import pyoracle as po
+    hz = code225.checks.z
+    rng = np.random.default_rng(5)
+    bp = po.OracleBP(hz, error_rate=0.03, max_iter=12, bp_method="ms", ms_scaling_factor=0.0)
+    bo = po.OracleBPOSD0(hz, error_rate=0.03, max_iter=12, bp_method="ms", ms_scaling_factor=0.0)
+    seen = set()
+    for _ in range(60):
+        e = (rng.random(hz.shape[1]) < 0.05).astype(np.uint8)
+        s = (hz @ e) % 2
+        a, b = bp.decode(s), bo.decode(s)
+        assert bo.converge == bp.converge and bo.iter == bp.iter
+        assert np.array_equal((hz @ b) % 2, s)                      # BP+OSD always returns a valid correction
+        if bp.converge:
+            assert np.array_equal(a, b)
+        else:
+            assert np.array_equal(b, po.osd0(hz, s, bo.soft))
+        seen.add(bp.converge)
+    assert seen == {0, 1}
