@@ -143,7 +143,7 @@ def cpu_port_throughput(code, p, opts, target_seconds=12.0, threads=0, decoder="
     from oracle import pyoracle as po
     hz, lz, q, prior = problem
     cores = po.num_threads() if threads <= 0 else threads
-    kw = dict(decoder=decoder, hx=code.checks.x, max_iter=opts["max_iter"], bp_method=opts["bp_method"],
+    kw = dict(decoder={"bposd": "bposd0"}.get(decoder, decoder), hx=code.checks.x, max_iter=opts["max_iter"], bp_method=opts["bp_method"],
               ms_scaling_factor=opts["ms_scaling_factor"], seed=0, threads=cores)
     probe = 64 * cores
     t0 = time.perf_counter()
@@ -165,7 +165,8 @@ def main():
     ap.add_argument("--workload", default="hgp_34_n1600", choices=sorted(WORKLOADS))
     ap.add_argument("--shots", type=int, default=1 << 20, help="shots per GPU per step")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--decoder", default="bp", choices=["bp", "ssf"])
+    ap.add_argument("--decoder", default="bp", choices=["bp", "ssf", "bposd"],
+                    help="bposd = BP, then OSD-0 on the shots BP left unconverged")
     ap.add_argument("--p", type=float, default=None)
     ap.add_argument("--max-iter", type=int, default=None)
     ap.add_argument("--bp-method", default=None)
@@ -200,10 +201,13 @@ def main():
     m, n = hz_dec.shape
     nnz = int(hz_dec.nnz)
     q, prior = float(q_vec[0]), float(prior_vec[0])
+    osd = args.decoder == "bposd"
     how = ("small-set-flip (candidate sets = subsets of the X-generator supports)" if ssf else
-           f"BP {opts['bp_method']} alpha={'1-2^-it' if opts['ms_scaling_factor'] == 0 else opts['ms_scaling_factor']} "
+           f"BP{' + OSD-0' if osd else ''} {opts['bp_method']} alpha={'1-2^-it' if opts['ms_scaling_factor'] == 0 else opts['ms_scaling_factor']} "
            f"max_iter={opts['max_iter']} early-exit")
-    metric = "decoded shots/sec (SSF, fixed p)" if ssf else "decoded shots/sec (BP, fixed p and iteration cap)"
+    metric = ("decoded shots/sec (SSF, fixed p)" if ssf else
+              "decoded shots/sec (BP + OSD-0, fixed p and iteration cap)" if osd else
+              "decoded shots/sec (BP, fixed p and iteration cap)")
     dtype = "u32" if ssf else args.precision
     config = {"workload": f"{args.workload}: {family} n={n} m={m} nnz={nnz} k={code.num_logicals}, "
                           f"{'phenomenological faults' if WORKLOADS[args.workload][0].startswith('spacetime:') else 'code capacity'}, "
@@ -248,7 +252,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from exp_ldpc_b200.decoders import Logicals, Sampler, TannerGraph, bp_decoder, row_words, ssf_decoder
+    from exp_ldpc_b200.decoders import Logicals, Sampler, TannerGraph, bp_decoder, bposd_decoder, row_words, ssf_decoder
     graph = TannerGraph(hz_dec, device=local_rank)
     logicals = Logicals(lz_dec, device=local_rank)
     sampler = Sampler(q_vec, n, device=local_rank)
@@ -256,7 +260,7 @@ def main():
         dec = ssf_decoder(graph, code.checks.x)
         cfg = {"kernel": "ssf"}
     else:
-        dec = bp_decoder(graph, channel_probs=prior_vec, precision=args.precision, **opts)
+        dec = (bposd_decoder if osd else bp_decoder)(graph, channel_probs=prior_vec, precision=args.precision, **opts)
         if args.threads or args.slots or args.ctas or args.teams:
             dec.configure(args.threads, args.slots, args.ctas, args.teams)
         cfg = dec.config()
@@ -351,8 +355,8 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": shots * world * e2e_steps / float(tt.item()), "unit": "shots/s",
                "h2d_bytes_per_step": int(shots * ss * 4), "d2h_bytes_per_step": int(shots * (es * 4 + 1 + 4)),
-               "api": f"{'ssf' if ssf else 'bp'}_decoder.decode_batch(packed host syndromes) -> "
-                      f"qd_{'ssf' if ssf else 'bp'}_decode_batch_host", "steps": e2e_steps}
+               "api": f"{args.decoder}_decoder.decode_batch(packed host syndromes) -> qd_{args.decoder}_decode_batch_host",
+               "steps": e2e_steps}
 
     if rank != 0:
         if world > 1:
@@ -408,7 +412,7 @@ def main():
     line = {"metric": metric, "value": value, "unit": "shots/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-            "config": config, "e2e": e2e, "gpu_launches": args.steps, "clocks": clk, "roofline": roofline,
+            "config": config, "e2e": e2e, "gpu_launches": args.steps * (2 if osd else 1), "clocks": clk, "roofline": roofline,
             "roofline_smem": roofline_smem, "cpu_baseline": cpu,
             "counters": {"failures": int(cnt[0]), "shots": int(cnt[1]), "non_converged": int(cnt[2]),
                          "iterations": int(cnt[3])},

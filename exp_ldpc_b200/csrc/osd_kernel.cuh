@@ -14,9 +14,9 @@
 //   * one CTA per shot; the augmented matrix [H | s] lives bit-packed in shared memory (m rows of
 //     ceil((n+1)/64) 64-bit words);
 //   * ranking = bitonic sort of (order-preserving 64-bit image of the key, column index);
-//   * per ranked column: one ballot pass collects the rows that hold the column's bit, warp 0
-//     picks the first such row that is not a pivot yet, then the warps XOR the pivot row into the
-//     other marked rows (Gauss-Jordan), one row per warp at a time, one 64-bit word per lane;
+//   * per ranked column: every thread looks at the column's bit in the rows it owns, the first such
+//     row that is not a pivot yet becomes the pivot (warp shuffle + one barrier), and every owner
+//     XORs the pivot row into its marked rows (Gauss-Jordan); one barrier per column;
 //   * stops after rank(H) pivots (computed once on the host).
 // Integer only => bit-identical to the oracle.
 #pragma once
@@ -61,7 +61,7 @@ __host__ __device__ inline OsdSmemLayout osd_smem_layout(int m, int W, int P, in
     return L;
 }
 
-__global__ void __launch_bounds__(512, 1) osd0_kernel(const OsdParams p)
+__global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = (int)threadIdx.x, NT = (int)blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(512, 1) osd0_kernel(const OsdParams p)
     uint16_t *pcol = reinterpret_cast<uint16_t *>(smem_raw + L.pcol);
     uint32_t *dec = reinterpret_cast<uint32_t *>(smem_raw + L.dec);
     __shared__ long long sh_shot;
-    __shared__ int sh_piv;
+    __shared__ int cand[64];
     const int W = p.W, m = p.m, n = p.n;
     long long c_delta = 0;                                    // thread 0: change of the failure count
 
@@ -139,49 +139,43 @@ __global__ void __launch_bounds__(512, 1) osd0_kernel(const OsdParams p)
         }
         __syncthreads();
 
-        // ---- 3. Gauss-Jordan over the ranked columns
-        const int m32 = (m + 31) & ~31;
+        // ---- 3. Gauss-Jordan over the ranked columns.  A thread owns rows tid, tid + NT, ...: it alone writes
+        // them, so one barrier per column (between choosing the pivot and using it) orders everything:
+        //   own bit of column c -> per-warp candidate (first unused row holding the bit) -> barrier ->
+        //   pivot = min over the warps -> every owner XORs the pivot row into its marked rows.
+        // cand[] is double-buffered by column parity, so a warp that runs ahead never overwrites it early.
         int rank = 0;
+        unsigned myused = 0u;                                    // bit q: row tid + q * NT is a pivot row
         for (int t = 0; t < n && rank < p.rank; ++t) {
             const int c = idx[t];
             const int cw = c >> 6, cb = c & 63;
-            for (int r0 = warp * 32; r0 < m32; r0 += nwarps * 32) {
-                const int r = r0 + lane;
-                const unsigned bit = r < m ? (unsigned)((R[(size_t)r * W + cw] >> cb) & 1ULL) : 0u;
-                const unsigned mask = __ballot_sync(0xffffffffu, bit);
-                if (lane == 0) rowmask[r0 >> 5] = mask;
+            unsigned mybits = 0u;
+            int first = 0x7fffffff;
+            for (int q = 0, r = tid; r < m; ++q, r += NT) {
+                const unsigned bit = (unsigned)((R[(size_t)r * W + cw] >> cb) & 1ULL);
+                mybits |= bit << q;
+                if (bit && !((myused >> q) & 1u)) first = min(first, r);
             }
-            __syncthreads();
-            if (warp == 0) {
-                int best = 0x7fffffff;
-                for (int w = lane; w < p.nwm; w += 32) {
-                    const uint32_t cand = rowmask[w] & ~used[w];
-                    if (cand) { best = min(best, w * 32 + __ffs(cand) - 1); break; }
-                }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-                if (lane == 0) {
-                    sh_piv = best == 0x7fffffff ? -1 : best;
-                    if (best != 0x7fffffff) { used[best >> 5] |= 1u << (best & 31); pcol[best] = (uint16_t)c; }
-                }
-            }
+            for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+            int *cd = cand + (t & 1) * 32;
+            if (lane == 0) cd[warp] = first;
             __syncthreads();
-            const int piv = sh_piv;
-            if (piv < 0) continue;                               // dependent on the columns ranked before it
+            int piv = lane < nwarps ? cd[lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) piv = min(piv, __shfl_xor_sync(0xffffffffu, piv, o));
+            if (piv == 0x7fffffff) continue;                    // dependent on the columns ranked before it
             ++rank;
             const unsigned long long *prow = R + (size_t)piv * W;
-            for (int w = warp; w < p.nwm; w += nwarps) {
-                uint32_t mask = rowmask[w];
-                if ((piv >> 5) == w) mask &= ~(1u << (piv & 31));
-                while (mask) {
-                    const int r = w * 32 + __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    unsigned long long *row = R + (size_t)r * W;
-                    for (int j = lane; j < W; j += 32) row[j] ^= prow[j];
-                }
+            for (int q = 0, r = tid; r < m; ++q, r += NT) {
+                if (r == piv) { myused |= 1u << q; pcol[r] = (uint16_t)c; continue; }
+                if (!((mybits >> q) & 1u)) continue;
+                unsigned long long *row = R + (size_t)r * W;
+#pragma unroll 4
+                for (int j = 0; j < W; ++j) row[j] ^= prow[j];
             }
-            __syncthreads();
         }
+        __syncthreads();
 
         // ---- 4. solution on the information set
         for (int w = tid; w < p.nwn; w += NT) dec[w] = 0u;

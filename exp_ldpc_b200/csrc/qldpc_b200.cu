@@ -1142,7 +1142,7 @@ extern "C" int qd_osd_create(qd_graph *g, qd_osd **out)
     int rc = use_device(g->device);
     if (rc) return rc;
     const GraphDev &gd = g->dev;
-    if (gd.n >= 65535) return fail(QD_EUNSUP, "OSD: more than 65534 columns");
+    if (gd.n > 8000) return fail(QD_EUNSUP, "OSD: more than 8000 columns");
     std::unique_ptr<qd_osd> o(new qd_osd);
     o->g = g; o->device = g->device;
     o->W = ((gd.n + 1 + 63) / 64) | 1;      // odd row pitch (in 64-bit words): column reads are bank-conflict free
@@ -1190,7 +1190,7 @@ static int osd_launch(qd_osd *o, int negate_key, const uint32_t *d_synd, int32_t
     QD_CUDA(cudaFuncSetAttribute(osd0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->smem));
     QD_CUDA(cudaMemsetAsync(p.next_shot, 0, sizeof(unsigned long long), st));
     int per_sm = 0;
-    const int threads = g.m >= 256 ? 512 : 256;
+    const int threads = g.m > 512 ? 1024 : (g.m > 256 ? 512 : 256);          // about one row per thread
     QD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, osd0_kernel, threads, o->smem));
     per_sm = std::max(1, per_sm);
     const unsigned grid = (unsigned)std::min<long long>((long long)o->g->sm_count * per_sm, shots);
