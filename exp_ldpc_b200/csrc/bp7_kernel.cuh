@@ -38,6 +38,7 @@ struct Bp7Params {
     int m, n, nwm, nwn;
     int m32;                    // rows rounded up to a multiple of 32
     int lines;                  // 128-byte message lines per slot
+    int off_flags, off_table, off_out, off_ctl;   // shared-memory carve-up (bp7_smem_layout), bytes
     int nrec;                   // column records (degree classes padded to multiples of 32)
     int max_iter;
     int staged;                 // record table copied to shared memory
@@ -213,11 +214,11 @@ __device__ __forceinline__ void col_ld(const uint32_t (&ea)[VMAX], real (&cv)[D]
     for (int t = 0; t < D; ++t) cv[t] = lds_off<s * 128>(ea[t], real());
 }
 
-struct Bp7LlrOut { double *llr; const uint16_t *col_id; int n; int raw; };
+struct Bp7LlrOut { double *llr; const uint16_t *col_id; int n; int raw; unsigned want; const long long *shot; };
 
 template <typename real, int METHOD, int D, int VMAX, int S, int FB, int s>
 __device__ __forceinline__ void col_cs(const uint32_t (&ea)[VMAX], const uint32_t (&fa)[VMAX], real (&cv)[D], real pj, int i,
-                                       unsigned &decbits, const Bp7LlrOut &lo, int r, long long shot)
+                                       unsigned &decbits, const Bp7LlrOut &lo, int r)
 {
     using A = Ar<real>;
     const int bi = i * S + s;
@@ -231,10 +232,10 @@ __device__ __forceinline__ void col_cs(const uint32_t (&ea)[VMAX], const uint32_
         for (int t = 0; t < D; ++t) sts_u8_off<s * FB>(fa[t], 1u);
     }
     decbits ^= flip << bi;
-    if (lo.llr && shot >= 0) {
+    if (lo.llr && ((lo.want >> s) & 1u)) {                   // rare: soft output requested for this slot and pass
         const unsigned col = lo.col_id[r];
         if (col != 0xFFFFu)
-            lo.llr[shot * (long long)lo.n + col] =
+            lo.llr[lo.shot[s] * (long long)lo.n + col] =
                 (METHOD == QD_BP_MIN_SUM_K || lo.raw) ? (double)soft : (double)A::lg(A::div((real)1, soft));
     }
 }
@@ -242,12 +243,12 @@ __device__ __forceinline__ void col_cs(const uint32_t (&ea)[VMAX], const uint32_
 // all slots of one column record of compile-time degree D
 template <typename real, int METHOD, int D, int VMAX, int S, int FB>
 __device__ __forceinline__ void col_update(const uint32_t (&ea)[VMAX], const uint32_t (&fa)[VMAX], real pj, int i, unsigned run,
-                                           unsigned &decbits, const Bp7LlrOut &lo, int r, const long long (&shot_of)[S])
+                                           unsigned &decbits, const Bp7LlrOut &lo, int r)
 {
     constexpr unsigned SMASK = (1u << S) - 1u;
     real ca[D], cb[D], cc[D];
 #define QD_LD(n, buf) col_ld<real, D, VMAX, (n) % S>(ea, buf)
-#define QD_CS(n, buf) col_cs<real, METHOD, D, VMAX, S, FB, (n) % S>(ea, fa, buf, pj, i, decbits, lo, r, shot_of[(n) % S])
+#define QD_CS(n, buf) col_cs<real, METHOD, D, VMAX, S, FB, (n) % S>(ea, fa, buf, pj, i, decbits, lo, r)
     if (run == SMASK) {                                  // three buffers: two slots of loads in flight
         QD_LD(0, ca);
         if (S > 1) QD_LD(1, cb);
@@ -294,17 +295,19 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = (int)threadIdx.x, NT = (int)blockDim.x, lane = tid & 31;
 
-    const Bp7SmemLayout L = bp7_smem_layout(p.m, p.nrec, p.nwn, p.lines, RD, VMAX, S, RB, p.staged != 0);
-    const uint32_t a_msg = smem_u32(smem_raw + L.msg), a_flags = smem_u32(smem_raw + L.flags),
-                   a_tab = smem_u32(smem_raw + L.table);
-    uint32_t *outbits = reinterpret_cast<uint32_t *>(smem_raw + L.out);          // [S][nwn]
-    Bp7Ctl *ctl = reinterpret_cast<Bp7Ctl *>(smem_raw + L.ctl);
+    // shared-memory carve-up comes from the host (bp7_smem_layout); the three hot base addresses are made
+    // opaque so that they live in registers instead of being re-derived inside the loops
+    uint32_t a_msg = smem_u32(smem_raw), a_flags = a_msg + (uint32_t)p.off_flags, a_tab = a_msg + (uint32_t)p.off_table;
+    asm volatile("" : "+r"(a_msg), "+r"(a_flags), "+r"(a_tab));
+    uint32_t *outbits = reinterpret_cast<uint32_t *>(smem_raw + p.off_out);      // [S][nwn]
+    Bp7Ctl *ctl = reinterpret_cast<Bp7Ctl *>(smem_raw + p.off_ctl);
+    const int max_iter = p.max_iter;
     const real *prior_rec = static_cast<const real *>(p.prior_rec);
     const real alpha_fixed = (real)p.alpha_fixed;
     const bool staged = p.staged != 0;
 
     if (staged) {
-        uint4 *st = reinterpret_cast<uint4 *>(smem_raw + L.table);
+        uint4 *st = reinterpret_cast<uint4 *>(smem_raw + p.off_table);
         for (int i = tid; i < p.nrec * (VMAX / 4); i += NT) st[i] = p.table[i];
     }
     if (tid < S) {
@@ -404,7 +407,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
             int born[S];
             unsigned act = 0u;
 #pragma unroll
-            for (int s = 0; s < S; ++s) { born[s] = ctl->born[s]; act |= (born[s] != BP_IDLE ? 1u : 0u) << s; }
+            for (int s = 0; s < S; ++s) { born[s] = ctl->born[s]; act |= (unsigned)(born[s] != BP_IDLE) << s; }
             unsigned un = 0u;
             int i = 0;
             for (int c = tid; c < p.m32; c += NT, ++i) {
@@ -462,7 +465,9 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
 #pragma unroll
             for (int s = 0; s < S; ++s) {
                 const int b = ctl->born[s], it = T - b - 1;
-                done |= (b != BP_IDLE && it >= 1 && (!((unsat >> s) & 1u) || it >= p.max_iter) ? 1u : 0u) << s;
+                const unsigned fin = (unsigned)(b != BP_IDLE) & (unsigned)(it >= 1) &
+                                     ((~(unsat >> s) & 1u) | (unsigned)(it >= max_iter));
+                done |= fin << s;
             }
             if (done) {
                 // hard decisions of the finished slots, back in column order
@@ -530,23 +535,24 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
 
         // ================================================================== bit pass
         {
-            unsigned run = 0u;
-            long long shot_of[S];
+            unsigned run = 0u, want = 0u;        // slots to update; slots whose soft output is written in this pass
 #pragma unroll
             for (int s = 0; s < S; ++s) {
                 const int b = ctl->born[s];
-                run |= (b != BP_IDLE && b != T ? 1u : 0u) << s;
-                // soft output of this slot wanted in this pass?  (mode 1: only the iteration that hits the cap)
-                shot_of[s] = p.llr && b != BP_IDLE && (p.llr_mode == 0 || T - b == p.max_iter) ? ctl->shot[s] : -1;
+                const unsigned on = (unsigned)(b != BP_IDLE) & (unsigned)(b != T);
+                run |= on << s;
+                // mode 1: only the iteration that hits the cap
+                want |= (on & ((unsigned)(p.llr_mode == 0) | (unsigned)(T - b == max_iter))) << s;
             }
+            if (!p.llr) want = 0u;
             int i = 0;
             for (int r = tid; r < p.nrec; r += NT, ++i) {
                 uint32_t ea[VMAX], fa[VMAX];
                 load_record(r, ea, fa);
                 const real pj = prior_of(r);
                 const int deg = __shfl_sync(0xffffffffu, (int)__ldg(p.chunk_deg + (r >> 5)), 0);
-                const Bp7LlrOut lo{p.llr, p.col_id, p.n, p.llr_mode};
-#define QD_COL(D_) col_update<real, METHOD, (D_), VMAX, S, FB>(ea, fa, pj, i, run, decbits, lo, r, shot_of)
+                const Bp7LlrOut lo{want ? p.llr : nullptr, p.col_id, p.n, p.llr_mode, want, ctl->shot};
+#define QD_COL(D_) col_update<real, METHOD, (D_), VMAX, S, FB>(ea, fa, pj, i, run, decbits, lo, r)
                 switch (deg) {
                 case 1: QD_COL(1); break;
                 case 2: QD_COL(2); break;

@@ -918,6 +918,11 @@ static int bp_launch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int6
         q.m32 = (g.m + 31) / 32 * 32;
         q.nrec = d->v7_nrec;
         q.lines = d->v7_lines;
+        {
+            const Bp7SmemLayout SL = bp7_smem_layout(g.m, d->v7_nrec, g.nwn, d->v7_lines, d->rd, d->vmax, d->slots,
+                                                     d->precision == QD_PREC_F64 ? 8 : 4, d->v7_staged != 0);
+            q.off_flags = (int)SL.flags; q.off_table = (int)SL.table; q.off_out = (int)SL.out; q.off_ctl = (int)SL.ctl;
+        }
         q.row_table = d->d7_row_table.as<uint4>();
         q.max_iter = d->max_iter;
         q.staged = d->v7_staged;

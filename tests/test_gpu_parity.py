@@ -455,3 +455,37 @@ def test_bposd_decoder_duck_type(gpu, code225):
         bposd_decoder(hz, error_rate=0.03, osd_method="osd_cs", osd_order=7)
     corr, conv, its = dec.decode_batch(np.zeros((3, hz.shape[0])))
     assert not corr.any() and conv.all()
+
+
+# ---------------------------------------------------------------------------------------------
+# statistical bar of the north star: logical error rate inside the oracle's 95 % binomial interval
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("p", [0.01, 0.02, 0.035])
+def test_f32_logical_error_rate_within_oracle_confidence_interval(gpu, code225, p):
+    """fp32 BP is not bit-reproducible; its LER must still fall inside the 95 % interval of the
+    fp64 reference-order decoder on the same shots (and the fp64 GPU path must equal the oracle)."""
+    from exp_ldpc_b200.experiment import CodeCapacityExperiment, binomial_ci
+    from oracle import pyoracle as po
+    q, prior = 2 * p / 3 + p - 4 / 3 * p * p, 2 * p / 3
+    shots = 20000
+    opts = dict(max_iter=32, bp_method="ms", ms_scaling_factor=0.625)
+    ref = po.run_code_capacity(code225.checks.z, code225.logicals.z, q, prior, decoder="bp", seed=8, shots=shots, **opts)
+    f64 = CodeCapacityExperiment(code225, q, prior, "bp", opts, precision="f64").run(shots, seed=8)
+    f32 = CodeCapacityExperiment(code225, q, prior, "bp", opts, precision="f32").run(shots, seed=8)
+    assert f64["failures"] == ref["failures"] and f64["non_converged"] == ref["non_converged"]
+    lo, hi = binomial_ci(ref["failures"], shots)
+    assert lo <= f32["failures"] / shots <= hi, (f32["failures"], ref["failures"], lo, hi)
+
+
+def test_p_sweep_rows_match_oracle_counts(gpu, code225):
+    """p_sweep (python/qldpc/misc/p_sweep.py:17-40) on one GPU: per-p failure counts equal the oracle's."""
+    from exp_ldpc_b200.experiment import depolarizing_noise, p_sweep
+    from oracle import pyoracle as po
+    opts = dict(max_iter=20, bp_method="ms", ms_scaling_factor=0.0)
+    ps = [0.01, 0.03]
+    df = p_sweep(3000, ps, depolarizing_noise, lambda p: {"p": p, "pm": p}, lambda p, x, z: 2 * p / 3,
+                 lambda p, x, z: 2 * p / 3, code=code225, rounds=0, decoder_mode="bp", bp_osd_options=opts, seed=4)
+    for row, p in zip(df.itertuples(), ps):
+        q = 2 * p / 3 + p - 4 / 3 * p * p
+        ref = po.run_code_capacity(code225.checks.z, code225.logicals.z, q, 2 * p / 3, decoder="bp", seed=4, shots=3000, **opts)
+        assert (row.failures, row.samples, row.non_converged) == (ref["failures"], 3000, ref["non_converged"])
