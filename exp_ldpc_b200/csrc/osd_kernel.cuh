@@ -166,13 +166,23 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
             for (int o = 16; o > 0; o >>= 1) piv = min(piv, __shfl_xor_sync(0xffffffffu, piv, o));
             if (piv == 0x7fffffff) continue;                    // dependent on the columns ranked before it
             ++rank;
-            const unsigned long long *prow = R + (size_t)piv * W;
+            // W is even and W/2 odd: rows are 16-byte aligned and the 128-bit accesses of a quarter-warp fall
+            // into different banks.  Zero words of the pivot row are skipped (warp-uniform test): the matrix
+            // starts sparse and fills in only gradually.
+            const ulonglong2 *prow = reinterpret_cast<const ulonglong2 *>(R + (size_t)piv * W);
             for (int q = 0, r = tid; r < m; ++q, r += NT) {
                 if (r == piv) { myused |= 1u << q; pcol[r] = (uint16_t)c; continue; }
                 if (!((mybits >> q) & 1u)) continue;
-                unsigned long long *row = R + (size_t)r * W;
-#pragma unroll 4
-                for (int j = 0; j < W; ++j) row[j] ^= prow[j];
+                ulonglong2 *row = reinterpret_cast<ulonglong2 *>(R + (size_t)r * W);
+#pragma unroll 3
+                for (int j = 0; j < W / 2; ++j) {
+                    const ulonglong2 pv = prow[j];
+                    if (pv.x | pv.y) {
+                        ulonglong2 v = row[j];
+                        v.x ^= pv.x; v.y ^= pv.y;
+                        row[j] = v;
+                    }
+                }
             }
         }
         __syncthreads();

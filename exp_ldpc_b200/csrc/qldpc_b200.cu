@@ -1150,7 +1150,8 @@ extern "C" int qd_osd_create(qd_graph *g, qd_osd **out)
     if (gd.n > 8000) return fail(QD_EUNSUP, "OSD: more than 8000 columns");
     std::unique_ptr<qd_osd> o(new qd_osd);
     o->g = g; o->device = g->device;
-    o->W = ((gd.n + 1 + 63) / 64) | 1;      // odd row pitch (in 64-bit words): column reads are bank-conflict free
+    o->W = (gd.n + 1 + 63) / 64;
+    while (o->W % 4 != 2) ++o->W;           // rows of an odd number of 16-byte units: aligned, bank-conflict free 128-bit XORs
     o->P = 1;
     while (o->P < gd.n) o->P <<= 1;
     o->smem = osd_smem_layout(gd.m, o->W, o->P, gd.nwm, gd.nwn).total;
