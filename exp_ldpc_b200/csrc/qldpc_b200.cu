@@ -107,6 +107,31 @@ __global__ void logical_fail_kernel(const uint32_t *__restrict__ lzT, int k, int
     }
 }
 
+// dst[s] (^)= bits [bit_offset, bit_offset + nbits) of src[s]; one thread per destination word.
+// The building block of the multi-round recipes: correction fold (spacetime_code.py:81-84),
+// syndrome history (spacetime_code.py:98-119 read backwards), data part of a single-shot decoding
+// (spacetime_code.py:31-33).
+__global__ void bits_extract_kernel(const uint32_t *__restrict__ src, int sstride, long long shots, long long bit_offset,
+                                    int nbits, uint32_t *__restrict__ dst, int dstride, int accumulate)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= shots * dstride) return;
+    const long long s = idx / dstride;
+    const int w = (int)(idx - s * dstride);
+    uint32_t v = 0u;
+    if (w * 32 < nbits) {
+        const uint32_t *row = src + s * (long long)sstride;
+        const long long b0 = bit_offset + (long long)w * 32;
+        const int sw = (int)(b0 >> 5), sh = (int)(b0 & 31);
+        const uint32_t lo = row[sw];
+        const uint32_t hi = (sh && sw + 1 < sstride) ? row[sw + 1] : 0u;
+        v = sh ? __funnelshift_r(lo, hi, sh) : lo;
+        const int rem = nbits - w * 32;
+        if (rem < 32) v &= (1u << rem) - 1u;
+    }
+    dst[idx] = accumulate ? dst[idx] ^ v : v;
+}
+
 // =============================================================================================
 // host-side handles
 // =============================================================================================
@@ -449,6 +474,19 @@ extern "C" int qd_sampler_run(qd_sampler *s, uint64_t seed, uint32_t stream_id, 
     const long long items = (long long)shots * stride;
     sample_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(
         s->d_thr.as<uint32_t>(), s->nbits, nw, (uint32_t)seed, (uint32_t)(seed >> 32), stream_id, shot0, shots, d_bits, stride);
+    QD_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int qd_bits_extract_batch(const uint32_t *d_src, int32_t src_stride, int64_t shots, int64_t bit_offset,
+                                     int32_t nbits, uint32_t *d_dst, int32_t dst_stride, int32_t accumulate, void *stream)
+{
+    if (!d_src || !d_dst || shots < 0 || bit_offset < 0 || nbits < 0) return fail(QD_EINVAL, "bad bits_extract_batch arguments");
+    if ((bit_offset + nbits + 31) / 32 > src_stride || (nbits + 31) / 32 > dst_stride) return fail(QD_EINVAL, "stride too small");
+    if (shots == 0) return 0;
+    const long long items = (long long)shots * dst_stride;
+    bits_extract_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(d_src, src_stride, shots, bit_offset, nbits,
+                                                                                d_dst, dst_stride, accumulate);
     QD_CUDA(cudaGetLastError());
     return 0;
 }

@@ -12,9 +12,10 @@ columns), with
   ``all_reduce(SUM)`` of ``int64[4] = {failures, shots, non_converged, iterations}`` per p-value.
 
 Supported ``decoder_mode``: ``'bp'`` (the first, pure-BP stage of the reference's
-``bposd_hybrid``; prior on every bit = ``data_prior``) and ``'ssf'``.  The OSD-based modes of the
-reference need the OSD post-processor, which is a "next" row; they raise
-``NotImplementedError`` rather than silently decoding differently.
+``bposd_hybrid``), ``'bposd'``, ``'bposd_hybrid'``, ``'bposd_single_shot'`` (OSD = OSD-0; the
+reference's default ``osd_cs`` of order 7 raises ``NotImplementedError``) and ``'ssf'`` (rounds = 0).
+For ``rounds > 0`` the faults are phenomenological (:class:`StorageExperiment`); ``'bpd_detector'``
+needs a Stim detector error model and raises ``NotImplementedError``.
 """
 from __future__ import annotations
 
@@ -30,7 +31,7 @@ from . import _lib
 from .codes import QuantumCode
 from .decoders import Logicals, Sampler, TannerGraph, bp_decoder, bposd_decoder, row_words, ssf_decoder, unpack_bits
 
-__all__ = ["depolarizing_noise", "NoiseModel", "CodeCapacityExperiment", "SpacetimeExperiment", "run_simulation", "p_sweep",
+__all__ = ["depolarizing_noise", "NoiseModel", "CodeCapacityExperiment", "SpacetimeExperiment", "StorageExperiment", "run_simulation", "p_sweep",
            "shard_range", "binomial_ci"]
 
 
@@ -173,17 +174,22 @@ class SpacetimeExperiment(CodeCapacityExperiment):
 
 def run_simulation(samples, code, meas_prior, data_prior, noise_model, noise_model_args, bp_osd_options, rounds,
                    decoder_mode, seed: int = 0, shot0: int = 0, device: int = 0, precision: str = "f64"):
-    """``run_simulation`` of ``_experiment.py:154-210`` for the code-capacity path (``rounds = 0``).
+    """``run_simulation`` of ``_experiment.py:154-210``: ``rounds = 0`` is the code-capacity circuit
+    under ``noise_model``; ``rounds > 0`` runs the multi-round recipes on phenomenological faults.
     Returns ``list[bool]``: the logical-failure flag of every shot."""
-    if rounds != 0:
-        raise NotImplementedError("multi-round storage simulation needs the circuit sampler (SURVEY.md §8 f2)")
     checks = code.checks
     x_steps = int(max(checks.x.sum(axis=0).max(), checks.x.sum(axis=1).max()))   # _experiment.py:160-161
     z_steps = int(max(checks.z.sum(axis=0).max(), checks.z.sum(axis=1).max()))
     nm = noise_model(**noise_model_args)
-    _ = meas_prior(x_steps, z_steps)
-    prior = data_prior(x_steps, z_steps)
-    exp = CodeCapacityExperiment(code, nm.code_capacity_flip_probability(), prior, decoder_mode, bp_osd_options,
+    mprior = meas_prior(x_steps, z_steps)
+    dprior = data_prior(x_steps, z_steps)
+    if rounds != 0:
+        # multi-round: phenomenological faults at the priors' rates (see StorageExperiment); the
+        # circuit-level sampler behind `noise_model` is SURVEY.md §8 f2
+        exp = StorageExperiment(code, rounds, dprior, mprior, decoder_mode, bp_osd_options, device=device, precision=precision)
+        res = exp.run(int(samples), seed=seed, shot0=shot0, per_shot=True)
+        return [bool(v) for v in res["fail"]]
+    exp = CodeCapacityExperiment(code, nm.code_capacity_flip_probability(), dprior, decoder_mode, bp_osd_options,
                                  device=device, precision=precision)
     res = exp.run(int(samples), seed=seed, shot0=shot0, per_shot=True)
     return [bool(v) for v in res["fail"]]
@@ -207,14 +213,16 @@ def p_sweep(samples, p_values, noise_model, noise_model_args, meas_prior, data_p
     world, rank = (dist.get_world_size(group), dist.get_rank(group)) if dist.is_available() and dist.is_initialized() else (1, 0)
     if device is None:
         device = torch.cuda.current_device() if torch.cuda.is_available() else 0
-    if rounds != 0:
-        raise NotImplementedError("multi-round storage simulation needs the circuit sampler (SURVEY.md §8 f2)")
     lo, hi = shard_range(int(samples), rank, world)
     rows = []
     for p_ph in p_values:
         t0 = time.time()
         nm = noise_model(**noise_model_args(p_ph))
-        if shard_runner is None:
+        if shard_runner is None and rounds != 0:
+            exp = StorageExperiment(code, rounds, data_prior(p_ph, 0, 0), meas_prior(p_ph, 0, 0), decoder_mode,
+                                    bp_osd_options, device=device, precision=precision)
+            res = exp.run(hi - lo, seed=seed, shot0=lo) if hi > lo else dict(failures=0, shots=0, non_converged=0, iters_total=0)
+        elif shard_runner is None:
             exp = CodeCapacityExperiment(code, nm.code_capacity_flip_probability(), data_prior(p_ph, 0, 0), decoder_mode,
                                          bp_osd_options, device=device, precision=precision)
             res = exp.run(hi - lo, seed=seed, shot0=lo)
@@ -296,7 +304,8 @@ def p_sweep_main(noise_model_args, noise_model, meas_prior, data_prior, argv=Non
                         help='lower and upper bounds of the sweep + number of points in the form (lower, upper, points)')
     parser.add_argument('--rounds', type=int, help='Number of rounds of syndrome extraction', default=0)
     parser.add_argument('--decoder_mode', default='bp',
-                        choices=['bp', 'ssf', 'bposd', 'bposd_single_shot', 'bposd_hybrid', 'bpd_detector'])
+                        choices=['bp', 'ssf', 'bposd', 'bposd_single_shot', 'bposd_hybrid', 'bpd_detector'],
+                        help="OSD-based modes need --bposd_osd_method osd0")
     parser.add_argument('--linspace', type=bool, default=False,
                         help='linearly spaced points (default: uniform spacing in log space)')
     parser.add_argument('--precision', default='f64', choices=['f64', 'f32'])
@@ -319,3 +328,140 @@ def p_sweep_main(noise_model_args, noise_model, meas_prior, data_prior, argv=Non
     if dist.is_initialized():
         dist.destroy_process_group()
     return result
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-round decoder recipes of the reference, on the device, phenomenological faults
+# ---------------------------------------------------------------------------------------------
+class StorageExperiment:
+    """The ``readout_correction`` recipes of ``python/qldpc/misc/_experiment.py`` as device pipelines:
+
+    ``bp``                 BP on the spacetime matrix, fold                     (first stage of the hybrid)
+    ``bposd``              BP+OSD on the spacetime matrix, fold                 (``BPOSDCorrect``, ``:62-83``)
+    ``bposd_hybrid``       BP on the spacetime matrix, fold, correct the readout, BP+OSD on H
+                                                                                (``BPOSDHybridCorrect``, ``:85-126``)
+    ``bposd_single_shot``  for every round: BP+OSD on ``[H | I]`` with the syndrome of the running
+                           correction added, then BP+OSD on H for the readout
+                                                                                (``BPOSDCorrectSingleShot``, ``:12-60``)
+
+    Faults are phenomenological: every column of ``SpacetimeCode(Hz, rounds)`` (data faults per round,
+    measurement faults per round) flips independently with its prior.  From the fault vector f the
+    quantities the reference slices out of a Stim record follow: data readout = XOR of the data
+    blocks of f; measured syndrome of round t = XOR of the first t+1 blocks of ``H_st f`` (the
+    reference differences the history, ``spacetime_code.py:113-117``; this undoes it).  Circuit-level
+    sampling needs the Pauli-frame simulator.  OSD means OSD-0.
+
+    Everything between the sampler and the failure flags runs on the GPU through the C ABI; torch
+    only owns the buffers."""
+
+    MODES = ("bp", "bposd", "bposd_hybrid", "bposd_single_shot")
+
+    def __init__(self, code: QuantumCode, rounds: int, data_prior: float, meas_prior: float, decoder_mode: str,
+                 bp_osd_options: Optional[Dict] = None, device: int = 0, precision: str = "f64"):
+        from .spacetime import SpacetimeCode, SpacetimeCodeSingleShot
+        if decoder_mode not in self.MODES:
+            if decoder_mode == "bpd_detector":
+                raise NotImplementedError("decoder_mode 'bpd_detector' needs a Stim detector error model (SURVEY.md §8 f2)")
+            raise RuntimeError("Unknown decoder operation mode")   # _experiment.py:189
+        opts = dict(bp_osd_options or {})
+        kw = dict(max_iter=opts.get("max_iter", 0), bp_method=opts.get("bp_method", "ps"),
+                  ms_scaling_factor=opts.get("ms_scaling_factor", 0.0), precision=precision, device=device)
+        okw = dict(osd_method=opts.get("osd_method", "osd0"), osd_order=opts.get("osd_order", 0))
+        self.code, self.mode, self.device, self.T = code, decoder_mode, int(device), int(rounds)
+        hz = code.checks.z
+        self.m, self.n = hz.shape
+        T, m, n = self.T, self.m, self.n
+        self.spacetime = SpacetimeCode(hz, T)
+        h_st = self.spacetime.spacetime_check_matrix
+        self.prior_st = np.concatenate([np.full((T + 1) * n, float(data_prior)), np.full(T * m, float(meas_prior))])
+        self.g_st = TannerGraph(h_st, device)
+        self.g_h = TannerGraph(hz, device)
+        self.sampler = Sampler(self.prior_st, h_st.shape[1], device)
+        self.logicals = Logicals(code.logicals.z, device)
+        self.dec_st = self.dec_h = self.dec_ss = None
+        if decoder_mode == "bp":
+            self.dec_st = bp_decoder(self.g_st, channel_probs=self.prior_st, **kw)
+        elif decoder_mode == "bposd":
+            self.dec_st = bposd_decoder(self.g_st, channel_probs=self.prior_st, **kw, **okw)
+        elif decoder_mode == "bposd_hybrid":
+            self.dec_st = bp_decoder(self.g_st, channel_probs=self.prior_st, **kw)
+            self.dec_h = bposd_decoder(self.g_h, error_rate=float(data_prior), **kw, **okw)
+        else:
+            h_ss = SpacetimeCodeSingleShot(hz).spacetime_check_matrix
+            self.g_ss = TannerGraph(h_ss, device)
+            self.prior_ss = np.concatenate([np.full(n, float(data_prior)), np.full(m, float(meas_prior))])
+            self.dec_ss = bposd_decoder(self.g_ss, channel_probs=self.prior_ss, **kw, **okw)
+            self.dec_h = bposd_decoder(self.g_h, error_rate=float(data_prior), **kw, **okw)
+
+    # ---- small helpers over packed device buffers
+    def _extract(self, src, bit_offset, nbits, dst, accumulate):
+        _lib.check(_lib.lib().qd_bits_extract_batch(_lib.ptr(src), src.shape[1], src.shape[0], int(bit_offset), int(nbits),
+                                                    _lib.ptr(dst), dst.shape[1], int(accumulate), self._stream))
+
+    def _fold(self, faults, dst, accumulate=False):
+        """``final_correction``: XOR of the T+1 data blocks (``spacetime_code.py:81-84``)."""
+        for t in range(self.T + 1):
+            self._extract(faults, t * self.n, self.n, dst, accumulate or t > 0)
+
+    def run(self, shots: int, seed: int = 0, shot0: int = 0, per_shot: bool = False) -> dict:
+        import torch
+        dev = torch.device(f"cuda:{self.device}")
+        torch.cuda.set_device(dev)
+        self._stream = torch.cuda.current_stream().cuda_stream
+        T, m, n = self.T, self.m, self.n
+        ncol = (T + 1) * n + T * m
+        wf, ws, wn, wm = row_words(ncol), row_words((T + 1) * m), row_words(n), row_words(m)
+        buf = lambda w, dt=torch.int32: torch.zeros((shots, w), dtype=dt, device=dev)   # noqa: E731
+        faults, sigma, fhat = buf(wf), buf(ws), buf(wf)
+        readout, corr = buf(wn), buf(wn)
+        conv = torch.zeros(shots, dtype=torch.uint8, device=dev)
+        its = torch.zeros(shots, dtype=torch.int32, device=dev)
+        fail = torch.zeros(shots, dtype=torch.uint8, device=dev)
+        st = self._stream
+        self.sampler.run_device(seed, 0, shot0, shots, faults, wf, st)
+        self.g_st.syndrome_batch_device(faults, wf, shots, sigma, ws, st)
+        self._fold(faults, readout)                                   # the data readout of the storage experiment
+        iters_total = torch.zeros((), dtype=torch.int64, device=dev)
+        if self.mode in ("bp", "bposd"):
+            self.dec_st.decode_batch_device(sigma, ws, shots, fhat, wf, conv, its, stream=st)
+            self._fold(fhat, corr)
+            self.logicals.fail_batch_device(readout, corr, wn, shots, fail, None, st)
+            iters_total += its.sum()
+        elif self.mode == "bposd_hybrid":
+            self.dec_st.decode_batch_device(sigma, ws, shots, fhat, wf, conv, its, stream=st)
+            iters_total += its.sum()
+            first = buf(wn)
+            self._fold(fhat, first)                                   # final_round_bp_correction
+            self._extract(first, 0, n, readout, True)                 # data_readout ^= it
+            s2, c2 = buf(wm), buf(wn)
+            self.g_h.syndrome_batch_device(readout, wn, shots, s2, wm, st)
+            conv2 = torch.zeros_like(conv)
+            self.dec_h.decode_batch_device(s2, wm, shots, c2, wn, conv2, its, None, readout, wn, self.logicals, fail, None, st)
+            iters_total += its.sum()
+            corr.copy_(first)
+            self._extract(c2, 0, n, corr, True)                       # final_correction + final_round_bp_correction
+        else:
+            acc, hist, s_t = buf(wn), buf(wm), buf(wm)
+            wss = row_words(n + m)
+            ehat = buf(wss)
+            for t in range(T):
+                self._extract(sigma, t * m, m, hist, True)            # history(t) = measured syndrome of round t
+                self.g_h.syndrome_batch_device(acc, wn, shots, s_t, wm, st)
+                self._extract(hist, 0, m, s_t, True)
+                self.dec_ss.decode_batch_device(s_t, wm, shots, ehat, wss, conv, its, stream=st)
+                iters_total += its.sum()
+                self._extract(ehat, 0, n, acc, True)                  # accumulated_correction += data part
+            self._extract(acc, 0, n, readout, True)
+            s2, c2 = buf(wm), buf(wn)
+            self.g_h.syndrome_batch_device(readout, wn, shots, s2, wm, st)
+            self.dec_h.decode_batch_device(s2, wm, shots, c2, wn, conv, its, None, readout, wn, self.logicals, fail, None, st)
+            iters_total += its.sum()
+            corr.copy_(acc)
+            self._extract(c2, 0, n, corr, True)
+        torch.cuda.synchronize(dev)
+        out = dict(failures=int(fail.sum().item()), shots=int(shots), non_converged=int((conv == 0).sum().item()),
+                   iters_total=int(iters_total.item()))
+        if per_shot:
+            out.update(corrections=unpack_bits(corr.cpu().numpy().view(np.uint32), n), fail=fail.cpu().numpy(),
+                       converged=conv.cpu().numpy(), faults=unpack_bits(faults.cpu().numpy().view(np.uint32), ncol))
+        return out

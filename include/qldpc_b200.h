@@ -93,6 +93,13 @@ int qd_sampler_run(qd_sampler *s, uint64_t seed, uint32_t stream_id, int64_t sho
 int qd_syndrome_batch(qd_graph *g, const uint32_t *d_vec, int32_t vec_stride, int64_t shots,
                       uint32_t *d_synd, int32_t synd_stride, void *stream);
 
+/* ---- d_dst[s] (^)= bits [bit_offset, bit_offset+nbits) of d_src[s] (accumulate != 0: XOR into d_dst).
+ *      Building block of the multi-round recipes: correction fold, syndrome history, data part of
+ *      a single-shot decoding (python/qldpc/spacetime_code.py:31-33,81-84,98-119). ------------- */
+int qd_bits_extract_batch(const uint32_t *d_src, int32_t src_stride, int64_t shots, int64_t bit_offset,
+                          int32_t nbits, uint32_t *d_dst, int32_t dst_stride, int32_t accumulate,
+                          void *stream);
+
 /* ---- fail[s] = any(L @ (a[s] ^ b[s]) mod 2); d_b may be NULL; d_fail_count (nullable) is
  *      incremented by the number of failing shots ------------------------------------------- */
 int qd_logical_fail_batch(qd_logicals *l, const uint32_t *d_a, const uint32_t *d_b, int32_t stride,

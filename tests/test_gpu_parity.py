@@ -489,3 +489,97 @@ def test_p_sweep_rows_match_oracle_counts(gpu, code225):
         q = 2 * p / 3 + p - 4 / 3 * p * p
         ref = po.run_code_capacity(code225.checks.z, code225.logicals.z, q, 2 * p / 3, decoder="bp", seed=4, shots=3000, **opts)
         assert (row.failures, row.samples, row.non_converged) == (ref["failures"], 3000, ref["non_converged"])
+
+
+# ---------------------------------------------------------------------------------------------
+# the multi-round readout_correction recipes (_experiment.py:12-126) on phenomenological faults
+# ---------------------------------------------------------------------------------------------
+def _oracle_recipe(code, rounds, data_prior, meas_prior, mode, opts, faults):
+    """Literal per-shot restatement of BPOSDCorrect / BPOSDHybridCorrect / BPOSDCorrectSingleShot
+    (_experiment.py:43-60,80-83,115-126) on top of the oracle decoders (OSD = OSD-0)."""
+    from exp_ldpc_b200.spacetime import SpacetimeCode, SpacetimeCodeSingleShot
+    from oracle import pyoracle as po
+    hz = code.checks.z
+    m, n = hz.shape
+    T = rounds
+    st = SpacetimeCode(hz, T)
+    h_st = st.spacetime_check_matrix
+    prior_st = np.concatenate([np.full((T + 1) * n, data_prior), np.full(T * m, meas_prior)])
+    hd = hz.toarray().astype(np.int64)
+    kw = dict(max_iter=opts["max_iter"], bp_method=opts["bp_method"], ms_scaling_factor=opts["ms_scaling_factor"])
+    if mode in ("bp", "bposd"):
+        dec_st = (po.OracleBP if mode == "bp" else po.OracleBPOSD0)(h_st, channel_probs=prior_st, **kw)
+    elif mode == "bposd_hybrid":
+        dec_st = po.OracleBP(h_st, channel_probs=prior_st, **kw)
+        dec_h = po.OracleBPOSD0(hz, error_rate=data_prior, **kw)
+    else:
+        ss = SpacetimeCodeSingleShot(hz)
+        dec_ss = po.OracleBPOSD0(ss.spacetime_check_matrix, channel_probs=np.concatenate([np.full(n, data_prior), np.full(m, meas_prior)]), **kw)
+        dec_h = po.OracleBPOSD0(hz, error_rate=data_prior, **kw)
+    corrs, fails = [], []
+    lz = np.asarray(code.logicals.z).astype(np.int64) & 1
+    for f in faults:
+        f = f.astype(np.int64)
+        # what the reference would slice out of the measurement record
+        data = f[:(T + 1) * n].reshape(T + 1, n)
+        meas = f[(T + 1) * n:].reshape(T, m)
+        cum = np.cumsum(data, axis=0) % 2
+        readout = cum[T]
+        history = lambda t: (hd @ cum[t] + meas[t]) % 2                      # noqa: E731
+        if mode in ("bp", "bposd", "bposd_hybrid"):
+            syndrome = st.syndrome_from_history(history, readout)
+            assert np.array_equal(syndrome.astype(np.int64) % 2, (h_st @ f) % 2)
+            first = st.final_correction(dec_st.decode(syndrome))
+            if mode == "bposd_hybrid":
+                r2 = (first + readout) % 2
+                final = dec_h.decode((hd @ r2) % 2)
+                corr = (final + first) % 2
+            else:
+                corr = first
+        else:
+            acc = np.zeros(n, dtype=np.int64)
+            for t in range(T):
+                syndrome = ((hd @ acc) % 2 + history(t)) % 2
+                acc = (acc + ss.final_correction(dec_ss.decode(syndrome))) % 2
+            r2 = (acc + readout) % 2
+            final = dec_h.decode((hd @ r2) % 2)
+            corr = (final + acc) % 2
+        corrs.append(corr)
+        fails.append(int(((lz @ ((readout + corr) % 2)) % 2).any()))
+    return np.array(corrs, dtype=np.uint8), np.array(fails, dtype=np.uint8)
+
+
+@pytest.mark.parametrize("mode", ["bp", "bposd", "bposd_hybrid", "bposd_single_shot"])
+@pytest.mark.parametrize("rounds", [1, 3])
+def test_storage_recipes_against_oracle_restatement(gpu, code225, mode, rounds):
+    from exp_ldpc_b200.experiment import StorageExperiment
+    from oracle import pyoracle as po
+    opts = dict(max_iter=12, bp_method="ms", ms_scaling_factor=0.0, osd_method="osd0")
+    data_prior, meas_prior = 0.012, 0.015
+    shots = 96
+    exp = StorageExperiment(code225, rounds, data_prior, meas_prior, mode, opts)
+    got = exp.run(shots, seed=31, per_shot=True)
+    faults = po.sample_bits(31, 0, 0, shots, po.thresholds(exp.prior_st))
+    assert np.array_equal(got["faults"], faults)
+    corr, fail = _oracle_recipe(code225, rounds, data_prior, meas_prior, mode, opts, faults)
+    assert np.array_equal(got["corrections"], corr), mode
+    assert np.array_equal(got["fail"], fail)
+    assert got["failures"] == int(fail.sum())
+
+
+def test_run_simulation_multi_round_modes(gpu, code225):
+    """run_simulation(rounds > 0, decoder_mode) mirrors _experiment.py:154-210 (list[bool] back)."""
+    from exp_ldpc_b200.experiment import StorageExperiment, depolarizing_noise, run_simulation
+    opts = dict(max_iter=10, bp_method="ms", ms_scaling_factor=0.0, osd_method="osd0", osd_order=0)
+    for mode in ("bposd", "bposd_hybrid", "bposd_single_shot"):
+        out = run_simulation(64, code225, lambda x, z: 0.01, lambda x, z: 0.012, depolarizing_noise, {"p": 0.018, "pm": 0.018},
+                             opts, 2, mode, seed=3)
+        ref = StorageExperiment(code225, 2, 0.012, 0.01, mode, opts).run(64, seed=3, per_shot=True)
+        assert isinstance(out, list) and len(out) == 64 and all(isinstance(v, bool) for v in out)
+        assert out == [bool(v) for v in ref["fail"]]
+    with pytest.raises(NotImplementedError):
+        run_simulation(8, code225, lambda x, z: 0.01, lambda x, z: 0.01, depolarizing_noise, {"p": 0.01, "pm": 0.01}, opts, 2,
+                       "bpd_detector")
+    with pytest.raises(RuntimeError):
+        run_simulation(8, code225, lambda x, z: 0.01, lambda x, z: 0.01, depolarizing_noise, {"p": 0.01, "pm": 0.01}, opts, 2,
+                       "no_such_mode")
