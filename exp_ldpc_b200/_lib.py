@@ -35,7 +35,10 @@ SIGNATURES = {
     "qd_sampler_create": (C.c_int, [i32, vp, C.c_int, P(vp)]),
     "qd_sampler_destroy": (C.c_int, [vp]),
     "qd_sampler_run": (C.c_int, [vp, u64, u32, i64, i64, vp, i32, vp]),
-    "qd_bits_extract_batch": (C.c_int, [vp, i32, i64, i64, i32, vp, i32, i32, vp]),
+    "qd_circuit_create": (C.c_int, [i32, vp, i32, vp, i32, i32, C.c_int, P(vp)]),
+    "qd_circuit_destroy": (C.c_int, [vp]),
+    "qd_circuit_sample": (C.c_int, [vp, u64, i64, i64, vp, i32, vp]),
+    "qd_bits_copy_batch": (C.c_int, [vp, i32, i64, i64, i32, vp, i32, i64, i32, vp]),
     "qd_syndrome_batch": (C.c_int, [vp, vp, i32, i64, vp, i32, vp]),
     "qd_logical_fail_batch": (C.c_int, [vp, vp, vp, i32, i64, vp, vp, vp]),
     "qd_bp_create": (C.c_int, [vp, vp, i32, i32, f64, i32, P(vp)]),

@@ -16,6 +16,7 @@
 #include "bp7_kernel.cuh"
 #include "bp7_layout.h"
 #include "bp_pick.h"
+#include "frame_sim.cuh"
 #include "osd_kernel.cuh"
 #include "ssf_kernel.cuh"
 
@@ -107,29 +108,31 @@ __global__ void logical_fail_kernel(const uint32_t *__restrict__ lzT, int k, int
     }
 }
 
-// dst[s] (^)= bits [bit_offset, bit_offset + nbits) of src[s]; one thread per destination word.
+// dst[s] bits [dst_offset, dst_offset + nbits)  (^)=  src[s] bits [src_offset, src_offset + nbits);
+// one thread per destination word, other destination bits are left alone.
 // The building block of the multi-round recipes: correction fold (spacetime_code.py:81-84),
-// syndrome history (spacetime_code.py:98-119 read backwards), data part of a single-shot decoding
-// (spacetime_code.py:31-33).
-__global__ void bits_extract_kernel(const uint32_t *__restrict__ src, int sstride, long long shots, long long bit_offset,
-                                    int nbits, uint32_t *__restrict__ dst, int dstride, int accumulate)
+// syndrome history and its differencing (spacetime_code.py:98-119), data part of a single-shot
+// decoding (spacetime_code.py:31-33), slices of a measurement record (storage_sim.py:187-196).
+__global__ void bits_copy_kernel(const uint32_t *__restrict__ src, int sstride, long long src_offset, long long shots,
+                                 int nbits, uint32_t *__restrict__ dst, int dstride, long long dst_offset, int accumulate)
 {
+    const int w0 = (int)(dst_offset >> 5), w1 = (int)((dst_offset + nbits - 1) >> 5), nw = w1 - w0 + 1;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= shots * dstride) return;
-    const long long s = idx / dstride;
-    const int w = (int)(idx - s * dstride);
-    uint32_t v = 0u;
-    if (w * 32 < nbits) {
-        const uint32_t *row = src + s * (long long)sstride;
-        const long long b0 = bit_offset + (long long)w * 32;
-        const int sw = (int)(b0 >> 5), sh = (int)(b0 & 31);
-        const uint32_t lo = row[sw];
-        const uint32_t hi = (sh && sw + 1 < sstride) ? row[sw + 1] : 0u;
-        v = sh ? __funnelshift_r(lo, hi, sh) : lo;
-        const int rem = nbits - w * 32;
-        if (rem < 32) v &= (1u << rem) - 1u;
-    }
-    dst[idx] = accumulate ? dst[idx] ^ v : v;
+    if (idx >= shots * nw) return;
+    const long long s = idx / nw;
+    const int w = w0 + (int)(idx - s * nw);
+    const long long b0 = max((long long)w * 32, dst_offset), b1 = min((long long)w * 32 + 32, dst_offset + nbits);
+    const int len = (int)(b1 - b0), sh = (int)(b0 - (long long)w * 32);
+    const long long s0 = src_offset + (b0 - dst_offset);
+    const uint32_t *row = src + s * (long long)sstride;
+    const int sw = (int)(s0 >> 5), ss = (int)(s0 & 31);
+    const uint32_t lo = row[sw];
+    const uint32_t hi = (ss && ss + len > 32) ? row[sw + 1] : 0u;
+    uint32_t v = ss ? __funnelshift_r(lo, hi, ss) : lo;
+    const uint32_t lm = len >= 32 ? 0xffffffffu : ((1u << len) - 1u);
+    v = (v & lm) << sh;
+    uint32_t *d = dst + s * (long long)dstride + w;
+    *d = accumulate ? (*d ^ v) : ((*d & ~(lm << sh)) | v);
 }
 
 // =============================================================================================
@@ -246,6 +249,12 @@ struct qd_bp {
             if (done[i]) cudaEventDestroy(done[i]);
         }
     }
+};
+
+struct qd_circuit {
+    int device = 0;
+    int nops = 0, nq = 0, nmeas = 0, nthr = 0;
+    DevBuf d_ops, d_thr;
 };
 
 struct qd_osd {
@@ -478,15 +487,19 @@ extern "C" int qd_sampler_run(qd_sampler *s, uint64_t seed, uint32_t stream_id, 
     return 0;
 }
 
-extern "C" int qd_bits_extract_batch(const uint32_t *d_src, int32_t src_stride, int64_t shots, int64_t bit_offset,
-                                     int32_t nbits, uint32_t *d_dst, int32_t dst_stride, int32_t accumulate, void *stream)
+extern "C" int qd_bits_copy_batch(const uint32_t *d_src, int32_t src_stride, int64_t src_bit_offset, int64_t shots,
+                                  int32_t nbits, uint32_t *d_dst, int32_t dst_stride, int64_t dst_bit_offset,
+                                  int32_t accumulate, void *stream)
 {
-    if (!d_src || !d_dst || shots < 0 || bit_offset < 0 || nbits < 0) return fail(QD_EINVAL, "bad bits_extract_batch arguments");
-    if ((bit_offset + nbits + 31) / 32 > src_stride || (nbits + 31) / 32 > dst_stride) return fail(QD_EINVAL, "stride too small");
-    if (shots == 0) return 0;
-    const long long items = (long long)shots * dst_stride;
-    bits_extract_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(d_src, src_stride, shots, bit_offset, nbits,
-                                                                                d_dst, dst_stride, accumulate);
+    if (!d_src || !d_dst || shots < 0 || src_bit_offset < 0 || dst_bit_offset < 0 || nbits < 0)
+        return fail(QD_EINVAL, "bad bits_copy_batch arguments");
+    if ((src_bit_offset + nbits + 31) / 32 > src_stride || (dst_bit_offset + nbits + 31) / 32 > dst_stride)
+        return fail(QD_EINVAL, "stride too small");
+    if (shots == 0 || nbits == 0) return 0;
+    const int nw = (int)(((dst_bit_offset + nbits - 1) >> 5) - (dst_bit_offset >> 5) + 1);
+    const long long items = (long long)shots * nw;
+    bits_copy_kernel<<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(d_src, src_stride, src_bit_offset, shots, nbits,
+                                                                             d_dst, dst_stride, dst_bit_offset, accumulate);
     QD_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1149,6 +1162,69 @@ extern "C" int qd_bp_decode_one(qd_bp *d, const uint8_t *h_syndrome, uint8_t *h_
     for (int j = 0; j < g.n; ++j) h_decoding[j] = (uint8_t)((c[j >> 5] >> (j & 31)) & 1u);
     if (converged) *converged = cv;
     if (iters) *iters = it;
+    return 0;
+}
+
+// =============================================================================================
+// circuit-level sampler (Pauli frames)
+// =============================================================================================
+extern "C" int qd_circuit_create(int32_t num_ops, const int32_t *h_ops, int32_t num_thresholds, const uint32_t *h_thresholds,
+                                 int32_t num_qubits, int32_t num_measurements, int device, qd_circuit **out)
+{
+    if (!out) return fail(QD_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (num_ops < 0 || (num_ops && !h_ops) || num_thresholds < 1 || !h_thresholds || num_qubits <= 0 || num_measurements < 0)
+        return fail(QD_EINVAL, "bad circuit_create arguments");
+    if (h_thresholds[0] != 0u) return fail(QD_EINVAL, "threshold 0 must be 0 (the noiseless entry)");
+    int meas = 0;
+    for (int i = 0; i < num_ops; ++i) {
+        const int code = h_ops[4 * i] & 0xff, ti = h_ops[4 * i] >> 8, q0 = h_ops[4 * i + 1], q1 = h_ops[4 * i + 2];
+        if (code > FR_ZERR || ti < 0 || ti >= num_thresholds || q0 < 0 || q0 >= num_qubits) return fail(QD_EINVAL, "bad circuit op");
+        if ((code == FR_CX || code == FR_CZ || code == FR_DEP2) && (q1 < 0 || q1 >= num_qubits || q1 == q0)) return fail(QD_EINVAL, "bad two-qubit op");
+        meas += code >= FR_MZ && code <= FR_MRX;
+    }
+    if (meas != num_measurements) return fail(QD_EINVAL, "num_measurements does not match the program");
+    int rc = use_device(device);
+    if (rc) return rc;
+    std::unique_ptr<qd_circuit> c(new qd_circuit);
+    c->device = device; c->nops = num_ops; c->nq = num_qubits; c->nmeas = num_measurements; c->nthr = num_thresholds;
+    std::vector<int32_t> ops(h_ops, h_ops + (size_t)4 * num_ops);
+    std::vector<uint32_t> thr(h_thresholds, h_thresholds + num_thresholds);
+    if ((rc = upload(c->d_ops, ops))) return rc;
+    if ((rc = upload(c->d_thr, thr))) return rc;
+    *out = c.release();
+    return 0;
+}
+
+extern "C" int qd_circuit_destroy(qd_circuit *c)
+{
+    if (c) { cudaSetDevice(c->device); delete c; }
+    return 0;
+}
+
+extern "C" int qd_circuit_sample(qd_circuit *c, uint64_t seed, int64_t shot0, int64_t shots, uint32_t *d_records,
+                                 int32_t stride, void *stream)
+{
+    if (!c || !d_records || shots < 0) return fail(QD_EINVAL, "bad circuit_sample arguments");
+    if (stride < words_for(c->nmeas)) return fail(QD_EINVAL, "stride smaller than ceil(measurements/32)");
+    if (shots == 0) return 0;
+    int rc = use_device(c->device);
+    if (rc) return rc;
+    int optin = 0;
+    QD_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    const int nqw = words_for(c->nq);
+    int threads = 128;
+    while (threads > 32 && (size_t)nqw * threads * 8 > (size_t)optin / 2) threads /= 2;
+    const size_t smem = (size_t)nqw * threads * 8;
+    if (smem > (size_t)optin) return fail(QD_EUNSUP, "circuit has too many qubits for the shared-memory frame sampler");
+    QD_CUDA(cudaFuncSetAttribute(frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FrameParams p{};
+    p.ops = c->d_ops.as<int4>(); p.nops = c->nops; p.thr = c->d_thr.as<uint32_t>();
+    p.nqw = nqw; p.nmeas = c->nmeas;
+    p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32);
+    p.shot0 = shot0; p.shots = shots; p.rec = d_records; p.stride = stride;
+    frame_kernel<<<grid_for(shots, threads), threads, smem, (cudaStream_t)stream>>>(p);
+    QD_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -357,7 +357,10 @@ class StorageExperiment:
     MODES = ("bp", "bposd", "bposd_hybrid", "bposd_single_shot")
 
     def __init__(self, code: QuantumCode, rounds: int, data_prior: float, meas_prior: float, decoder_mode: str,
-                 bp_osd_options: Optional[Dict] = None, device: int = 0, precision: str = "f64"):
+                 bp_osd_options: Optional[Dict] = None, device: int = 0, precision: str = "f64", circuit=None):
+        """``circuit``: Stim text of the storage simulation (``StorageSim.circuit`` of the reference for this
+        code and ``rounds``): shots are then sampled from that noisy circuit on the device (Pauli frames)
+        instead of from phenomenological faults; the priors only parameterise the decoders."""
         from .spacetime import SpacetimeCode, SpacetimeCodeSingleShot
         if decoder_mode not in self.MODES:
             if decoder_mode == "bpd_detector":
@@ -377,6 +380,15 @@ class StorageExperiment:
         self.g_st = TannerGraph(h_st, device)
         self.g_h = TannerGraph(hz, device)
         self.sampler = Sampler(self.prior_st, h_st.shape[1], device)
+        self.circuit_sampler = None
+        if circuit is not None:
+            from .circuits import CircuitSampler
+            self.circuit_sampler = CircuitSampler(circuit, device)
+            self.mx = code.checks.x.shape[0]
+            want = T * (self.mx + m) + n                       # storage_sim.py:187-196
+            if self.circuit_sampler.num_measurements != want:
+                raise ValueError(f"circuit has {self.circuit_sampler.num_measurements} measurements, the storage "
+                                 f"simulation of this code with {T} rounds has {want}")
         self.logicals = Logicals(code.logicals.z, device)
         self.dec_st = self.dec_h = self.dec_ss = None
         if decoder_mode == "bp":
@@ -394,9 +406,9 @@ class StorageExperiment:
             self.dec_h = bposd_decoder(self.g_h, error_rate=float(data_prior), **kw, **okw)
 
     # ---- small helpers over packed device buffers
-    def _extract(self, src, bit_offset, nbits, dst, accumulate):
-        _lib.check(_lib.lib().qd_bits_extract_batch(_lib.ptr(src), src.shape[1], src.shape[0], int(bit_offset), int(nbits),
-                                                    _lib.ptr(dst), dst.shape[1], int(accumulate), self._stream))
+    def _extract(self, src, bit_offset, nbits, dst, accumulate, dst_offset=0):
+        _lib.check(_lib.lib().qd_bits_copy_batch(_lib.ptr(src), src.shape[1], int(bit_offset), src.shape[0], int(nbits),
+                                                 _lib.ptr(dst), dst.shape[1], int(dst_offset), int(accumulate), self._stream))
 
     def _fold(self, faults, dst, accumulate=False):
         """``final_correction``: XOR of the T+1 data blocks (``spacetime_code.py:81-84``)."""
@@ -418,9 +430,24 @@ class StorageExperiment:
         its = torch.zeros(shots, dtype=torch.int32, device=dev)
         fail = torch.zeros(shots, dtype=torch.uint8, device=dev)
         st = self._stream
-        self.sampler.run_device(seed, 0, shot0, shots, faults, wf, st)
-        self.g_st.syndrome_batch_device(faults, wf, shots, sigma, ws, st)
-        self._fold(faults, readout)                                   # the data readout of the storage experiment
+        records = None
+        if self.circuit_sampler is None:
+            self.sampler.run_device(seed, 0, shot0, shots, faults, wf, st)
+            self.g_st.syndrome_batch_device(faults, wf, shots, sigma, ws, st)
+            self._fold(faults, readout)                               # the data readout of the storage experiment
+        else:
+            # measurement record -> data readout and differenced syndrome table (spacetime_code.py:98-119)
+            per_round = self.mx + m
+            records = buf(row_words(self.circuit_sampler.num_measurements))
+            self.circuit_sampler.sample_device(seed, shot0, shots, records, records.shape[1], st)
+            self._extract(records, per_round * T, n, readout, False)                 # data_view
+            for t in range(T):
+                z_off = per_round * t + self.mx                                       # measurement_view(t, get_x_checks=False)
+                self._extract(records, z_off, m, sigma, True, dst_offset=t * m)
+                self._extract(records, z_off, m, sigma, True, dst_offset=(t + 1) * m)
+            last = buf(wm)
+            self.g_h.syndrome_batch_device(readout, wn, shots, last, wm, st)
+            self._extract(last, 0, m, sigma, True, dst_offset=T * m)
         iters_total = torch.zeros((), dtype=torch.int64, device=dev)
         if self.mode in ("bp", "bposd"):
             self.dec_st.decode_batch_device(sigma, ws, shots, fhat, wf, conv, its, stream=st)
@@ -463,5 +490,9 @@ class StorageExperiment:
                    iters_total=int(iters_total.item()))
         if per_shot:
             out.update(corrections=unpack_bits(corr.cpu().numpy().view(np.uint32), n), fail=fail.cpu().numpy(),
-                       converged=conv.cpu().numpy(), faults=unpack_bits(faults.cpu().numpy().view(np.uint32), ncol))
+                       converged=conv.cpu().numpy())
+            if records is None:
+                out["faults"] = unpack_bits(faults.cpu().numpy().view(np.uint32), ncol)
+            else:
+                out["records"] = unpack_bits(records.cpu().numpy().view(np.uint32), self.circuit_sampler.num_measurements)
         return out

@@ -17,6 +17,9 @@
  *                                                            python/qldpc/misc/_experiment.py:208-209
  *   qd_sampler_*          <- stim sampler.sample(samples) restricted to the code-capacity circuit
  *                            (rounds = 0)                    python/qldpc/misc/_experiment.py:193-197
+ *   qd_circuit_*          <- stim.Circuit(text).compile_sampler().sample(samples) for the circuits of
+ *                            build_storage_simulation        python/qldpc/misc/_experiment.py:171-197
+ *                                                            python/qldpc/storage_sim.py:38-75,134-185
  *   qd_code_capacity_run  <- run_simulation(samples, ...) for rounds = 0, returning the counts that
  *                            p_sweep sums                    python/qldpc/misc/_experiment.py:154-210
  *                                                            python/qldpc/misc/p_sweep.py:28-32
@@ -66,6 +69,7 @@ typedef struct qd_sampler  qd_sampler;
 typedef struct qd_bp       qd_bp;
 typedef struct qd_ssf      qd_ssf;
 typedef struct qd_osd      qd_osd;
+typedef struct qd_circuit  qd_circuit;
 
 int         qd_abi_version(void);
 const char *qd_last_error(void);
@@ -89,16 +93,30 @@ int qd_sampler_destroy(qd_sampler *s);
 int qd_sampler_run(qd_sampler *s, uint64_t seed, uint32_t stream_id, int64_t shot0, int64_t shots,
                    uint32_t *d_bits, int32_t stride, void *stream);
 
+/* ---- circuit-level sampler (Pauli frames).  Program: num_ops rows {opcode | threshold << 8, q0, q1, site}
+ *      with opcodes 0 reset, 1 CX, 2 CZ, 3 MZ, 4 MX, 5 MRZ, 6 MRX, 7 DEPOLARIZE1, 8 DEPOLARIZE2,
+ *      9 X_ERROR, 10 Z_ERROR; h_thresholds[t] = floor(p * 2^32), entry 0 = 0; `site` numbers the noisy
+ *      operations (Philox counter).  Records are bit-packed like stim's bit_packed samples:
+ *      bit k of shot s = k-th measurement, relative to the noiseless reference sample. ---------- */
+int qd_circuit_create(int32_t num_ops, const int32_t *h_ops, int32_t num_thresholds,
+                      const uint32_t *h_thresholds, int32_t num_qubits, int32_t num_measurements,
+                      int device, qd_circuit **out);
+int qd_circuit_destroy(qd_circuit *c);
+int qd_circuit_sample(qd_circuit *c, uint64_t seed, int64_t shot0, int64_t shots,
+                      uint32_t *d_records, int32_t stride, void *stream);
+
 /* ---- H @ v mod 2, batched and bit-packed --------------------------------------------------- */
 int qd_syndrome_batch(qd_graph *g, const uint32_t *d_vec, int32_t vec_stride, int64_t shots,
                       uint32_t *d_synd, int32_t synd_stride, void *stream);
 
-/* ---- d_dst[s] (^)= bits [bit_offset, bit_offset+nbits) of d_src[s] (accumulate != 0: XOR into d_dst).
- *      Building block of the multi-round recipes: correction fold, syndrome history, data part of
- *      a single-shot decoding (python/qldpc/spacetime_code.py:31-33,81-84,98-119). ------------- */
-int qd_bits_extract_batch(const uint32_t *d_src, int32_t src_stride, int64_t shots, int64_t bit_offset,
-                          int32_t nbits, uint32_t *d_dst, int32_t dst_stride, int32_t accumulate,
-                          void *stream);
+/* ---- d_dst[s] bits [dst_bit_offset, +nbits) (^)= d_src[s] bits [src_bit_offset, +nbits); other bits
+ *      of d_dst are left alone (accumulate != 0: XOR into them).  Building block of the multi-round
+ *      recipes: correction fold, syndrome history and its differencing, data part of a single-shot
+ *      decoding, slices of a measurement record (python/qldpc/spacetime_code.py:31-33,81-84,98-119;
+ *      python/qldpc/storage_sim.py:187-196). ----------------------------------------------------- */
+int qd_bits_copy_batch(const uint32_t *d_src, int32_t src_stride, int64_t src_bit_offset, int64_t shots,
+                       int32_t nbits, uint32_t *d_dst, int32_t dst_stride, int64_t dst_bit_offset,
+                       int32_t accumulate, void *stream);
 
 /* ---- fail[s] = any(L @ (a[s] ^ b[s]) mod 2); d_b may be NULL; d_fail_count (nullable) is
  *      incremented by the number of failing shots ------------------------------------------- */

@@ -59,6 +59,7 @@ def lib():
         L.orc_osd0.restype = C.c_int
         L.orc_bposd0_decode.argtypes = [C.c_void_p, u8p, u8p, C.POINTER(C.c_int)]
         L.orc_bposd0_decode.restype = C.c_int
+        L.orc_circuit_sample.argtypes = [C.c_int, i32p, u32p, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int64, u8p]
         L.orc_ssf_create.argtypes = [C.c_int, C.c_int, i32p, i32p, C.c_int, i32p, i32p]
         L.orc_ssf_create.restype = C.c_void_p
         L.orc_ssf_destroy.argtypes = [C.c_void_p]
@@ -175,6 +176,16 @@ def osd0(h, synd, key_ascending) -> np.ndarray:
     if not ok:
         raise ValueError("syndrome is not in the column space of H")
     return dec
+
+
+def circuit_sample(ops, thresholds, num_qubits, num_measurements, seed, shot0, shots) -> np.ndarray:
+    """Pauli-frame sampler on the host: ``(shots, num_measurements)`` 0/1 records."""
+    ops = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1, 4)
+    thr = np.ascontiguousarray(thresholds, dtype=np.uint32)
+    rec = np.zeros((shots, num_measurements), dtype=np.uint8)
+    lib().orc_circuit_sample(ops.shape[0], _p(ops, C.c_int32), _p(thr, C.c_uint32), int(num_qubits), int(num_measurements),
+                             int(seed), int(shot0), int(shots), _p(rec, C.c_uint8))
+    return rec
 
 
 class OracleSSF:

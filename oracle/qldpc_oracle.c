@@ -335,6 +335,64 @@ int orc_bposd0_decode(orc_bp *d, const uint8_t *synd, uint8_t *decoding, int *it
 const double *orc_bp_soft(const orc_bp *d) { return d->soft; }
 
 /* ============================================================================================
+ * Pauli-frame circuit sampler — restatement of what stim's compiled sampler returns for the circuits
+ * of build_storage_simulation (python/qldpc/storage_sim.py:38-75,134-185; reference call sites
+ * python/qldpc/misc/_experiment.py:171-197), relative to the noiseless reference sample.
+ * Program rows {opcode | threshold << 8, q0, q1, site}; opcodes 0 reset, 1 CX, 2 CZ, 3 MZ, 4 MX,
+ * 5 MRZ, 6 MRX, 7 DEPOLARIZE1, 8 DEPOLARIZE2, 9 X_ERROR, 10 Z_ERROR.  Noise site k of shot g draws
+ * philox(key = seed, ctr = (g_lo, g_hi, k, 0x51)).  PARITY: stim is absent; what is pinned is the
+ * circuit text (reference-generated fixtures) and the textbook frame propagation rules.
+ * ========================================================================================== */
+void orc_circuit_sample(int nops, const int32_t *ops, const uint32_t *thr, int nq, int nmeas, uint64_t seed,
+                        int64_t shot0, int64_t shots, uint8_t *records)
+{
+    uint8_t *fx = (uint8_t *)malloc((size_t)(nq ? nq : 1)), *fz = (uint8_t *)malloc((size_t)(nq ? nq : 1));
+    const uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    for (int64_t s = 0; s < shots; ++s) {
+        const uint64_t g = (uint64_t)(shot0 + s);
+        uint8_t *rec = records + s * (int64_t)nmeas;
+        int k = 0;
+        memset(fx, 0, (size_t)nq); memset(fz, 0, (size_t)nq);
+        for (int i = 0; i < nops; ++i) {
+            const int code = ops[4 * i] & 0xff, ti = ops[4 * i] >> 8, q0 = ops[4 * i + 1], q1 = ops[4 * i + 2];
+            uint32_t r[4] = {0, 0, 0, 0};
+            int hit = 0;
+            if (ti) {
+                const uint32_t ctr[4] = { (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)ops[4 * i + 3], 0x51u };
+                orc_philox4x32_10(ctr, key, r);
+                hit = r[0] < thr[ti];
+            }
+            switch (code) {
+            case 0: fx[q0] = fz[q0] = 0; break;
+            case 1: fx[q1] ^= fx[q0]; fz[q0] ^= fz[q1]; break;
+            case 2: { const uint8_t a = fx[q0], b = fx[q1]; fz[q0] ^= b; fz[q1] ^= a; } break;
+            case 3: rec[k++] = (uint8_t)(fx[q0] ^ hit); break;
+            case 4: rec[k++] = (uint8_t)(fz[q0] ^ hit); break;
+            case 5: rec[k++] = (uint8_t)(fx[q0] ^ hit); fx[q0] = fz[q0] = 0; break;
+            case 6: rec[k++] = (uint8_t)(fz[q0] ^ hit); fx[q0] = fz[q0] = 0; break;
+            case 7:
+                if (hit) {
+                    const uint32_t c = 1u + (uint32_t)(((uint64_t)r[1] * 3u) >> 32);
+                    fx[q0] ^= (uint8_t)(c != 3u); fz[q0] ^= (uint8_t)(c != 1u);
+                }
+                break;
+            case 8:
+                if (hit) {
+                    const uint32_t c = 1u + (uint32_t)(((uint64_t)r[1] * 15u) >> 32), pa = c & 3u, pb = c >> 2;
+                    fx[q0] ^= (uint8_t)(pa == 1u || pa == 2u); fz[q0] ^= (uint8_t)(pa >= 2u);
+                    fx[q1] ^= (uint8_t)(pb == 1u || pb == 2u); fz[q1] ^= (uint8_t)(pb >= 2u);
+                }
+                break;
+            case 9: if (hit) fx[q0] ^= 1; break;
+            case 10: if (hit) fz[q0] ^= 1; break;
+            default: break;
+            }
+        }
+    }
+    free(fx); free(fz);
+}
+
+/* ============================================================================================
  * Small-set-flip.  Candidate sets: non-empty subsets F of the support of
  * a generator g (row of Hx).  delta(F) = |sigma| - |sigma ^ Hz 1_F|.  Every round flips the F
  * maximising delta/|F| (exact integer cross-multiplication) among those with delta > 0; ties go

@@ -494,7 +494,7 @@ def test_p_sweep_rows_match_oracle_counts(gpu, code225):
 # ---------------------------------------------------------------------------------------------
 # the multi-round readout_correction recipes (_experiment.py:12-126) on phenomenological faults
 # ---------------------------------------------------------------------------------------------
-def _oracle_recipe(code, rounds, data_prior, meas_prior, mode, opts, faults):
+def _oracle_recipe(code, rounds, data_prior, meas_prior, mode, opts, faults=None, records=None):
     """Literal per-shot restatement of BPOSDCorrect / BPOSDHybridCorrect / BPOSDCorrectSingleShot
     (_experiment.py:43-60,80-83,115-126) on top of the oracle decoders (OSD = OSD-0)."""
     from exp_ldpc_b200.spacetime import SpacetimeCode, SpacetimeCodeSingleShot
@@ -518,17 +518,24 @@ def _oracle_recipe(code, rounds, data_prior, meas_prior, mode, opts, faults):
         dec_h = po.OracleBPOSD0(hz, error_rate=data_prior, **kw)
     corrs, fails = [], []
     lz = np.asarray(code.logicals.z).astype(np.int64) & 1
-    for f in faults:
-        f = f.astype(np.int64)
-        # what the reference would slice out of the measurement record
-        data = f[:(T + 1) * n].reshape(T + 1, n)
-        meas = f[(T + 1) * n:].reshape(T, m)
-        cum = np.cumsum(data, axis=0) % 2
-        readout = cum[T]
-        history = lambda t: (hd @ cum[t] + meas[t]) % 2                      # noqa: E731
+    mx = code.checks.x.shape[0]
+    for item in (faults if records is None else records):
+        if records is None:
+            f = item.astype(np.int64)
+            # what the reference would slice out of the measurement record
+            data = f[:(T + 1) * n].reshape(T + 1, n)
+            meas = f[(T + 1) * n:].reshape(T, m)
+            cum = np.cumsum(data, axis=0) % 2
+            readout = cum[T]
+            history = lambda t: (hd @ cum[t] + meas[t]) % 2                      # noqa: E731
+        else:
+            rec = item.astype(np.int64)                                          # storage_sim.py:187-196
+            readout = rec[(mx + m) * T:(mx + m) * T + n]
+            history = lambda t: rec[(mx + m) * t + mx:(mx + m) * t + mx + m]     # noqa: E731
         if mode in ("bp", "bposd", "bposd_hybrid"):
             syndrome = st.syndrome_from_history(history, readout)
-            assert np.array_equal(syndrome.astype(np.int64) % 2, (h_st @ f) % 2)
+            if records is None:
+                assert np.array_equal(syndrome.astype(np.int64) % 2, (h_st @ f) % 2)
             first = st.final_correction(dec_st.decode(syndrome))
             if mode == "bposd_hybrid":
                 r2 = (first + readout) % 2
@@ -583,3 +590,47 @@ def test_run_simulation_multi_round_modes(gpu, code225):
     with pytest.raises(RuntimeError):
         run_simulation(8, code225, lambda x, z: 0.01, lambda x, z: 0.01, depolarizing_noise, {"p": 0.01, "pm": 0.01}, opts, 2,
                        "no_such_mode")
+
+
+
+# ---------------------------------------------------------------------------------------------
+# circuit-level sampling (Pauli frames) of the reference-generated storage-simulation circuits
+# ---------------------------------------------------------------------------------------------
+def _golden_circuit(name):
+    import gzip
+    with gzip.open(os.path.join(GOLDEN, f"storage_sim_n225_{name}.stim.gz"), "rt") as fh:
+        return fh.read().split("\n")
+
+
+@pytest.mark.parametrize("name", ["T0_depol", "T1_depol", "T3_depol", "T1_circuit"])
+def test_circuit_sampler_bit_exact(gpu, name):
+    from exp_ldpc_b200.circuits import CircuitSampler
+    from oracle import pyoracle as po
+    smp = CircuitSampler(_golden_circuit(name))
+    p = smp.program
+    for shot0, shots in ((0, 300), (10 ** 9 + 7, 65)):                      # ragged batch, 64-bit shot index
+        got = smp.sample(shots, seed=12345, shot0=shot0)
+        ref = po.circuit_sample(p.ops, p.thresholds, p.num_qubits, p.num_measurements, 12345, shot0, shots)
+        assert got.shape == (shots, p.num_measurements) and got.dtype == bool
+        assert np.array_equal(got.astype(np.uint8), ref)
+
+
+@pytest.mark.parametrize("mode", ["bposd", "bposd_hybrid", "bposd_single_shot"])
+@pytest.mark.parametrize("name,rounds", [("T1_circuit", 1), ("T3_depol", 3)])
+def test_storage_recipes_on_circuit_level_noise(gpu, code225, mode, name, rounds):
+    """The full reference pipeline of _experiment.py:154-210 on the device: noisy circuit -> record
+    -> measurement_view / data_view -> readout_correction recipe -> logical flag."""
+    from exp_ldpc_b200.experiment import StorageExperiment
+    from oracle import pyoracle as po
+    opts = dict(max_iter=12, bp_method="ms", ms_scaling_factor=0.0, osd_method="osd0")
+    data_prior, meas_prior = 0.03, 0.05
+    shots = 64
+    circuit = _golden_circuit(name)
+    exp = StorageExperiment(code225, rounds, data_prior, meas_prior, mode, opts, circuit=circuit)
+    got = exp.run(shots, seed=77, per_shot=True)
+    p = exp.circuit_sampler.program
+    records = po.circuit_sample(p.ops, p.thresholds, p.num_qubits, p.num_measurements, 77, 0, shots)
+    assert np.array_equal(got["records"], records)
+    corr, fail = _oracle_recipe(code225, rounds, data_prior, meas_prior, mode, opts, records=records)
+    assert np.array_equal(got["corrections"], corr), mode
+    assert np.array_equal(got["fail"], fail)
