@@ -5,7 +5,8 @@ Host-side mirror of ``python/qldpc/misc/_experiment.py:154-210`` (``run_simulati
 return types (``list[bool]`` of per-shot logical failures; a pandas DataFrame with the reference's
 columns), with
 
-* the Stim sampler replaced by the Philox code-capacity sampler on the device (``rounds = 0``);
+* the Stim sampler replaced by the Philox code-capacity sampler (``rounds = 0``) or the Pauli-frame
+  circuit sampler (``rounds > 0``) on the device;
 * the per-shot Python loop replaced by ``qd_code_capacity_run``
   (sample -> syndrome -> decode -> residual -> logical flag, all on the GPU);
 * ``multiprocessing.Pool(cpu_count())`` + ``sum`` replaced by one rank per GPU and a single
@@ -14,8 +15,9 @@ columns), with
 Supported ``decoder_mode``: ``'bp'`` (the first, pure-BP stage of the reference's
 ``bposd_hybrid``), ``'bposd'``, ``'bposd_hybrid'``, ``'bposd_single_shot'`` (OSD = OSD-0; the
 reference's default ``osd_cs`` of order 7 raises ``NotImplementedError``) and ``'ssf'`` (rounds = 0).
-For ``rounds > 0`` the faults are phenomenological (:class:`StorageExperiment`); ``'bpd_detector'``
-needs a Stim detector error model and raises ``NotImplementedError``.
+For ``rounds > 0`` the noisy storage circuit is built (``exp_ldpc_b200.storage``) and sampled with Pauli
+frames on the device (:class:`StorageExperiment`); ``'bpd_detector'`` needs a detector error model and
+raises ``NotImplementedError``.
 """
 from __future__ import annotations
 
@@ -31,29 +33,14 @@ from . import _lib
 from .codes import QuantumCode
 from .decoders import Logicals, Sampler, TannerGraph, bp_decoder, bposd_decoder, row_words, ssf_decoder, unpack_bits
 
-__all__ = ["depolarizing_noise", "NoiseModel", "CodeCapacityExperiment", "SpacetimeExperiment", "StorageExperiment", "run_simulation", "p_sweep",
+__all__ = ["depolarizing_noise", "circuit_noise", "trivial_noise", "NoiseModel", "build_storage_simulation", "CodeCapacityExperiment", "SpacetimeExperiment", "StorageExperiment", "run_simulation", "p_sweep",
            "shard_range", "binomial_ci"]
 
 
-@dataclass(frozen=True)
-class NoiseModel:
-    """What the circuit-rewriting noise models of ``noise_model.py`` amount to for ``rounds = 0``."""
-    name: str
-    p: float
-    pm: float
-
-    def code_capacity_flip_probability(self) -> float:
-        """Marginal probability that a data-qubit Z-basis readout is flipped.
-
-        ``depolarizing_noise(p, pm)`` (``noise_model.py:117-123``) puts ``DEPOLARIZE1(p)`` on the data
-        qubits before the only measurement step of the rounds=0 circuit and rewrites ``MZ`` into
-        ``MZ(pm)``: X or Y with probability 2p/3, then an independent readout flip pm."""
-        a = 2.0 * self.p / 3.0
-        return a + self.pm - 2.0 * a * self.pm
-
-
-def depolarizing_noise(p: float, pm: float) -> NoiseModel:
-    return NoiseModel("depolarizing", float(p), float(pm))
+# the noise models are the reference's text rewriters (exp_ldpc_b200.storage); for rounds = 0 their closed-form
+# code-capacity flip probability replaces the circuit
+from .storage import (NoiseRewriter as NoiseModel, build_storage_simulation, circuit_noise,  # noqa: E402,F401
+                      depolarizing_noise, trivial_noise)
 
 
 def shard_range(total: int, rank: int, world: int):
@@ -174,9 +161,9 @@ class SpacetimeExperiment(CodeCapacityExperiment):
 
 def run_simulation(samples, code, meas_prior, data_prior, noise_model, noise_model_args, bp_osd_options, rounds,
                    decoder_mode, seed: int = 0, shot0: int = 0, device: int = 0, precision: str = "f64"):
-    """``run_simulation`` of ``_experiment.py:154-210``: ``rounds = 0`` is the code-capacity circuit
-    under ``noise_model``; ``rounds > 0`` runs the multi-round recipes on phenomenological faults.
-    Returns ``list[bool]``: the logical-failure flag of every shot."""
+    """``run_simulation`` of ``_experiment.py:154-210``: builds the storage-simulation circuit under
+    ``noise_model`` (``rounds = 0``: its closed-form code-capacity equivalent), samples it on the device,
+    decodes with the ``decoder_mode`` recipe.  Returns ``list[bool]``: the logical-failure flag of every shot."""
     checks = code.checks
     x_steps = int(max(checks.x.sum(axis=0).max(), checks.x.sum(axis=1).max()))   # _experiment.py:160-161
     z_steps = int(max(checks.z.sum(axis=0).max(), checks.z.sum(axis=1).max()))
@@ -184,9 +171,10 @@ def run_simulation(samples, code, meas_prior, data_prior, noise_model, noise_mod
     mprior = meas_prior(x_steps, z_steps)
     dprior = data_prior(x_steps, z_steps)
     if rounds != 0:
-        # multi-round: phenomenological faults at the priors' rates (see StorageExperiment); the
-        # circuit-level sampler behind `noise_model` is SURVEY.md §8 f2
-        exp = StorageExperiment(code, rounds, dprior, mprior, decoder_mode, bp_osd_options, device=device, precision=precision)
+        # _experiment.py:165-197: build the noisy storage circuit, sample it (Pauli frames on the device)
+        sim = build_storage_simulation(rounds, nm, code, use_x_logicals=False)
+        exp = StorageExperiment(code, rounds, dprior, mprior, decoder_mode, bp_osd_options, device=device, precision=precision,
+                                circuit=sim.circuit)
         res = exp.run(int(samples), seed=seed, shot0=shot0, per_shot=True)
         return [bool(v) for v in res["fail"]]
     exp = CodeCapacityExperiment(code, nm.code_capacity_flip_probability(), dprior, decoder_mode, bp_osd_options,
@@ -219,8 +207,9 @@ def p_sweep(samples, p_values, noise_model, noise_model_args, meas_prior, data_p
         t0 = time.time()
         nm = noise_model(**noise_model_args(p_ph))
         if shard_runner is None and rounds != 0:
+            sim = build_storage_simulation(rounds, nm, code, use_x_logicals=False)
             exp = StorageExperiment(code, rounds, data_prior(p_ph, 0, 0), meas_prior(p_ph, 0, 0), decoder_mode,
-                                    bp_osd_options, device=device, precision=precision)
+                                    bp_osd_options, device=device, precision=precision, circuit=sim.circuit)
             res = exp.run(hi - lo, seed=seed, shot0=lo) if hi > lo else dict(failures=0, shots=0, non_converged=0, iters_total=0)
         elif shard_runner is None:
             exp = CodeCapacityExperiment(code, nm.code_capacity_flip_probability(), data_prior(p_ph, 0, 0), decoder_mode,

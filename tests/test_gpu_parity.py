@@ -575,13 +575,17 @@ def test_storage_recipes_against_oracle_restatement(gpu, code225, mode, rounds):
 
 
 def test_run_simulation_multi_round_modes(gpu, code225):
-    """run_simulation(rounds > 0, decoder_mode) mirrors _experiment.py:154-210 (list[bool] back)."""
-    from exp_ldpc_b200.experiment import StorageExperiment, depolarizing_noise, run_simulation
+    """run_simulation(rounds > 0, decoder_mode) mirrors _experiment.py:154-210: circuit under the noise
+    model -> record -> recipe -> list[bool]."""
+    from exp_ldpc_b200.experiment import (StorageExperiment, build_storage_simulation, circuit_noise, depolarizing_noise,
+                                          run_simulation)
     opts = dict(max_iter=10, bp_method="ms", ms_scaling_factor=0.0, osd_method="osd0", osd_order=0)
-    for mode in ("bposd", "bposd_hybrid", "bposd_single_shot"):
-        out = run_simulation(64, code225, lambda x, z: 0.01, lambda x, z: 0.012, depolarizing_noise, {"p": 0.018, "pm": 0.018},
-                             opts, 2, mode, seed=3)
-        ref = StorageExperiment(code225, 2, 0.012, 0.01, mode, opts).run(64, seed=3, per_shot=True)
+    for mode, nm, args in (("bposd", depolarizing_noise, {"p": 0.018, "pm": 0.018}),
+                           ("bposd_hybrid", circuit_noise, {"p": 0.002, "pm": 0.004}),
+                           ("bposd_single_shot", depolarizing_noise, {"p": 0.02, "pm": 0.01})):
+        out = run_simulation(64, code225, lambda x, z: 0.01, lambda x, z: 0.012, nm, args, opts, 2, mode, seed=3)
+        circuit = build_storage_simulation(2, nm(**args), code225, use_x_logicals=False).circuit
+        ref = StorageExperiment(code225, 2, 0.012, 0.01, mode, opts, circuit=circuit).run(64, seed=3, per_shot=True)
         assert isinstance(out, list) and len(out) == 64 and all(isinstance(v, bool) for v in out)
         assert out == [bool(v) for v in ref["fail"]]
     with pytest.raises(NotImplementedError):
