@@ -38,6 +38,7 @@ SIGNATURES = {
     "qd_circuit_create": (C.c_int, [i32, vp, i32, vp, i32, i32, C.c_int, P(vp)]),
     "qd_circuit_destroy": (C.c_int, [vp]),
     "qd_circuit_sample": (C.c_int, [vp, u64, i64, i64, vp, i32, vp]),
+    "qd_circuit_propagate_faults": (C.c_int, [vp, i64, vp, vp, i32, vp]),
     "qd_bits_copy_batch": (C.c_int, [vp, i32, i64, i64, i32, vp, i32, i64, i32, vp]),
     "qd_syndrome_batch": (C.c_int, [vp, vp, i32, i64, vp, i32, vp]),
     "qd_logical_fail_batch": (C.c_int, [vp, vp, vp, i32, i64, vp, vp, vp]),

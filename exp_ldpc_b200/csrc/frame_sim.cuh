@@ -34,6 +34,8 @@ struct FrameParams {
     uint32_t k0, k1;            // Philox key = seed
     long long shot0, shots;
     uint32_t *rec; int stride;  // [shots][stride] packed measurement records
+    const int2 *forced;         // fault-propagation mode (detector error models): "shot" g runs the NOISELESS circuit
+                                // with exactly one fault, {noise site, Pauli code} = forced[g]; no random numbers
 };
 
 __global__ void frame_kernel(const FrameParams p)
@@ -60,9 +62,16 @@ __global__ void frame_kernel(const FrameParams p)
         const int code = op.x & 0xff, ti = op.x >> 8, q0 = op.y, q1 = op.z;
         uint32_t r[4] = {0u, 0u, 0u, 0u};
         bool hit = false;
+        int forced_code = 0;
         if (ti) {
-            philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)op.w, 0x51u, p.k0, p.k1, r);
-            hit = r[0] < __ldg(p.thr + ti);
+            if (p.forced) {
+                const int2 f = __ldg(p.forced + g);
+                hit = f.x == op.w;
+                forced_code = f.y;
+            } else {
+                philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)op.w, 0x51u, p.k0, p.k1, r);
+                hit = r[0] < __ldg(p.thr + ti);
+            }
         }
         switch (code) {
         case FR_RESET: clrb(fx, q0); clrb(fz, q0); break;
@@ -74,13 +83,15 @@ __global__ void frame_kernel(const FrameParams p)
         case FR_MRX: emit(getb(fz, q0) ^ (hit ? 1u : 0u)); clrb(fx, q0); clrb(fz, q0); break;
         case FR_DEP1:
             if (hit) {
-                const uint32_t c = 1u + (uint32_t)(((unsigned long long)r[1] * 3ull) >> 32);      // 1 X, 2 Y, 3 Z
+                const uint32_t c = p.forced ? (uint32_t)forced_code
+                                            : 1u + (uint32_t)(((unsigned long long)r[1] * 3ull) >> 32);      // 1 X, 2 Y, 3 Z
                 xorb(fx, q0, c != 3u ? 1u : 0u); xorb(fz, q0, c != 1u ? 1u : 0u);
             }
             break;
         case FR_DEP2:
             if (hit) {
-                const uint32_t c = 1u + (uint32_t)(((unsigned long long)r[1] * 15ull) >> 32);     // (pa, pb) != (I, I)
+                const uint32_t c = p.forced ? (uint32_t)forced_code
+                                            : 1u + (uint32_t)(((unsigned long long)r[1] * 15ull) >> 32);     // (pa, pb) != (I, I)
                 const uint32_t pa = c & 3u, pb = c >> 2;                                            // 0 I, 1 X, 2 Y, 3 Z
                 xorb(fx, q0, (pa == 1u || pa == 2u) ? 1u : 0u); xorb(fz, q0, pa >= 2u ? 1u : 0u);
                 xorb(fx, q1, (pb == 1u || pb == 2u) ? 1u : 0u); xorb(fz, q1, pb >= 2u ? 1u : 0u);

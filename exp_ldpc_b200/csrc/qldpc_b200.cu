@@ -1202,8 +1202,24 @@ extern "C" int qd_circuit_destroy(qd_circuit *c)
     return 0;
 }
 
+static int circuit_launch(qd_circuit *c, uint64_t seed, int64_t shot0, int64_t shots, uint32_t *d_records, int32_t stride,
+                          const int2 *d_forced, void *stream);
+
 extern "C" int qd_circuit_sample(qd_circuit *c, uint64_t seed, int64_t shot0, int64_t shots, uint32_t *d_records,
                                  int32_t stride, void *stream)
+{
+    return circuit_launch(c, seed, shot0, shots, d_records, stride, nullptr, stream);
+}
+
+extern "C" int qd_circuit_propagate_faults(qd_circuit *c, int64_t num_faults, const int32_t *d_site_and_pauli,
+                                           uint32_t *d_records, int32_t stride, void *stream)
+{
+    if (!d_site_and_pauli) return fail(QD_EINVAL, "bad circuit_propagate_faults arguments");
+    return circuit_launch(c, 0, 0, num_faults, d_records, stride, reinterpret_cast<const int2 *>(d_site_and_pauli), stream);
+}
+
+static int circuit_launch(qd_circuit *c, uint64_t seed, int64_t shot0, int64_t shots, uint32_t *d_records, int32_t stride,
+                          const int2 *d_forced, void *stream)
 {
     if (!c || !d_records || shots < 0) return fail(QD_EINVAL, "bad circuit_sample arguments");
     if (stride < words_for(c->nmeas)) return fail(QD_EINVAL, "stride smaller than ceil(measurements/32)");
@@ -1223,6 +1239,7 @@ extern "C" int qd_circuit_sample(qd_circuit *c, uint64_t seed, int64_t shot0, in
     p.nqw = nqw; p.nmeas = c->nmeas;
     p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32);
     p.shot0 = shot0; p.shots = shots; p.rec = d_records; p.stride = stride;
+    p.forced = d_forced;
     frame_kernel<<<grid_for(shots, threads), threads, smem, (cudaStream_t)stream>>>(p);
     QD_CUDA(cudaGetLastError());
     return 0;

@@ -16,8 +16,8 @@ Supported ``decoder_mode``: ``'bp'`` (the first, pure-BP stage of the reference'
 ``bposd_hybrid``), ``'bposd'``, ``'bposd_hybrid'``, ``'bposd_single_shot'`` (OSD = OSD-0; the
 reference's default ``osd_cs`` of order 7 raises ``NotImplementedError``) and ``'ssf'`` (rounds = 0).
 For ``rounds > 0`` the noisy storage circuit is built (``exp_ldpc_b200.storage``) and sampled with Pauli
-frames on the device (:class:`StorageExperiment`); ``'bpd_detector'`` needs a detector error model and
-raises ``NotImplementedError``.
+frames on the device (:class:`StorageExperiment`); ``'bpd_detector'`` decodes on the circuit's detector
+error model (:class:`DetectorExperiment`).
 """
 from __future__ import annotations
 
@@ -33,7 +33,7 @@ from . import _lib
 from .codes import QuantumCode
 from .decoders import Logicals, Sampler, TannerGraph, bp_decoder, bposd_decoder, row_words, ssf_decoder, unpack_bits
 
-__all__ = ["depolarizing_noise", "circuit_noise", "trivial_noise", "NoiseModel", "build_storage_simulation", "CodeCapacityExperiment", "SpacetimeExperiment", "StorageExperiment", "run_simulation", "p_sweep",
+__all__ = ["depolarizing_noise", "circuit_noise", "trivial_noise", "NoiseModel", "build_storage_simulation", "CodeCapacityExperiment", "SpacetimeExperiment", "StorageExperiment", "DetectorExperiment", "run_simulation", "p_sweep",
            "shard_range", "binomial_ci"]
 
 
@@ -170,6 +170,11 @@ def run_simulation(samples, code, meas_prior, data_prior, noise_model, noise_mod
     nm = noise_model(**noise_model_args)
     mprior = meas_prior(x_steps, z_steps)
     dprior = data_prior(x_steps, z_steps)
+    if decoder_mode == "bpd_detector":
+        sim = build_storage_simulation(rounds, nm, code, use_x_logicals=False)
+        res = DetectorExperiment(sim.circuit, bp_osd_options, device=device, precision=precision).run(
+            int(samples), seed=seed, shot0=shot0, per_shot=True)
+        return [bool(v) for v in res["fail"]]
     if rounds != 0:
         # _experiment.py:165-197: build the noisy storage circuit, sample it (Pauli frames on the device)
         sim = build_storage_simulation(rounds, nm, code, use_x_logicals=False)
@@ -206,7 +211,11 @@ def p_sweep(samples, p_values, noise_model, noise_model_args, meas_prior, data_p
     for p_ph in p_values:
         t0 = time.time()
         nm = noise_model(**noise_model_args(p_ph))
-        if shard_runner is None and rounds != 0:
+        if shard_runner is None and decoder_mode == "bpd_detector":
+            sim = build_storage_simulation(rounds, nm, code, use_x_logicals=False)
+            exp = DetectorExperiment(sim.circuit, bp_osd_options, device=device, precision=precision)
+            res = exp.run(hi - lo, seed=seed, shot0=lo) if hi > lo else dict(failures=0, shots=0, non_converged=0, iters_total=0)
+        elif shard_runner is None and rounds != 0:
             sim = build_storage_simulation(rounds, nm, code, use_x_logicals=False)
             exp = StorageExperiment(code, rounds, data_prior(p_ph, 0, 0), meas_prior(p_ph, 0, 0), decoder_mode,
                                     bp_osd_options, device=device, precision=precision, circuit=sim.circuit)
@@ -353,7 +362,7 @@ class StorageExperiment:
         from .spacetime import SpacetimeCode, SpacetimeCodeSingleShot
         if decoder_mode not in self.MODES:
             if decoder_mode == "bpd_detector":
-                raise NotImplementedError("decoder_mode 'bpd_detector' needs a Stim detector error model (SURVEY.md §8 f2)")
+                raise ValueError("decoder_mode 'bpd_detector' decodes detectors, not a readout: use DetectorExperiment")
             raise RuntimeError("Unknown decoder operation mode")   # _experiment.py:189
         opts = dict(bp_osd_options or {})
         kw = dict(max_iter=opts.get("max_iter", 0), bp_method=opts.get("bp_method", "ps"),
@@ -484,4 +493,62 @@ class StorageExperiment:
                 out["faults"] = unpack_bits(faults.cpu().numpy().view(np.uint32), ncol)
             else:
                 out["records"] = unpack_bits(records.cpu().numpy().view(np.uint32), self.circuit_sampler.num_measurements)
+        return out
+
+
+class DetectorExperiment:
+    """``decoder_mode = 'bpd_detector'`` (``BPDetectorCorrect``, ``_experiment.py:128-151``) on the device:
+    sample the noisy circuit, form the detectors, BP on the fault check matrix of the circuit's detector
+    error model, and flag the shot iff a corrected logical observable is non-zero
+    (``logicals ^= fault_map @ fault_set``, ``:147-151,202-204``).
+
+    The detector error model comes from :func:`exp_ldpc_b200.circuits.detector_error_model` (fault
+    propagation on the GPU) with the detector / observable ids as row indices — i.e. what the reference's
+    ``DetectorSpacetimeCode`` means, not what its ``lil_to_coo`` writes (``spacetime_code.py:168-171``)."""
+
+    def __init__(self, circuit, bp_osd_options: Optional[Dict] = None, device: int = 0, precision: str = "f64"):
+        from scipy import sparse
+
+        from .circuits import CircuitSampler, compile_circuit, detector_error_model
+        opts = dict(bp_osd_options or {})
+        self.device = int(device)
+        self.program = compile_circuit(circuit)
+        self.dem = detector_error_model(self.program, device)
+        self.sampler = CircuitSampler(self.program, device)
+        self.nmeas = self.program.num_measurements
+        self.ndet, self.nfaults = self.dem.fault_check_matrix.shape
+        self.g_det = TannerGraph(self.dem.detector_matrix, device)
+        self.decoder = bp_decoder(self.dem.fault_check_matrix, channel_probs=self.dem.fault_priors,
+                                  max_iter=opts.get("max_iter", 0), bp_method=opts.get("bp_method", "ps"),
+                                  ms_scaling_factor=opts.get("ms_scaling_factor", 0.0), precision=precision, device=device)
+        both = sparse.hstack([self.dem.observable_matrix, self.dem.fault_map]).toarray()
+        self.logicals = Logicals(both, device)
+
+    def run(self, shots: int, seed: int = 0, shot0: int = 0, per_shot: bool = False) -> dict:
+        import torch
+        dev = torch.device(f"cuda:{self.device}")
+        torch.cuda.set_device(dev)
+        st = torch.cuda.current_stream().cuda_stream
+        wr, wd, wf = row_words(self.nmeas), row_words(self.ndet), row_words(self.nfaults)
+        wc = row_words(self.nmeas + self.nfaults)
+        buf = lambda w: torch.zeros((shots, w), dtype=torch.int32, device=dev)           # noqa: E731
+        rec, det, fhat, cat = buf(wr), buf(wd), buf(wf), buf(wc)
+        conv = torch.zeros(shots, dtype=torch.uint8, device=dev)
+        its = torch.zeros(shots, dtype=torch.int32, device=dev)
+        fail = torch.zeros(shots, dtype=torch.uint8, device=dev)
+        self.sampler.sample_device(seed, shot0, shots, rec, wr, st)
+        self.g_det.syndrome_batch_device(rec, wr, shots, det, wd, st)
+        self.decoder.decode_batch_device(det, wd, shots, fhat, wf, conv, its, stream=st)
+        copy = _lib.lib().qd_bits_copy_batch
+        _lib.check(copy(_lib.ptr(rec), wr, 0, shots, self.nmeas, _lib.ptr(cat), wc, 0, 0, st))
+        _lib.check(copy(_lib.ptr(fhat), wf, 0, shots, self.nfaults, _lib.ptr(cat), wc, self.nmeas, 0, st))
+        self.logicals.fail_batch_device(cat, None, wc, shots, fail, None, st)
+        torch.cuda.synchronize(dev)
+        out = dict(failures=int(fail.sum().item()), shots=int(shots), non_converged=int((conv == 0).sum().item()),
+                   iters_total=int(its.sum().item()))
+        if per_shot:
+            out.update(fail=fail.cpu().numpy(), converged=conv.cpu().numpy(),
+                       records=unpack_bits(rec.cpu().numpy().view(np.uint32), self.nmeas),
+                       detectors=unpack_bits(det.cpu().numpy().view(np.uint32), self.ndet),
+                       fault_sets=unpack_bits(fhat.cpu().numpy().view(np.uint32), self.nfaults))
         return out

@@ -104,6 +104,13 @@ int qd_circuit_create(int32_t num_ops, const int32_t *h_ops, int32_t num_thresho
 int qd_circuit_destroy(qd_circuit *c);
 int qd_circuit_sample(qd_circuit *c, uint64_t seed, int64_t shot0, int64_t shots,
                       uint32_t *d_records, int32_t stride, void *stream);
+/* Fault propagation for detector error models (what circuit.detector_error_model() needs,
+ * python/qldpc/misc/_experiment.py:174, python/qldpc/spacetime_code.py:122-183): record f = the
+ * NOISELESS circuit with exactly one fault, d_site_and_pauli[2f] = noise site, [2f+1] = Pauli code
+ * (DEPOLARIZE1: 1 X, 2 Y, 3 Z; DEPOLARIZE2: 1..15 = pa + 4 pb with 0 I, 1 X, 2 Y, 3 Z; ignored
+ * for measurement flips and X/Z_ERROR). */
+int qd_circuit_propagate_faults(qd_circuit *c, int64_t num_faults, const int32_t *d_site_and_pauli,
+                                uint32_t *d_records, int32_t stride, void *stream);
 
 /* ---- H @ v mod 2, batched and bit-packed --------------------------------------------------- */
 int qd_syndrome_batch(qd_graph *g, const uint32_t *d_vec, int32_t vec_stride, int64_t shots,

@@ -60,6 +60,7 @@ def lib():
         L.orc_bposd0_decode.argtypes = [C.c_void_p, u8p, u8p, C.POINTER(C.c_int)]
         L.orc_bposd0_decode.restype = C.c_int
         L.orc_circuit_sample.argtypes = [C.c_int, i32p, u32p, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int64, u8p]
+        L.orc_circuit_propagate_faults.argtypes = [C.c_int, i32p, C.c_int, C.c_int, C.c_int64, i32p, u8p]
         L.orc_ssf_create.argtypes = [C.c_int, C.c_int, i32p, i32p, C.c_int, i32p, i32p]
         L.orc_ssf_create.restype = C.c_void_p
         L.orc_ssf_destroy.argtypes = [C.c_void_p]
@@ -185,6 +186,16 @@ def circuit_sample(ops, thresholds, num_qubits, num_measurements, seed, shot0, s
     rec = np.zeros((shots, num_measurements), dtype=np.uint8)
     lib().orc_circuit_sample(ops.shape[0], _p(ops, C.c_int32), _p(thr, C.c_uint32), int(num_qubits), int(num_measurements),
                              int(seed), int(shot0), int(shots), _p(rec, C.c_uint8))
+    return rec
+
+
+def circuit_propagate_faults(ops, num_qubits, num_measurements, site_and_pauli) -> np.ndarray:
+    """Records of the noiseless circuit with exactly one forced fault each: ``(nfaults, num_measurements)``."""
+    ops = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1, 4)
+    f = np.ascontiguousarray(site_and_pauli, dtype=np.int32).reshape(-1, 2)
+    rec = np.zeros((f.shape[0], num_measurements), dtype=np.uint8)
+    lib().orc_circuit_propagate_faults(ops.shape[0], _p(ops, C.c_int32), int(num_qubits), int(num_measurements), f.shape[0],
+                                       _p(f, C.c_int32), _p(rec, C.c_uint8))
     return rec
 
 

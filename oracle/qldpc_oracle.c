@@ -343,8 +343,24 @@ const double *orc_bp_soft(const orc_bp *d) { return d->soft; }
  * philox(key = seed, ctr = (g_lo, g_hi, k, 0x51)).  PARITY: stim is absent; what is pinned is the
  * circuit text (reference-generated fixtures) and the textbook frame propagation rules.
  * ========================================================================================== */
+static void orc_circuit_run(int nops, const int32_t *ops, const uint32_t *thr, int nq, int nmeas, uint64_t seed,
+                            int64_t shot0, int64_t shots, const int32_t *forced, uint8_t *records);
+
 void orc_circuit_sample(int nops, const int32_t *ops, const uint32_t *thr, int nq, int nmeas, uint64_t seed,
                         int64_t shot0, int64_t shots, uint8_t *records)
+{
+    orc_circuit_run(nops, ops, thr, nq, nmeas, seed, shot0, shots, NULL, records);
+}
+
+/* record f = the noiseless circuit with exactly one fault {site, Pauli code} = forced[2f], forced[2f+1] */
+void orc_circuit_propagate_faults(int nops, const int32_t *ops, int nq, int nmeas, int64_t nfaults, const int32_t *forced,
+                                  uint8_t *records)
+{
+    orc_circuit_run(nops, ops, NULL, nq, nmeas, 0, 0, nfaults, forced, records);
+}
+
+static void orc_circuit_run(int nops, const int32_t *ops, const uint32_t *thr, int nq, int nmeas, uint64_t seed,
+                            int64_t shot0, int64_t shots, const int32_t *forced, uint8_t *records)
 {
     uint8_t *fx = (uint8_t *)malloc((size_t)(nq ? nq : 1)), *fz = (uint8_t *)malloc((size_t)(nq ? nq : 1));
     const uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
@@ -357,7 +373,11 @@ void orc_circuit_sample(int nops, const int32_t *ops, const uint32_t *thr, int n
             const int code = ops[4 * i] & 0xff, ti = ops[4 * i] >> 8, q0 = ops[4 * i + 1], q1 = ops[4 * i + 2];
             uint32_t r[4] = {0, 0, 0, 0};
             int hit = 0;
-            if (ti) {
+            uint32_t fcode = 0;
+            if (ti && forced) {
+                hit = forced[2 * s] == ops[4 * i + 3];
+                fcode = (uint32_t)forced[2 * s + 1];
+            } else if (ti) {
                 const uint32_t ctr[4] = { (uint32_t)g, (uint32_t)(g >> 32), (uint32_t)ops[4 * i + 3], 0x51u };
                 orc_philox4x32_10(ctr, key, r);
                 hit = r[0] < thr[ti];
@@ -372,13 +392,13 @@ void orc_circuit_sample(int nops, const int32_t *ops, const uint32_t *thr, int n
             case 6: rec[k++] = (uint8_t)(fz[q0] ^ hit); fx[q0] = fz[q0] = 0; break;
             case 7:
                 if (hit) {
-                    const uint32_t c = 1u + (uint32_t)(((uint64_t)r[1] * 3u) >> 32);
+                    const uint32_t c = forced ? fcode : 1u + (uint32_t)(((uint64_t)r[1] * 3u) >> 32);
                     fx[q0] ^= (uint8_t)(c != 3u); fz[q0] ^= (uint8_t)(c != 1u);
                 }
                 break;
             case 8:
                 if (hit) {
-                    const uint32_t c = 1u + (uint32_t)(((uint64_t)r[1] * 15u) >> 32), pa = c & 3u, pb = c >> 2;
+                    const uint32_t c = forced ? fcode : 1u + (uint32_t)(((uint64_t)r[1] * 15u) >> 32), pa = c & 3u, pb = c >> 2;
                     fx[q0] ^= (uint8_t)(pa == 1u || pa == 2u); fz[q0] ^= (uint8_t)(pa >= 2u);
                     fx[q1] ^= (uint8_t)(pb == 1u || pb == 2u); fz[q1] ^= (uint8_t)(pb >= 2u);
                 }

@@ -588,9 +588,6 @@ def test_run_simulation_multi_round_modes(gpu, code225):
         ref = StorageExperiment(code225, 2, 0.012, 0.01, mode, opts, circuit=circuit).run(64, seed=3, per_shot=True)
         assert isinstance(out, list) and len(out) == 64 and all(isinstance(v, bool) for v in out)
         assert out == [bool(v) for v in ref["fail"]]
-    with pytest.raises(NotImplementedError):
-        run_simulation(8, code225, lambda x, z: 0.01, lambda x, z: 0.01, depolarizing_noise, {"p": 0.01, "pm": 0.01}, opts, 2,
-                       "bpd_detector")
     with pytest.raises(RuntimeError):
         run_simulation(8, code225, lambda x, z: 0.01, lambda x, z: 0.01, depolarizing_noise, {"p": 0.01, "pm": 0.01}, opts, 2,
                        "no_such_mode")
@@ -638,3 +635,90 @@ def test_storage_recipes_on_circuit_level_noise(gpu, code225, mode, name, rounds
     corr, fail = _oracle_recipe(code225, rounds, data_prior, meas_prior, mode, opts, records=records)
     assert np.array_equal(got["corrections"], corr), mode
     assert np.array_equal(got["fail"], fail)
+
+
+
+# ---------------------------------------------------------------------------------------------
+# detector error model + decoder_mode 'bpd_detector' (_experiment.py:128-151,174,186-204)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def dem_t2(gpu, code225):
+    from exp_ldpc_b200.circuits import compile_circuit, detector_error_model
+    from exp_ldpc_b200.storage import build_storage_simulation, circuit_noise
+    circuit = build_storage_simulation(2, circuit_noise(0.004, 0.006), code225).circuit
+    prog = compile_circuit(circuit)
+    return circuit, prog, detector_error_model(prog)
+
+
+def test_detector_error_model_columns_are_fault_symptoms(dem_t2):
+    """Every column of the model is the symptom of at least one elementary fault propagated by the oracle,
+    and every sampled elementary fault's symptom is a column (or empty)."""
+    from oracle import pyoracle as po
+    _, prog, dem = dem_t2
+    ndet, nfaults = dem.fault_check_matrix.shape
+    assert ndet == len(prog.detectors) == 108 + 216 + 108 and dem.fault_map.shape == (9, nfaults)
+    assert (dem.fault_priors > 0).all() and (dem.fault_priors < 0.5).all()
+    cols = {(tuple(dem.fault_check_matrix[:, j].nonzero()[0]), tuple(dem.fault_map[:, j].nonzero()[0])) for j in range(nfaults)}
+    assert len(cols) == nfaults                                          # merged: no duplicate symptoms
+    rng = np.random.default_rng(0)
+    noisy = prog.ops[(prog.ops[:, 0] >> 8) > 0]
+    pick = noisy[rng.choice(len(noisy), 200, replace=False)]
+    faults = []
+    for code_ti, _a, _b, site in pick:
+        code = int(code_ti) & 0xff
+        faults.append((site, int(rng.integers(1, 4)) if code == 7 else int(rng.integers(1, 16)) if code == 8 else 0))
+    rec = po.circuit_propagate_faults(prog.ops, prog.num_qubits, prog.num_measurements, faults).astype(np.int64)
+    det = (rec @ dem.detector_matrix.T.toarray()) % 2
+    obs = (rec @ dem.observable_matrix.T.toarray()) % 2
+    for k in range(len(faults)):
+        key = (tuple(np.flatnonzero(det[k])), tuple(np.flatnonzero(obs[k])))
+        assert key == ((), ()) or key in cols, faults[k]
+
+
+def test_detector_error_model_predicts_detector_rates(dem_t2):
+    """P(detector fires) from the model = XOR-combination of the priors of the faults that touch it; the
+    circuit sampler must reproduce it (this ties the sampler, the annotations and the model together)."""
+    from exp_ldpc_b200.circuits import CircuitSampler
+    circuit, prog, dem = dem_t2
+    shots = 40000
+    rec = CircuitSampler(prog).sample(shots, seed=5).astype(np.int64)
+    fired = ((rec @ dem.detector_matrix.T.toarray()) % 2).mean(axis=0)
+    h = dem.fault_check_matrix.tocsr()
+    pred = np.array([(1 - np.prod(1 - 2 * dem.fault_priors[h.indices[h.indptr[i]:h.indptr[i + 1]]])) / 2 for i in range(h.shape[0])])
+    sigma = np.sqrt(pred * (1 - pred) / shots)
+    assert np.all(np.abs(fired - pred) < 5 * sigma + 2e-4)
+
+
+def test_bpd_detector_mode_against_oracle(gpu, code225):
+    """Measurement-step noise (depolarizing_noise): its detector error model is small enough for the
+    shared-memory BP kernel; the circuit_noise model of the same code (15 k faults, 45 k edges) is not and
+    is rejected with QD_EUNSUP."""
+    from exp_ldpc_b200._lib import QdError
+    from exp_ldpc_b200.circuits import compile_circuit
+    from exp_ldpc_b200.experiment import DetectorExperiment, run_simulation
+    from exp_ldpc_b200.storage import build_storage_simulation, circuit_noise, depolarizing_noise
+    from oracle import pyoracle as po
+    circuit = build_storage_simulation(2, depolarizing_noise(0.01, 0.012), code225).circuit
+    prog = compile_circuit(circuit)
+    opts = dict(max_iter=15, bp_method="ms", ms_scaling_factor=0.0)
+    shots = 48
+    exp = DetectorExperiment(circuit, opts)
+    dem = exp.dem
+    out = run_simulation(shots, code225, lambda x, z: 0.01, lambda x, z: 0.01, depolarizing_noise, {"p": 0.01, "pm": 0.012},
+                         opts, 2, "bpd_detector", seed=9)
+    with pytest.raises(QdError):
+        DetectorExperiment(build_storage_simulation(2, circuit_noise(0.004, 0.006), code225).circuit, opts)
+    got = exp.run(shots, seed=9, per_shot=True)
+    rec = po.circuit_sample(prog.ops, prog.thresholds, prog.num_qubits, prog.num_measurements, 9, 0, shots).astype(np.int64)
+    assert np.array_equal(got["records"], rec)
+    det = (rec @ dem.detector_matrix.T.toarray()) % 2
+    obs = (rec @ dem.observable_matrix.T.toarray()) % 2
+    assert np.array_equal(got["detectors"], det)
+    ref = po.OracleBP(exp.dem.fault_check_matrix, channel_probs=exp.dem.fault_priors, **opts)
+    fm = exp.dem.fault_map.toarray().astype(np.int64)
+    for s in range(shots):
+        fault_set = ref.decode(det[s])                                  # _experiment.py:147-151
+        assert np.array_equal(got["fault_sets"][s], fault_set), s
+        logicals = (obs[s] + fm @ fault_set) % 2
+        assert got["fail"][s] == int(logicals.any())
+    assert out == [bool(v) for v in got["fail"]]
