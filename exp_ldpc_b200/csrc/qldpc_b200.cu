@@ -16,6 +16,7 @@
 #include "bp7_kernel.cuh"
 #include "bp7_layout.h"
 #include "bp_pick.h"
+#include "bpg_kernel.cuh"
 #include "frame_sim.cuh"
 #include "osd_kernel.cuh"
 #include "ssf_kernel.cuh"
@@ -201,6 +202,9 @@ struct qd_graph {
     std::vector<int32_t> row_ptr, col_idx, col_ptr;
     std::vector<uint32_t> row_desc, col_desc, csc_pos, csc_row, fpos_of_pos;
     std::vector<uint8_t> csc_k;      // index of the edge within its row
+    std::vector<int32_t> csc_edge;   // CSR edge id of every CSC entry
+    DevBuf d_col_ptr, d_csc_edge;
+    int big = 0;                     // degrees / size beyond the shared-memory kernels: global-memory BP only
     // message placements of the thread-owned-state BP kernel, keyed by (banks, column tile)
     std::list<std::pair<int, Bp7Layout>> bp7_layouts;   // list: references stay valid
     DevBuf d_row_desc, d_col_desc, d_csc_pos, d_csc_row, d_row_ptr, d_col_idx, d_fpos;
@@ -235,6 +239,8 @@ struct qd_bp {
     double v7_prior0 = 0.0, alpha_fixed = 0.0;
     std::vector<double> prior_dom;   // priors in the decoder's domain, per column
     int v7_lines = 0;
+    int global_mem = 0;    // messages in global memory (bpg_kernel.cuh): graphs the shared-memory kernels cannot take
+    DevBuf d_scratch;
     int llr_mode = 0;      // what d_llr receives (0: log-ratio every iteration, 1: raw soft output of the last iteration)
     DevBuf d7_table, d7_row_table, d7_chunk_deg, d7_prior_rec, d7_col_id, d7_const_bits;
     // host-buffer pipeline state
@@ -340,7 +346,7 @@ extern "C" int qd_graph_create(int32_t m, int32_t n, int64_t nnz, const int32_t 
             if (e > lo && h_col_idx[e] <= h_col_idx[e - 1]) return fail(QD_EINVAL, "column indices must be sorted and unique");
         }
     }
-    if (max_row > 255) return fail(QD_EUNSUP, "row degree > 255");
+    if (max_row > 255) g->big = 1;
     int min_row = max_row;
     for (int i = 0; i < m; ++i) min_row = std::min(min_row, h_row_ptr[i + 1] - h_row_ptr[i]);
     const int regular_deg = (m > 0 && min_row == max_row) ? max_row : 0;
@@ -370,10 +376,11 @@ extern "C" int qd_graph_create(int32_t m, int32_t n, int64_t nnz, const int32_t 
         max_col = std::max(max_col, g->col_ptr[j + 1]);
         g->col_ptr[j + 1] += g->col_ptr[j];
     }
-    if (max_col > 255) return fail(QD_EUNSUP, "column degree > 255");
+    if (max_col > 255) g->big = 1;
     g->csc_pos.resize(std::max<int64_t>(nnz, 1));
     g->csc_row.resize(std::max<int64_t>(nnz, 1));
     g->csc_k.resize(std::max<int64_t>(nnz, 1));
+    g->csc_edge.resize(std::max<int64_t>(nnz, 1));
     g->col_desc.resize(n);
     {
         std::vector<int> fill(g->col_ptr.begin(), g->col_ptr.end() - 1);
@@ -382,7 +389,8 @@ extern "C" int qd_graph_create(int32_t m, int32_t n, int64_t nnz, const int32_t 
                 const int t = fill[h_col_idx[e]]++;
                 g->csc_pos[t] = (uint32_t)pos_of_edge[e];
                 g->csc_row[t] = (uint32_t)i;
-                g->csc_k[t] = (uint8_t)(e - h_row_ptr[i]);
+                g->csc_k[t] = (uint8_t)std::min(e - h_row_ptr[i], 255);
+                g->csc_edge[t] = e;
             }
         for (int j = 0; j < n; ++j)
             g->col_desc[j] = (uint32_t)g->col_ptr[j] | ((uint32_t)(g->col_ptr[j + 1] - g->col_ptr[j]) << 24);
@@ -394,6 +402,8 @@ extern "C" int qd_graph_create(int32_t m, int32_t n, int64_t nnz, const int32_t 
     if ((rc = upload(g->d_row_ptr, g->row_ptr))) return rc;
     if ((rc = upload(g->d_col_idx, g->col_idx))) return rc;
     if ((rc = upload(g->d_fpos, g->fpos_of_pos))) return rc;
+    if ((rc = upload(g->d_col_ptr, g->col_ptr))) return rc;
+    if ((rc = upload(g->d_csc_edge, g->csc_edge))) return rc;
     GraphDev &d = g->dev;
     d.m = m; d.n = n; d.nnz = (int)nnz;
     d.nwm = words_for(m); d.nwn = words_for(n);
@@ -793,12 +803,15 @@ static int bp7_configure(qd_bp *d, int threads, int slots, int ctas)
 // pick the kernel family and its default launch geometry.  Row-regular graphs with a compiled
 // (row degree, column tile) pair take the thread-owned-state kernel (bp7_kernel.cuh) when they fit;
 // everything else the generic kernel (bp_kernel.cuh).
-static int bp_choose_kernel(qd_bp *d, bool allow_regular)
+static int bp_choose_kernel(qd_bp *d, bool allow_regular, bool family_global = false)
 {
     const GraphDev &gd = d->g->dev;
     int rc;
     d->v7 = 0;
-    if (allow_regular && gd.max_row_deg >= 2 && gd.max_col_deg >= 1 && gd.max_col_deg <= 8) {
+    d->global_mem = 0;
+    const bool shared_ok = !d->g->big && gd.max_col_deg <= 16 && !(d->method == QD_BP_PRODUCT_SUM && gd.max_row_deg > 16);
+    if (family_global || !shared_ok) { d->global_mem = 1; }
+    else if (allow_regular && gd.max_row_deg >= 2 && gd.max_col_deg >= 1 && gd.max_col_deg <= 8) {
         // candidates: exact (row degree, column tile) for row-regular graphs, else the padded variants
         const int vm0 = gd.max_col_deg <= 4 ? 4 : 8;
         bool found = false;
@@ -819,13 +832,21 @@ static int bp_choose_kernel(qd_bp *d, bool allow_regular)
             if (bp7_configure(d, 0, 0, 0) != 0) d->v7 = 0;     // does not fit: generic kernel
         }
     }
-    if (!d->v7) {
+    if (!d->v7 && !d->global_mem) {
         d->rd = 0;
         d->v7_irreg = 0;
         d->vmax = gd.max_col_deg <= 8 ? 8 : 16;
         d->idx_bytes = 4;
         if ((rc = bp6_prepare(d))) return rc;
-        if ((rc = bp_default_config(d))) return rc;
+        if (bp_default_config(d) != 0) d->global_mem = 1;       // does not fit shared memory
+    }
+    if (d->global_mem) {
+        d->rd = 0; d->v7_irreg = 0;
+        const size_t smem = (size_t)((gd.n + 15) & ~15) + ((gd.m + 15) & ~15) + (size_t)gd.nwn * 4 + 16;
+        if (smem > (size_t)d->g->smem_optin)
+            return fail(QD_EUNSUP, "graph too large even for the global-memory BP kernel (decisions + syndrome exceed shared memory)");
+        d->threads = 512; d->slots = 1; d->ctas_per_sm = std::max(1, std::min(4, (int)((200u * 1024u) / (smem + 1024)))); d->groups = 1;
+        d->smem = smem;
     }
     return 0;
 }
@@ -833,18 +854,20 @@ static int bp_choose_kernel(qd_bp *d, bool allow_regular)
 extern "C" int qd_bp_select_kernel(qd_bp *d, int32_t family)
 {
     if (!d) return fail(QD_EINVAL, "NULL handle");
-    if (family != 0 && family != 6 && family != 7) return fail(QD_EINVAL, "kernel family must be 0 (automatic), 6 (generic) or 7 (row-regular)");
+    if (family != 0 && family != 5 && family != 6 && family != 7)
+        return fail(QD_EINVAL, "kernel family must be 0 (automatic), 5 (global memory), 6 (generic) or 7 (thread-owned state)");
     int rc = use_device(d->g->device);
     if (rc) return rc;
-    if ((rc = bp_choose_kernel(d, family != 6))) return rc;
-    if (family == 7 && !d->v7) return fail(QD_EUNSUP, "the row-regular BP kernel does not support this graph");
+    if ((rc = bp_choose_kernel(d, family != 6, family == 5))) return rc;
+    if (family == 7 && !d->v7) return fail(QD_EUNSUP, "the thread-owned-state BP kernel does not support this graph");
+    if (family == 6 && d->global_mem) return fail(QD_EUNSUP, "the generic shared-memory BP kernel does not support this graph");
     return 0;
 }
 
 extern "C" int qd_bp_get_kernel(qd_bp *d, int32_t *family, int32_t *row_degree, int32_t *column_tile)
 {
     if (!d) return fail(QD_EINVAL, "NULL handle");
-    if (family) *family = d->v7 ? 7 : 6;
+    if (family) *family = d->global_mem ? 5 : (d->v7 ? 7 : 6);
     if (row_degree) *row_degree = d->rd;
     if (column_tile) *column_tile = d->vmax;
     return 0;
@@ -868,13 +891,10 @@ extern "C" int qd_bp_create(qd_graph *g, const double *h_channel_probs, int32_t 
     d->max_iter = max_iter > 0 ? max_iter : gd.n;   // ldpc convention: 0 -> n
     d->method = method;
     d->precision = precision;
-    if (gd.max_col_deg > 16) return fail(QD_EUNSUP, "column degree > 16 not supported by the shared-memory BP kernel");
     d->alpha_fixed = ms_scaling_factor;
     d->rd = 0;
     d->vmax = gd.max_col_deg <= 8 ? 8 : 16;
     d->idx_bytes = 4;
-    if (method == QD_BP_PRODUCT_SUM && gd.max_row_deg > 16)
-        return fail(QD_EUNSUP, "product-sum: row degree > 16 not supported by the shared-memory BP kernel");
     // priors in the decoder's domain, computed in double with the host libm (same as the oracle)
     std::vector<double> pr(gd.n), al(d->max_iter + 1, 0.0);
     for (int j = 0; j < gd.n; ++j) {
@@ -916,6 +936,11 @@ extern "C" int qd_bp_destroy(qd_bp *d)
 extern "C" int qd_bp_configure(qd_bp *d, int32_t threads, int32_t slots, int32_t ctas_per_sm, int32_t teams)
 {
     if (!d) return fail(QD_EINVAL, "NULL handle");
+    if (d->global_mem) {
+        if (threads > 0) { if (threads % 32 || threads > 512) return fail(QD_EINVAL, "threads must be a multiple of 32 <= 512"); d->threads = threads; }
+        if (ctas_per_sm > 0) d->ctas_per_sm = ctas_per_sm;
+        return 0;
+    }
     if (d->v7) {
         if (teams > 1) return fail(QD_EINVAL, "the row-regular BP kernel runs one team per CTA");
         int rc = use_device(d->g->device);
@@ -963,6 +988,35 @@ static int bp_launch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int6
     int rc = use_device(d->g->device);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (d->global_mem) {
+        qd_graph *gr = d->g;
+        const unsigned grid = (unsigned)std::min<long long>((long long)gr->sm_count * d->ctas_per_sm, shots);
+        const size_t rb = d->precision == QD_PREC_F64 ? 8 : 4;
+        if ((rc = d->d_scratch.ensure((size_t)gr->sm_count * d->ctas_per_sm * 2 * std::max(g.nnz, 1) * rb))) return rc;
+        BpgParams q{};
+        q.m = g.m; q.n = g.n; q.nnz = g.nnz; q.nwm = g.nwm; q.nwn = g.nwn;
+        q.row_ptr = g.row_ptr; q.col_idx = g.col_idx;
+        q.col_ptr = gr->d_col_ptr.as<int32_t>(); q.csc_edge = gr->d_csc_edge.as<int32_t>();
+        q.prior = d->d_prior.p; q.alpha_fixed = d->alpha_fixed; q.max_iter = d->max_iter;
+        q.scratch = d->d_scratch.p;
+        q.synd = d_synd; q.synd_stride = synd_stride; q.shots = shots;
+        q.corr = d_corr; q.corr_stride = corr_stride;
+        q.conv = d_converged; q.iters = d_iters; q.llr = d_llr; q.llr_mode = d->llr_mode;
+        q.err = d_err; q.err_stride = err_stride;
+        q.lzT = d_err ? logicals->d_lzT.as<uint32_t>() : nullptr;
+        q.k = d_err ? logicals->k : 0;
+        q.fail = d_fail;
+        q.counters = (long long *)d_counters;
+        q.next_shot = d->d_next.as<unsigned long long>() + queue;
+        void (*fn)(const BpgParams) =
+            d->precision == QD_PREC_F64 ? (d->method == QD_BP_MIN_SUM ? bpg_kernel<double, QD_BP_MIN_SUM> : bpg_kernel<double, QD_BP_PRODUCT_SUM>)
+                                        : (d->method == QD_BP_MIN_SUM ? bpg_kernel<float, QD_BP_MIN_SUM> : bpg_kernel<float, QD_BP_PRODUCT_SUM>);
+        QD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem));
+        QD_CUDA(cudaMemsetAsync(q.next_shot, 0, sizeof(unsigned long long), st));
+        fn<<<grid, d->threads, d->smem, st>>>(q);
+        QD_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (d->v7) {
         Bp7Params q{};
         q.m = g.m; q.n = g.n; q.nwm = g.nwm; q.nwn = g.nwn;

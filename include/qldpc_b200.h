@@ -144,9 +144,10 @@ int qd_bp_configure(qd_bp *d, int32_t threads, int32_t slots, int32_t ctas_per_s
 int qd_bp_get_config(qd_bp *d, int32_t *threads, int32_t *slots, int32_t *ctas_per_sm,
                      int32_t *teams, int32_t *smem_bytes, int32_t *grid);
 
-/* Kernel family (testing / tuning).  qd_bp_create picks automatically: 7 = row-regular kernel
- * (all rows of H have the same degree and a kernel is compiled for it), 6 = generic kernel (any
- * row degrees).  select: 0 = automatic, 6 / 7 = force; resets the launch geometry. */
+/* Kernel family (testing / tuning).  qd_bp_create picks automatically: 7 = thread-owned-state
+ * shared-memory kernel (a variant is compiled for the graph's degrees), 6 = generic shared-memory
+ * kernel, 5 = messages in global memory (graphs too large or too dense for shared memory; slower).
+ * select: 0 = automatic, 5 / 6 / 7 = force; resets the launch geometry. */
 int qd_bp_select_kernel(qd_bp *d, int32_t family);
 int qd_bp_get_kernel(qd_bp *d, int32_t *family, int32_t *row_degree, int32_t *column_tile);
 

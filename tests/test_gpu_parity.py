@@ -691,9 +691,8 @@ def test_detector_error_model_predicts_detector_rates(dem_t2):
 
 def test_bpd_detector_mode_against_oracle(gpu, code225):
     """Measurement-step noise (depolarizing_noise): its detector error model is small enough for the
-    shared-memory BP kernel; the circuit_noise model of the same code (15 k faults, 45 k edges) is not and
-    is rejected with QD_EUNSUP."""
-    from exp_ldpc_b200._lib import QdError
+    shared-memory BP kernel; the circuit_noise model of the same code (15 k faults, 45 k edges) falls back
+    to the global-memory kernel."""
     from exp_ldpc_b200.circuits import compile_circuit
     from exp_ldpc_b200.experiment import DetectorExperiment, run_simulation
     from exp_ldpc_b200.storage import build_storage_simulation, circuit_noise, depolarizing_noise
@@ -706,8 +705,8 @@ def test_bpd_detector_mode_against_oracle(gpu, code225):
     dem = exp.dem
     out = run_simulation(shots, code225, lambda x, z: 0.01, lambda x, z: 0.01, depolarizing_noise, {"p": 0.01, "pm": 0.012},
                          opts, 2, "bpd_detector", seed=9)
-    with pytest.raises(QdError):
-        DetectorExperiment(build_storage_simulation(2, circuit_noise(0.004, 0.006), code225).circuit, opts)
+    big = DetectorExperiment(build_storage_simulation(2, circuit_noise(0.004, 0.006), code225).circuit, opts)
+    assert big.decoder.config()["kernel"] == "global"       # 15 k faults / 45 k edges: messages live in global memory
     got = exp.run(shots, seed=9, per_shot=True)
     rec = po.circuit_sample(prog.ops, prog.thresholds, prog.num_qubits, prog.num_measurements, 9, 0, shots).astype(np.int64)
     assert np.array_equal(got["records"], rec)
@@ -722,3 +721,57 @@ def test_bpd_detector_mode_against_oracle(gpu, code225):
         logicals = (obs[s] + fm @ fault_set) % 2
         assert got["fail"][s] == int(logicals.any())
     assert out == [bool(v) for v in got["fail"]]
+
+
+
+# ---------------------------------------------------------------------------------------------
+# global-memory BP kernel: the fallback for graphs the shared-memory kernels cannot take
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", _bp_case_names())
+def test_global_memory_bp_kernel_matches_committed_golden_vectors(gpu, codes, name):
+    g = np.load(os.path.join(GOLDEN, "decoder_vectors.npz"))
+    out = _run_gpu_case(name, codes, kernel="global")
+    assert np.array_equal(np.packbits(out["decodings"], axis=1), g[name + "_dec"])
+    assert np.array_equal(out["iters"], g[name + "_iters"])
+    assert np.array_equal(out["fail"], g[name + "_fail"])
+    assert np.array_equal(out["converged"], g[name + "_conv"])
+
+
+def test_large_graphs_fall_back_to_global_memory(gpu, code1600):
+    """Spacetime matrix of the n = 1600 code, T = 3: 26 k edges do not fit one SM in fp64."""
+    from exp_ldpc_b200.experiment import SpacetimeExperiment
+    from oracle import pyoracle as po
+    opts = dict(max_iter=8, bp_method="ms", ms_scaling_factor=0.0)
+    exp = SpacetimeExperiment(code1600, 3, 0.004, 0.006, opts)
+    assert exp.decoder.config()["kernel"] == "global"
+    shots = 24
+    got = exp.run(shots, seed=2, per_shot=True)
+    h_st = exp.spacetime.spacetime_check_matrix
+    m, n = code1600.checks.z.shape
+    lz = np.asarray(code1600.logicals.z) & 1
+    l_st = np.concatenate([lz] * 4 + [np.zeros((lz.shape[0], 3 * m), dtype=lz.dtype)], axis=1)
+    ref = po.run_code_capacity(h_st, l_st, exp.prior, exp.prior, decoder="bp", seed=2, shots=shots, per_shot=True, **opts)
+    assert (got["decodings"] == ref["decodings"]).all()
+    assert np.array_equal(got["iters"], ref["iters"]) and np.array_equal(got["fail"], ref["fail"])
+
+
+def test_dense_rows_take_the_global_kernel(gpu):
+    """Row degree 300 (> 255) and product-sum with row degree > 16: beyond the shared-memory kernels."""
+    from scipy import sparse
+    from exp_ldpc_b200.decoders import bp_decoder
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(4)
+    a = (rng.random((40, 600)) < 0.05).astype(np.uint32)
+    a[0, :300] = 1
+    h = sparse.csr_matrix(a)
+    probs = rng.uniform(0.01, 0.05, 600)
+    err = (rng.random((20, 600)) < probs).astype(np.int64)
+    synd = (err @ a.T.astype(np.int64)) % 2
+    for method in ("ms", "ps"):
+        dec = bp_decoder(h, channel_probs=probs, max_iter=10, bp_method=method, ms_scaling_factor=0.0)
+        assert dec.config()["kernel"] == "global"
+        ref = po.OracleBP(h, channel_probs=probs, max_iter=10, bp_method=method, ms_scaling_factor=0.0)
+        corr, conv, its = dec.decode_batch(synd)
+        for s in range(synd.shape[0]):
+            assert np.array_equal(corr[s], ref.decode(synd[s])), (method, s)
+            assert its[s] == ref.iter and conv[s] == ref.converge
