@@ -51,7 +51,7 @@ SIGNATURES = {
     "qd_bp_decode_batch": (C.c_int, [vp, vp, i32, i64, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp]),
     "qd_bp_decode_batch_host": (C.c_int, [vp, vp, i32, i64, vp, i32, vp, vp]),
     "qd_bp_decode_one": (C.c_int, [vp, vp, vp, P(i32), P(i32), vp]),
-    "qd_osd_create": (C.c_int, [vp, P(vp)]),
+    "qd_osd_create": (C.c_int, [vp, i32, i32, P(vp)]),
     "qd_osd_destroy": (C.c_int, [vp]),
     "qd_osd_rank": (C.c_int, [vp]),
     "qd_bposd_decode_batch": (C.c_int, [vp, vp, vp, i32, i64, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]),

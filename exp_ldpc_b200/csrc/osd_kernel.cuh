@@ -31,6 +31,7 @@ struct OsdParams {
     int P;                      // sort size: power of two >= n
     int rank;                   // rank of H
     int negate_key;             // product-sum: rank by descending ratio
+    int method, order;          // 0 OSD-0; 1 osd_e, 2 osd_cs with search depth `order`
     const int32_t *row_ptr, *col_idx;
     const uint32_t *synd; int synd_stride;
     const double *soft;         // [shots][n] raw soft output of the last BP iteration
@@ -187,12 +188,136 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
         }
         __syncthreads();
 
-        // ---- 4. solution on the information set
+        // ---- 4. higher-order search (osd_e / osd_cs): patterns on the columns outside the information set
+        // T (ranking order).  A pattern t changes the information-set part to x_S = x_S(OSD-0) + R_T t, so
+        // its weight is |t| + sum over pivot rows of (s_r ^ parity of the row's bits on t).  Smallest
+        // weight wins; OSD-0 first, ties to the earlier candidate (oracle: orc_osd).
+        long long best_ci = -1;                                  // -1: keep the OSD-0 solution
+        uint32_t *Mrow = reinterpret_cast<uint32_t *>(keys);     // the ranking keys are dead: reuse them
+        uint16_t *tlist = reinterpret_cast<uint16_t *>(Mrow + m);
+        int k = 0, ord_k = 0;
+        if (p.method != 0 && p.order > 0) {
+            uint32_t *colpiv = dec;                               // bit per column: in the information set
+            for (int w = tid; w < p.nwn; w += NT) colpiv[w] = 0u;
+            __syncthreads();
+            for (int r = tid; r < m; r += NT) {
+                const unsigned pc = pcol[r];
+                if (pc != 0xFFFFu) atomicOr(&colpiv[pc >> 5], 1u << (pc & 31));
+            }
+            __syncthreads();
+            if (warp == 0) {                                      // compaction of T in ranking order
+                int count = 0;
+                for (int base = 0; base < n; base += 32) {
+                    const int t = base + lane;
+                    const int c = t < n ? (int)idx[t] : 0;
+                    const bool isT = t < n && !((colpiv[c >> 5] >> (c & 31)) & 1u);
+                    const unsigned bal = __ballot_sync(0xffffffffu, isT);
+                    if (isT) tlist[count + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)c;
+                    count += __popc(bal);
+                }
+                if (lane == 0) cand[0] = count;
+            }
+            __syncthreads();
+            k = cand[0];
+            ord_k = min(p.order, k);
+            // per row: bit b = the row's bit on T[b] (b < ord_k <= 24), bit 30 = pivot row, bit 31 = OSD-0 bit
+            int w0 = 0;
+            for (int r = tid; r < m; r += NT) {
+                uint32_t v = 0u;
+                if (pcol[r] != 0xFFFFu) {
+                    const unsigned long long *row = R + (size_t)r * W;
+                    const uint32_t sb = (uint32_t)((row[n >> 6] >> (n & 63)) & 1ULL);
+                    v = (1u << 30) | (sb << 31);
+                    for (int b = 0; b < ord_k; ++b) { const int c = tlist[b]; v |= (uint32_t)((row[c >> 6] >> (c & 63)) & 1ULL) << b; }
+                    w0 += (int)sb;
+                }
+                Mrow[r] = v;
+            }
+            __syncthreads();
+            // block sum of the OSD-0 weight
+            {
+                int v = w0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) cand[32 + warp] = v;
+                __syncthreads();
+                v = lane < nwarps ? cand[32 + lane] : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                w0 = v;
+                __syncthreads();
+            }
+            const long long ncand = p.method == 1 ? ((1LL << ord_k) - 1) : (long long)k + (long long)ord_k * (ord_k - 1) / 2;
+            unsigned long long mybest = ~0ULL;                   // (weight << 32) | candidate index
+            for (long long ci = tid; ci < ncand; ci += NT) {
+                int wt;
+                if (p.method == 2 && ci < k) {                   // one column of T
+                    const int c = tlist[ci];
+                    const int cw = c >> 6, cb = c & 63;
+                    wt = 1;
+                    for (int r = 0; r < m; ++r) {
+                        const uint32_t v = Mrow[r];
+                        wt += (int)((v >> 30) & ((v >> 31) ^ (uint32_t)((R[(size_t)r * W + cw] >> cb) & 1ULL)) & 1u);
+                    }
+                } else {
+                    uint32_t mask;
+                    if (p.method == 1) mask = (uint32_t)(ci + 1);
+                    else {                                       // pair (i, j), i < j < ord_k, lexicographic
+                        long long q = ci - k;
+                        int i = 0;
+                        while (q >= ord_k - 1 - i) { q -= ord_k - 1 - i; ++i; }
+                        mask = (1u << i) | (1u << (i + 1 + (int)q));
+                    }
+                    wt = __popc(mask);
+                    for (int r = 0; r < m; ++r) {
+                        const uint32_t v = Mrow[r];
+                        wt += (int)((v >> 30) & ((v >> 31) ^ (uint32_t)__popc(v & mask)) & 1u);
+                    }
+                }
+                const unsigned long long key = ((unsigned long long)(unsigned)wt << 32) | (unsigned long long)ci;
+                mybest = key < mybest ? key : mybest;
+            }
+            {                                                     // block minimum
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, mybest, o); mybest = o2 < mybest ? o2 : mybest; }
+                unsigned long long *red = keys + (((size_t)m * 4 + (size_t)n * 2 + 7) >> 3);      // past Mrow and tlist
+                if (lane == 0) red[warp] = mybest;
+                __syncthreads();
+                mybest = lane < nwarps ? red[lane] : ~0ULL;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, mybest, o); mybest = o2 < mybest ? o2 : mybest; }
+            }
+            if (mybest != ~0ULL && (int)(mybest >> 32) < w0) best_ci = (long long)(mybest & 0xffffffffULL);
+            __syncthreads();
+        }
+
+        // ---- 5. the chosen solution
         for (int w = tid; w < p.nwn; w += NT) dec[w] = 0u;
         __syncthreads();
-        for (int r = tid; r < m; r += NT) {
-            const unsigned pc = pcol[r];
-            if (pc != 0xFFFFu && ((R[(size_t)r * W + (n >> 6)] >> (n & 63)) & 1ULL)) atomicOr(&dec[pc >> 5], 1u << (pc & 31));
+        {
+            uint32_t mask = 0u;
+            int single = -1;
+            if (best_ci >= 0) {
+                if (p.method == 2 && best_ci < k) single = tlist[best_ci];
+                else if (p.method == 1) mask = (uint32_t)(best_ci + 1);
+                else {
+                    long long q = best_ci - k;
+                    int i = 0;
+                    while (q >= ord_k - 1 - i) { q -= ord_k - 1 - i; ++i; }
+                    mask = (1u << i) | (1u << (i + 1 + (int)q));
+                }
+                if (tid == 0 && single >= 0) atomicOr(&dec[single >> 5], 1u << (single & 31));
+                if (tid < 32 && ((mask >> tid) & 1u)) { const int c = tlist[tid]; atomicOr(&dec[c >> 5], 1u << (c & 31)); }
+            }
+            for (int r = tid; r < m; r += NT) {
+                const unsigned pc = pcol[r];
+                if (pc == 0xFFFFu) continue;
+                const unsigned long long *row = R + (size_t)r * W;
+                uint32_t bit = (uint32_t)((row[n >> 6] >> (n & 63)) & 1ULL);
+                if (single >= 0) bit ^= (uint32_t)((row[single >> 6] >> (single & 63)) & 1ULL);
+                if (mask) bit ^= (uint32_t)__popc(Mrow[r] & mask) & 1u;
+                if (bit) atomicOr(&dec[pc >> 5], 1u << (pc & 31));
+            }
         }
         __syncthreads();
         uint32_t *dst = p.corr + shot * (long long)p.corr_stride;

@@ -267,6 +267,7 @@ struct qd_osd {
     qd_graph *g = nullptr;
     int device = 0;
     int rank = 0, W = 0, P = 0;
+    int method = 0, order = 0;    // 0 OSD-0, 1 osd_e, 2 osd_cs
     size_t smem = 0;
     DevBuf d_next, d_soft, d_conv;
 };
@@ -1324,21 +1325,27 @@ static int gf2_rank_of_csr(int m, int n, const std::vector<int32_t> &row_ptr, co
     return rank;
 }
 
-extern "C" int qd_osd_create(qd_graph *g, qd_osd **out)
+extern "C" int qd_osd_create(qd_graph *g, int32_t method, int32_t order, qd_osd **out)
 {
     if (!out) return fail(QD_EINVAL, "out is NULL");
     *out = nullptr;
     if (!g) return fail(QD_EINVAL, "graph is NULL");
+    if (method < 0 || method > 2 || order < 0) return fail(QD_EINVAL, "OSD method must be 0 (osd0), 1 (osd_e) or 2 (osd_cs), order >= 0");
+    if (method == 1 && order > 16) return fail(QD_EUNSUP, "osd_e: search depth > 16 (65535 patterns) not supported");
+    if (method == 2 && order > 24) return fail(QD_EUNSUP, "osd_cs: search depth > 24 not supported");
     int rc = use_device(g->device);
     if (rc) return rc;
     const GraphDev &gd = g->dev;
     if (gd.n > 8000) return fail(QD_EUNSUP, "OSD: more than 8000 columns");
     std::unique_ptr<qd_osd> o(new qd_osd);
     o->g = g; o->device = g->device;
+    o->method = order > 0 ? method : 0; o->order = method ? order : 0;
     o->W = (gd.n + 1 + 63) / 64;
     while (o->W % 4 != 2) ++o->W;           // rows of an odd number of 16-byte units: aligned, bank-conflict free 128-bit XORs
     o->P = 1;
     while (o->P < gd.n) o->P <<= 1;
+    if (o->method && (size_t)gd.m * 4 + (size_t)gd.n * 2 + 8 * 33 > (size_t)o->P * 8)
+        return fail(QD_EUNSUP, "higher-order OSD: scratch for this shape does not fit");
     o->smem = osd_smem_layout(gd.m, o->W, o->P, gd.nwm, gd.nwn).total;
     if (o->smem > (size_t)g->smem_optin)
         return fail(QD_EUNSUP, "OSD: [H | s] (" + std::to_string(o->smem) + " B bit-packed) does not fit shared memory");
@@ -1368,6 +1375,7 @@ static int osd_launch(qd_osd *o, int negate_key, const uint32_t *d_synd, int32_t
     OsdParams p{};
     p.m = g.m; p.n = g.n; p.nwm = g.nwm; p.nwn = g.nwn;
     p.W = o->W; p.P = o->P; p.rank = o->rank; p.negate_key = negate_key;
+    p.method = o->method; p.order = o->order;
     p.row_ptr = g.row_ptr; p.col_idx = g.col_idx;
     p.synd = d_synd; p.synd_stride = synd_stride;
     p.soft = d_soft; p.conv = d_conv; p.shots = shots;

@@ -287,9 +287,9 @@ class bposd_decoder(bp_decoder):
     """Drop-in for ``ldpc.bposd_decoder`` (``_experiment.py:23-27,96-100``): belief propagation, then
     ordered-statistics post-processing on the shots BP did not converge on.
 
-    ``osd_method`` 'osd0' / 'osd_0' (information set = the first rank(H) independent columns in the
-    order of the BP soft output, no higher-order search) is implemented; the reference's default
-    'osd_cs' (order 7) and 'osd_e' are not and raise ``NotImplementedError``.
+    ``osd_method`` 'osd0' (information set = the first rank(H) independent columns in the order of the
+    BP soft output), 'osd_e' (exhaustive over the first ``osd_order`` other columns) and 'osd_cs'
+    (combination sweep, the reference's default with ``osd_order = 7``, ``_experiment.py:218-219``).
     Side outputs as upstream: ``bp_decoding`` (BP's own hard decision), ``osdw_decoding`` = the returned
     vector, ``converge`` / ``iter`` describe the BP stage."""
 
@@ -297,19 +297,23 @@ class bposd_decoder(bp_decoder):
                  channel_probs=(None,), osd_order=-1, osd_method="osd0", precision="f64", device=0, kernel="auto",
                  **_ignored):
         key = str(osd_method).lower()
-        if key in ("osd_e", "osde", "exhaustive", "e", "osd_cs", "1", "cs", "combination_sweep"):
-            if int(osd_order) > 0:
-                raise NotImplementedError(f"osd_method '{osd_method}' with osd_order > 0 is not implemented (only OSD-0)")
-        elif key not in ("osd0", "osd_0", "0", "zero"):
+        if key in ("osd_e", "osde", "exhaustive", "e"):
+            method = 1
+        elif key in ("osd_cs", "1", "cs", "combination_sweep"):
+            method = 2
+        elif key in ("osd0", "osd_0", "0", "zero"):
+            method = 0
+        else:
             raise ValueError(f"ERROR: OSD method '{osd_method}' invalid. Please choose from the following methods: "
                              "'OSD_0', 'OSD_E' or 'OSD_CS'.")
+        order = max(int(osd_order), 0) if method else 0
         super().__init__(parity_check_matrix, error_rate=error_rate, max_iter=max_iter, bp_method=bp_method,
                          ms_scaling_factor=ms_scaling_factor, channel_probs=channel_probs, precision=precision,
                          device=device, kernel=kernel)
-        self.osd_method = "osd0"
-        self.osd_order = 0
+        self.osd_method = ("osd0", "osd_e", "osd_cs")[method if order else 0]
+        self.osd_order = order
         self._osd = C.c_void_p()
-        _lib.check(_lib.lib().qd_osd_create(self.graph.handle, C.byref(self._osd)))
+        _lib.check(_lib.lib().qd_osd_create(self.graph.handle, method, order, C.byref(self._osd)))
         self.osd0_decoding = np.zeros(self.n, dtype=np.int64)
         self.osdw_decoding = np.zeros(self.n, dtype=np.int64)
 

@@ -23,8 +23,8 @@
  *   qd_code_capacity_run  <- run_simulation(samples, ...) for rounds = 0, returning the counts that
  *                            p_sweep sums                    python/qldpc/misc/_experiment.py:154-210
  *                                                            python/qldpc/misc/p_sweep.py:28-32
- *   qd_osd_*, qd_bposd_*  <- ldpc.bposd_decoder(..., osd_method="osd0").decode(syndrome): BP, then
- *                            OSD-0 on the shots BP left unconverged
+ *   qd_osd_*, qd_bposd_*  <- ldpc.bposd_decoder(..., osd_method=, osd_order=).decode(syndrome): BP, then
+ *                            OSD (osd0 / osd_e / osd_cs) on the shots BP left unconverged
  *                                                            python/qldpc/misc/_experiment.py:23-27,51,59,82,96-100,125
  *   qd_ssf_*              <- (absent from the reference; SURVEY.md Appendix C is the specification)
  *
@@ -168,11 +168,14 @@ int qd_bp_decode_batch_host(qd_bp *d, const uint32_t *h_synd, int32_t synd_strid
 int qd_bp_decode_one(qd_bp *d, const uint8_t *h_syndrome, uint8_t *h_decoding, int32_t *converged,
                      int32_t *iters, double *h_llr);
 
-/* ---- BP + OSD-0 ----------------------------------------------------------------------------- */
+/* ---- BP + OSD ------------------------------------------------------------------------------- */
 /* OSD-0: rank the columns by the soft output of the last BP iteration (most likely in error
  * first, ties by index), take the first rank(H) independent ones as information set, solve.
+ * method 1 ("osd_e"): then try all non-zero patterns on the first `order` columns outside the
+ * information set; method 2 ("osd_cs"): every single such column, then every pair among the
+ * first `order`; the lightest candidate wins (OSD-0 first, ties to the earlier candidate).
  * Needs [H | s] bit-packed in shared memory (m * ceil((n+1)/64) * 8 bytes): QD_EUNSUP otherwise. */
-int qd_osd_create(qd_graph *g, qd_osd **out);
+int qd_osd_create(qd_graph *g, int32_t method, int32_t order, qd_osd **out);
 int qd_osd_destroy(qd_osd *o);
 int qd_osd_rank(qd_osd *o);                       /* rank of H over GF(2) */
 /* As qd_bp_decode_batch; shots with converged == 0 get the OSD-0 decoding (d_converged keeps the

@@ -57,6 +57,10 @@ def lib():
         L.orc_bp_soft.restype = f64p
         L.orc_osd0.argtypes = [C.c_int, C.c_int, i32p, i32p, u8p, f64p, u8p]
         L.orc_osd0.restype = C.c_int
+        L.orc_osd.argtypes = [C.c_int, C.c_int, i32p, i32p, u8p, f64p, C.c_int, C.c_int, u8p]
+        L.orc_osd.restype = C.c_int
+        L.orc_bposd_decode.argtypes = [C.c_void_p, u8p, C.c_int, C.c_int, u8p, C.POINTER(C.c_int)]
+        L.orc_bposd_decode.restype = C.c_int
         L.orc_bposd0_decode.argtypes = [C.c_void_p, u8p, u8p, C.POINTER(C.c_int)]
         L.orc_bposd0_decode.restype = C.c_int
         L.orc_circuit_sample.argtypes = [C.c_int, i32p, u32p, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int64, u8p]
@@ -167,13 +171,34 @@ class OracleBPOSD0(OracleBP):
         return dec.astype(np.int64)
 
 
-def osd0(h, synd, key_ascending) -> np.ndarray:
-    """OSD-0 solution for an explicit ranking key (ascending = most likely in error first)."""
+OSD_METHODS = {"osd0": 0, "osd_0": 0, "osd_e": 1, "osd_cs": 2}
+
+
+class OracleBPOSD(OracleBP):
+    """``ldpc.bposd_decoder(..., osd_method=, osd_order=)`` restatement."""
+
+    def __init__(self, h, osd_method="osd0", osd_order=0, **kw):
+        super().__init__(h, **kw)
+        self.osd_method, self.osd_order = OSD_METHODS[osd_method], int(osd_order)
+
+    def decode(self, synd) -> np.ndarray:
+        s = np.ascontiguousarray(np.asarray(synd).astype(np.int64) & 1, dtype=np.uint8)
+        dec = np.zeros(self.n, dtype=np.uint8)
+        it = C.c_int(0)
+        self.converge = lib().orc_bposd_decode(self._h, _p(s, C.c_uint8), self.osd_method, self.osd_order, _p(dec, C.c_uint8),
+                                               C.byref(it))
+        self.iter = it.value
+        return dec.astype(np.int64)
+
+
+def osd0(h, synd, key_ascending, method="osd0", order=0) -> np.ndarray:
+    """OSD solution for an explicit ranking key (ascending = most likely in error first)."""
     m, n, ptr, idx = _csr(h)
     s = np.ascontiguousarray(np.asarray(synd).astype(np.int64) & 1, dtype=np.uint8)
     key = np.ascontiguousarray(key_ascending, dtype=np.float64)
     dec = np.zeros(n, dtype=np.uint8)
-    ok = lib().orc_osd0(m, n, _p(ptr, C.c_int32), _p(idx, C.c_int32), _p(s, C.c_uint8), _p(key, C.c_double), _p(dec, C.c_uint8))
+    ok = lib().orc_osd(m, n, _p(ptr, C.c_int32), _p(idx, C.c_int32), _p(s, C.c_uint8), _p(key, C.c_double),
+                       OSD_METHODS[method], int(order), _p(dec, C.c_uint8))
     if not ok:
         raise ValueError("syndrome is not in the column space of H")
     return dec
@@ -232,11 +257,12 @@ class _Experiment(C.Structure):
                 ("row_ptr", C.POINTER(C.c_int32)), ("col_idx", C.POINTER(C.c_int32)),
                 ("Lz", C.POINTER(C.c_uint8)), ("thr", C.POINTER(C.c_uint32)), ("probs", C.POINTER(C.c_double)),
                 ("max_iter", C.c_int), ("method", C.c_int), ("alpha", C.c_double),
-                ("mg", C.c_int), ("hx_row_ptr", C.POINTER(C.c_int32)), ("hx_col_idx", C.POINTER(C.c_int32))]
+                ("mg", C.c_int), ("hx_row_ptr", C.POINTER(C.c_int32)), ("hx_col_idx", C.POINTER(C.c_int32)),
+                ("osd_order", C.c_int)]
 
 
 def run_code_capacity(hz, lz, q_sample, prior, *, decoder="bp", hx=None, max_iter=0, bp_method="ms",
-                      ms_scaling_factor=0.0, seed=0, shot0=0, shots=1, threads=0, per_shot=False):
+                      ms_scaling_factor=0.0, seed=0, shot0=0, shots=1, threads=0, per_shot=False, osd_order=0):
     """Sample -> syndrome -> decode -> logical flag for ``shots`` shots on the host cores.
     Returns ``dict(failures, shots, non_converged, iters_total[, decodings, converged, iters, fail])``."""
     m, n, ptr, idx = _csr(hz)
@@ -248,6 +274,7 @@ def run_code_capacity(hz, lz, q_sample, prior, *, decoder="bp", hx=None, max_ite
     x.row_ptr, x.col_idx = _p(ptr, C.c_int32), _p(idx, C.c_int32)
     x.Lz, x.thr, x.probs = _p(lz, C.c_uint8), _p(thr, C.c_uint32), _p(probs, C.c_double)
     x.max_iter, x.method, x.alpha = int(max_iter), METHODS.get(str(bp_method).lower(), 3), float(ms_scaling_factor)
+    x.osd_order = int(osd_order)
     keep = [ptr, idx, lz, thr, probs]
     if decoder == "ssf":
         mg, _, xp, xi = _csr(hx)
@@ -262,7 +289,7 @@ def run_code_capacity(hz, lz, q_sample, prior, *, decoder="bp", hx=None, max_ite
         fail = np.zeros(shots, dtype=np.uint8)
     null8, null32 = C.POINTER(C.c_uint8)(), C.POINTER(C.c_int32)()
     rc = lib().orc_run_code_capacity(
-        C.byref(x), {"bp": 0, "ssf": 1, "bposd0": 2}[decoder], int(seed), int(shot0), int(shots), int(threads),
+        C.byref(x), {"bp": 0, "ssf": 1, "bposd0": 2, "bposd_e": 3, "bposd_cs": 4}[decoder], int(seed), int(shot0), int(shots), int(threads),
         _p(counters, C.c_int64),
         _p(dec, C.c_uint8) if per_shot else null8, _p(conv, C.c_uint8) if per_shot else null8,
         _p(its, C.c_int32) if per_shot else null32, _p(fail, C.c_uint8) if per_shot else null8)

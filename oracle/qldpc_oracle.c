@@ -282,13 +282,20 @@ static int orc_rank_cmp(const void *a, const void *b)
     return x->idx - y->idx;
 }
 
-int orc_osd0(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, const uint8_t *synd,
-             const double *key_ascending, uint8_t *decoding)
+/* method 0: OSD-0.  method 1 ("osd_e", exhaustive): all 2^order - 1 non-zero patterns on the first `order`
+ * non-information-set columns (in ranking order; pattern c sets column b iff bit b of c), c ascending.
+ * method 2 ("osd_cs", combination sweep): every single non-information-set column (ranking order), then
+ * every pair among the first `order` of them (i < j, lexicographic).  Each pattern t fixes the
+ * information-set part as x_S = x_S(OSD-0) + R_T t; the candidate of smallest Hamming weight wins, the
+ * OSD-0 solution first and ties to the earlier candidate (strict improvement only). */
+int orc_osd(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, const uint8_t *synd,
+            const double *key_ascending, int method, int order, uint8_t *decoding)
 {
     const int W = (n + 1 + 63) / 64;
     uint64_t *R = (uint64_t *)calloc((size_t)(m ? m : 1) * W, sizeof(uint64_t));
     orc_rank_t *ord = (orc_rank_t *)malloc(sizeof(orc_rank_t) * (n ? n : 1));
     int *pcol = (int *)malloc(sizeof(int) * (m ? m : 1));
+    uint8_t *is_piv = (uint8_t *)calloc((size_t)(n ? n : 1), 1);
     for (int i = 0; i < m; ++i) {
         for (int32_t e = row_ptr[i]; e < row_ptr[i + 1]; ++e) R[(size_t)i * W + (col_idx[e] >> 6)] |= (uint64_t)1 << (col_idx[e] & 63);
         if (synd[i]) R[(size_t)i * W + (n >> 6)] |= (uint64_t)1 << (n & 63);
@@ -304,6 +311,7 @@ int orc_osd0(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, const
             if (pcol[i] < 0 && ((R[(size_t)i * W + (c >> 6)] >> (c & 63)) & 1)) { piv = i; break; }
         if (piv < 0) continue;
         pcol[piv] = c;
+        is_piv[c] = 1;
         ++rank;
         for (int i = 0; i < m; ++i)
             if (i != piv && ((R[(size_t)i * W + (c >> 6)] >> (c & 63)) & 1))
@@ -316,8 +324,62 @@ int orc_osd0(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, const
         if (pcol[i] >= 0) decoding[pcol[i]] = (uint8_t)sbit;
         else if (sbit) consistent = 0;      /* syndrome outside the column space: cannot happen for s = H e */
     }
-    free(R); free(ord); free(pcol);
+    if (method != 0 && order > 0 && consistent) {
+        /* T: the columns outside the information set, in ranking order */
+        int k = 0;
+        int *T = (int *)malloc(sizeof(int) * (n ? n : 1));
+        for (int t = 0; t < n; ++t) if (!is_piv[ord[t].idx]) T[k++] = ord[t].idx;
+        const int ord_k = order < k ? order : k;
+        uint8_t *cand = (uint8_t *)malloc((size_t)(n ? n : 1)), *best = (uint8_t *)malloc((size_t)(n ? n : 1));
+        int best_w = 0;
+        for (int j = 0; j < n; ++j) best_w += decoding[j];
+        memcpy(best, decoding, (size_t)n);
+        #define ORC_GETBIT(i, c) ((int)((R[(size_t)(i) * W + ((c) >> 6)] >> ((c) & 63)) & 1))
+        /* evaluate the pattern that sets T[a] (and T[b] if b >= 0, ... generic list) */
+        int pat[32];
+        long ncand = method == 1 ? ((1L << ord_k) - 1) : (long)k + (long)ord_k * (ord_k - 1) / 2;
+        long ci = 0;
+        int i2 = 0, j2 = 1;                                   /* pair cursor for osd_cs */
+        for (; ci < ncand; ++ci) {
+            int np = 0;
+            if (method == 1) { for (int bpos = 0; bpos < ord_k; ++bpos) if (((ci + 1) >> bpos) & 1) pat[np++] = T[bpos]; }
+            else if (ci < k) pat[np++] = T[ci];
+            else { pat[np++] = T[i2]; pat[np++] = T[j2]; if (++j2 >= ord_k) { ++i2; j2 = i2 + 1; } }
+            memset(cand, 0, (size_t)n);
+            int w = np;
+            for (int q = 0; q < np; ++q) cand[pat[q]] = 1;
+            for (int i = 0; i < m; ++i) {
+                if (pcol[i] < 0) continue;
+                int bit = ORC_GETBIT(i, n);
+                for (int q = 0; q < np; ++q) bit ^= ORC_GETBIT(i, pat[q]);
+                cand[pcol[i]] = (uint8_t)bit;
+                w += bit;
+            }
+            if (w < best_w) { best_w = w; memcpy(best, cand, (size_t)n); }
+        }
+        #undef ORC_GETBIT
+        memcpy(decoding, best, (size_t)n);
+        free(T); free(cand); free(best);
+    }
+    free(R); free(ord); free(pcol); free(is_piv);
     return consistent;
+}
+
+int orc_osd0(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, const uint8_t *synd,
+             const double *key_ascending, uint8_t *decoding)
+{
+    return orc_osd(m, n, row_ptr, col_idx, synd, key_ascending, 0, 0, decoding);
+}
+
+int orc_bposd_decode(orc_bp *d, const uint8_t *synd, int method, int order, uint8_t *decoding, int *iters)
+{
+    const int conv = orc_bp_decode(d, synd, decoding, NULL, iters);
+    if (conv) return 1;
+    double *key = (double *)malloc(sizeof(double) * (d->n ? d->n : 1));
+    for (int j = 0; j < d->n; ++j) key[j] = d->method == 0 ? -d->soft[j] : d->soft[j];
+    orc_osd(d->m, d->n, d->row_ptr, d->col_idx, synd, key, method, order, decoding);
+    free(key);
+    return 0;
 }
 
 /* BP, then OSD-0 on the shots BP did not converge on.  Returns the BP convergence flag. */
@@ -569,7 +631,7 @@ static void *orc_worker_main(void *arg)
     const orc_experiment *x = w->x;
     orc_bp *bp = NULL;
     orc_ssf *ssf = NULL;
-    if (w->decoder == 0 || w->decoder == 2)
+    if (w->decoder == 0 || w->decoder >= 2)
         bp = orc_bp_create(x->m, x->n, x->row_ptr, x->col_idx, x->probs, x->max_iter, x->method, x->alpha);
     else
         ssf = orc_ssf_create(x->m, x->n, x->row_ptr, x->col_idx, x->mg, x->hx_row_ptr, x->hx_col_idx);
@@ -585,6 +647,7 @@ static void *orc_worker_main(void *arg)
             orc_sample_bits(w->seed, 0u, w->shot0 + s, 1, x->n, x->thr, err);
             orc_syndrome(x->m, x->row_ptr, x->col_idx, err, syn);
             if (bp && w->decoder == 2) conv = orc_bposd0_decode(bp, syn, dec, &it);
+            else if (bp && (w->decoder == 3 || w->decoder == 4)) conv = orc_bposd_decode(bp, syn, w->decoder - 2, x->osd_order, dec, &it);
             else if (bp) conv = orc_bp_decode(bp, syn, dec, NULL, &it);
             else conv = orc_ssf_decode(ssf, syn, x->max_iter, dec, &it, NULL);
             if (w->decodings) memcpy(w->decodings + s * (int64_t)x->n, dec, (size_t)x->n);

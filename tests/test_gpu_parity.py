@@ -260,8 +260,12 @@ def test_run_simulation_signature_and_counts(gpu, code225):
     assert flags == [bool(v) for v in ref["fail"]]
     with pytest.raises(RuntimeError):
         run_simulation(10, code225, partial(prior, p), partial(prior, p), depolarizing_noise, {"p": p, "pm": p}, opts, 0, "nope")
-    with pytest.raises(NotImplementedError):
-        run_simulation(10, code225, partial(prior, p), partial(prior, p), depolarizing_noise, {"p": p, "pm": p}, opts, 0, "bposd")
+    # the reference's default mode and OSD settings (bposd, osd_cs order 7) run as they are
+    flags = run_simulation(400, code225, partial(prior, p), partial(prior, p), depolarizing_noise, {"p": p, "pm": p}, opts, 0,
+                           "bposd", seed=3)
+    ref = po.run_code_capacity(code225.checks.z, code225.logicals.z, q, 2 * p / 3, decoder="bposd_cs", osd_order=7, max_iter=30,
+                               bp_method="ms", seed=3, shots=400, per_shot=True)
+    assert flags == [bool(v) for v in ref["fail"]]
 
 
 def test_full_size_properties_n6400(gpu, code6400):
@@ -451,8 +455,8 @@ def test_bposd_decoder_duck_type(gpu, code225):
         s = ((hz @ e) % 2).astype(float)                            # the reference hands in float64 0/1
         assert np.array_equal(dec.decode(s), ref.decode(s))
         assert (dec.converge, dec.iter) == (ref.converge, ref.iter)
-    with pytest.raises(NotImplementedError):
-        bposd_decoder(hz, error_rate=0.03, osd_method="osd_cs", osd_order=7)
+    with pytest.raises(ValueError):
+        bposd_decoder(hz, error_rate=0.03, osd_method="no_such_osd")
     corr, conv, its = dec.decode_batch(np.zeros((3, hz.shape[0])))
     assert not corr.any() and conv.all()
 
@@ -775,3 +779,28 @@ def test_dense_rows_take_the_global_kernel(gpu):
         for s in range(synd.shape[0]):
             assert np.array_equal(corr[s], ref.decode(synd[s])), (method, s)
             assert its[s] == ref.iter and conv[s] == ref.converge
+
+
+
+@pytest.mark.parametrize("which,method,osd,order,p", [("hgp225", "ms", "osd_cs", 7, 0.04), ("hgp225", "ps", "osd_cs", 10, 0.03),
+                                                      ("hgp225", "ms", "osd_e", 6, 0.05), ("hgp1600", "ms", "osd_cs", 7, 0.025)])
+def test_higher_order_osd_against_live_oracle(gpu, codes, which, method, osd, order, p):
+    """The reference's default post-processing is osd_cs of order 7 (_experiment.py:218-219)."""
+    from exp_ldpc_b200.experiment import CodeCapacityExperiment
+    from oracle import pyoracle as po
+    code = codes[which]
+    q, prior = 2 * p / 3 + p - 4 / 3 * p * p, 2 * p / 3
+    shots = 300 if which == "hgp225" else 64
+    opts = dict(max_iter=16, bp_method=method, ms_scaling_factor=0.0, osd_method=osd, osd_order=order)
+    exp = CodeCapacityExperiment(code, q, prior, "bposd", opts)
+    assert (exp.decoder.osd_method, exp.decoder.osd_order) == (osd, order)
+    got = exp.run(shots, seed=23, per_shot=True)
+    ref = po.run_code_capacity(code.checks.z, code.logicals.z, q, prior, decoder={"osd_cs": "bposd_cs", "osd_e": "bposd_e"}[osd],
+                               osd_order=order, max_iter=16, bp_method=method, ms_scaling_factor=0.0, seed=23, shots=shots,
+                               per_shot=True)
+    zero = po.run_code_capacity(code.checks.z, code.logicals.z, q, prior, decoder="bposd0", max_iter=16, bp_method=method,
+                                ms_scaling_factor=0.0, seed=23, shots=shots, per_shot=True)
+    assert (ref["decodings"] != zero["decodings"]).any()               # the search does change some solutions
+    assert (got["decodings"] == ref["decodings"]).all()
+    assert np.array_equal(got["fail"], ref["fail"]) and got["failures"] == ref["failures"]
+    assert ref["decodings"].sum() <= zero["decodings"].sum()

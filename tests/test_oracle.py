@@ -311,3 +311,19 @@ def test_bposd0_keeps_converged_bp_and_fixes_the_rest(code225):
             assert np.array_equal(b, po.osd0(hz, s, bo.soft))
         seen.add(bp.converge)
     assert seen == {0, 1}
+
+
+
+def test_higher_order_osd_never_heavier_and_valid(code225):
+    from oracle import pyoracle as po
+    hz = code225.checks.z
+    rng = np.random.default_rng(3)
+    for _ in range(6):
+        e = (rng.random(hz.shape[1]) < 0.07).astype(np.uint8)
+        s = (hz @ e) % 2
+        key = rng.normal(size=hz.shape[1])
+        w0 = po.osd0(hz, s, key).sum()
+        for method, order in (("osd_e", 6), ("osd_cs", 7)):
+            x = po.osd0(hz, s, key, method, order)
+            assert np.array_equal((hz @ x) % 2, s) and x.sum() <= w0
+        assert np.array_equal(po.osd0(hz, s, key, "osd_cs", 0), po.osd0(hz, s, key))
