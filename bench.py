@@ -143,7 +143,8 @@ def cpu_port_throughput(code, p, opts, target_seconds=12.0, threads=0, decoder="
     from oracle import pyoracle as po
     hz, lz, q, prior = problem
     cores = po.num_threads() if threads <= 0 else threads
-    kw = dict(decoder={"bposd": "bposd0"}.get(decoder, decoder), hx=code.checks.x, max_iter=opts["max_iter"], bp_method=opts["bp_method"],
+    osd_dec = {"osd0": "bposd0", "osd_e": "bposd_e", "osd_cs": "bposd_cs"}[opts.get("osd_method", "osd0")]
+    kw = dict(decoder={"bposd": osd_dec}.get(decoder, decoder), hx=code.checks.x, osd_order=opts.get("osd_order", 0), max_iter=opts["max_iter"], bp_method=opts["bp_method"],
               ms_scaling_factor=opts["ms_scaling_factor"], seed=0, threads=cores)
     probe = 64 * cores
     t0 = time.perf_counter()
@@ -165,6 +166,8 @@ def main():
     ap.add_argument("--workload", default="hgp_34_n1600", choices=sorted(WORKLOADS))
     ap.add_argument("--shots", type=int, default=1 << 20, help="shots per GPU per step")
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--osd-method", default="osd0", choices=["osd0", "osd_e", "osd_cs"])
+    ap.add_argument("--osd-order", type=int, default=0)
     ap.add_argument("--decoder", default="bp", choices=["bp", "ssf", "bposd"],
                     help="bposd = BP, then OSD-0 on the shots BP left unconverged")
     ap.add_argument("--p", type=float, default=None)
@@ -195,6 +198,8 @@ def main():
         opts["max_iter"] = args.max_iter
     if args.bp_method is not None:
         opts["bp_method"] = args.bp_method
+    if args.decoder == "bposd":
+        opts["osd_method"], opts["osd_order"] = args.osd_method, args.osd_order
     code = load_workload(args.workload)
     problem = decoding_problem(args.workload, code, p)
     hz_dec, lz_dec, q_vec, prior_vec = problem
@@ -203,10 +208,10 @@ def main():
     q, prior = float(q_vec[0]), float(prior_vec[0])
     osd = args.decoder == "bposd"
     how = ("small-set-flip (candidate sets = subsets of the X-generator supports)" if ssf else
-           f"BP{' + OSD-0' if osd else ''} {opts['bp_method']} alpha={'1-2^-it' if opts['ms_scaling_factor'] == 0 else opts['ms_scaling_factor']} "
+           f"BP{' + ' + args.osd_method + ' order ' + str(args.osd_order) if osd else ''} {opts['bp_method']} alpha={'1-2^-it' if opts['ms_scaling_factor'] == 0 else opts['ms_scaling_factor']} "
            f"max_iter={opts['max_iter']} early-exit")
     metric = ("decoded shots/sec (SSF, fixed p)" if ssf else
-              "decoded shots/sec (BP + OSD-0, fixed p and iteration cap)" if osd else
+              "decoded shots/sec (BP + OSD, fixed p and iteration cap)" if osd else
               "decoded shots/sec (BP, fixed p and iteration cap)")
     dtype = "u32" if ssf else args.precision
     config = {"workload": f"{args.workload}: {family} n={n} m={m} nnz={nnz} k={code.num_logicals}, "
