@@ -804,3 +804,78 @@ def test_higher_order_osd_against_live_oracle(gpu, codes, which, method, osd, or
     assert (got["decodings"] == ref["decodings"]).all()
     assert np.array_equal(got["fail"], ref["fail"]) and got["failures"] == ref["failures"]
     assert ref["decodings"].sum() <= zero["decodings"].sum()
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases: empty and single-shot batches, padded strides, isolated qubits, tiny row degrees
+# ---------------------------------------------------------------------------------------------
+def _odd_matrix():
+    """7 x 12: an isolated column (no check), a column of degree 5, rows of degree 1 and 2."""
+    from scipy import sparse
+    a = np.zeros((7, 12), dtype=np.uint32)
+    a[0, [0, 1, 2, 3]] = 1
+    a[1, [1, 4]] = 1
+    a[2, [5]] = 1
+    a[3, [1, 6, 7, 8, 9]] = 1
+    a[4, [1, 2, 10]] = 1
+    a[5, [1, 3, 9, 10]] = 1
+    a[6, [0, 4, 8]] = 1
+    return sparse.csr_matrix(a)          # column 11 is isolated
+
+
+@pytest.mark.parametrize("kernel", ["auto", "generic", "global"])
+@pytest.mark.parametrize("method", ["ms", "ps"])
+def test_irregular_tiny_graph_all_kernels(gpu, kernel, method):
+    from exp_ldpc_b200.decoders import bp_decoder
+    from oracle import pyoracle as po
+    h = _odd_matrix()
+    probs = np.linspace(0.02, 0.3, 12)
+    probs[11] = 0.7                                   # isolated qubit with prior > 1/2: decision is 1 forever
+    synd = np.array([[(k >> r) & 1 for r in range(7)] for k in range(128)], dtype=np.uint8)      # every syndrome
+    dec = bp_decoder(h, channel_probs=probs, max_iter=9, bp_method=method, ms_scaling_factor=0.0, kernel=kernel)
+    ref = po.OracleBP(h, channel_probs=probs, max_iter=9, bp_method=method, ms_scaling_factor=0.0)
+    corr, conv, its = dec.decode_batch(synd)
+    for s in range(synd.shape[0]):
+        want = ref.decode(synd[s])
+        assert np.array_equal(corr[s], want), (kernel, method, s)
+        assert its[s] == ref.iter and conv[s] == ref.converge
+    assert corr[:, 11].all()
+
+
+def test_empty_and_single_shot_batches(gpu, code225):
+    from exp_ldpc_b200.decoders import bp_decoder, bposd_decoder, ssf_decoder
+    hz, hx = code225.checks.z, code225.checks.x
+    for dec in (bp_decoder(hz, error_rate=0.02, max_iter=5, bp_method="ms"),
+                bposd_decoder(hz, error_rate=0.02, max_iter=5, bp_method="ms", osd_method="osd_cs", osd_order=3),
+                ssf_decoder(hz, hx)):
+        corr, conv, its = dec.decode_batch(np.zeros((0, hz.shape[0]), dtype=np.uint8))
+        assert corr.shape == (0, hz.shape[1]) and conv.shape == (0,) and its.shape == (0,)
+        corr, conv, its = dec.decode_batch(np.zeros((1, hz.shape[0]), dtype=np.uint8))
+        assert not corr.any() and conv[0] == 1
+        with pytest.raises(ValueError):
+            dec.decode_batch(np.zeros((2, hz.shape[0] + 1), dtype=np.uint8))
+
+
+def test_padded_strides_and_dirty_output_buffers(gpu, code225):
+    """Strides larger than needed: padding words of the output are written as zero, inputs beyond
+    ceil(m/32) words are ignored."""
+    import torch
+    from exp_ldpc_b200.decoders import TannerGraph, bp_decoder, pack_bits, row_words, unpack_bits
+    hz = code225.checks.z
+    m, n = hz.shape
+    rng = np.random.default_rng(0)
+    err = (rng.random((64, n)) < 0.03).astype(np.uint8)
+    synd = ((err @ hz.T.toarray()) % 2).astype(np.uint8)
+    dec = bp_decoder(TannerGraph(hz), error_rate=0.02, max_iter=20, bp_method="ms", ms_scaling_factor=0.0)
+    base, _, _ = dec.decode_batch(synd)
+    ss, cs = row_words(m) + 3, row_words(n) + 5
+    packed = np.full((64, ss), 0xFFFFFFFF, dtype=np.uint32)
+    packed[:, :row_words(m)] = pack_bits(synd)
+    dev = torch.device("cuda:0")
+    d_syn = torch.from_numpy(packed.view(np.int32)).to(dev)
+    d_cor = torch.full((64, cs), -1, dtype=torch.int32, device=dev)
+    dec.decode_batch_device(d_syn, ss, 64, d_cor, cs)
+    torch.cuda.synchronize()
+    out = d_cor.cpu().numpy().view(np.uint32)
+    assert np.array_equal(unpack_bits(out[:, :row_words(n)], n), base)
+    assert not out[:, (n + 31) // 32:].any()
