@@ -45,7 +45,9 @@ struct OsdParams {
     unsigned long long *next_shot;
 };
 
-struct OsdSmemLayout { size_t rows, keys, idx, rowmask, used, pcol, dec, total; };
+struct OsdSmemLayout { size_t rows, keys, idx, rowmask, used, pcol, dec, stage, nz, prow, total; };
+
+constexpr int OSD_BLOCK = 32;     // ranked columns handled per lazy elimination block
 
 __host__ __device__ inline OsdSmemLayout osd_smem_layout(int m, int W, int P, int nwm, int nwn)
 {
@@ -58,6 +60,10 @@ __host__ __device__ inline OsdSmemLayout osd_smem_layout(int m, int W, int P, in
     L.used = o;    o += ((size_t)nwm * 4 + 7) & ~(size_t)7;
     L.pcol = o;    o += ((size_t)m * 2 + 7) & ~(size_t)7;
     L.dec = o;     o += ((size_t)nwn * 4 + 7) & ~(size_t)7;
+    o = (o + 15) & ~(size_t)15;
+    L.stage = o;   o += (size_t)OSD_BLOCK * W * 8;                 // copies of the block's pivot rows
+    L.nz = o;      o += ((size_t)(W / 2) * 4 + 7) & ~(size_t)7;    // per 16-byte chunk: which staged rows are non-zero there
+    L.prow = o;    o += (size_t)OSD_BLOCK * 2;
     L.total = o;
     return L;
 }
@@ -140,48 +146,130 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
         }
         __syncthreads();
 
-        // ---- 3. Gauss-Jordan over the ranked columns.  A thread owns rows tid, tid + NT, ...: it alone writes
-        // them, so one barrier per column (between choosing the pivot and using it) orders everything:
-        //   own bit of column c -> per-warp candidate (first unused row holding the bit) -> barrier ->
-        //   pivot = min over the warps -> every owner XORs the pivot row into its marked rows.
-        // cand[] is double-buffered by column parity, so a warp that runs ahead never overwrites it early.
-        int rank = 0;
-        unsigned myused = 0u;                                    // bit q: row tid + q * NT is a pivot row
-        for (int t = 0; t < n && rank < p.rank; ++t) {
-            const int c = idx[t];
-            const int cw = c >> 6, cb = c & 63;
-            unsigned mybits = 0u;
-            int first = 0x7fffffff;
-            for (int q = 0, r = tid; r < m; ++q, r += NT) {
-                const unsigned bit = (unsigned)((R[(size_t)r * W + cw] >> cb) & 1ULL);
-                mybits |= bit << q;
-                if (bit && !((myused >> q) & 1u)) first = min(first, r);
+        // ---- 3. Gauss-Jordan over the ranked columns, one thread per row, in lazy blocks of OSD_BLOCK columns.
+        // At the start of a block a thread pulls its row's bits on the block's columns into a register (B).
+        // Choosing pivots then only needs those bits: when row r absorbs pivot i, B_r ^= B_piv and the set Y_r
+        // of block-start pivot rows that make up the pending update becomes Y_r ^ Y_piv ^ {i}.  (B, Y) pairs are
+        // published in shared memory (the pivot's pair is read by everyone, its owner does not write it in
+        // that step), so a column costs one barrier and a few register operations.  After the block the pivot
+        // rows are copied aside and every row applies its pending update in one pass:
+        //     row_r ^= XOR_{i in Y_r} staged_i,
+        // reading the staged rows with warp-wide broadcast loads (one wavefront per 16 bytes and pivot instead
+        // of a load/xor/store of the own row per pivot).  16-byte chunks where no staged row has a bit are skipped.
+        if (NT >= m) {
+            uint2 *BY = reinterpret_cast<uint2 *>(keys);              // the ranking keys are dead
+            ulonglong2 *S = reinterpret_cast<ulonglong2 *>(smem_raw + L.stage);
+            uint32_t *nz = reinterpret_cast<uint32_t *>(smem_raw + L.nz);
+            uint16_t *prow = reinterpret_cast<uint16_t *>(smem_raw + L.prow);
+            const bool mine = tid < m;
+            const int W2 = W / 2;
+            unsigned long long *myrow = R + (size_t)(mine ? tid : 0) * W;
+            bool isused = false;
+            int rank = 0;
+            for (int t0 = 0; t0 < n && rank < p.rank; t0 += OSD_BLOCK) {
+                const int K = min(OSD_BLOCK, n - t0);
+                uint32_t B = 0u, Y = 0u;
+                if (mine) {
+                    for (int j = 0; j < K; ++j) {
+                        const int c = idx[t0 + j];
+                        B |= (uint32_t)((myrow[c >> 6] >> (c & 63)) & 1ULL) << j;
+                    }
+                    BY[tid] = make_uint2(B, 0u);
+                }
+                int npiv = 0;
+                for (int j = 0; j < K && rank < p.rank; ++j) {
+                    const bool has = mine && !isused && ((B >> j) & 1u);
+                    const unsigned bal = __ballot_sync(0xffffffffu, has);
+                    int *cd = cand + (j & 1) * 32;
+                    if (lane == 0) cd[warp] = bal ? (warp << 5) + __ffs((int)bal) - 1 : 0x7fffffff;
+                    __syncthreads();
+                    const int piv = __reduce_min_sync(0xffffffffu, lane < nwarps ? cd[lane] : 0x7fffffff);
+                    if (piv == 0x7fffffff) continue;            // dependent on the columns ranked before it
+                    ++rank;
+                    if (tid == piv) { isused = true; pcol[tid] = idx[t0 + j]; prow[npiv] = (uint16_t)tid; }
+                    else if ((B >> j) & 1u) {
+                        const uint2 pv = BY[piv];
+                        B ^= pv.x; Y ^= pv.y ^ (1u << npiv);
+                        BY[tid] = make_uint2(B, Y);
+                    }
+                    ++npiv;
+                }
+                __syncthreads();
+                if (npiv == 0) continue;
+                for (int i = warp; i < npiv; i += nwarps) {
+                    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(R + (size_t)prow[i] * W);
+                    for (int w = lane; w < W2; w += 32) S[i * W2 + w] = src[w];
+                }
+                __syncthreads();
+                for (int jc = warp; jc < W2; jc += nwarps) {
+                    bool nzb = false;
+                    if (lane < npiv) { const ulonglong2 v = S[lane * W2 + jc]; nzb = (v.x | v.y) != 0ULL; }
+                    const unsigned b = __ballot_sync(0xffffffffu, nzb);
+                    if (lane == 0) nz[jc] = b;
+                }
+                __syncthreads();
+                {
+                    ulonglong2 *row = reinterpret_cast<ulonglong2 *>(myrow);
+                    for (int jc = 0; jc < W2; ++jc) {
+                        const uint32_t y = mine ? (Y & nz[jc]) : 0u;
+                        uint32_t u = __reduce_or_sync(0xffffffffu, y);
+                        if (!u) continue;
+                        ulonglong2 acc = make_ulonglong2(0ULL, 0ULL);
+                        while (u) {
+                            const int i = __ffs((int)u) - 1;
+                            u &= u - 1u;
+                            const ulonglong2 sv = S[i * W2 + jc];
+                            if ((y >> i) & 1u) { acc.x ^= sv.x; acc.y ^= sv.y; }
+                        }
+                        if (y) { ulonglong2 v = row[jc]; v.x ^= acc.x; v.y ^= acc.y; row[jc] = v; }
+                    }
+                }
+                __syncthreads();
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-            int *cd = cand + (t & 1) * 32;
-            if (lane == 0) cd[warp] = first;
-            __syncthreads();
-            int piv = lane < nwarps ? cd[lane] : 0x7fffffff;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) piv = min(piv, __shfl_xor_sync(0xffffffffu, piv, o));
-            if (piv == 0x7fffffff) continue;                    // dependent on the columns ranked before it
-            ++rank;
-            // W is even and W/2 odd: rows are 16-byte aligned and the 128-bit accesses of a quarter-warp fall
-            // into different banks.  Zero words of the pivot row are skipped (warp-uniform test): the matrix
-            // starts sparse and fills in only gradually.
-            const ulonglong2 *prow = reinterpret_cast<const ulonglong2 *>(R + (size_t)piv * W);
-            for (int q = 0, r = tid; r < m; ++q, r += NT) {
-                if (r == piv) { myused |= 1u << q; pcol[r] = (uint16_t)c; continue; }
-                if (!((mybits >> q) & 1u)) continue;
-                ulonglong2 *row = reinterpret_cast<ulonglong2 *>(R + (size_t)r * W);
-#pragma unroll 3
-                for (int j = 0; j < W / 2; ++j) {
-                    const ulonglong2 pv = prow[j];
-                    if (pv.x | pv.y) {
-                        ulonglong2 v = row[j];
-                        v.x ^= pv.x; v.y ^= pv.y;
-                        row[j] = v;
+        } else {
+            // ---- 3. Gauss-Jordan over the ranked columns.  A thread owns rows tid, tid + NT, ...: it alone writes
+            // them, so one barrier per column (between choosing the pivot and using it) orders everything:
+            //   own bit of column c -> per-warp candidate (first unused row holding the bit) -> barrier ->
+            //   pivot = min over the warps -> every owner XORs the pivot row into its marked rows.
+            // cand[] is double-buffered by column parity, so a warp that runs ahead never overwrites it early.
+            int rank = 0;
+            unsigned myused = 0u;                                    // bit q: row tid + q * NT is a pivot row
+            for (int t = 0; t < n && rank < p.rank; ++t) {
+                const int c = idx[t];
+                const int cw = c >> 6, cb = c & 63;
+                unsigned mybits = 0u;
+                int first = 0x7fffffff;
+                for (int q = 0, r = tid; r < m; ++q, r += NT) {
+                    const unsigned bit = (unsigned)((R[(size_t)r * W + cw] >> cb) & 1ULL);
+                    mybits |= bit << q;
+                    if (bit && !((myused >> q) & 1u)) first = min(first, r);
+                }
+    #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+                int *cd = cand + (t & 1) * 32;
+                if (lane == 0) cd[warp] = first;
+                __syncthreads();
+                int piv = lane < nwarps ? cd[lane] : 0x7fffffff;
+    #pragma unroll
+                for (int o = 16; o > 0; o >>= 1) piv = min(piv, __shfl_xor_sync(0xffffffffu, piv, o));
+                if (piv == 0x7fffffff) continue;                    // dependent on the columns ranked before it
+                ++rank;
+                // W is even and W/2 odd: rows are 16-byte aligned and the 128-bit accesses of a quarter-warp fall
+                // into different banks.  Zero words of the pivot row are skipped (warp-uniform test): the matrix
+                // starts sparse and fills in only gradually.
+                const ulonglong2 *prow = reinterpret_cast<const ulonglong2 *>(R + (size_t)piv * W);
+                for (int q = 0, r = tid; r < m; ++q, r += NT) {
+                    if (r == piv) { myused |= 1u << q; pcol[r] = (uint16_t)c; continue; }
+                    if (!((mybits >> q) & 1u)) continue;
+                    ulonglong2 *row = reinterpret_cast<ulonglong2 *>(R + (size_t)r * W);
+    #pragma unroll 3
+                    for (int j = 0; j < W / 2; ++j) {
+                        const ulonglong2 pv = prow[j];
+                        if (pv.x | pv.y) {
+                            ulonglong2 v = row[j];
+                            v.x ^= pv.x; v.y ^= pv.y;
+                            row[j] = v;
+                        }
                     }
                 }
             }
