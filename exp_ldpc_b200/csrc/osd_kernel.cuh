@@ -1,22 +1,24 @@
-// osd_kernel.cuh — ordered-statistics post-processing, order 0 (OSD-0), for the shots belief
+// osd_kernel.cuh — ordered-statistics post-processing (OSD-0, osd_e, osd_cs) for the shots belief
 // propagation did not converge on.
 //
-// Stands in for the OSD stage of ldpc.bposd_decoder(osd_method="osd0") as the reference calls it at
-// python/qldpc/misc/_experiment.py:23-27,51,59,77,82,96-100,125; CPU restatement:
-// oracle/qldpc_oracle.c orc_osd0 (parity unpinned, see oracle/qldpc_oracle.h).
+// Stands in for the OSD stage of ldpc.bposd_decoder as the reference calls it at
+// python/qldpc/misc/_experiment.py:23-27,51,59,77,82,96-100,125 (defaults osd_cs order 7, :218-219);
+// CPU restatement: oracle/qldpc_oracle.c orc_osd0 / orc_osd (parity unpinned, see oracle/qldpc_oracle.h).
 //
 // Definition: rank the columns most-likely-in-error first by the soft output of the last BP
 // iteration (ascending total LLR for min-sum, descending posterior ratio for product-sum, ties by
 // column index); the first rank(H) linearly independent columns in that order are the information
-// set S; the decoding is the unique solution of H_S x_S = s, zero elsewhere.  The answer does not
-// depend on how the elimination is carried out, only on the ranking, so the kernel is free to
+// set S; the OSD-0 decoding is the unique solution of H_S x_S = s, zero elsewhere.  The answer does
+// not depend on how the elimination is carried out, only on the ranking, so the kernel is free to
 // pick its own pivots:
-//   * one CTA per shot; the augmented matrix [H | s] lives bit-packed in shared memory (m rows of
-//     ceil((n+1)/64) 64-bit words);
-//   * ranking = bitonic sort of (order-preserving 64-bit image of the key, column index);
-//   * per ranked column: every thread looks at the column's bit in the rows it owns, the first such
-//     row that is not a pivot yet becomes the pivot (warp shuffle + one barrier), and every owner
-//     XORs the pivot row into its marked rows (Gauss-Jordan); one barrier per column;
+//   * one CTA per shot; ranking = bitonic sort of (order-preserving 64-bit image of the key, column);
+//   * the augmented matrix [H | s] is built bit-packed in shared memory WITH ITS COLUMNS IN RANKED
+//     ORDER (m rows of W 64-bit words), so a block of 32 consecutive ranked columns is one aligned
+//     32-bit word of every row and, for OSD-0, everything left of the current block is dead;
+//   * Gauss-Jordan in lazy blocks of 32 columns, one thread per row: pivots are chosen on
+//     register-resident column bits (one barrier per column), the pending row operations are
+//     applied once per block through 4-bit lookup tables of the block's pivot rows
+//     (method of the four Russians): one 128-bit table load + XOR per 4 pivots and 16 bytes of row;
 //   * stops after rank(H) pivots (computed once on the host).
 // Integer only => bit-identical to the oracle.
 #pragma once
@@ -45,7 +47,7 @@ struct OsdParams {
     unsigned long long *next_shot;
 };
 
-struct OsdSmemLayout { size_t rows, keys, idx, rowmask, used, pcol, dec, stage, nz, prow, total; };
+struct OsdSmemLayout { size_t rows, keys, idx, pcol, dec, tables, nz, prow, total; };
 
 constexpr int OSD_BLOCK = 32;     // ranked columns handled per lazy elimination block
 
@@ -54,15 +56,13 @@ __host__ __device__ inline OsdSmemLayout osd_smem_layout(int m, int W, int P, in
     OsdSmemLayout L;
     size_t o = 0;
     L.rows = o;    o += (size_t)m * W * 8;
-    L.keys = o;    o += (size_t)P * 8;
+    L.keys = o;    o += (size_t)P * 8;                             // sort keys; then inverse ranking; then (B, Y) pairs; then search scratch
     L.idx = o;     o += ((size_t)P * 2 + 7) & ~(size_t)7;
-    L.rowmask = o; o += ((size_t)nwm * 4 + 7) & ~(size_t)7;
-    L.used = o;    o += ((size_t)nwm * 4 + 7) & ~(size_t)7;
     L.pcol = o;    o += ((size_t)m * 2 + 7) & ~(size_t)7;
     L.dec = o;     o += ((size_t)nwn * 4 + 7) & ~(size_t)7;
     o = (o + 15) & ~(size_t)15;
-    L.stage = o;   o += (size_t)OSD_BLOCK * W * 8;                 // copies of the block's pivot rows
-    L.nz = o;      o += ((size_t)(W / 2) * 4 + 7) & ~(size_t)7;    // per 16-byte chunk: which staged rows are non-zero there
+    L.tables = o;  o += (size_t)(W / 2) * (OSD_BLOCK / 4) * 16 * 16;  // per 16-byte chunk: 8 nibble tables of 16 entries
+    L.nz = o;      o += ((size_t)(W / 2) * 4 + 7) & ~(size_t)7;    // per chunk: which of the block's pivot rows are non-zero there
     L.prow = o;    o += (size_t)OSD_BLOCK * 2;
     L.total = o;
     return L;
@@ -76,14 +76,17 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
     unsigned long long *R = reinterpret_cast<unsigned long long *>(smem_raw + L.rows);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw + L.keys);
     uint16_t *idx = reinterpret_cast<uint16_t *>(smem_raw + L.idx);
-    uint32_t *rowmask = reinterpret_cast<uint32_t *>(smem_raw + L.rowmask);
-    uint32_t *used = reinterpret_cast<uint32_t *>(smem_raw + L.used);
     uint16_t *pcol = reinterpret_cast<uint16_t *>(smem_raw + L.pcol);
     uint32_t *dec = reinterpret_cast<uint32_t *>(smem_raw + L.dec);
     __shared__ long long sh_shot;
     __shared__ int cand[64];
-    const int W = p.W, m = p.m, n = p.n;
+    __shared__ int sh_k;
+    __shared__ int red32[32];
+    __shared__ unsigned long long red64[32];
+    const int W = p.W, W2 = p.W / 2, m = p.m, n = p.n;
     long long c_delta = 0;                                    // thread 0: change of the failure count
+
+    if (tid < 64) cand[tid] = 0x7fffffff;                     // entries of absent warps stay "no candidate"
 
     for (;;) {
         if (tid == 0) {
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
         const long long shot = sh_shot;
         if (shot < 0) break;
 
-        // ---- 1. ranking
+        // ---- 1. ranking: idx[t] = column ranked t-th
         for (int i = tid; i < p.P; i += NT) {
             unsigned long long key = ~0ULL;
             if (i < n) {
@@ -128,115 +131,125 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                 __syncthreads();
             }
 
-        // ---- 2. [H | s]
-        for (int i = tid; i < m * W; i += NT) R[i] = 0ULL;
-        for (int i = tid; i < p.nwm; i += NT) used[i] = 0u;
-        for (int i = tid; i < m; i += NT) pcol[i] = (uint16_t)0xFFFF;
-        __syncthreads();
+        // ---- 2. [H | s] with the columns in ranked order: column idx[t] sits at bit position t, s at position n
         {
+            uint16_t *pos = reinterpret_cast<uint16_t *>(keys);      // the sort keys are dead
+            for (int i = tid; i < m * W; i += NT) R[i] = 0ULL;
+            for (int t = tid; t < n; t += NT) pos[idx[t]] = (uint16_t)t;
+            for (int i = tid; i < m; i += NT) pcol[i] = (uint16_t)0xFFFF;
+            __syncthreads();
             const uint32_t *s = p.synd + shot * (long long)p.synd_stride;
             for (int r = tid; r < m; r += NT) {
                 unsigned long long *row = R + (size_t)r * W;
                 for (int e = p.row_ptr[r]; e < p.row_ptr[r + 1]; ++e) {
-                    const int c = p.col_idx[e];
-                    row[c >> 6] |= 1ULL << (c & 63);
+                    const int q = pos[p.col_idx[e]];
+                    row[q >> 6] |= 1ULL << (q & 63);
                 }
                 if ((s[r >> 5] >> (r & 31)) & 1u) row[n >> 6] |= 1ULL << (n & 63);
             }
+            __syncthreads();
         }
-        __syncthreads();
 
-        // ---- 3. Gauss-Jordan over the ranked columns, one thread per row, in lazy blocks of OSD_BLOCK columns.
-        // At the start of a block a thread pulls its row's bits on the block's columns into a register (B).
-        // Choosing pivots then only needs those bits: when row r absorbs pivot i, B_r ^= B_piv and the set Y_r
-        // of block-start pivot rows that make up the pending update becomes Y_r ^ Y_piv ^ {i}.  (B, Y) pairs are
-        // published in shared memory (the pivot's pair is read by everyone, its owner does not write it in
-        // that step), so a column costs one barrier and a few register operations.  After the block the pivot
-        // rows are copied aside and every row applies its pending update in one pass:
-        //     row_r ^= XOR_{i in Y_r} staged_i,
-        // reading the staged rows with warp-wide broadcast loads (one wavefront per 16 bytes and pivot instead
-        // of a load/xor/store of the own row per pivot).  16-byte chunks where no staged row has a bit are skipped.
         if (NT >= m) {
-            uint2 *BY = reinterpret_cast<uint2 *>(keys);              // the ranking keys are dead
-            ulonglong2 *S = reinterpret_cast<ulonglong2 *>(smem_raw + L.stage);
+            // ---- 3. Gauss-Jordan, one thread per row, in lazy blocks of 32 ranked columns.
+            // A thread pulls its row's 32 bits of the block into a register (B).  Choosing pivots only needs
+            // those bits: when row r absorbs pivot i, B_r ^= B_piv and the set Y_r of block-start pivot rows
+            // making up the row's pending update becomes Y_r ^ Y_piv ^ {i}.  (B, Y) pairs are published in
+            // shared memory (everyone reads the pivot's pair; its owner does not write it in that step), so a
+            // column costs one barrier and a few register operations.  After the block,
+            //     row_r ^= XOR_{i in Y_r} (pivot row i as it was at the start of the block)
+            // is applied through nibble tables: T[chunk][g][e] = XOR of the pivot rows 4g+b, b in e, restricted
+            // to the 16-byte chunk.  For OSD-0 the chunks left of the block are never read again and are skipped.
+            uint2 *BY = reinterpret_cast<uint2 *>(keys);
+            ulonglong2 *T = reinterpret_cast<ulonglong2 *>(smem_raw + L.tables);
             uint32_t *nz = reinterpret_cast<uint32_t *>(smem_raw + L.nz);
             uint16_t *prow = reinterpret_cast<uint16_t *>(smem_raw + L.prow);
             const bool mine = tid < m;
-            const int W2 = W / 2;
             unsigned long long *myrow = R + (size_t)(mine ? tid : 0) * W;
+            const int wb = (warp << 5) - 1;
             bool isused = false;
             int rank = 0;
             for (int t0 = 0; t0 < n && rank < p.rank; t0 += OSD_BLOCK) {
-                const int K = min(OSD_BLOCK, n - t0);
                 uint32_t B = 0u, Y = 0u;
                 if (mine) {
-                    for (int j = 0; j < K; ++j) {
-                        const int c = idx[t0 + j];
-                        B |= (uint32_t)((myrow[c >> 6] >> (c & 63)) & 1ULL) << j;
-                    }
+                    B = (uint32_t)(myrow[t0 >> 6] >> (t0 & 32));
+                    if (n - t0 < 32) B &= (1u << (n - t0)) - 1u;       // position n is s, never a pivot column
                     BY[tid] = make_uint2(B, 0u);
                 }
+                uint32_t avail = isused ? 0u : B;
                 int npiv = 0;
-                for (int j = 0; j < K && rank < p.rank; ++j) {
-                    const bool has = mine && !isused && ((B >> j) & 1u);
-                    const unsigned bal = __ballot_sync(0xffffffffu, has);
+#pragma unroll
+                for (int j = 0; j < OSD_BLOCK; ++j) {
+                    if (rank >= p.rank) break;
+                    const unsigned bal = __ballot_sync(0xffffffffu, (avail >> j) & 1u);
                     int *cd = cand + (j & 1) * 32;
-                    if (lane == 0) cd[warp] = bal ? (warp << 5) + __ffs((int)bal) - 1 : 0x7fffffff;
+                    if (lane == 0) cd[warp] = bal ? wb + __ffs((int)bal) : 0x7fffffff;
                     __syncthreads();
-                    const int piv = __reduce_min_sync(0xffffffffu, lane < nwarps ? cd[lane] : 0x7fffffff);
+                    const int piv = __reduce_min_sync(0xffffffffu, cd[lane]);
                     if (piv == 0x7fffffff) continue;            // dependent on the columns ranked before it
                     ++rank;
-                    if (tid == piv) { isused = true; pcol[tid] = idx[t0 + j]; prow[npiv] = (uint16_t)tid; }
-                    else if ((B >> j) & 1u) {
+                    if (tid == piv) {
+                        isused = true; avail = 0u;
+                        pcol[tid] = (uint16_t)(t0 + j); prow[npiv] = (uint16_t)tid;
+                    } else if ((B >> j) & 1u) {
                         const uint2 pv = BY[piv];
                         B ^= pv.x; Y ^= pv.y ^ (1u << npiv);
                         BY[tid] = make_uint2(B, Y);
+                        if (!isused) avail = B;
                     }
                     ++npiv;
                 }
                 __syncthreads();
                 if (npiv == 0) continue;
-                for (int i = warp; i < npiv; i += nwarps) {
-                    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(R + (size_t)prow[i] * W);
-                    for (int w = lane; w < W2; w += 32) S[i * W2 + w] = src[w];
+                const int jc0 = p.method == 0 ? min((t0 + OSD_BLOCK) >> 7, n >> 7) : 0;
+                const int ng = (npiv + 3) >> 2;
+                for (int x = tid; x < (W2 - jc0) * ng * 16; x += NT) {
+                    const int e = x & 15, gq = x >> 4, g = gq % ng, jc = jc0 + gq / ng;
+                    ulonglong2 acc = make_ulonglong2(0ULL, 0ULL);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (((e >> b) & 1) && 4 * g + b < npiv) {
+                            const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(R + (size_t)prow[4 * g + b] * W)[jc];
+                            acc.x ^= v.x; acc.y ^= v.y;
+                        }
+                    T[(jc * (OSD_BLOCK / 4) + g) * 16 + e] = acc;
                 }
-                __syncthreads();
-                for (int jc = warp; jc < W2; jc += nwarps) {
+                for (int jc = jc0 + warp; jc < W2; jc += nwarps) {
                     bool nzb = false;
-                    if (lane < npiv) { const ulonglong2 v = S[lane * W2 + jc]; nzb = (v.x | v.y) != 0ULL; }
+                    if (lane < npiv) {
+                        const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(R + (size_t)prow[lane] * W)[jc];
+                        nzb = (v.x | v.y) != 0ULL;
+                    }
                     const unsigned b = __ballot_sync(0xffffffffu, nzb);
                     if (lane == 0) nz[jc] = b;
                 }
                 __syncthreads();
-                {
+                if (Y) {
                     ulonglong2 *row = reinterpret_cast<ulonglong2 *>(myrow);
-                    for (int jc = 0; jc < W2; ++jc) {
-                        const uint32_t y = mine ? (Y & nz[jc]) : 0u;
-                        uint32_t u = __reduce_or_sync(0xffffffffu, y);
-                        if (!u) continue;
-                        ulonglong2 acc = make_ulonglong2(0ULL, 0ULL);
-                        while (u) {
-                            const int i = __ffs((int)u) - 1;
-                            u &= u - 1u;
-                            const ulonglong2 sv = S[i * W2 + jc];
-                            if ((y >> i) & 1u) { acc.x ^= sv.x; acc.y ^= sv.y; }
+                    for (int jc = jc0; jc < W2; ++jc) {
+                        const uint32_t y = Y & nz[jc];
+                        if (!y) continue;
+                        const ulonglong2 *Tj = T + jc * (OSD_BLOCK / 4) * 16;
+                        ulonglong2 acc = row[jc];
+#pragma unroll
+                        for (int g = 0; g < OSD_BLOCK / 4; ++g) {
+                            if (g >= ng) break;
+                            const ulonglong2 tv = Tj[g * 16 + ((y >> (4 * g)) & 15u)];
+                            acc.x ^= tv.x; acc.y ^= tv.y;
                         }
-                        if (y) { ulonglong2 v = row[jc]; v.x ^= acc.x; v.y ^= acc.y; row[jc] = v; }
+                        row[jc] = acc;
                     }
                 }
                 __syncthreads();
             }
         } else {
-            // ---- 3. Gauss-Jordan over the ranked columns.  A thread owns rows tid, tid + NT, ...: it alone writes
-            // them, so one barrier per column (between choosing the pivot and using it) orders everything:
-            //   own bit of column c -> per-warp candidate (first unused row holding the bit) -> barrier ->
-            //   pivot = min over the warps -> every owner XORs the pivot row into its marked rows.
+            // ---- 3'. more rows than threads: plain Gauss-Jordan, a thread owns rows tid, tid + NT, ... and is
+            // their only writer, so one barrier per column (between choosing the pivot and using it) suffices.
             // cand[] is double-buffered by column parity, so a warp that runs ahead never overwrites it early.
             int rank = 0;
             unsigned myused = 0u;                                    // bit q: row tid + q * NT is a pivot row
             for (int t = 0; t < n && rank < p.rank; ++t) {
-                const int c = idx[t];
-                const int cw = c >> 6, cb = c & 63;
+                const int cw = t >> 6, cb = t & 63;
                 unsigned mybits = 0u;
                 int first = 0x7fffffff;
                 for (int q = 0, r = tid; r < m; ++q, r += NT) {
@@ -244,27 +257,21 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                     mybits |= bit << q;
                     if (bit && !((myused >> q) & 1u)) first = min(first, r);
                 }
-    #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+                first = __reduce_min_sync(0xffffffffu, first);
                 int *cd = cand + (t & 1) * 32;
                 if (lane == 0) cd[warp] = first;
                 __syncthreads();
-                int piv = lane < nwarps ? cd[lane] : 0x7fffffff;
-    #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) piv = min(piv, __shfl_xor_sync(0xffffffffu, piv, o));
+                const int piv = __reduce_min_sync(0xffffffffu, cd[lane]);
                 if (piv == 0x7fffffff) continue;                    // dependent on the columns ranked before it
                 ++rank;
-                // W is even and W/2 odd: rows are 16-byte aligned and the 128-bit accesses of a quarter-warp fall
-                // into different banks.  Zero words of the pivot row are skipped (warp-uniform test): the matrix
-                // starts sparse and fills in only gradually.
-                const ulonglong2 *prow = reinterpret_cast<const ulonglong2 *>(R + (size_t)piv * W);
+                const ulonglong2 *prw = reinterpret_cast<const ulonglong2 *>(R + (size_t)piv * W);
                 for (int q = 0, r = tid; r < m; ++q, r += NT) {
-                    if (r == piv) { myused |= 1u << q; pcol[r] = (uint16_t)c; continue; }
+                    if (r == piv) { myused |= 1u << q; pcol[r] = (uint16_t)t; continue; }
                     if (!((mybits >> q) & 1u)) continue;
                     ulonglong2 *row = reinterpret_cast<ulonglong2 *>(R + (size_t)r * W);
-    #pragma unroll 3
-                    for (int j = 0; j < W / 2; ++j) {
-                        const ulonglong2 pv = prow[j];
+#pragma unroll 3
+                    for (int j = 0; j < W2; ++j) {
+                        const ulonglong2 pv = prw[j];
                         if (pv.x | pv.y) {
                             ulonglong2 v = row[j];
                             v.x ^= pv.x; v.y ^= pv.y;
@@ -273,19 +280,20 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                     }
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
 
         // ---- 4. higher-order search (osd_e / osd_cs): patterns on the columns outside the information set
         // T (ranking order).  A pattern t changes the information-set part to x_S = x_S(OSD-0) + R_T t, so
         // its weight is |t| + sum over pivot rows of (s_r ^ parity of the row's bits on t).  Smallest
-        // weight wins; OSD-0 first, ties to the earlier candidate (oracle: orc_osd).
+        // weight wins; OSD-0 first, ties to the earlier candidate (oracle: orc_osd).  Columns are addressed by
+        // their ranked position here; idx[] maps back to column numbers in step 5.
         long long best_ci = -1;                                  // -1: keep the OSD-0 solution
-        uint32_t *Mrow = reinterpret_cast<uint32_t *>(keys);     // the ranking keys are dead: reuse them
+        uint32_t *Mrow = reinterpret_cast<uint32_t *>(keys);     // the (B, Y) pairs are dead: reuse them
         uint16_t *tlist = reinterpret_cast<uint16_t *>(Mrow + m);
         int k = 0, ord_k = 0;
         if (p.method != 0 && p.order > 0) {
-            uint32_t *colpiv = dec;                               // bit per column: in the information set
+            uint32_t *colpiv = dec;                               // bit per ranked position: in the information set
             for (int w = tid; w < p.nwn; w += NT) colpiv[w] = 0u;
             __syncthreads();
             for (int r = tid; r < m; r += NT) {
@@ -297,16 +305,15 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                 int count = 0;
                 for (int base = 0; base < n; base += 32) {
                     const int t = base + lane;
-                    const int c = t < n ? (int)idx[t] : 0;
-                    const bool isT = t < n && !((colpiv[c >> 5] >> (c & 31)) & 1u);
+                    const bool isT = t < n && !((colpiv[t >> 5] >> (t & 31)) & 1u);
                     const unsigned bal = __ballot_sync(0xffffffffu, isT);
-                    if (isT) tlist[count + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)c;
+                    if (isT) tlist[count + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)t;
                     count += __popc(bal);
                 }
-                if (lane == 0) cand[0] = count;
+                if (lane == 0) sh_k = count;
             }
             __syncthreads();
-            k = cand[0];
+            k = sh_k;
             ord_k = min(p.order, k);
             // per row: bit b = the row's bit on T[b] (b < ord_k <= 24), bit 30 = pivot row, bit 31 = OSD-0 bit
             int w0 = 0;
@@ -321,19 +328,11 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                 }
                 Mrow[r] = v;
             }
-            __syncthreads();
-            // block sum of the OSD-0 weight
-            {
-                int v = w0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0) cand[32 + warp] = v;
+            {                                                     // block sum of the OSD-0 weight
+                int v = __reduce_add_sync(0xffffffffu, w0);
+                if (lane == 0) red32[warp] = v;
                 __syncthreads();
-                v = lane < nwarps ? cand[32 + lane] : 0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                w0 = v;
-                __syncthreads();
+                w0 = __reduce_add_sync(0xffffffffu, lane < nwarps ? red32[lane] : 0);
             }
             const long long ncand = p.method == 1 ? ((1LL << ord_k) - 1) : (long long)k + (long long)ord_k * (ord_k - 1) / 2;
             unsigned long long mybest = ~0ULL;                   // (weight << 32) | candidate index
@@ -368,10 +367,9 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
             {                                                     // block minimum
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) { const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, mybest, o); mybest = o2 < mybest ? o2 : mybest; }
-                unsigned long long *red = keys + (((size_t)m * 4 + (size_t)n * 2 + 7) >> 3);      // past Mrow and tlist
-                if (lane == 0) red[warp] = mybest;
+                if (lane == 0) red64[warp] = mybest;
                 __syncthreads();
-                mybest = lane < nwarps ? red[lane] : ~0ULL;
+                mybest = lane < nwarps ? red64[lane] : ~0ULL;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) { const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, mybest, o); mybest = o2 < mybest ? o2 : mybest; }
             }
@@ -379,7 +377,7 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
             __syncthreads();
         }
 
-        // ---- 5. the chosen solution
+        // ---- 5. the chosen solution, back in column numbers
         for (int w = tid; w < p.nwn; w += NT) dec[w] = 0u;
         __syncthreads();
         {
@@ -394,8 +392,8 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                     while (q >= ord_k - 1 - i) { q -= ord_k - 1 - i; ++i; }
                     mask = (1u << i) | (1u << (i + 1 + (int)q));
                 }
-                if (tid == 0 && single >= 0) atomicOr(&dec[single >> 5], 1u << (single & 31));
-                if (tid < 32 && ((mask >> tid) & 1u)) { const int c = tlist[tid]; atomicOr(&dec[c >> 5], 1u << (c & 31)); }
+                if (tid == 0 && single >= 0) { const int c = idx[single]; atomicOr(&dec[c >> 5], 1u << (c & 31)); }
+                if (tid < 32 && ((mask >> tid) & 1u)) { const int c = idx[tlist[tid]]; atomicOr(&dec[c >> 5], 1u << (c & 31)); }
             }
             for (int r = tid; r < m; r += NT) {
                 const unsigned pc = pcol[r];
@@ -404,7 +402,7 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                 uint32_t bit = (uint32_t)((row[n >> 6] >> (n & 63)) & 1ULL);
                 if (single >= 0) bit ^= (uint32_t)((row[single >> 6] >> (single & 63)) & 1ULL);
                 if (mask) bit ^= (uint32_t)__popc(Mrow[r] & mask) & 1u;
-                if (bit) atomicOr(&dec[pc >> 5], 1u << (pc & 31));
+                if (bit) { const int c = idx[pc]; atomicOr(&dec[c >> 5], 1u << (c & 31)); }
             }
         }
         __syncthreads();

@@ -1389,7 +1389,7 @@ static int osd_launch(qd_osd *o, int negate_key, const uint32_t *d_synd, int32_t
     QD_CUDA(cudaFuncSetAttribute(osd0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->smem));
     QD_CUDA(cudaMemsetAsync(p.next_shot, 0, sizeof(unsigned long long), st));
     int per_sm = 0;
-    const int threads = g.m > 512 ? 1024 : (g.m > 256 ? 512 : 256);          // about one row per thread
+    const int threads = std::min(1024, std::max(128, (g.m + 31) & ~31));       // one row per thread (lazy blocked elimination) when m <= 1024
     QD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, osd0_kernel, threads, o->smem));
     per_sm = std::max(1, per_sm);
     const unsigned grid = (unsigned)std::min<long long>((long long)o->g->sm_count * per_sm, shots);
