@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
             unsigned long long *myrow = R + (size_t)(mine ? tid : 0) * W;
             const int wb = (warp << 5) - 1;
             bool isused = false;
-            int rank = 0;
+            int rank = 0, par = 0;
             for (int t0 = 0; t0 < n && rank < p.rank; t0 += OSD_BLOCK) {
                 uint32_t B = 0u, Y = 0u;
                 if (mine) {
@@ -176,17 +176,27 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                     if (n - t0 < 32) B &= (1u << (n - t0)) - 1u;       // position n is s, never a pivot column
                     BY[tid] = make_uint2(B, 0u);
                 }
+                // One barrier per PIVOT: every warp proposes (lowest block column in which one of its unused rows
+                // has a bit, first such row); the minimum over the warps is the next independent column in ranking
+                // order together with a pivot row for it.  Columns that depend on earlier ones never show a bit in
+                // an unused row (and keep none), so they cost nothing.
                 uint32_t avail = isused ? 0u : B;
                 int npiv = 0;
-#pragma unroll
-                for (int j = 0; j < OSD_BLOCK; ++j) {
-                    if (rank >= p.rank) break;
-                    const unsigned bal = __ballot_sync(0xffffffffu, (avail >> j) & 1u);
-                    int *cd = cand + (j & 1) * 32;
-                    if (lane == 0) cd[warp] = bal ? wb + __ffs((int)bal) : 0x7fffffff;
+                while (rank < p.rank) {
+                    const uint32_t orw = __reduce_or_sync(0xffffffffu, avail);
+                    int key = 0x7fffffff;
+                    if (orw) {
+                        const int cw = __ffs((int)orw) - 1;
+                        const unsigned bal = __ballot_sync(0xffffffffu, (avail >> cw) & 1u);
+                        key = (cw << 16) | (wb + __ffs((int)bal));
+                    }
+                    int *cd = cand + par;
+                    par ^= 32;
+                    if (lane == 0) cd[warp] = key;
                     __syncthreads();
-                    const int piv = __reduce_min_sync(0xffffffffu, cd[lane]);
-                    if (piv == 0x7fffffff) continue;            // dependent on the columns ranked before it
+                    const int best = __reduce_min_sync(0xffffffffu, cd[lane]);
+                    if (best == 0x7fffffff) break;              // the rest of the block depends on earlier columns
+                    const int j = best >> 16, piv = best & 0xffff;
                     ++rank;
                     if (tid == piv) {
                         isused = true; avail = 0u;
