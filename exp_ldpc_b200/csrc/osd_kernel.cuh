@@ -68,6 +68,7 @@ __host__ __device__ inline OsdSmemLayout osd_smem_layout(int m, int W, int P, in
     return L;
 }
 
+template <int RPT>
 __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -87,6 +88,8 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
     long long c_delta = 0;                                    // thread 0: change of the failure count
 
     if (tid < 64) cand[tid] = 0x7fffffff;                     // entries of absent warps stay "no candidate"
+    for (int x = tid; x < W2 * (OSD_BLOCK / 4); x += NT)      // entry 0 of every nibble table: the empty XOR
+        reinterpret_cast<ulonglong2 *>(smem_raw + L.tables)[x * 16] = make_ulonglong2(0ULL, 0ULL);
 
     for (;;) {
         if (tid == 0) {
@@ -150,8 +153,8 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
             __syncthreads();
         }
 
-        if (NT >= m) {
-            // ---- 3. Gauss-Jordan, one thread per row, in lazy blocks of 32 ranked columns.
+        if (NT * RPT >= m) {
+            // ---- 3. Gauss-Jordan, one thread per row (or two), in lazy blocks of 32 ranked columns.
             // A thread pulls its row's 32 bits of the block into a register (B).  Choosing pivots only needs
             // those bits: when row r absorbs pivot i, B_r ^= B_piv and the set Y_r of block-start pivot rows
             // making up the row's pending update becomes Y_r ^ Y_piv ^ {i}.  (B, Y) pairs are published in
@@ -164,32 +167,40 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
             ulonglong2 *T = reinterpret_cast<ulonglong2 *>(smem_raw + L.tables);
             uint32_t *nz = reinterpret_cast<uint32_t *>(smem_raw + L.nz);
             uint16_t *prow = reinterpret_cast<uint16_t *>(smem_raw + L.prow);
-            const bool mine = tid < m;
-            unsigned long long *myrow = R + (size_t)(mine ? tid : 0) * W;
-            const int wb = (warp << 5) - 1;
-            bool isused = false;
+            // Thread tid owns rows tid + q * NT, q < RPT (RPT = 2 halves the warps that take part in the
+            // latency-bound pivot rounds).
+            unsigned long long *myrow[RPT];
+            bool mine[RPT], isused[RPT];
+            uint32_t B[RPT], Y[RPT], avail[RPT];
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) {
+                mine[q] = tid + q * NT < m;
+                myrow[q] = R + (size_t)(mine[q] ? tid + q * NT : 0) * W;
+                isused[q] = false;
+            }
             int rank = 0, par = 0;
             for (int t0 = 0; t0 < n && rank < p.rank; t0 += OSD_BLOCK) {
-                uint32_t B = 0u, Y = 0u;
-                if (mine) {
-                    B = (uint32_t)(myrow[t0 >> 6] >> (t0 & 32));
-                    if (n - t0 < 32) B &= (1u << (n - t0)) - 1u;       // position n is s, never a pivot column
-                    BY[tid] = make_uint2(B, 0u);
+#pragma unroll
+                for (int q = 0; q < RPT; ++q) {
+                    B[q] = 0u; Y[q] = 0u;
+                    if (mine[q]) {
+                        B[q] = (uint32_t)(myrow[q][t0 >> 6] >> (t0 & 32));
+                        if (n - t0 < 32) B[q] &= (1u << (n - t0)) - 1u;       // position n is s, never a pivot column
+                        BY[tid + q * NT] = make_uint2(B[q], 0u);
+                    }
+                    avail[q] = isused[q] ? 0u : B[q];
                 }
-                // One barrier per PIVOT: every warp proposes (lowest block column in which one of its unused rows
-                // has a bit, first such row); the minimum over the warps is the next independent column in ranking
+                // One barrier per PIVOT: every thread proposes (lowest block column in which one of its unused
+                // rows has a bit, that row); the minimum over the CTA is the next independent column in ranking
                 // order together with a pivot row for it.  Columns that depend on earlier ones never show a bit in
                 // an unused row (and keep none), so they cost nothing.
-                uint32_t avail = isused ? 0u : B;
                 int npiv = 0;
                 while (rank < p.rank) {
-                    const uint32_t orw = __reduce_or_sync(0xffffffffu, avail);
                     int key = 0x7fffffff;
-                    if (orw) {
-                        const int cw = __ffs((int)orw) - 1;
-                        const unsigned bal = __ballot_sync(0xffffffffu, (avail >> cw) & 1u);
-                        key = (cw << 16) | (wb + __ffs((int)bal));
-                    }
+#pragma unroll
+                    for (int q = 0; q < RPT; ++q)
+                        if (avail[q]) key = min(key, ((__ffs((int)avail[q]) - 1) << 16) | (tid + q * NT));
+                    key = __reduce_min_sync(0xffffffffu, key);
                     int *cd = cand + par;
                     par ^= 32;
                     if (lane == 0) cd[warp] = key;
@@ -198,14 +209,17 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                     if (best == 0x7fffffff) break;              // the rest of the block depends on earlier columns
                     const int j = best >> 16, piv = best & 0xffff;
                     ++rank;
-                    if (tid == piv) {
-                        isused = true; avail = 0u;
-                        pcol[tid] = (uint16_t)(t0 + j); prow[npiv] = (uint16_t)tid;
-                    } else if ((B >> j) & 1u) {
-                        const uint2 pv = BY[piv];
-                        B ^= pv.x; Y ^= pv.y ^ (1u << npiv);
-                        BY[tid] = make_uint2(B, Y);
-                        if (!isused) avail = B;
+                    const uint2 pv = BY[piv];
+#pragma unroll
+                    for (int q = 0; q < RPT; ++q) {
+                        if (tid + q * NT == piv) {
+                            isused[q] = true; avail[q] = 0u;
+                            pcol[piv] = (uint16_t)(t0 + j); prow[npiv] = (uint16_t)piv;
+                        } else if ((B[q] >> j) & 1u) {
+                            B[q] ^= pv.x; Y[q] ^= pv.y ^ (1u << npiv);
+                            BY[tid + q * NT] = make_uint2(B[q], Y[q]);
+                            if (!isused[q]) avail[q] = B[q];
+                        }
                     }
                     ++npiv;
                 }
@@ -234,18 +248,23 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                     if (lane == 0) nz[jc] = b;
                 }
                 __syncthreads();
-                if (Y) {
-                    ulonglong2 *row = reinterpret_cast<ulonglong2 *>(myrow);
+#pragma unroll
+                for (int q = 0; q < RPT; ++q) {
+                    if (!Y[q]) continue;
+                    ulonglong2 *row = reinterpret_cast<ulonglong2 *>(myrow[q]);
                     for (int jc = jc0; jc < W2; ++jc) {
-                        const uint32_t y = Y & nz[jc];
+                        const uint32_t y = Y[q] & nz[jc];
                         if (!y) continue;
                         const ulonglong2 *Tj = T + jc * (OSD_BLOCK / 4) * 16;
+                        // all 8 lookups are issued unconditionally: nibbles beyond the block's pivots are 0 and
+                        // entry 0 of every table is zero (set once per launch, only ever rewritten with zero)
+                        ulonglong2 tv[OSD_BLOCK / 4];
+#pragma unroll
+                        for (int g = 0; g < OSD_BLOCK / 4; ++g) tv[g] = Tj[g * 16 + ((y >> (4 * g)) & 15u)];
                         ulonglong2 acc = row[jc];
 #pragma unroll
-                        for (int g = 0; g < OSD_BLOCK / 4; ++g) {
-                            if (g >= ng) break;
-                            const ulonglong2 tv = Tj[g * 16 + ((y >> (4 * g)) & 15u)];
-                            acc.x ^= tv.x; acc.y ^= tv.y;
+                        for (int g = 0; g < OSD_BLOCK / 4; g += 2) {
+                            acc.x ^= tv[g].x ^ tv[g + 1].x; acc.y ^= tv[g].y ^ tv[g + 1].y;
                         }
                         row[jc] = acc;
                     }

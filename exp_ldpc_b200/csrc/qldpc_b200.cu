@@ -1386,14 +1386,19 @@ static int osd_launch(qd_osd *o, int negate_key, const uint32_t *d_synd, int32_t
     p.fail = d_fail;
     p.counters = (long long *)d_counters;
     p.next_shot = o->d_next.as<unsigned long long>() + queue;
-    QD_CUDA(cudaFuncSetAttribute(osd0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->smem));
+    // one row per thread up to 1024 rows (measured faster than two at m = 768), two up to 2048; beyond that the
+    // kernel falls back to its strided-rows elimination
+    int rpt = g.m > 1024 ? 2 : 1;
+    if (const char *e = getenv("QD_OSD_RPT")) rpt = atoi(e) == 2 ? 2 : 1;
+    const int threads = std::min(1024, std::max(128, ((g.m + rpt - 1) / rpt + 31) & ~31));
+    auto kern = rpt == 2 ? osd0_kernel<2> : osd0_kernel<1>;
+    QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->smem));
     QD_CUDA(cudaMemsetAsync(p.next_shot, 0, sizeof(unsigned long long), st));
     int per_sm = 0;
-    const int threads = std::min(1024, std::max(128, (g.m + 31) & ~31));       // one row per thread (lazy blocked elimination) when m <= 1024
-    QD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, osd0_kernel, threads, o->smem));
+    QD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, o->smem));
     per_sm = std::max(1, per_sm);
     const unsigned grid = (unsigned)std::min<long long>((long long)o->g->sm_count * per_sm, shots);
-    osd0_kernel<<<grid, threads, o->smem, st>>>(p);
+    kern<<<grid, threads, o->smem, st>>>(p);
     QD_CUDA(cudaGetLastError());
     return 0;
 }
