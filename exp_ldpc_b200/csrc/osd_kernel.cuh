@@ -153,8 +153,8 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
             __syncthreads();
         }
 
-        if (NT * RPT >= m) {
-            // ---- 3. Gauss-Jordan, one thread per row (or two), in lazy blocks of 32 ranked columns.
+        {
+            // ---- 3. Gauss-Jordan (the host guarantees NT * RPT >= m), one thread per row (or two), in lazy blocks of 32 ranked columns.
             // A thread pulls its row's 32 bits of the block into a register (B).  Choosing pivots only needs
             // those bits: when row r absorbs pivot i, B_r ^= B_piv and the set Y_r of block-start pivot rows
             // making up the row's pending update becomes Y_r ^ Y_piv ^ {i}.  (B, Y) pairs are published in
@@ -271,45 +271,6 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                 }
                 __syncthreads();
             }
-        } else {
-            // ---- 3'. more rows than threads: plain Gauss-Jordan, a thread owns rows tid, tid + NT, ... and is
-            // their only writer, so one barrier per column (between choosing the pivot and using it) suffices.
-            // cand[] is double-buffered by column parity, so a warp that runs ahead never overwrites it early.
-            int rank = 0;
-            unsigned myused = 0u;                                    // bit q: row tid + q * NT is a pivot row
-            for (int t = 0; t < n && rank < p.rank; ++t) {
-                const int cw = t >> 6, cb = t & 63;
-                unsigned mybits = 0u;
-                int first = 0x7fffffff;
-                for (int q = 0, r = tid; r < m; ++q, r += NT) {
-                    const unsigned bit = (unsigned)((R[(size_t)r * W + cw] >> cb) & 1ULL);
-                    mybits |= bit << q;
-                    if (bit && !((myused >> q) & 1u)) first = min(first, r);
-                }
-                first = __reduce_min_sync(0xffffffffu, first);
-                int *cd = cand + (t & 1) * 32;
-                if (lane == 0) cd[warp] = first;
-                __syncthreads();
-                const int piv = __reduce_min_sync(0xffffffffu, cd[lane]);
-                if (piv == 0x7fffffff) continue;                    // dependent on the columns ranked before it
-                ++rank;
-                const ulonglong2 *prw = reinterpret_cast<const ulonglong2 *>(R + (size_t)piv * W);
-                for (int q = 0, r = tid; r < m; ++q, r += NT) {
-                    if (r == piv) { myused |= 1u << q; pcol[r] = (uint16_t)t; continue; }
-                    if (!((mybits >> q) & 1u)) continue;
-                    ulonglong2 *row = reinterpret_cast<ulonglong2 *>(R + (size_t)r * W);
-#pragma unroll 3
-                    for (int j = 0; j < W2; ++j) {
-                        const ulonglong2 pv = prw[j];
-                        if (pv.x | pv.y) {
-                            ulonglong2 v = row[j];
-                            v.x ^= pv.x; v.y ^= pv.y;
-                            row[j] = v;
-                        }
-                    }
-                }
-            }
-            __syncthreads();
         }
 
         // ---- 4. higher-order search (osd_e / osd_cs): patterns on the columns outside the information set

@@ -1336,7 +1336,7 @@ extern "C" int qd_osd_create(qd_graph *g, int32_t method, int32_t order, qd_osd 
     int rc = use_device(g->device);
     if (rc) return rc;
     const GraphDev &gd = g->dev;
-    if (gd.n > 8000) return fail(QD_EUNSUP, "OSD: more than 8000 columns");
+    if (gd.n > 8000 || gd.m > 2048) return fail(QD_EUNSUP, "OSD: more than 8000 columns or 2048 rows");
     std::unique_ptr<qd_osd> o(new qd_osd);
     o->g = g; o->device = g->device;
     o->method = order > 0 ? method : 0; o->order = method ? order : 0;
@@ -1386,8 +1386,8 @@ static int osd_launch(qd_osd *o, int negate_key, const uint32_t *d_synd, int32_t
     p.fail = d_fail;
     p.counters = (long long *)d_counters;
     p.next_shot = o->d_next.as<unsigned long long>() + queue;
-    // one row per thread up to 1024 rows (measured faster than two at m = 768), two up to 2048; beyond that the
-    // kernel falls back to its strided-rows elimination
+    // one row per thread up to 1024 rows (measured faster than two at m = 768), two up to 2048 (more rows never
+    // fit shared memory: qd_osd_create refuses them)
     int rpt = g.m > 1024 ? 2 : 1;
     if (const char *e = getenv("QD_OSD_RPT")) rpt = atoi(e) == 2 ? 2 : 1;
     const int threads = std::min(1024, std::max(128, ((g.m + rpt - 1) / rpt + 31) & ~31));

@@ -441,6 +441,28 @@ def test_bposd0_experiment_against_live_oracle(gpu, codes, which, method, p, ker
     assert not (((err ^ got["decodings"]) @ hz.T.toarray()) % 2).any()
 
 
+@pytest.mark.parametrize("which,osd,order", [("hgp1600", "osd0", 0), ("hgp225", "osd_cs", 5)])
+def test_osd_two_rows_per_thread_variant(gpu, codes, which, osd, order, monkeypatch):
+    """The OSD kernel instantiation that gives a thread two rows (chosen by itself only beyond 1024 checks)
+    must produce the same decodings; QD_OSD_RPT forces it on codes the oracle finishes quickly."""
+    from exp_ldpc_b200.experiment import CodeCapacityExperiment
+    from oracle import pyoracle as po
+    code = codes[which]
+    p = 0.03
+    q, prior = 2 * p / 3 + p - 4 / 3 * p * p, 2 * p / 3
+    shots = 64 if which == "hgp1600" else 300
+    opts = dict(max_iter=12, bp_method="ms", ms_scaling_factor=0.0, osd_method=osd, osd_order=order)
+    monkeypatch.setenv("QD_OSD_RPT", "2")
+    got = CodeCapacityExperiment(code, q, prior, "bposd", opts).run(shots, seed=23, per_shot=True)
+    monkeypatch.delenv("QD_OSD_RPT")
+    ref = po.run_code_capacity(code.checks.z, code.logicals.z, q, prior, decoder="bposd0" if order == 0 else "bposd_cs",
+                               osd_order=order, max_iter=12, bp_method="ms", ms_scaling_factor=0.0, seed=23, shots=shots,
+                               per_shot=True)
+    assert ref["non_converged"] > 0
+    assert (got["decodings"] == ref["decodings"]).all()
+    assert np.array_equal(got["fail"], ref["fail"]) and got["failures"] == ref["failures"]
+
+
 def test_bposd_decoder_duck_type(gpu, code225):
     """ldpc.bposd_decoder call shape of _experiment.py:96-100,125."""
     from exp_ldpc_b200.decoders import bposd_decoder
