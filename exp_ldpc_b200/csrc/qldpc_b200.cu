@@ -17,6 +17,7 @@
 #include "bp7_layout.h"
 #include "bp_pick.h"
 #include "bpg_kernel.cuh"
+#include "bpc_kernel.cuh"
 #include "frame_sim.cuh"
 #include "osd_kernel.cuh"
 #include "ssf_kernel.cuh"
@@ -241,6 +242,9 @@ struct qd_bp {
     int v7_lines = 0;
     int global_mem = 0;    // messages in global memory (bpg_kernel.cuh): graphs the shared-memory kernels cannot take
     DevBuf d_scratch;
+    // cluster kernel (bpc_kernel.cuh): messages spread over the shared memories of `cl_C` CTAs
+    int cluster = 0, cl_C = 0, cl_max_edges = 0, cl_max_rows = 0, cl_nwpos = 0, cl_clusters = 0;
+    DevBuf dc_row_lo, dc_edge_pos, dc_lc_lo, dc_lc_col, dc_lc_ptr, dc_desc, dc_word_lo, dc_col_pos, dc_prior;
     int llr_mode = 0;      // what d_llr receives (0: log-ratio every iteration, 1: raw soft output of the last iteration)
     DevBuf d7_table, d7_row_table, d7_chunk_deg, d7_prior_rec, d7_col_id, d7_const_bits;
     // host-buffer pipeline state
@@ -801,17 +805,122 @@ static int bp7_configure(qd_bp *d, int threads, int slots, int ctas)
 }
 
 
+template <typename real, int METHOD>
+static void (*bpc_fn())(const BpcParams) { return bpc_kernel<real, METHOD>; }
+
+static void (*bpc_kernel_for(const qd_bp *d))(const BpcParams)
+{
+    return d->precision == QD_PREC_F64 ? (d->method == QD_BP_MIN_SUM ? bpc_fn<double, QD_BP_MIN_SUM>() : bpc_fn<double, QD_BP_PRODUCT_SUM>())
+                                       : (d->method == QD_BP_MIN_SUM ? bpc_fn<float, QD_BP_MIN_SUM>() : bpc_fn<float, QD_BP_PRODUCT_SUM>());
+}
+
+// Partition the graph over a cluster of C CTAs (smallest C of 2, 4, 8 whose per-CTA share fits shared memory) and
+// upload the tables of bpc_kernel.cuh.  Rows: contiguous ranges of about nnz / C edges.  Columns: the CTA holding
+// most of the column's edges (ties: the lowest rank).
+static int bpc_prepare(qd_bp *d)
+{
+    qd_graph *g = d->g;
+    const GraphDev &gd = g->dev;
+    const int rb = d->precision == QD_PREC_F64 ? 8 : 4;
+    const int m = gd.m, n = gd.n, nnz = gd.nnz;
+    if (m < 8 || nnz < 8) return fail(QD_EUNSUP, "cluster BP kernel: graph too small to split");
+    for (int C = 2; C <= 8; C *= 2) {
+        std::vector<int32_t> row_lo(C + 1, 0);
+        row_lo[C] = m;
+        for (int c = 1, r = 0; c < C; ++c) {
+            const long long want = (long long)nnz * c / C;
+            while (r < m && g->row_ptr[r] < want) ++r;
+            row_lo[c] = std::max(r, row_lo[c - 1]);
+        }
+        int max_edges = 0, max_rows = 0;
+        for (int c = 0; c < C; ++c) {
+            max_edges = std::max(max_edges, g->row_ptr[row_lo[c + 1]] - g->row_ptr[row_lo[c]]);
+            max_rows = std::max(max_rows, row_lo[c + 1] - row_lo[c]);
+        }
+        if (max_edges >= (1 << 24)) continue;
+        std::vector<int> row_owner(m);
+        for (int c = 0; c < C; ++c) for (int r = row_lo[c]; r < row_lo[c + 1]; ++r) row_owner[r] = c;
+        std::vector<int> col_owner(n, 0);
+        std::vector<std::vector<int32_t>> cols(C);
+        for (int j = 0; j < n; ++j) {
+            int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int t = g->col_ptr[j]; t < g->col_ptr[j + 1]; ++t) ++cnt[row_owner[g->csc_row[t]]];
+            int best = g->col_ptr[j + 1] == g->col_ptr[j] ? (int)((long long)j * C / n) : 0;   // isolated columns: spread
+            for (int c = 1; c < C; ++c) if (cnt[c] > cnt[best]) best = c;
+            col_owner[j] = best;
+            cols[best].push_back(j);
+        }
+        std::vector<int32_t> lc_lo(C + 1, 0), word_lo(C + 1, 0);
+        int max_cols = 0;
+        for (int c = 0; c < C; ++c) {
+            lc_lo[c + 1] = lc_lo[c] + (int)cols[c].size();
+            word_lo[c + 1] = word_lo[c] + ((int)cols[c].size() + 31) / 32;
+            max_cols = std::max(max_cols, (int)cols[c].size());
+        }
+        const int nwpos = std::max(word_lo[C], 1);
+        const size_t smem = bpc_smem_layout(max_edges, max_rows, nwpos, gd.nwn, rb).total;
+        if (smem + 256 > (size_t)g->smem_optin) continue;
+        // tables
+        std::vector<int32_t> lc_col(std::max(n, 1)), lc_ptr(n + 1, 0), col_pos(std::max(n, 1)), edge_pos(std::max(nnz, 1));
+        std::vector<uint32_t> desc(std::max(nnz, 1));
+        std::vector<double> prior(std::max(n, 1));
+        int li = 0, dp = 0;
+        for (int c = 0; c < C; ++c)
+            for (size_t i = 0; i < cols[c].size(); ++i, ++li) {
+                const int j = cols[c][i];
+                lc_col[li] = j;
+                prior[li] = d->prior_dom[j];
+                col_pos[j] = (word_lo[c] << 5) + (int)i;
+                lc_ptr[li] = dp;
+                for (int t = g->col_ptr[j]; t < g->col_ptr[j + 1]; ++t) {
+                    const int e = g->csc_edge[t], o = row_owner[g->csc_row[t]];
+                    desc[dp++] = ((uint32_t)o << 24) | (uint32_t)(e - g->row_ptr[row_lo[o]]);
+                }
+            }
+        lc_ptr[n] = dp;
+        for (int e = 0; e < nnz; ++e) edge_pos[e] = col_pos[g->col_idx[e]];
+        int rc;
+        if ((rc = upload(d->dc_row_lo, row_lo)) || (rc = upload(d->dc_edge_pos, edge_pos)) || (rc = upload(d->dc_lc_lo, lc_lo)) ||
+            (rc = upload(d->dc_lc_col, lc_col)) || (rc = upload(d->dc_lc_ptr, lc_ptr)) || (rc = upload(d->dc_desc, desc)) ||
+            (rc = upload(d->dc_word_lo, word_lo)) || (rc = upload(d->dc_col_pos, col_pos)))
+            return rc;
+        if (rb == 8) { if ((rc = upload(d->dc_prior, prior))) return rc; }
+        else { std::vector<float> pf(prior.begin(), prior.end()); if ((rc = upload(d->dc_prior, pf))) return rc; }
+        const int threads = std::min(1024, std::max(128, (std::max(max_rows, max_cols) + 31) & ~31));
+        // how many clusters of this shape the device runs at once
+        auto fn = bpc_kernel_for(d);
+        QD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3((unsigned)(C * std::max(1, g->sm_count / C)));
+        cfg.blockDim = dim3((unsigned)threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) != cudaSuccess || nclusters < 1) {
+            cudaGetLastError();
+            continue;
+        }
+        d->cl_C = C; d->cl_max_edges = max_edges; d->cl_max_rows = max_rows; d->cl_nwpos = nwpos; d->cl_clusters = nclusters;
+        d->threads = threads; d->slots = 1; d->ctas_per_sm = 1; d->groups = 1; d->smem = smem;
+        return 0;
+    }
+    return fail(QD_EUNSUP, "cluster BP kernel: the graph does not fit the shared memory of 8 SMs");
+}
+
 // pick the kernel family and its default launch geometry.  Row-regular graphs with a compiled
 // (row degree, column tile) pair take the thread-owned-state kernel (bp7_kernel.cuh) when they fit;
 // everything else the generic kernel (bp_kernel.cuh).
-static int bp_choose_kernel(qd_bp *d, bool allow_regular, bool family_global = false)
+static int bp_choose_kernel(qd_bp *d, bool allow_regular, bool family_global = false, bool family_cluster = false)
 {
     const GraphDev &gd = d->g->dev;
     int rc;
     d->v7 = 0;
     d->global_mem = 0;
     const bool shared_ok = !d->g->big && gd.max_col_deg <= 16 && !(d->method == QD_BP_PRODUCT_SUM && gd.max_row_deg > 16);
-    if (family_global || !shared_ok) { d->global_mem = 1; }
+    if (family_global || family_cluster || !shared_ok) { d->global_mem = 1; }
     else if (allow_regular && gd.max_row_deg >= 2 && gd.max_col_deg >= 1 && gd.max_col_deg <= 8) {
         // candidates: exact (row degree, column tile) for row-regular graphs, else the padded variants
         const int vm0 = gd.max_col_deg <= 4 ? 4 : 8;
@@ -841,6 +950,11 @@ static int bp_choose_kernel(qd_bp *d, bool allow_regular, bool family_global = f
         if ((rc = bp6_prepare(d))) return rc;
         if (bp_default_config(d) != 0) d->global_mem = 1;       // does not fit shared memory
     }
+    d->cluster = 0;
+    if (d->global_mem && !family_global && bpc_prepare(d) == 0) {   // too large for one SM: spread over a cluster
+        d->global_mem = 0; d->cluster = 1;
+        d->rd = 0; d->v7_irreg = 0;
+    }
     if (d->global_mem) {
         d->rd = 0; d->v7_irreg = 0;
         const size_t smem = (size_t)((gd.n + 15) & ~15) + ((gd.m + 15) & ~15) + (size_t)gd.nwn * 4 + 16;
@@ -855,11 +969,12 @@ static int bp_choose_kernel(qd_bp *d, bool allow_regular, bool family_global = f
 extern "C" int qd_bp_select_kernel(qd_bp *d, int32_t family)
 {
     if (!d) return fail(QD_EINVAL, "NULL handle");
-    if (family != 0 && family != 5 && family != 6 && family != 7)
-        return fail(QD_EINVAL, "kernel family must be 0 (automatic), 5 (global memory), 6 (generic) or 7 (thread-owned state)");
+    if (family != 0 && family != 5 && family != 6 && family != 7 && family != 8)
+        return fail(QD_EINVAL, "kernel family must be 0 (automatic), 5 (global memory), 6 (generic), 7 (thread-owned state) or 8 (cluster)");
     int rc = use_device(d->g->device);
     if (rc) return rc;
-    if ((rc = bp_choose_kernel(d, family != 6, family == 5))) return rc;
+    if ((rc = bp_choose_kernel(d, family != 6, family == 5, family == 8))) return rc;
+    if (family == 8 && !d->cluster) return fail(QD_EUNSUP, "the cluster BP kernel does not support this graph");
     if (family == 7 && !d->v7) return fail(QD_EUNSUP, "the thread-owned-state BP kernel does not support this graph");
     if (family == 6 && d->global_mem) return fail(QD_EUNSUP, "the generic shared-memory BP kernel does not support this graph");
     return 0;
@@ -868,7 +983,7 @@ extern "C" int qd_bp_select_kernel(qd_bp *d, int32_t family)
 extern "C" int qd_bp_get_kernel(qd_bp *d, int32_t *family, int32_t *row_degree, int32_t *column_tile)
 {
     if (!d) return fail(QD_EINVAL, "NULL handle");
-    if (family) *family = d->global_mem ? 5 : (d->v7 ? 7 : 6);
+    if (family) *family = d->cluster ? 8 : (d->global_mem ? 5 : (d->v7 ? 7 : 6));
     if (row_degree) *row_degree = d->rd;
     if (column_tile) *column_tile = d->vmax;
     return 0;
@@ -989,6 +1104,39 @@ static int bp_launch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int6
     int rc = use_device(d->g->device);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (d->cluster) {
+        BpcParams q{};
+        q.m = g.m; q.n = g.n; q.nnz = g.nnz; q.nwn = g.nwn; q.C = d->cl_C;
+        q.max_edges = d->cl_max_edges; q.max_rows = d->cl_max_rows; q.nwpos = d->cl_nwpos;
+        q.row_lo = d->dc_row_lo.as<int32_t>(); q.row_ptr = g.row_ptr; q.edge_pos = d->dc_edge_pos.as<int32_t>();
+        q.lc_lo = d->dc_lc_lo.as<int32_t>(); q.lc_col = d->dc_lc_col.as<int32_t>(); q.lc_ptr = d->dc_lc_ptr.as<int32_t>();
+        q.desc = d->dc_desc.as<uint32_t>(); q.word_lo = d->dc_word_lo.as<int32_t>(); q.col_pos = d->dc_col_pos.as<int32_t>();
+        q.prior = d->dc_prior.p; q.alpha_fixed = d->alpha_fixed; q.max_iter = d->max_iter;
+        q.synd = d_synd; q.synd_stride = synd_stride; q.shots = shots;
+        q.corr = d_corr; q.corr_stride = corr_stride;
+        q.conv = d_converged; q.iters = d_iters; q.llr = d_llr; q.llr_mode = d->llr_mode;
+        q.err = d_err; q.err_stride = err_stride;
+        q.lzT = d_err ? logicals->d_lzT.as<uint32_t>() : nullptr;
+        q.k = d_err ? logicals->k : 0;
+        q.fail = d_fail;
+        q.counters = (long long *)d_counters;
+        q.next_shot = d->d_next.as<unsigned long long>() + queue;
+        auto fn = bpc_kernel_for(d);
+        QD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem));
+        QD_CUDA(cudaMemsetAsync(q.next_shot, 0, sizeof(unsigned long long), st));
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)d->cl_C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        const long long nclusters = std::min<long long>(d->cl_clusters, shots);
+        cfg.gridDim = dim3((unsigned)(nclusters * d->cl_C));
+        cfg.blockDim = dim3((unsigned)d->threads);
+        cfg.dynamicSmemBytes = d->smem;
+        cfg.stream = st;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        QD_CUDA(cudaLaunchKernelEx(&cfg, fn, q));
+        return 0;
+    }
     if (d->global_mem) {
         qd_graph *gr = d->g;
         const unsigned grid = (unsigned)std::min<long long>((long long)gr->sm_count * d->ctas_per_sm, shots);

@@ -146,8 +146,9 @@ int qd_bp_get_config(qd_bp *d, int32_t *threads, int32_t *slots, int32_t *ctas_p
 
 /* Kernel family (testing / tuning).  qd_bp_create picks automatically: 7 = thread-owned-state
  * shared-memory kernel (a variant is compiled for the graph's degrees), 6 = generic shared-memory
- * kernel, 5 = messages in global memory (graphs too large or too dense for shared memory; slower).
- * select: 0 = automatic, 5 / 6 / 7 = force; resets the launch geometry. */
+ * kernel, 8 = messages spread over the shared memories of a thread-block cluster of 2 / 4 / 8 SMs
+ * (graphs too large or too dense for one SM), 5 = messages in global memory (graphs beyond that; slower).
+ * select: 0 = automatic, 5 / 6 / 7 / 8 = force; resets the launch geometry. */
 int qd_bp_select_kernel(qd_bp *d, int32_t family);
 int qd_bp_get_kernel(qd_bp *d, int32_t *family, int32_t *row_degree, int32_t *column_tile);
 

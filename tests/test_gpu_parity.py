@@ -732,7 +732,7 @@ def test_bpd_detector_mode_against_oracle(gpu, code225):
     out = run_simulation(shots, code225, lambda x, z: 0.01, lambda x, z: 0.01, depolarizing_noise, {"p": 0.01, "pm": 0.012},
                          opts, 2, "bpd_detector", seed=9)
     big = DetectorExperiment(build_storage_simulation(2, circuit_noise(0.004, 0.006), code225).circuit, opts)
-    assert big.decoder.config()["kernel"] == "global"       # 15 k faults / 45 k edges: messages live in global memory
+    assert big.decoder.config()["kernel"] == "cluster"      # 15 k faults / 45 k edges: messages spread over a cluster
     got = exp.run(shots, seed=9, per_shot=True)
     rec = po.circuit_sample(prog.ops, prog.thresholds, prog.num_qubits, prog.num_measurements, 9, 0, shots).astype(np.int64)
     assert np.array_equal(got["records"], rec)
@@ -763,13 +763,27 @@ def test_global_memory_bp_kernel_matches_committed_golden_vectors(gpu, codes, na
     assert np.array_equal(out["converged"], g[name + "_conv"])
 
 
-def test_large_graphs_fall_back_to_global_memory(gpu, code1600):
-    """Spacetime matrix of the n = 1600 code, T = 3: 26 k edges do not fit one SM in fp64."""
+@pytest.mark.parametrize("name", _bp_case_names())
+def test_cluster_bp_kernel_matches_committed_golden_vectors(gpu, codes, name):
+    """Every golden BP case replayed with the messages split over a thread-block cluster (forced: these graphs
+    would fit one SM)."""
+    g = np.load(os.path.join(GOLDEN, "decoder_vectors.npz"))
+    out = _run_gpu_case(name, codes, kernel="cluster")
+    assert np.array_equal(np.packbits(out["decodings"], axis=1), g[name + "_dec"])
+    assert np.array_equal(out["iters"], g[name + "_iters"])
+    assert np.array_equal(out["fail"], g[name + "_fail"])
+    assert np.array_equal(out["converged"], g[name + "_conv"])
+
+
+@pytest.mark.parametrize("kernel", ["auto", "global"])
+def test_large_graphs_take_the_cluster_kernel(gpu, code1600, kernel):
+    """Spacetime matrix of the n = 1600 code, T = 3: 26 k edges do not fit one SM in fp64; they are spread over
+    a cluster (automatic choice) or, forced, kept in global memory."""
     from exp_ldpc_b200.experiment import SpacetimeExperiment
     from oracle import pyoracle as po
     opts = dict(max_iter=8, bp_method="ms", ms_scaling_factor=0.0)
-    exp = SpacetimeExperiment(code1600, 3, 0.004, 0.006, opts)
-    assert exp.decoder.config()["kernel"] == "global"
+    exp = SpacetimeExperiment(code1600, 3, 0.004, 0.006, opts, kernel=kernel)
+    assert exp.decoder.config()["kernel"] == ("cluster" if kernel == "auto" else "global")
     shots = 24
     got = exp.run(shots, seed=2, per_shot=True)
     h_st = exp.spacetime.spacetime_check_matrix
@@ -781,7 +795,7 @@ def test_large_graphs_fall_back_to_global_memory(gpu, code1600):
     assert np.array_equal(got["iters"], ref["iters"]) and np.array_equal(got["fail"], ref["fail"])
 
 
-def test_dense_rows_take_the_global_kernel(gpu):
+def test_dense_rows_take_the_cluster_kernel(gpu):
     """Row degree 300 (> 255) and product-sum with row degree > 16: beyond the shared-memory kernels."""
     from scipy import sparse
     from exp_ldpc_b200.decoders import bp_decoder
