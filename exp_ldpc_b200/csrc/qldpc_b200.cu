@@ -243,8 +243,8 @@ struct qd_bp {
     int global_mem = 0;    // messages in global memory (bpg_kernel.cuh): graphs the shared-memory kernels cannot take
     DevBuf d_scratch;
     // cluster kernel (bpc_kernel.cuh): messages spread over the shared memories of `cl_C` CTAs
-    int cluster = 0, cl_C = 0, cl_max_edges = 0, cl_max_rows = 0, cl_nwpos = 0, cl_clusters = 0;
-    DevBuf dc_row_lo, dc_edge_pos, dc_lc_lo, dc_lc_col, dc_lc_ptr, dc_desc, dc_word_lo, dc_col_pos, dc_prior;
+    int cluster = 0, cl_C = 0, cl_max_edges = 0, cl_max_rows = 0, cl_max_cols = 0, cl_max_cedges = 0, cl_nwpos = 0, cl_clusters = 0;
+    DevBuf dc_row_lo, dc_row_start, dc_edge_pos, dc_lc_lo, dc_lc_col, dc_lc_ptr, dc_desc, dc_word_lo, dc_col_pos, dc_prior;
     int llr_mode = 0;      // what d_llr receives (0: log-ratio every iteration, 1: raw soft output of the last iteration)
     DevBuf d7_table, d7_row_table, d7_chunk_deg, d7_prior_rec, d7_col_id, d7_const_bits;
     // host-buffer pipeline state
@@ -833,8 +833,15 @@ static int bpc_prepare(qd_bp *d)
             row_lo[c] = std::max(r, row_lo[c - 1]);
         }
         int max_edges = 0, max_rows = 0;
+        std::vector<int32_t> row_start(std::max(m, 1), 0);
         for (int c = 0; c < C; ++c) {
-            max_edges = std::max(max_edges, g->row_ptr[row_lo[c + 1]] - g->row_ptr[row_lo[c]]);
+            int pos = 0;
+            for (int r = row_lo[c]; r < row_lo[c + 1]; ++r) {
+                const int deg = g->row_ptr[r + 1] - g->row_ptr[r];
+                row_start[r] = pos;
+                pos += deg | 1;                                   // odd pitch
+            }
+            max_edges = std::max(max_edges, pos);
             max_rows = std::max(max_rows, row_lo[c + 1] - row_lo[c]);
         }
         if (max_edges >= (1 << 24)) continue;
@@ -851,14 +858,20 @@ static int bpc_prepare(qd_bp *d)
             cols[best].push_back(j);
         }
         std::vector<int32_t> lc_lo(C + 1, 0), word_lo(C + 1, 0);
-        int max_cols = 0;
+        int max_cols = 0, max_cedges = 0;
         for (int c = 0; c < C; ++c) {
             lc_lo[c + 1] = lc_lo[c] + (int)cols[c].size();
             word_lo[c + 1] = word_lo[c] + ((int)cols[c].size() + 31) / 32;
             max_cols = std::max(max_cols, (int)cols[c].size());
+            int ce = 0;
+            for (int j : cols[c]) ce += g->col_ptr[j + 1] - g->col_ptr[j];
+            max_cedges = std::max(max_cedges, ce);
         }
         const int nwpos = std::max(word_lo[C], 1);
-        const size_t smem = bpc_smem_layout(max_edges, max_rows, nwpos, gd.nwn, rb).total;
+        const size_t smem = bpc_smem_layout(max_edges, max_rows, max_cols, max_cedges, nwpos, gd.nwn, rb).total;
+        const bool dbg = getenv("QD_BPC_DEBUG") != nullptr;
+        if (dbg) fprintf(stderr, "bpc: C=%d max_edges=%d max_rows=%d max_cols=%d max_cedges=%d smem=%zu (optin %d)\n", C, max_edges,
+                         max_rows, max_cols, max_cedges, smem, g->smem_optin);
         if (smem + 256 > (size_t)g->smem_optin) continue;
         // tables
         std::vector<int32_t> lc_col(std::max(n, 1)), lc_ptr(n + 1, 0), col_pos(std::max(n, 1)), edge_pos(std::max(nnz, 1));
@@ -873,20 +886,20 @@ static int bpc_prepare(qd_bp *d)
                 col_pos[j] = (word_lo[c] << 5) + (int)i;
                 lc_ptr[li] = dp;
                 for (int t = g->col_ptr[j]; t < g->col_ptr[j + 1]; ++t) {
-                    const int e = g->csc_edge[t], o = row_owner[g->csc_row[t]];
-                    desc[dp++] = ((uint32_t)o << 24) | (uint32_t)(e - g->row_ptr[row_lo[o]]);
+                    const int e = g->csc_edge[t], row = (int)g->csc_row[t], o = row_owner[row];
+                    desc[dp++] = ((uint32_t)o << 24) | (uint32_t)(row_start[row] + (e - g->row_ptr[row]));
                 }
             }
         lc_ptr[n] = dp;
         for (int e = 0; e < nnz; ++e) edge_pos[e] = col_pos[g->col_idx[e]];
         int rc;
-        if ((rc = upload(d->dc_row_lo, row_lo)) || (rc = upload(d->dc_edge_pos, edge_pos)) || (rc = upload(d->dc_lc_lo, lc_lo)) ||
+        if ((rc = upload(d->dc_row_lo, row_lo)) || (rc = upload(d->dc_row_start, row_start)) || (rc = upload(d->dc_edge_pos, edge_pos)) || (rc = upload(d->dc_lc_lo, lc_lo)) ||
             (rc = upload(d->dc_lc_col, lc_col)) || (rc = upload(d->dc_lc_ptr, lc_ptr)) || (rc = upload(d->dc_desc, desc)) ||
             (rc = upload(d->dc_word_lo, word_lo)) || (rc = upload(d->dc_col_pos, col_pos)))
             return rc;
         if (rb == 8) { if ((rc = upload(d->dc_prior, prior))) return rc; }
         else { std::vector<float> pf(prior.begin(), prior.end()); if ((rc = upload(d->dc_prior, pf))) return rc; }
-        const int threads = std::min(1024, std::max(128, (std::max(max_rows, max_cols) + 31) & ~31));
+        const int threads = std::min(768, std::max(128, (std::max(max_rows, max_cols) + 31) & ~31));   // 768: 85 registers, no spills
         // how many clusters of this shape the device runs at once
         auto fn = bpc_kernel_for(d);
         QD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -899,11 +912,14 @@ static int bpc_prepare(qd_bp *d)
         cfg.dynamicSmemBytes = smem;
         cfg.attrs = attr; cfg.numAttrs = 1;
         int nclusters = 0;
-        if (cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg) != cudaSuccess || nclusters < 1) {
+        const cudaError_t oe = cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg);
+        if (dbg) fprintf(stderr, "bpc: C=%d threads=%d clusters=%d (%s)\n", C, threads, nclusters, cudaGetErrorString(oe));
+        if (oe != cudaSuccess || nclusters < 1) {
             cudaGetLastError();
             continue;
         }
-        d->cl_C = C; d->cl_max_edges = max_edges; d->cl_max_rows = max_rows; d->cl_nwpos = nwpos; d->cl_clusters = nclusters;
+        d->cl_C = C; d->cl_max_edges = max_edges; d->cl_max_rows = max_rows; d->cl_max_cols = max_cols; d->cl_max_cedges = max_cedges;
+        d->cl_nwpos = nwpos; d->cl_clusters = nclusters;
         d->threads = threads; d->slots = 1; d->ctas_per_sm = 1; d->groups = 1; d->smem = smem;
         return 0;
     }
@@ -1107,8 +1123,9 @@ static int bp_launch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int6
     if (d->cluster) {
         BpcParams q{};
         q.m = g.m; q.n = g.n; q.nnz = g.nnz; q.nwn = g.nwn; q.C = d->cl_C;
-        q.max_edges = d->cl_max_edges; q.max_rows = d->cl_max_rows; q.nwpos = d->cl_nwpos;
-        q.row_lo = d->dc_row_lo.as<int32_t>(); q.row_ptr = g.row_ptr; q.edge_pos = d->dc_edge_pos.as<int32_t>();
+        q.max_edges = d->cl_max_edges; q.max_rows = d->cl_max_rows; q.max_cols = d->cl_max_cols; q.max_cedges = d->cl_max_cedges;
+        q.nwpos = d->cl_nwpos;
+        q.row_lo = d->dc_row_lo.as<int32_t>(); q.row_ptr = g.row_ptr; q.row_start = d->dc_row_start.as<int32_t>(); q.edge_pos = d->dc_edge_pos.as<int32_t>();
         q.lc_lo = d->dc_lc_lo.as<int32_t>(); q.lc_col = d->dc_lc_col.as<int32_t>(); q.lc_ptr = d->dc_lc_ptr.as<int32_t>();
         q.desc = d->dc_desc.as<uint32_t>(); q.word_lo = d->dc_word_lo.as<int32_t>(); q.col_pos = d->dc_col_pos.as<int32_t>();
         q.prior = d->dc_prior.p; q.alpha_fixed = d->alpha_fixed; q.max_iter = d->max_iter;

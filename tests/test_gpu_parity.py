@@ -732,7 +732,7 @@ def test_bpd_detector_mode_against_oracle(gpu, code225):
     out = run_simulation(shots, code225, lambda x, z: 0.01, lambda x, z: 0.01, depolarizing_noise, {"p": 0.01, "pm": 0.012},
                          opts, 2, "bpd_detector", seed=9)
     big = DetectorExperiment(build_storage_simulation(2, circuit_noise(0.004, 0.006), code225).circuit, opts)
-    assert big.decoder.config()["kernel"] == "cluster"      # 15 k faults / 45 k edges: messages spread over a cluster
+    assert big.decoder.config()["kernel"] == "global"       # 15 k faults / 96 k edges: beyond 8 SMs' shared memory
     got = exp.run(shots, seed=9, per_shot=True)
     rec = po.circuit_sample(prog.ops, prog.thresholds, prog.num_qubits, prog.num_measurements, 9, 0, shots).astype(np.int64)
     assert np.array_equal(got["records"], rec)
@@ -809,7 +809,7 @@ def test_dense_rows_take_the_cluster_kernel(gpu):
     synd = (err @ a.T.astype(np.int64)) % 2
     for method in ("ms", "ps"):
         dec = bp_decoder(h, channel_probs=probs, max_iter=10, bp_method=method, ms_scaling_factor=0.0)
-        assert dec.config()["kernel"] == "global"
+        assert dec.config()["kernel"] == "cluster"                      # beyond the single-SM kernels' degree limits
         ref = po.OracleBP(h, channel_probs=probs, max_iter=10, bp_method=method, ms_scaling_factor=0.0)
         corr, conv, its = dec.decode_batch(synd)
         for s in range(synd.shape[0]):
