@@ -1654,6 +1654,7 @@ extern "C" int qd_ssf_create(qd_graph *hz, int32_t num_generators, const int32_t
     for (int gi = 0; gi < mg; ++gi) {
         const int lo = gen_ptr[gi], w = gen_ptr[gi + 1] - lo;
         if (w <= 0 || w > SSF_MAX_W) return fail(QD_EUNSUP, "SSF: generator weight must be in [1, 12]");
+        if (mg > 65535) return fail(QD_EUNSUP, "SSF: more than 65535 generators");
         max_w = std::max(max_w, w);
         std::vector<int32_t> win;
         for (int t = lo; t < lo + w; ++t) {

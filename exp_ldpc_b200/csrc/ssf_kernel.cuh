@@ -4,13 +4,16 @@
 // One CTA per shot in flight (persistent, shots pulled from a global atomic queue).  Per round:
 //   * the best candidate of every generator is CACHED in shared memory; a flip only invalidates the
 //     generators whose check window contains a check that changed (host-built check -> generators
-//     lists), so after the first round a thread rescans a handful of generators instead of all;
-//   * scanning a generator: the syndrome restricted to the generator's check window is gathered
-//     into one 64-bit word; the 2^w - 1 candidate subsets are walked in Gray-code order, one XOR +
-//     two popcounts each:  delta = 2 popc(local & T) - popc(T);
+//     lists), so after the first round only a few hundred generators are rescanned instead of all;
+//   * the stale generators are compacted into a list; the syndrome restricted to a generator's check
+//     window is gathered into one 64-bit word (one thread per stale generator);
+//   * the rescans are spread evenly over the CTA as (generator, chunk) work items: a chunk fixes the
+//     subset's bits above the lowest five and walks the 32 settings of the low five in a compile-time
+//     Gray-code order (toggle masks in registers, no indexing), one XOR + two popcounts per candidate:
+//     delta = 2 popc(local & T) - popc(T); chunk winners merge with a shared-memory atomicMax;
 //   * candidates are ranked by an exact integer key  (delta * 27720 / |F|, lowest generator,
 //     lowest subset mask)  — 27720 = lcm(1..12) makes the ratio an integer, so the arg-max is a
-//     plain 64-bit max and ties break exactly like the serial oracle;
+//     plain 64-bit max and ties break exactly like the serial oracle, whatever the evaluation order;
 //   * warp shuffles + one shared-memory stage pick the CTA-wide winner, which is flipped.
 // Integer arithmetic only => results are bit-identical to the oracle.
 #pragma once
@@ -45,7 +48,8 @@ struct SsfParams {
 
 __host__ __device__ inline size_t ssf_smem_bytes(int nwn, int nwm, int mg, int threads)
 {
-    return (size_t)8 * (threads / 32 + 2) + (size_t)8 * mg + (size_t)4 * (nwn + nwm) + (size_t)((mg + 15) & ~15) + 32;
+    return (size_t)8 * (threads / 32 + 2) + (size_t)16 * mg + (size_t)4 * (nwn + nwm) + (size_t)((mg + 15) & ~15) +
+           (size_t)((2 * mg + 15) & ~15) + 32;
 }
 
 // 27720 / size for size in 1..12
@@ -68,12 +72,14 @@ __global__ void __launch_bounds__(256) ssf_kernel(const SsfParams p)
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
     unsigned long long *red = reinterpret_cast<unsigned long long *>(smem_raw);   // [nwarps + 2]
     unsigned long long *gkeys = red + nwarps + 2;                                  // [mg] cached best key per generator
-    uint32_t *sigma = reinterpret_cast<uint32_t *>(gkeys + s.mg);                  // [nwm]
+    unsigned long long *glocal = gkeys + s.mg;                                     // [mg] window syndrome of the d-th stale generator
+    uint32_t *sigma = reinterpret_cast<uint32_t *>(glocal + s.mg);                 // [nwm]
     uint32_t *dec = sigma + s.nwm;                                                // [nwn]
     uint8_t *dirty = reinterpret_cast<uint8_t *>(dec + s.nwn);                    // [mg] cached key is stale
+    uint16_t *dlist = reinterpret_cast<uint16_t *>(dirty + ((s.mg + 15) & ~15));  // [mg] the stale generators
     __shared__ long long sh_shot;
-    __shared__ int sh_weight;
-
+    __shared__ int sh_weight, sh_ndirty;
+    constexpr int LOWB = 5;                                                       // subset bits walked inside a work item
 
     long long c_fail = 0, c_shots = 0, c_nc = 0, c_it = 0;
 
@@ -82,6 +88,7 @@ __global__ void __launch_bounds__(256) ssf_kernel(const SsfParams p)
             const unsigned long long id = atomicAdd(p.next_shot, 1ULL);
             sh_shot = id < (unsigned long long)p.shots ? (long long)id : -1;
             sh_weight = 0;
+            sh_ndirty = 0;
         }
         __syncthreads();
         const long long shot = sh_shot;
@@ -99,43 +106,70 @@ __global__ void __launch_bounds__(256) ssf_kernel(const SsfParams p)
         int weight = sh_weight;
         int rounds = 0;
         while (weight > 0 && (p.max_rounds == 0 || rounds < p.max_rounds)) {
-            unsigned long long best = 0ULL;
-            for (int g = tid; g < s.mg; g += NT) {
-                if (!dirty[g]) { const unsigned long long k = gkeys[g]; best = k > best ? k : best; continue; }
-                dirty[g] = 0;
-                unsigned long long gbest = 0ULL;
-                const int lo = s.gen_ptr[g], w = s.gen_ptr[g + 1] - lo;
+            // ---- stale generators -> list (order irrelevant: keys carry the generator index)
+            for (int g = tid; g < s.mg; g += NT)
+                if (dirty[g]) { dirty[g] = 0; gkeys[g] = 0ULL; dlist[atomicAdd(&sh_ndirty, 1)] = (uint16_t)g; }
+            __syncthreads();
+            const int ndirty = sh_ndirty;
+            // ---- their window syndromes
+            for (int d = tid; d < ndirty; d += NT) {
+                const int g = dlist[d];
                 const int wlo = s.win_ptr[g], nw = s.win_ptr[g + 1] - wlo;
                 unsigned long long local = 0ULL;
                 for (int z = 0; z < nw; ++z) {
                     const int c = s.win_chk[wlo + z];
                     local |= (unsigned long long)((sigma[c >> 5] >> (c & 31)) & 1u) << z;
                 }
-                if (!local) { gkeys[g] = 0ULL; continue; }
-                unsigned long long qm[SSF_MAX_W];
-#pragma unroll
-                for (int t = 0; t < SSF_MAX_W; ++t) qm[t] = t < w ? s.qmask[lo + t] : 0ULL;
-                unsigned long long T = 0ULL;
-                unsigned gray = 0u;
+                glocal[d] = local;
+            }
+            __syncthreads();
+            if (tid == 0) sh_ndirty = 0;                        // next round's list (read again only after two barriers)
+            // ---- rescans: work item = (stale generator d, chunk of its subsets); generators of different size
+            // have different chunk counts, so items are numbered over the largest and the surplus skipped
+            const int maxch = s.max_w > LOWB ? 1 << (s.max_w - LOWB) : 1;
+            for (int x = tid; x < ndirty * maxch; x += NT) {
+                const int d = x / maxch, chunk = x - d * maxch;
+                const unsigned long long local = glocal[d];
+                if (!local) continue;
+                const int g = dlist[d];
+                const int lo = s.gen_ptr[g], w = s.gen_ptr[g + 1] - lo;
+                if (chunk >= (w > LOWB ? 1 << (w - LOWB) : 1)) continue;
+                unsigned long long q0 = 0ULL, q1 = 0ULL, q2 = 0ULL, q3 = 0ULL, q4 = 0ULL, T = 0ULL;
+                if (w > 0) q0 = s.qmask[lo];
+                if (w > 1) q1 = s.qmask[lo + 1];
+                if (w > 2) q2 = s.qmask[lo + 2];
+                if (w > 3) q3 = s.qmask[lo + 3];
+                if (w > 4) q4 = s.qmask[lo + 4];
+                for (int t = LOWB; t < w; ++t)
+                    if ((chunk >> (t - LOWB)) & 1) T ^= s.qmask[lo + t];
+                const unsigned hi_mask = (unsigned)chunk << LOWB;
+                const int hi_size = __popc((unsigned)chunk);
+                const unsigned low_lim = w < LOWB ? 1u << w : 1u << LOWB;      // low settings that stay inside the support
                 const unsigned long long gkey = (unsigned long long)(0xFFFFFFu - (unsigned)g) << 16;
-                for (unsigned i = 1; i < (1u << w); ++i) {
-                    const int b = __ffs(i) - 1;
-                    gray ^= 1u << b;
-                    unsigned long long q = qm[0];
+                unsigned long long gbest = 0ULL;
+                unsigned gray = 0u;
 #pragma unroll
-                    for (int t = 1; t < SSF_MAX_W; ++t) q = (b == t) ? qm[t] : q;
-                    T ^= q;
+                for (unsigned i = 0; i < (1u << LOWB); ++i) {
+                    if (i > 0) {
+                        const int b = (i & 1u) ? 0 : (i & 2u) ? 1 : (i & 4u) ? 2 : (i & 8u) ? 3 : 4;   // compile time
+                        gray ^= 1u << b;
+                        T ^= b == 0 ? q0 : b == 1 ? q1 : b == 2 ? q2 : b == 3 ? q3 : q4;
+                    }
+                    const unsigned mask = hi_mask | gray;
+                    if (mask == 0u || gray >= low_lim) continue;
                     const int delta = 2 * __popcll(local & T) - __popcll(T);
                     if (delta > 0) {
                         const unsigned long long key =
-                            ((unsigned long long)((unsigned)delta * inv_size[__popc(gray)]) << 40) | gkey |
-                            (unsigned long long)(0xFFFFu - gray);
+                            ((unsigned long long)((unsigned)delta * inv_size[hi_size + __popc(gray)]) << 40) | gkey |
+                            (unsigned long long)(0xFFFFu - mask);
                         gbest = key > gbest ? key : gbest;
                     }
                 }
-                gkeys[g] = gbest;
-                best = gbest > best ? gbest : best;
+                if (gbest) atomicMax(&gkeys[g], gbest);
             }
+            __syncthreads();
+            unsigned long long best = 0ULL;
+            for (int g = tid; g < s.mg; g += NT) { const unsigned long long k = gkeys[g]; best = k > best ? k : best; }
             best = warp_max_u64(best);
             if (lane == 0) red[warp] = best;
             __syncthreads();
