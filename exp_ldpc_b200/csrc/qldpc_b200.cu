@@ -281,6 +281,7 @@ struct qd_ssf {
     int device = 0;
     SsfDev dev{};
     int max_rounds = 0;
+    int max_window = 64;   // checks in the largest generator window (<= 32: the 32-bit scan)
     int threads = 128;
     size_t smem = 0;
     DevBuf d_gen_ptr, d_gen_idx, d_win_ptr, d_win_chk, d_qmask, d_chk_ptr, d_chk_gen, d_next;
@@ -1650,7 +1651,7 @@ extern "C" int qd_ssf_create(qd_graph *hz, int32_t num_generators, const int32_t
     std::vector<int32_t> gen_ptr(h_gen_row_ptr, h_gen_row_ptr + mg + 1), gen_idx(h_gen_col_idx, h_gen_col_idx + gnnz);
     std::vector<int32_t> win_ptr(mg + 1, 0), win_chk;
     std::vector<unsigned long long> qmask(std::max(gnnz, 1), 0ULL);
-    int max_w = 0;
+    int max_w = 0, max_window = 0;
     for (int gi = 0; gi < mg; ++gi) {
         const int lo = gen_ptr[gi], w = gen_ptr[gi + 1] - lo;
         if (w <= 0 || w > SSF_MAX_W) return fail(QD_EUNSUP, "SSF: generator weight must be in [1, 12]");
@@ -1674,6 +1675,7 @@ extern "C" int qd_ssf_create(qd_graph *hz, int32_t num_generators, const int32_t
         }
         win_chk.insert(win_chk.end(), win.begin(), win.end());
         win_ptr[gi + 1] = (int)win_chk.size();
+        max_window = std::max(max_window, win_ptr[gi + 1] - win_ptr[gi]);
     }
     // check -> generators whose window contains it (what a flip invalidates)
     std::vector<int32_t> chk_ptr(g.m + 1, 0), chk_gen(win_chk.size());
@@ -1703,6 +1705,7 @@ extern "C" int qd_ssf_create(qd_graph *hz, int32_t num_generators, const int32_t
     s.qmask = d->d_qmask.as<unsigned long long>();
     s.chk_ptr = d->d_chk_ptr.as<int32_t>(); s.chk_gen = d->d_chk_gen.as<int32_t>();
     d->threads = 128;
+    d->max_window = max_window;
     d->smem = ssf_smem_bytes(g.nwn, g.nwm, mg, d->threads);
     *out = d.release();
     return 0;
@@ -1740,13 +1743,14 @@ static int ssf_launch(qd_ssf *d, const uint32_t *d_synd, int32_t synd_stride, in
     p.fail = d_fail;
     p.counters = (long long *)d_counters;
     p.next_shot = d->d_next.as<unsigned long long>() + queue;
-    QD_CUDA(cudaFuncSetAttribute(ssf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem));
+    auto kern = d->max_window <= 32 ? ssf_kernel<uint32_t> : ssf_kernel<unsigned long long>;
+    QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem));
     QD_CUDA(cudaMemsetAsync(p.next_shot, 0, sizeof(unsigned long long), st));
     int per_sm = 0;
-    QD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ssf_kernel, d->threads, d->smem));
+    QD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, d->threads, d->smem));
     per_sm = std::max(1, per_sm);
     unsigned grid = (unsigned)std::min<long long>((long long)d->g->sm_count * per_sm, shots);
-    ssf_kernel<<<grid, d->threads, d->smem, st>>>(p);
+    kern<<<grid, d->threads, d->smem, st>>>(p);
     QD_CUDA(cudaGetLastError());
     return 0;
 }

@@ -65,6 +65,12 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
     return v;
 }
 
+__device__ __forceinline__ int popc_w(unsigned long long v) { return __popcll(v); }
+__device__ __forceinline__ int popc_w(uint32_t v) { return __popc(v); }
+
+// WT: the window word — uint32_t when every generator's check window has at most 32 checks ((3,4) HGP: 28),
+// which halves the popcounts of the scan; unsigned long long otherwise
+template <typename WT>
 __global__ void __launch_bounds__(256) ssf_kernel(const SsfParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -129,19 +135,19 @@ __global__ void __launch_bounds__(256) ssf_kernel(const SsfParams p)
             const int maxch = s.max_w > LOWB ? 1 << (s.max_w - LOWB) : 1;
             for (int x = tid; x < ndirty * maxch; x += NT) {
                 const int d = x / maxch, chunk = x - d * maxch;
-                const unsigned long long local = glocal[d];
+                const WT local = (WT)glocal[d];
                 if (!local) continue;
                 const int g = dlist[d];
                 const int lo = s.gen_ptr[g], w = s.gen_ptr[g + 1] - lo;
                 if (chunk >= (w > LOWB ? 1 << (w - LOWB) : 1)) continue;
-                unsigned long long q0 = 0ULL, q1 = 0ULL, q2 = 0ULL, q3 = 0ULL, q4 = 0ULL, T = 0ULL;
-                if (w > 0) q0 = s.qmask[lo];
-                if (w > 1) q1 = s.qmask[lo + 1];
-                if (w > 2) q2 = s.qmask[lo + 2];
-                if (w > 3) q3 = s.qmask[lo + 3];
-                if (w > 4) q4 = s.qmask[lo + 4];
+                WT q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0, T = 0;
+                if (w > 0) q0 = (WT)s.qmask[lo];
+                if (w > 1) q1 = (WT)s.qmask[lo + 1];
+                if (w > 2) q2 = (WT)s.qmask[lo + 2];
+                if (w > 3) q3 = (WT)s.qmask[lo + 3];
+                if (w > 4) q4 = (WT)s.qmask[lo + 4];
                 for (int t = LOWB; t < w; ++t)
-                    if ((chunk >> (t - LOWB)) & 1) T ^= s.qmask[lo + t];
+                    if ((chunk >> (t - LOWB)) & 1) T ^= (WT)s.qmask[lo + t];
                 const unsigned hi_mask = (unsigned)chunk << LOWB;
                 const int hi_size = __popc((unsigned)chunk);
                 const unsigned low_lim = w < LOWB ? 1u << w : 1u << LOWB;      // low settings that stay inside the support
@@ -157,7 +163,7 @@ __global__ void __launch_bounds__(256) ssf_kernel(const SsfParams p)
                     }
                     const unsigned mask = hi_mask | gray;
                     if (mask == 0u || gray >= low_lim) continue;
-                    const int delta = 2 * __popcll(local & T) - __popcll(T);
+                    const int delta = 2 * popc_w((WT)(local & T)) - popc_w(T);
                     if (delta > 0) {
                         const unsigned long long key =
                             ((unsigned long long)((unsigned)delta * inv_size[hi_size + __popc(gray)]) << 40) | gkey |
