@@ -383,7 +383,9 @@ def main():
     sm_mhz = clk.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
     smem_peak = sm_count * 128 * sm_mhz * 1e6 / 1e9
     smem_achieved = smem_bytes_per_shot * shots / (kernel_ms * 1e-3) / 1e9
-    kernel_name = {"regular": "bp7_kernel", "ssf": "ssf_kernel"}.get(cfg.get("kernel"), "bp_kernel")
+    kernel_name = {"regular": "bp7_kernel", "ssf": "ssf_kernel", "cluster": "bpc_kernel", "global": "bpg_kernel"}.get(cfg.get("kernel"), "bp_kernel")
+    if osd:
+        kernel_name += " + osd0_kernel"
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full`
     # capture of this workload (per launch of the captured shot count, scaled to this launch)
     traffic = None
