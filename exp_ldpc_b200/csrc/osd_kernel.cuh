@@ -139,7 +139,6 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
             uint16_t *pos = reinterpret_cast<uint16_t *>(keys);      // the sort keys are dead
             for (int i = tid; i < m * W; i += NT) R[i] = 0ULL;
             for (int t = tid; t < n; t += NT) pos[idx[t]] = (uint16_t)t;
-            for (int i = tid; i < m; i += NT) pcol[i] = (uint16_t)0xFFFF;
             __syncthreads();
             const uint32_t *s = p.synd + shot * (long long)p.synd_stride;
             for (int r = tid; r < m; r += NT) {
@@ -172,13 +171,15 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
             unsigned long long *myrow[RPT];
             bool mine[RPT], isused[RPT];
             uint32_t B[RPT], Y[RPT], avail[RPT];
+            int mypcol[RPT];
 #pragma unroll
             for (int q = 0; q < RPT; ++q) {
                 mine[q] = tid + q * NT < m;
                 myrow[q] = R + (size_t)(mine[q] ? tid + q * NT : 0) * W;
                 isused[q] = false;
+                mypcol[q] = 0xFFFF;
             }
-            int rank = 0, par = 0;
+            int rank = 0, myprow = 0;
             for (int t0 = 0; t0 < n && rank < p.rank; t0 += OSD_BLOCK) {
 #pragma unroll
                 for (int q = 0; q < RPT; ++q) {
@@ -195,34 +196,34 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                 // order together with a pivot row for it.  Columns that depend on earlier ones never show a bit in
                 // an unused row (and keep none), so they cost nothing.
                 int npiv = 0;
-                while (rank < p.rank) {
+                auto pivot_round = [&](int *cd) -> bool {       // false: the block is finished
                     int key = 0x7fffffff;
 #pragma unroll
                     for (int q = 0; q < RPT; ++q)
                         if (avail[q]) key = min(key, ((__ffs((int)avail[q]) - 1) << 16) | (tid + q * NT));
                     key = __reduce_min_sync(0xffffffffu, key);
-                    int *cd = cand + par;
-                    par ^= 32;
                     if (lane == 0) cd[warp] = key;
                     __syncthreads();
                     const int best = __reduce_min_sync(0xffffffffu, cd[lane]);
-                    if (best == 0x7fffffff) break;              // the rest of the block depends on earlier columns
+                    if (best == 0x7fffffff) return false;       // the rest of the block depends on earlier columns
                     const int j = best >> 16, piv = best & 0xffff;
-                    ++rank;
                     const uint2 pv = BY[piv];
+                    if (lane == npiv) myprow = piv;             // lane i of every warp remembers the block's i-th pivot row
 #pragma unroll
                     for (int q = 0; q < RPT; ++q) {
-                        if (tid + q * NT == piv) {
-                            isused[q] = true; avail[q] = 0u;
-                            pcol[piv] = (uint16_t)(t0 + j); prow[npiv] = (uint16_t)piv;
-                        } else if ((B[q] >> j) & 1u) {
+                        if (tid + q * NT == piv) { isused[q] = true; mypcol[q] = t0 + j; }
+                        else if ((B[q] >> j) & 1u) {
                             B[q] ^= pv.x; Y[q] ^= pv.y ^ (1u << npiv);
                             BY[tid + q * NT] = make_uint2(B[q], Y[q]);
-                            if (!isused[q]) avail[q] = B[q];
                         }
+                        avail[q] = isused[q] ? 0u : B[q];
                     }
                     ++npiv;
-                }
+                    return ++rank < p.rank;
+                };
+                // cand[] is double-buffered: a warp that runs ahead into the next round never overwrites a slot early
+                while (pivot_round(cand) && pivot_round(cand + 32)) { }
+                if (warp == 0 && lane < npiv) prow[lane] = (uint16_t)myprow;
                 __syncthreads();
                 if (npiv == 0) continue;
                 const int jc0 = p.method == 0 ? min((t0 + OSD_BLOCK) >> 7, n >> 7) : 0;
@@ -271,6 +272,10 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                 }
                 __syncthreads();
             }
+#pragma unroll
+            for (int q = 0; q < RPT; ++q)
+                if (mine[q]) pcol[tid + q * NT] = (uint16_t)mypcol[q];   // ranked position of the row's pivot column, 0xFFFF: none
+            __syncthreads();
         }
 
         // ---- 4. higher-order search (osd_e / osd_cs): patterns on the columns outside the information set
