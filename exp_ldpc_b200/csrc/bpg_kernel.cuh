@@ -5,14 +5,22 @@
 // or degrees beyond their limits.  Same decoder (ldpc.bp_decoder semantics, SURVEY.md Appendix B;
 // reference call sites python/qldpc/misc/_experiment.py:110-117,137-149), same operation order as the
 // serial restatement (oracle/qldpc_oracle.c: bp_min_sum_log / bp_prob_ratios), so fp64 results are
-// bit-identical to it; an order of magnitude slower than the shared-memory kernels.
+// bit-identical to it; slower than the shared-memory kernels.
 //
 // One CTA per shot in flight (persistent, atomic shot queue).  Two message arrays per CTA in a global
-// scratch buffer, CSR edge order: b2c (bit -> check) and c2b (check -> bit).  Check pass: one thread
-// per row, forward sweep writes the exclusive prefix (min + sign parity packed in the sign bit, or
-// the prefix product), backward sweep folds in the suffix.  Bit pass: one thread per column over its
-// edges in row order (prefix sums, then suffix sums).  Hard decisions (bytes) and the syndrome live
-// in shared memory; convergence is tested exactly after every iteration.
+// scratch buffer, CSR edge order: b2c (bit -> check) and c2b (check -> bit).
+//   * Min-sum check pass: one WARP per row, lanes strided over the row's (contiguous) edges, all loads
+//     issued before the first use.  The serial prefix/suffix sweeps give edge k the minimum of the other
+//     edges' magnitudes and the parity of the other edges' signs; both are exact and order-free, so the
+//     warp computes smallest / second-smallest magnitude (+ position of the smallest) and the sign
+//     parity with shuffles and every lane writes its edges — detector-error-model rows have hundreds
+//     of edges, a thread per row spent the whole iteration on serial L2 round trips.
+//   * Product-sum check pass: one thread per row, the two literal sweeps (ordered products).
+//   * Bit pass: one thread per column; columns
+//     of degree <= 8 load all their messages first and keep the prefix sums in registers (one gather + one
+//     scatter; tiles of 4 / 8), longer ones run the two literal sweeps.
+//   * Hard decisions (bytes) and the syndrome live in shared memory; convergence is tested exactly after
+//     every iteration, one warp per row.
 #pragma once
 
 #include "bp_kernel.cuh"
@@ -38,8 +46,59 @@ struct BpgParams {
     unsigned long long *next_shot;
 };
 
+constexpr int BPG_RT = 8;      // rows up to 32 * BPG_RT edges keep their messages in registers during the check update
+
+// merge (smallest, second smallest, position of the smallest) over the warp; equal magnitudes may pick either
+// position: the second smallest then equals the smallest, so every edge receives the same value either way
+template <typename real>
+__device__ __forceinline__ void warp_two_min(real &m1, real &m2, int &arg)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const real om1 = __shfl_xor_sync(0xffffffffu, m1, o), om2 = __shfl_xor_sync(0xffffffffu, m2, o);
+        const int oarg = __shfl_xor_sync(0xffffffffu, arg, o);
+        const bool take = om1 < m1 || (om1 == m1 && (unsigned)oarg < (unsigned)arg);
+        const real hi1 = take ? m1 : om1;                         // the larger of the two smallest
+        const real lo2 = om2 < m2 ? om2 : m2;
+        m2 = hi1 < lo2 ? hi1 : lo2;
+        if (take) { m1 = om1; arg = oarg; }
+    }
+}
+
+// Column update with the column's messages in registers: one gather of check->bit messages, the prefix products /
+// sums in the serial order, one scatter of bit->check messages.  Returns the soft output (total LLR / posterior ratio).
+template <typename real, int METHOD, int CT>
+__device__ __forceinline__ real bpg_column_in_registers(const int32_t *__restrict__ csc_edge, int lo, int hi, const real *c2b,
+                                                        real *b2c, real prior)
+{
+    using A = Ar<real>;
+    int ee[CT];
+    real cv[CT], pre[CT];
+#pragma unroll
+    for (int k = 0; k < CT; ++k) if (lo + k < hi) ee[k] = csc_edge[lo + k];
+#pragma unroll
+    for (int k = 0; k < CT; ++k) if (lo + k < hi) cv[k] = c2b[ee[k]];
+    real temp = prior;
+#pragma unroll
+    for (int k = 0; k < CT; ++k)
+        if (lo + k < hi) {
+            pre[k] = temp;
+            if (METHOD == QD_BP_MIN_SUM_K) temp = A::add(temp, cv[k]);
+            else { temp = A::mul(temp, cv[k]); if (temp != temp) temp = (real)1; }
+        }
+    const real soft = temp;
+    temp = METHOD == QD_BP_MIN_SUM_K ? (real)0 : (real)1;
+#pragma unroll
+    for (int k = CT - 1; k >= 0; --k)
+        if (lo + k < hi) {
+            if (METHOD == QD_BP_MIN_SUM_K) { b2c[ee[k]] = A::add(pre[k], temp); temp = A::add(temp, cv[k]); }
+            else { b2c[ee[k]] = A::mul(pre[k], temp); temp = A::mul(temp, cv[k]); if (temp != temp) temp = (real)1; }
+        }
+    return soft;
+}
+
 template <typename real, int METHOD>
-__global__ void __launch_bounds__(512) bpg_kernel(const BpgParams p)
+__global__ void __launch_bounds__(512, 2) bpg_kernel(const BpgParams p)
 {
     using A = Ar<real>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -47,7 +106,7 @@ __global__ void __launch_bounds__(512) bpg_kernel(const BpgParams p)
     uint8_t *syn = dec + ((p.n + 15) & ~15);                   // [m]
     uint32_t *bits = reinterpret_cast<uint32_t *>(syn + ((p.m + 15) & ~15));   // [nwn]
     __shared__ long long sh_shot;
-    const int tid = (int)threadIdx.x, NT = (int)blockDim.x;
+    const int tid = (int)threadIdx.x, NT = (int)blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
     real *b2c = static_cast<real *>(p.scratch) + (size_t)blockIdx.x * 2 * p.nnz;
     real *c2b = b2c + p.nnz;
     const real *prior = static_cast<const real *>(p.prior);
@@ -74,32 +133,52 @@ __global__ void __launch_bounds__(512) bpg_kernel(const BpgParams p)
         while (it < p.max_iter) {
             ++it;
             // ---- check pass
-            for (int r = tid; r < p.m; r += NT) {
-                const int lo = p.row_ptr[r], hi = p.row_ptr[r + 1];
-                if (METHOD == QD_BP_MIN_SUM_K) {
-                    const real al = alpha_fixed != (real)0 ? alpha_fixed : A::sub((real)1, pow2_neg<real>(it));
-                    real temp = A::big();
-                    unsigned sgn = syn[r];
-                    for (int e = lo; e < hi; ++e) {             // exclusive prefix: min, sign parity in the sign bit
-                        const real v = b2c[e];
-                        c2b[e] = A::flip(temp, sgn & 1u);
-                        const real a = abs_bits(v);
-                        if (a < temp) temp = a;
-                        sgn += v <= (real)0 ? 1u : 0u;         // the serial rule: a zero message counts as negative
+            if (METHOD == QD_BP_MIN_SUM_K) {
+                const real al = alpha_fixed != (real)0 ? alpha_fixed : A::sub((real)1, pow2_neg<real>(it));
+                for (int r = warp; r < p.m; r += nwarps) {
+                    const int lo = p.row_ptr[r], hi = p.row_ptr[r + 1];
+                    real m1 = A::big(), m2 = A::big();
+                    int arg = -1;
+                    unsigned tot = 0u;
+                    if (hi - lo <= 32 * BPG_RT) {
+                        real v[BPG_RT];
+#pragma unroll
+                        for (int k = 0; k < BPG_RT; ++k) { const int e = lo + lane + 32 * k; v[k] = e < hi ? b2c[e] : A::big(); }
+#pragma unroll
+                        for (int k = 0; k < BPG_RT; ++k) {
+                            const int e = lo + lane + 32 * k;
+                            if (e < hi) {
+                                const real a = abs_bits(v[k]);
+                                tot ^= v[k] <= (real)0 ? 1u : 0u;   // the serial rule: a zero message counts as negative
+                                if (a < m1) { m2 = m1; m1 = a; arg = e; }
+                                else if (a < m2) m2 = a;
+                            }
+                        }
+                        warp_two_min(m1, m2, arg);
+                        tot = (__reduce_xor_sync(0xffffffffu, tot) ^ syn[r]) & 1u;
+                        const real o1 = A::mul(m1, al), o2 = A::mul(m2, al);
+#pragma unroll
+                        for (int k = 0; k < BPG_RT; ++k) {
+                            const int e = lo + lane + 32 * k;
+                            if (e < hi) c2b[e] = A::flip(e == arg ? o2 : o1, tot ^ (v[k] <= (real)0 ? 1u : 0u));
+                        }
+                    } else {
+                        for (int e = lo + lane; e < hi; e += 32) {
+                            const real x = b2c[e], a = abs_bits(x);
+                            tot ^= x <= (real)0 ? 1u : 0u;
+                            if (a < m1) { m2 = m1; m1 = a; arg = e; }
+                            else if (a < m2) m2 = a;
+                        }
+                        warp_two_min(m1, m2, arg);
+                        tot = (__reduce_xor_sync(0xffffffffu, tot) ^ syn[r]) & 1u;
+                        const real o1 = A::mul(m1, al), o2 = A::mul(m2, al);
+                        for (int e = lo + lane; e < hi; e += 32)
+                            c2b[e] = A::flip(e == arg ? o2 : o1, tot ^ (b2c[e] <= (real)0 ? 1u : 0u));
                     }
-                    temp = A::big();
-                    sgn = 0u;
-                    for (int e = hi - 1; e >= lo; --e) {
-                        const real pre = c2b[e], v = b2c[e];
-                        real mag = abs_bits(pre);
-                        if (temp < mag) mag = temp;
-                        const unsigned par = ((hi_bits(pre) >> 31) + sgn) & 1u;
-                        c2b[e] = A::flip(A::mul(mag, al), par);
-                        const real a = abs_bits(v);
-                        if (a < temp) temp = a;
-                        sgn += v <= (real)0 ? 1u : 0u;
-                    }
-                } else {
+                }
+            } else {
+                for (int r = tid; r < p.m; r += NT) {
+                    const int lo = p.row_ptr[r], hi = p.row_ptr[r + 1];
                     real temp = syn[r] ? (real)-1 : (real)1;
                     for (int e = lo; e < hi; ++e) {
                         c2b[e] = temp;
@@ -119,7 +198,17 @@ __global__ void __launch_bounds__(512) bpg_kernel(const BpgParams p)
             for (int j = tid; j < p.n; j += NT) {
                 const int lo = p.col_ptr[j], hi = p.col_ptr[j + 1];
                 real temp = prior[j];
-                if (METHOD == QD_BP_MIN_SUM_K) {
+                if (hi - lo <= 8) {
+                    const real soft = hi - lo <= 4 ? bpg_column_in_registers<real, METHOD, 4>(p.csc_edge, lo, hi, c2b, b2c, temp)
+                                                   : bpg_column_in_registers<real, METHOD, 8>(p.csc_edge, lo, hi, c2b, b2c, temp);
+                    if (METHOD == QD_BP_MIN_SUM_K) {
+                        dec[j] = soft <= (real)0 ? 1 : 0;
+                        if (want_llr) p.llr[shot * (long long)p.n + j] = (double)soft;
+                    } else {
+                        dec[j] = soft >= (real)1 ? 1 : 0;
+                        if (want_llr) p.llr[shot * (long long)p.n + j] = p.llr_mode ? (double)soft : (double)A::lg(A::div((real)1, soft));
+                    }
+                } else if (METHOD == QD_BP_MIN_SUM_K) {
                     for (int t = lo; t < hi; ++t) { const int e = p.csc_edge[t]; b2c[e] = temp; temp = A::add(temp, c2b[e]); }
                     dec[j] = temp <= (real)0 ? 1 : 0;
                     if (want_llr) p.llr[shot * (long long)p.n + j] = (double)temp;
@@ -146,10 +235,11 @@ __global__ void __launch_bounds__(512) bpg_kernel(const BpgParams p)
             __syncthreads();
             // ---- H dec == s ?
             int unsat = 0;
-            for (int r = tid; r < p.m; r += NT) {
-                unsigned par = syn[r];
-                for (int e = p.row_ptr[r]; e < p.row_ptr[r + 1]; ++e) par ^= dec[p.col_idx[e]];
-                unsat |= (int)(par & 1u);
+            for (int r = warp; r < p.m; r += nwarps) {
+                unsigned par = 0u;
+                for (int e = p.row_ptr[r] + lane; e < p.row_ptr[r + 1]; e += 32) par ^= dec[p.col_idx[e]];
+                par = (__reduce_xor_sync(0xffffffffu, par) ^ syn[r]) & 1u;
+                unsat |= (int)par;
             }
             if (!__syncthreads_or(unsat)) { converged = 1; break; }
         }
