@@ -112,7 +112,7 @@ __device__ __forceinline__ void cluster_sync_once_fenced()
 }
 
 template <typename real, int METHOD>
-__global__ void __launch_bounds__(768, 1) bpc_kernel(const BpcParams p)
+__global__ void __launch_bounds__(800, 1) bpc_kernel(const BpcParams p)
 {
     namespace cg = cooperative_groups;
     using A = Ar<real>;

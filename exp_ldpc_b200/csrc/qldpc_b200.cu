@@ -828,10 +828,15 @@ static int bpc_prepare(qd_bp *d)
     for (int C = 2; C <= 8; C *= 2) {
         std::vector<int32_t> row_lo(C + 1, 0);
         row_lo[C] = m;
-        for (int c = 1, r = 0; c < C; ++c) {
-            const long long want = (long long)nnz * c / C;
-            while (r < m && g->row_ptr[r] < want) ++r;
-            row_lo[c] = std::max(r, row_lo[c - 1]);
+        if (gd.max_row_deg <= 32) {
+            // a thread per row: equal row counts, so that no CTA needs one more pass over its rows than the others
+            for (int c = 1; c < C; ++c) row_lo[c] = (int)((long long)m * c / C);
+        } else {
+            for (int c = 1, r = 0; c < C; ++c) {
+                const long long want = (long long)nnz * c / C;
+                while (r < m && g->row_ptr[r] < want) ++r;
+                row_lo[c] = std::max(r, row_lo[c - 1]);
+            }
         }
         int max_edges = 0, max_rows = 0;
         std::vector<int32_t> row_start(std::max(m, 1), 0);
@@ -900,7 +905,16 @@ static int bpc_prepare(qd_bp *d)
             return rc;
         if (rb == 8) { if ((rc = upload(d->dc_prior, prior))) return rc; }
         else { std::vector<float> pf(prior.begin(), prior.end()); if ((rc = upload(d->dc_prior, pf))) return rc; }
-        const int threads = std::min(768, std::max(128, (std::max(max_rows, max_cols) + 31) & ~31));   // 768: 85 registers, no spills
+        // threads per CTA: the fewest passes over the CTA's rows and columns (a column pass costs about as much as a
+        // row pass), then the fewest threads; 800 threads leave 81 registers
+        int threads = 128;
+        {
+            long best = -1;
+            for (int t = 128; t <= 800; t += 32) {
+                const long cost = (long)((max_rows + t - 1) / t) + (long)((max_cols + t - 1) / t);
+                if (best < 0 || cost < best) { best = cost; threads = t; }
+            }
+        }
         // how many clusters of this shape the device runs at once
         auto fn = bpc_kernel_for(d);
         QD_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
