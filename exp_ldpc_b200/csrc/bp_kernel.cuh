@@ -48,6 +48,8 @@ struct GraphDev {
     const uint32_t *fpos_of_pos;  // [npos] flag-byte index (row * fb + k) of a message position
     const int32_t *row_ptr;       // CSR (syndrome kernel)
     const int32_t *col_idx;
+    const int32_t *ell;           // [32][ell_deg][nwm]: column of the e-th edge of check 32 k + b at (b * ell_deg + e) * nwm + k, -1 = none
+    int ell_deg;                  // max row degree if the table exists (<= 64), else 0
 };
 
 struct BpParams {

@@ -83,6 +83,86 @@ __global__ void syndrome_kernel(GraphDev g, const uint32_t *__restrict__ vec, in
     synd[idx] = word;
 }
 
+// 32 x 32 bit transpose in registers (bit b of a[s]  <->  bit s of a[b])
+__device__ __forceinline__ void transpose32(uint32_t (&a)[32])
+{
+    uint32_t msk = 0x0000FFFFu;
+#pragma unroll
+    for (int j = 16; j != 0; j >>= 1, msk ^= msk << j) {
+#pragma unroll
+        for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
+            const uint32_t t = ((a[k] >> j) ^ a[k + j]) & msk;
+            a[k] ^= t << j;
+            a[k + j] ^= t;
+        }
+    }
+}
+
+// Bit-sliced H e mod 2: a warp takes a tile of 32 shots.  The packed error rows are read coalesced (lane = word),
+// every lane transposes its 32 x 32 bit block in registers, so that shared memory holds one word per COLUMN with
+// the 32 shots in its bits (pitch 33: conflict free).  A check is then the XOR of the words of its columns — 32
+// shots per operation instead of one bit gather per shot and edge — computed by lane k for the checks 32k..32k+31,
+// transposed back in registers and written as word k of the 32 syndrome rows (coalesced).  HBM traffic is the
+// algorithmic minimum: 4 * (ceil(n/32) + ceil(m/32)) bytes per shot.
+// DEG: compile-time bound of the row degree (8 or 16: the edge loop unrolls and its table loads are issued ahead of
+// the shared-memory gathers), 0 = run-time
+template <int DEG>
+__global__ void __launch_bounds__(256) syndrome_sliced_kernel(GraphDev g, const uint32_t *__restrict__ vec, int vstride, long long shots,
+                                                              uint32_t *__restrict__ synd, int sstride)
+{
+    extern __shared__ uint32_t sliced_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint32_t *cw = sliced_smem + (size_t)warp * g.nwn * 33;       // column c at (c >> 5) * 33 + (c & 31)
+    const long long ntiles = (shots + 31) / 32;
+    for (long long tile = (long long)blockIdx.x * nwarps + warp; tile < ntiles; tile += (long long)gridDim.x * nwarps) {
+        const long long s0 = tile * 32;
+        const int ns = (int)min(32LL, shots - s0);
+        for (int wc = 0; wc < g.nwn; wc += 32) {
+            const int w = wc + lane;
+            uint32_t a[32];
+#pragma unroll
+            for (int s = 0; s < 32; ++s) a[s] = (s < ns && w < g.nwn) ? vec[(s0 + s) * (long long)vstride + w] : 0u;
+            transpose32(a);
+            if (w < g.nwn) {
+#pragma unroll
+                for (int b = 0; b < 32; ++b) cw[w * 33 + b] = a[b];
+            }
+        }
+        __syncwarp();
+        for (int kc = 0; kc < sstride; kc += 32) {
+            const int k = kc + lane;
+            uint32_t o[32];
+#pragma unroll
+            for (int b = 0; b < 32; ++b) {
+                uint32_t x = 0u;
+                if (k < g.nwm) {
+                    const int32_t *t = g.ell + (size_t)b * g.ell_deg * g.nwm + k;      // lanes read consecutive entries
+                    if (DEG > 0) {
+                        int c[DEG > 0 ? DEG : 1];
+#pragma unroll
+                        for (int e = 0; e < DEG; ++e) c[e] = e < g.ell_deg ? __ldg(t + (size_t)e * g.nwm) : -1;
+#pragma unroll
+                        for (int e = 0; e < DEG; ++e) if (c[e] >= 0) x ^= cw[(c[e] >> 5) * 33 + (c[e] & 31)];
+                    } else {
+                        for (int e = 0; e < g.ell_deg; ++e) {
+                            const int c = __ldg(t + (size_t)e * g.nwm);
+                            if (c >= 0) x ^= cw[(c >> 5) * 33 + (c & 31)];
+                        }
+                    }
+                }
+                o[b] = x;
+            }
+            transpose32(o);
+            if (k < sstride) {
+#pragma unroll
+                for (int s = 0; s < 32; ++s)
+                    if (s < ns) synd[(s0 + s) * (long long)sstride + k] = o[s];
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // one warp per shot: fail = any_i parity(L_i & (a ^ b))
 __global__ void logical_fail_kernel(const uint32_t *__restrict__ lzT, int k, int nwn, const uint32_t *__restrict__ a,
                                     const uint32_t *__restrict__ b, int stride, long long shots,
@@ -204,7 +284,7 @@ struct qd_graph {
     std::vector<uint32_t> row_desc, col_desc, csc_pos, csc_row, fpos_of_pos;
     std::vector<uint8_t> csc_k;      // index of the edge within its row
     std::vector<int32_t> csc_edge;   // CSR edge id of every CSC entry
-    DevBuf d_col_ptr, d_csc_edge;
+    DevBuf d_col_ptr, d_csc_edge, d_ell;
     int big = 0;                     // degrees / size beyond the shared-memory kernels: global-memory BP only
     // message placements of the thread-owned-state BP kernel, keyed by (banks, column tile)
     std::list<std::pair<int, Bp7Layout>> bp7_layouts;   // list: references stay valid
@@ -425,6 +505,17 @@ extern "C" int qd_graph_create(int32_t m, int32_t n, int64_t nnz, const int32_t 
     d.csc_row = g->d_csc_row.as<uint32_t>();
     d.row_ptr = g->d_row_ptr.as<int32_t>();
     d.col_idx = g->d_col_idx.as<int32_t>();
+    d.ell = nullptr; d.ell_deg = 0;
+    if (max_row >= 1 && max_row <= 64) {
+        // the syndrome kernel's view of H: for fixed (bit b, edge e) the 32-check groups k are contiguous
+        const int nwm = d.nwm;
+        std::vector<int32_t> ell((size_t)32 * max_row * std::max(nwm, 1), -1);
+        for (int r = 0; r < m; ++r)
+            for (int e = h_row_ptr[r]; e < h_row_ptr[r + 1]; ++e)
+                ell[((size_t)(r & 31) * max_row + (e - h_row_ptr[r])) * nwm + (r >> 5)] = h_col_idx[e];
+        if ((rc = upload(g->d_ell, ell))) return rc;
+        d.ell = g->d_ell.as<int32_t>(); d.ell_deg = max_row;
+    }
     QD_CUDA(cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device));
     QD_CUDA(cudaDeviceGetAttribute(&g->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     *out = g.release();
@@ -528,8 +619,20 @@ extern "C" int qd_syndrome_batch(qd_graph *g, const uint32_t *d_vec, int32_t vec
     if (shots == 0) return 0;
     int rc = use_device(g->device);
     if (rc) return rc;
-    const long long items = (long long)shots * synd_stride;
-    syndrome_kernel<<<grid_for(items, 128), 128, 0, (cudaStream_t)stream>>>(g->dev, d_vec, vec_stride, shots, d_synd, synd_stride);
+    const size_t per_warp = (size_t)g->dev.nwn * 33 * 4;
+    if (per_warp <= 96u * 1024u && g->dev.ell && !getenv("QD_SYNDROME_GATHER")) {
+        // bit-sliced kernel: as many warps per CTA as ~96 KB of shared memory hold (two CTAs per SM), at most 8
+        const int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (96u * 1024u) / per_warp));
+        const size_t smem = per_warp * warps;
+        auto kern = g->dev.ell_deg <= 8 ? syndrome_sliced_kernel<8> : g->dev.ell_deg <= 16 ? syndrome_sliced_kernel<16> : syndrome_sliced_kernel<0>;
+        QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const long long tiles = (shots + 31) / 32;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((tiles + warps - 1) / warps, (long long)g->sm_count * 4));
+        kern<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(g->dev, d_vec, vec_stride, shots, d_synd, synd_stride);
+    } else {
+        const long long items = (long long)shots * synd_stride;
+        syndrome_kernel<<<grid_for(items, 128), 128, 0, (cudaStream_t)stream>>>(g->dev, d_vec, vec_stride, shots, d_synd, synd_stride);
+    }
     QD_CUDA(cudaGetLastError());
     return 0;
 }
