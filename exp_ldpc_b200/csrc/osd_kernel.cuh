@@ -19,7 +19,10 @@
 //     register-resident column bits (one barrier per column), the pending row operations are
 //     applied once per block through 4-bit lookup tables of the block's pivot rows
 //     (method of the four Russians): one 128-bit table load + XOR per 4 pivots and 16 bytes of row;
-//   * stops after rank(H) pivots (computed once on the host).
+//   * stops after rank(H) pivots (computed once on the host);
+//   * matrices beyond one SM's shared memory (m * W * 8 bytes: the n = 6400 HGP code needs 2.5 MB) stay in a
+//     per-CTA global scratch (L2-resident for a bounded number of CTAs); ranking, (B, Y) pairs and lookup tables
+//     remain in shared memory.  Same code, slower.
 // Integer only => bit-identical to the oracle.
 #pragma once
 
@@ -45,17 +48,18 @@ struct OsdParams {
     uint8_t *fail;              // in: flag of the BP decoding; out: flag of the OSD decoding
     long long *counters;        // counters[0] (failures) is corrected by the change of the flag
     unsigned long long *next_shot;
+    unsigned long long *rows_global;   // non-null: [gridDim.x][m * W] — the matrix does not fit shared memory and lives in L2 / HBM
 };
 
 struct OsdSmemLayout { size_t rows, keys, idx, pcol, dec, tables, nz, prow, total; };
 
 constexpr int OSD_BLOCK = 32;     // ranked columns handled per lazy elimination block
 
-__host__ __device__ inline OsdSmemLayout osd_smem_layout(int m, int W, int P, int nwm, int nwn)
+__host__ __device__ inline OsdSmemLayout osd_smem_layout(int m, int W, int P, int nwm, int nwn, bool rows_in_smem)
 {
     OsdSmemLayout L;
     size_t o = 0;
-    L.rows = o;    o += (size_t)m * W * 8;
+    L.rows = o;    o += rows_in_smem ? (size_t)m * W * 8 : 0;
     L.keys = o;    o += (size_t)P * 8;                             // sort keys; then inverse ranking; then (B, Y) pairs; then search scratch
     L.idx = o;     o += ((size_t)P * 2 + 7) & ~(size_t)7;
     L.pcol = o;    o += ((size_t)m * 2 + 7) & ~(size_t)7;
@@ -73,8 +77,9 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = (int)threadIdx.x, NT = (int)blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
-    const OsdSmemLayout L = osd_smem_layout(p.m, p.W, p.P, p.nwm, p.nwn);
-    unsigned long long *R = reinterpret_cast<unsigned long long *>(smem_raw + L.rows);
+    const OsdSmemLayout L = osd_smem_layout(p.m, p.W, p.P, p.nwm, p.nwn, p.rows_global == nullptr);
+    unsigned long long *R = p.rows_global ? p.rows_global + (size_t)blockIdx.x * p.m * p.W
+                                          : reinterpret_cast<unsigned long long *>(smem_raw + L.rows);
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw + L.keys);
     uint16_t *idx = reinterpret_cast<uint16_t *>(smem_raw + L.idx);
     uint16_t *pcol = reinterpret_cast<uint16_t *>(smem_raw + L.pcol);

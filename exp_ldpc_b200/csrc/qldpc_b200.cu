@@ -353,7 +353,8 @@ struct qd_osd {
     int rank = 0, W = 0, P = 0;
     int method = 0, order = 0;    // 0 OSD-0, 1 osd_e, 2 osd_cs
     size_t smem = 0;
-    DevBuf d_next, d_soft, d_conv;
+    int rows_global = 0;          // [H | s] in a global scratch buffer (does not fit shared memory)
+    DevBuf d_next, d_soft, d_conv, d_rows;
 };
 
 struct qd_ssf {
@@ -1619,7 +1620,7 @@ extern "C" int qd_osd_create(qd_graph *g, int32_t method, int32_t order, qd_osd 
     int rc = use_device(g->device);
     if (rc) return rc;
     const GraphDev &gd = g->dev;
-    if (gd.n > 8000 || gd.m > 2048) return fail(QD_EUNSUP, "OSD: more than 8000 columns or 2048 rows");
+    if (gd.n > 16000 || gd.m > 4096) return fail(QD_EUNSUP, "OSD: more than 16000 columns or 4096 rows");
     std::unique_ptr<qd_osd> o(new qd_osd);
     o->g = g; o->device = g->device;
     o->method = order > 0 ? method : 0; o->order = method ? order : 0;
@@ -1629,9 +1630,13 @@ extern "C" int qd_osd_create(qd_graph *g, int32_t method, int32_t order, qd_osd 
     while (o->P < gd.n) o->P <<= 1;
     if (o->method && (size_t)gd.m * 4 + (size_t)gd.n * 2 + 8 * 33 > (size_t)o->P * 8)
         return fail(QD_EUNSUP, "higher-order OSD: scratch for this shape does not fit");
-    o->smem = osd_smem_layout(gd.m, o->W, o->P, gd.nwm, gd.nwn).total;
-    if (o->smem > (size_t)g->smem_optin)
-        return fail(QD_EUNSUP, "OSD: [H | s] (" + std::to_string(o->smem) + " B bit-packed) does not fit shared memory");
+    o->smem = osd_smem_layout(gd.m, o->W, o->P, gd.nwm, gd.nwn, true).total;
+    if (o->smem > (size_t)g->smem_optin || getenv("QD_OSD_GLOBAL")) {      // (the variable forces the scratch path for tests)
+        o->rows_global = 1;
+        o->smem = osd_smem_layout(gd.m, o->W, o->P, gd.nwm, gd.nwn, false).total;
+        if (o->smem > (size_t)g->smem_optin)
+            return fail(QD_EUNSUP, "OSD: ranking keys and lookup tables (" + std::to_string(o->smem) + " B) do not fit shared memory");
+    }
     o->rank = gf2_rank_of_csr(gd.m, gd.n, g->row_ptr, g->col_idx);
     if ((rc = o->d_next.alloc(sizeof(unsigned long long) * 2))) return rc;
     *out = o.release();
@@ -1671,16 +1676,24 @@ static int osd_launch(qd_osd *o, int negate_key, const uint32_t *d_synd, int32_t
     p.next_shot = o->d_next.as<unsigned long long>() + queue;
     // one row per thread up to 1024 rows (measured faster than two at m = 768), two up to 2048 (more rows never
     // fit shared memory: qd_osd_create refuses them)
-    int rpt = g.m > 1024 ? 2 : 1;
-    if (const char *e = getenv("QD_OSD_RPT")) rpt = atoi(e) == 2 ? 2 : 1;
+    int rpt = g.m > 2048 ? 4 : g.m > 1024 ? 2 : 1;
+    if (const char *e = getenv("QD_OSD_RPT")) rpt = std::max(rpt, atoi(e) == 4 ? 4 : atoi(e) == 2 ? 2 : 1);
     const int threads = std::min(1024, std::max(128, ((g.m + rpt - 1) / rpt + 31) & ~31));
-    auto kern = rpt == 2 ? osd0_kernel<2> : osd0_kernel<1>;
+    auto kern = rpt == 4 ? osd0_kernel<4> : rpt == 2 ? osd0_kernel<2> : osd0_kernel<1>;
     QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)o->smem));
     QD_CUDA(cudaMemsetAsync(p.next_shot, 0, sizeof(unsigned long long), st));
     int per_sm = 0;
     QD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, o->smem));
     per_sm = std::max(1, per_sm);
-    const unsigned grid = (unsigned)std::min<long long>((long long)o->g->sm_count * per_sm, shots);
+    long long ctas = (long long)o->g->sm_count * per_sm;
+    if (o->rows_global) {
+        // keep the matrices of the CTAs in flight L2-resident: at most ~96 MB of them, at least 8 CTAs
+        const size_t per = (size_t)g.m * o->W * 8;
+        ctas = std::max<long long>(8, std::min<long long>(ctas, (long long)((96ull << 20) / per)));
+        if (int rc2 = o->d_rows.ensure(per * (size_t)ctas)) return rc2;
+        p.rows_global = o->d_rows.as<unsigned long long>();
+    }
+    const unsigned grid = (unsigned)std::min<long long>(ctas, shots);
     kern<<<grid, threads, o->smem, st>>>(p);
     QD_CUDA(cudaGetLastError());
     return 0;

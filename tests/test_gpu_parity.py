@@ -463,6 +463,52 @@ def test_osd_two_rows_per_thread_variant(gpu, codes, which, osd, order, monkeypa
     assert np.array_equal(got["fail"], ref["fail"]) and got["failures"] == ref["failures"]
 
 
+@pytest.mark.parametrize("which,env,osd,order", [("hgp1600", {"QD_OSD_GLOBAL": "1"}, "osd0", 0),
+                                                  ("hgp225", {"QD_OSD_GLOBAL": "1", "QD_OSD_RPT": "4"}, "osd_cs", 6),
+                                                  ("hgp1600", {"QD_OSD_RPT": "4"}, "osd0", 0)])
+def test_osd_global_scratch_and_four_rows_per_thread(gpu, codes, which, env, osd, order, monkeypatch):
+    """Codes whose [H | s] exceeds shared memory (n = 6400: 2.5 MB) keep it in a global scratch buffer and give a
+    thread up to four rows; both paths are forced here on codes the oracle finishes quickly."""
+    from exp_ldpc_b200.experiment import CodeCapacityExperiment
+    from oracle import pyoracle as po
+    code = codes[which]
+    p = 0.03
+    q, prior = 2 * p / 3 + p - 4 / 3 * p * p, 2 * p / 3
+    shots = 48 if which == "hgp1600" else 300
+    opts = dict(max_iter=12, bp_method="ms", ms_scaling_factor=0.0, osd_method=osd, osd_order=order)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    got = CodeCapacityExperiment(code, q, prior, "bposd", opts).run(shots, seed=29, per_shot=True)
+    for k in env:
+        monkeypatch.delenv(k)
+    ref = po.run_code_capacity(code.checks.z, code.logicals.z, q, prior, decoder="bposd0" if order == 0 else "bposd_cs",
+                               osd_order=order, max_iter=12, bp_method="ms", ms_scaling_factor=0.0, seed=29, shots=shots,
+                               per_shot=True)
+    assert ref["non_converged"] > 0
+    assert (got["decodings"] == ref["decodings"]).all()
+    assert np.array_equal(got["fail"], ref["fail"]) and got["failures"] == ref["failures"]
+
+
+def test_bposd_on_a_code_beyond_shared_memory(gpu):
+    """A5-lift n = 2700 (m = 1080): [H | s] takes 397 KB; BP + OSD-0 must still give valid, oracle-identical corrections."""
+    from exp_ldpc_b200 import code_builders
+    from exp_ldpc_b200.experiment import CodeCapacityExperiment
+    from oracle import pyoracle as po
+    code = code_builders.a5_lift_2700()
+    p = 0.04
+    q, prior = 2 * p / 3 + p - 4 / 3 * p * p, 2 * p / 3
+    shots = 16
+    opts = dict(max_iter=8, bp_method="ms", ms_scaling_factor=0.0, osd_method="osd0")
+    got = CodeCapacityExperiment(code, q, prior, "bposd", opts).run(shots, seed=31, per_shot=True)
+    ref = po.run_code_capacity(code.checks.z, code.logicals.z, q, prior, decoder="bposd0", max_iter=8, bp_method="ms",
+                               ms_scaling_factor=0.0, seed=31, shots=shots, per_shot=True)
+    assert ref["non_converged"] > 0
+    assert (got["decodings"] == ref["decodings"]).all()
+    hz = code.checks.z
+    err = po.sample_bits(31, 0, 0, shots, po.thresholds(q, hz.shape[1]))
+    assert not (((err ^ got["decodings"]) @ hz.T.toarray()) % 2).any()
+
+
 def test_bposd_decoder_duck_type(gpu, code225):
     """ldpc.bposd_decoder call shape of _experiment.py:96-100,125."""
     from exp_ldpc_b200.decoders import bposd_decoder
