@@ -175,7 +175,8 @@ int qd_bp_decode_one(qd_bp *d, const uint8_t *h_syndrome, uint8_t *h_decoding, i
  * method 1 ("osd_e"): then try all non-zero patterns on the first `order` columns outside the
  * information set; method 2 ("osd_cs"): every single such column, then every pair among the
  * first `order`; the lightest candidate wins (OSD-0 first, ties to the earlier candidate).
- * Needs [H | s] bit-packed in shared memory (m * ceil((n+1)/64) * 8 bytes): QD_EUNSUP otherwise. */
+ * [H | s] is eliminated bit-packed in shared memory when its m * ceil((n+1)/64) * 8 bytes fit, else in a
+ * global scratch buffer (slower); QD_EUNSUP beyond 4096 checks / 16000 columns. */
 int qd_osd_create(qd_graph *g, int32_t method, int32_t order, qd_osd **out);
 int qd_osd_destroy(qd_osd *o);
 int qd_osd_rank(qd_osd *o);                       /* rank of H over GF(2) */
