@@ -470,6 +470,10 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                 done |= fin << s;
             }
             if (done) {
+                // the queue's answer is not needed before the epilogue is through: ask first
+                unsigned long long next_id = 0ULL;
+                if (tid < S && ((done >> tid) & 1u)) next_id = atomicAdd(p.next_shot, 1ULL);
+                if (tid == 0) ctl->pad[0] = 0;                  // bit s: the residual of slot s anticommutes with a logical
                 // hard decisions of the finished slots, back in column order
                 for (int w = tid; w < S * p.nwn; w += NT) outbits[w] = p.const_bits[w % p.nwn];
                 __syncthreads();
@@ -488,28 +492,36 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                     }
                 }
                 __syncthreads();
-                for (int s = 0; s < S; ++s) {
+                // all finished slots together: corrections out, residuals in place (each word by one thread)
+                for (int x = tid; x < S * p.corr_stride; x += NT) {
+                    const int s = x / p.corr_stride, w = x - s * p.corr_stride;
                     if (!((done >> s) & 1u)) continue;
-                    const int it = T - ctl->born[s] - 1;
-                    const int conv = !((unsat >> s) & 1u);
                     const long long shot = ctl->shot[s];
-                    uint32_t *D = outbits + s * p.nwn;
-                    uint32_t *dst = p.corr + shot * (long long)p.corr_stride;
-                    for (int w = tid; w < p.corr_stride; w += NT) dst[w] = w < p.nwn ? D[w] : 0u;
-                    int f = 0;
-                    if (p.err) {
-                        const uint32_t *e = p.err + shot * (long long)p.err_stride;
-                        __syncthreads();
-                        for (int w = tid; w < p.nwn; w += NT) D[w] ^= e[w];
-                        __syncthreads();
-                        for (int i = tid; i < p.k; i += NT) {
-                            uint32_t acc = 0u;
-                            for (int w = 0; w < p.nwn; ++w) acc ^= p.lzT[(size_t)w * p.k + i] & D[w];
-                            f |= __popc(acc) & 1;
-                        }
-                        f = __syncthreads_or(f);
+                    const uint32_t v = w < p.nwn ? outbits[s * p.nwn + w] : 0u;
+                    p.corr[shot * (long long)p.corr_stride + w] = v;
+                    if (p.err && w < p.nwn) outbits[s * p.nwn + w] = v ^ p.err[shot * (long long)p.err_stride + w];
+                }
+                if (p.err) {
+                    __syncthreads();
+                    // logical parities: a thread per (slot, logical); consecutive threads read consecutive logicals
+                    for (int item = tid; item < S * p.k; item += NT) {
+                        const int s = item / p.k, i = item - s * p.k;
+                        if (!((done >> s) & 1u)) continue;
+                        const uint32_t *D = outbits + s * p.nwn;
+                        uint32_t acc = 0u;
+                        for (int w = 0; w < p.nwn; ++w) acc ^= __ldg(p.lzT + (size_t)w * p.k + i) & D[w];
+                        if (__popc(acc) & 1) atomicOr(&ctl->pad[0], 1 << s);
                     }
-                    if (tid == 0) {
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    const unsigned failing = (unsigned)ctl->pad[0];
+                    for (int s = 0; s < S; ++s) {
+                        if (!((done >> s) & 1u)) continue;
+                        const int it = T - ctl->born[s] - 1;
+                        const int conv = !((unsat >> s) & 1u);
+                        const int f = (int)((failing >> s) & 1u);
+                        const long long shot = ctl->shot[s];
                         if (p.conv) p.conv[shot] = (uint8_t)conv;
                         if (p.iters) p.iters[shot] = it;
                         if (p.fail) p.fail[shot] = (uint8_t)f;
@@ -518,9 +530,8 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                 }
                 __syncthreads();
                 if (tid < S && ((done >> tid) & 1u)) {
-                    const unsigned long long id = atomicAdd(p.next_shot, 1ULL);
-                    const bool more = id < (unsigned long long)p.shots;
-                    ctl->shot[tid] = more ? (long long)id : -1;
+                    const bool more = next_id < (unsigned long long)p.shots;
+                    ctl->shot[tid] = more ? (long long)next_id : -1;
                     ctl->born[tid] = more ? T : BP_IDLE;
                 }
                 __syncthreads();
