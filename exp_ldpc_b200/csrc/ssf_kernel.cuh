@@ -152,7 +152,13 @@ __global__ void __launch_bounds__(256) ssf_kernel(const SsfParams p)
                 const int hi_size = __popc((unsigned)chunk);
                 const unsigned low_lim = w < LOWB ? 1u << w : 1u << LOWB;      // low settings that stay inside the support
                 const unsigned long long gkey = (unsigned long long)(0xFFFFFFu - (unsigned)g) << 16;
-                unsigned long long gbest = 0ULL;
+                // inside a work item the generator and the high subset bits are fixed, so candidates compare by
+                // (delta * 27720 / |F|, lowest low setting): a 32-bit key  score * 32 + (31 - gray), three
+                // instructions per candidate; the 64-bit key is formed once for the winner.  31 = "nothing positive".
+                int iv[LOWB + 1];
+#pragma unroll
+                for (int t = 0; t <= LOWB; ++t) iv[t] = (int)inv_size[min(hi_size + t, 12)] * 32;
+                int best32 = 31;
                 unsigned gray = 0u;
 #pragma unroll
                 for (unsigned i = 0; i < (1u << LOWB); ++i) {
@@ -164,12 +170,12 @@ __global__ void __launch_bounds__(256) ssf_kernel(const SsfParams p)
                     const unsigned mask = hi_mask | gray;
                     if (mask == 0u || gray >= low_lim) continue;
                     const int delta = 2 * popc_w((WT)(local & T)) - popc_w(T);
-                    if (delta > 0) {
-                        const unsigned long long key =
-                            ((unsigned long long)((unsigned)delta * inv_size[hi_size + __popc(gray)]) << 40) | gkey |
-                            (unsigned long long)(0xFFFFu - mask);
-                        gbest = key > gbest ? key : gbest;
-                    }
+                    best32 = max(best32, delta * iv[__popc(gray)] + (31 - (int)gray));
+                }
+                unsigned long long gbest = 0ULL;
+                if (best32 > 31) {
+                    const unsigned wg = 31u - ((unsigned)best32 & 31u);
+                    gbest = ((unsigned long long)((unsigned)best32 >> 5) << 40) | gkey | (unsigned long long)(0xFFFFu - (hi_mask | wg));
                 }
                 if (gbest) atomicMax(&gkeys[g], gbest);
             }
