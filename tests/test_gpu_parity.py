@@ -489,8 +489,9 @@ def test_osd_global_scratch_and_four_rows_per_thread(gpu, codes, which, env, osd
     assert np.array_equal(got["fail"], ref["fail"]) and got["failures"] == ref["failures"]
 
 
-def test_bposd_on_a_code_beyond_shared_memory(gpu):
-    """A5-lift n = 2700 (m = 1080): [H | s] takes 397 KB; BP + OSD-0 must still give valid, oracle-identical corrections."""
+@pytest.mark.parametrize("osd,order", [("osd0", 0), ("osd_cs", 5)])
+def test_bposd_on_a_code_beyond_shared_memory(gpu, osd, order):
+    """A5-lift n = 2700 (m = 1080): [H | s] takes 397 KB; BP + OSD must still give valid, oracle-identical corrections."""
     from exp_ldpc_b200 import code_builders
     from exp_ldpc_b200.experiment import CodeCapacityExperiment
     from oracle import pyoracle as po
@@ -498,10 +499,11 @@ def test_bposd_on_a_code_beyond_shared_memory(gpu):
     p = 0.04
     q, prior = 2 * p / 3 + p - 4 / 3 * p * p, 2 * p / 3
     shots = 16
-    opts = dict(max_iter=8, bp_method="ms", ms_scaling_factor=0.0, osd_method="osd0")
+    opts = dict(max_iter=8, bp_method="ms", ms_scaling_factor=0.0, osd_method=osd, osd_order=order)
     got = CodeCapacityExperiment(code, q, prior, "bposd", opts).run(shots, seed=31, per_shot=True)
-    ref = po.run_code_capacity(code.checks.z, code.logicals.z, q, prior, decoder="bposd0", max_iter=8, bp_method="ms",
-                               ms_scaling_factor=0.0, seed=31, shots=shots, per_shot=True)
+    ref = po.run_code_capacity(code.checks.z, code.logicals.z, q, prior, decoder="bposd0" if order == 0 else "bposd_cs",
+                               osd_order=order, max_iter=8, bp_method="ms", ms_scaling_factor=0.0, seed=31, shots=shots,
+                               per_shot=True)
     assert ref["non_converged"] > 0
     assert (got["decodings"] == ref["decodings"]).all()
     hz = code.checks.z
