@@ -153,7 +153,7 @@ __device__ __forceinline__ void check_ps7(real (&v)[RD], unsigned sbit)
     real temp = sbit ? (real)-1 : (real)1;
 #pragma unroll
     for (int k = 0; k < RD; ++k) {
-        t[k] = A::sub(A::div((real)2, A::add((real)1, v[k])), (real)1);
+        t[k] = A::sub(A::two_over(A::add((real)1, v[k])), (real)1);
         pre[k] = temp;
         temp = A::mul(temp, t[k]);
     }

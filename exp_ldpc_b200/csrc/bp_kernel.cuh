@@ -80,6 +80,9 @@ template <> struct Ar<double> {
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    // 2 / b: doubling is exact, so twice the correctly rounded reciprocal IS the correctly rounded quotient
+    // (b = 1 + ratio >= 1 here: no overflow, no subnormal result) — a reciprocal is cheaper than a division
+    static __device__ __forceinline__ double two_over(double b) { return __dmul_rn(2.0, __drcp_rn(b)); }
     static __device__ __forceinline__ double big() { return 1e308; }
     static __device__ __forceinline__ double lg(double a) { return log(a); }
     // no NaNs on the min-sum path, so plain compare-select (fmin/fmax cost ~8 instructions each)
@@ -95,6 +98,7 @@ template <> struct Ar<float> {
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float two_over(float b) { return __fmul_rn(2.0f, __frcp_rn(b)); }
     static __device__ __forceinline__ float big() { return 3.0e38f; }
     static __device__ __forceinline__ float lg(float a) { return logf(a); }
     static __device__ __forceinline__ float mn(float a, float b) { return fminf(a, b); }
@@ -490,7 +494,7 @@ __global__ void __launch_bounds__(MAXT, 1) bp_kernel(const BpParams p)
                             for (int k = 0; k < DMAX; ++k) {
                                 if (k < deg) {
                                     const real v = lds_real(row + k * RB, real());
-                                    t[k] = A::sub(A::div((real)2, A::add((real)1, v)), (real)1);
+                                    t[k] = A::sub(A::two_over(A::add((real)1, v)), (real)1);
                                     sts_real(row + k * RB, temp);
                                     temp = A::mul(temp, t[k]);
                                 }

@@ -242,13 +242,13 @@ __global__ void __launch_bounds__(800, 1) bpc_kernel(const BpcParams p)
                     real temp = syn[r] ? (real)-1 : (real)1;
                     for (int e = lo; e < hi; ++e) {
                         c2b[e] = temp;
-                        temp = A::mul(temp, A::sub(A::div((real)2, A::add((real)1, b2c[e])), (real)1));
+                        temp = A::mul(temp, A::sub(A::two_over(A::add((real)1, b2c[e])), (real)1));
                     }
                     temp = (real)1;
                     for (int e = hi - 1; e >= lo; --e) {
                         const real x = A::mul(c2b[e], temp);
                         c2b[e] = A::div(A::sub((real)1, x), A::add((real)1, x));
-                        temp = A::mul(temp, A::sub(A::div((real)2, A::add((real)1, b2c[e])), (real)1));
+                        temp = A::mul(temp, A::sub(A::two_over(A::add((real)1, b2c[e])), (real)1));
                     }
                 }
             }
