@@ -178,6 +178,8 @@ def main():
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--teams", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=None,
+                    help="wall seconds of CPU work per reference-arm step / for the cpu_baseline sample (default: bounded automatically)")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -228,9 +230,9 @@ def main():
         rates = []
         cores = 0
         sample = ""
-        per_step = max(2.0, min(20.0, 120.0 / (args.steps + args.warmup)))
+        per_step = args.cpu_seconds or max(2.0, min(20.0, 120.0 / (args.steps + args.warmup)))
         for i in range(args.warmup + args.steps):
-            r, cores, sample, _ = cpu_port_throughput(code, p, opts, target_seconds=per_step if i >= args.warmup else 1.0,
+            r, cores, sample, _ = cpu_port_throughput(code, p, opts, target_seconds=per_step if i >= args.warmup else min(1.0, per_step),
                                                       decoder=args.decoder, problem=problem)
             if i >= args.warmup:
                 rates.append(r)
@@ -409,7 +411,7 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        v, cores, sample, cpu_iters = cpu_port_throughput(code, p, opts, target_seconds=12.0, decoder=args.decoder,
+        v, cores, sample, cpu_iters = cpu_port_throughput(code, p, opts, target_seconds=args.cpu_seconds or 12.0, decoder=args.decoder,
                                                           problem=problem)
         cpu = {"value": v, "unit": "shots/s", "cores": cores, "kind": "port", "sample": sample,
                "mean_iterations": cpu_iters}
