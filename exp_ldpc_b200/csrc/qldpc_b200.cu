@@ -321,7 +321,8 @@ struct qd_bp {
     std::vector<double> prior_dom;   // priors in the decoder's domain, per column
     int v7_lines = 0;
     int global_mem = 0;    // messages in global memory (bpg_kernel.cuh): graphs the shared-memory kernels cannot take
-    DevBuf d_scratch;
+    DevBuf d_scratch[2];        // global-memory kernel: message arrays of the CTAs in flight, one buffer per work queue
+                                // (the host pipeline keeps two launches in flight on two streams)
     // cluster kernel (bpc_kernel.cuh): messages spread over the shared memories of `cl_C` CTAs
     int cluster = 0, cl_C = 0, cl_max_edges = 0, cl_max_rows = 0, cl_max_cols = 0, cl_max_cedges = 0, cl_nwpos = 0, cl_clusters = 0;
     DevBuf dc_row_lo, dc_row_start, dc_edge_pos, dc_lc_lo, dc_lc_col, dc_lc_ptr, dc_desc, dc_word_lo, dc_col_pos, dc_prior;
@@ -354,7 +355,7 @@ struct qd_osd {
     int method = 0, order = 0;    // 0 OSD-0, 1 osd_e, 2 osd_cs
     size_t smem = 0;
     int rows_global = 0;          // [H | s] in a global scratch buffer (does not fit shared memory)
-    DevBuf d_next, d_soft, d_conv, d_rows;
+    DevBuf d_next, d_soft, d_conv, d_rows, d_failbuf;
 };
 
 struct qd_ssf {
@@ -1277,13 +1278,14 @@ static int bp_launch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int6
         qd_graph *gr = d->g;
         const unsigned grid = (unsigned)std::min<long long>((long long)gr->sm_count * d->ctas_per_sm, shots);
         const size_t rb = d->precision == QD_PREC_F64 ? 8 : 4;
-        if ((rc = d->d_scratch.ensure((size_t)gr->sm_count * d->ctas_per_sm * 2 * std::max(g.nnz, 1) * rb))) return rc;
+        DevBuf &scratch = d->d_scratch[queue & 1];
+        if ((rc = scratch.ensure((size_t)gr->sm_count * d->ctas_per_sm * 2 * std::max(g.nnz, 1) * rb))) return rc;
         BpgParams q{};
         q.m = g.m; q.n = g.n; q.nnz = g.nnz; q.nwm = g.nwm; q.nwn = g.nwn;
         q.row_ptr = g.row_ptr; q.col_idx = g.col_idx;
         q.col_ptr = gr->d_col_ptr.as<int32_t>(); q.csc_edge = gr->d_csc_edge.as<int32_t>();
         q.prior = d->d_prior.p; q.alpha_fixed = d->alpha_fixed; q.max_iter = d->max_iter;
-        q.scratch = d->d_scratch.p;
+        q.scratch = scratch.p;
         q.synd = d_synd; q.synd_stride = synd_stride; q.shots = shots;
         q.corr = d_corr; q.corr_stride = corr_stride;
         q.conv = d_converged; q.iters = d_iters; q.llr = d_llr; q.llr_mode = d->llr_mode;
@@ -1395,6 +1397,7 @@ static int host_pipeline(H *d, int device, int nwm, int nwn, const uint32_t *h_s
     const int is = (nwm + 3) & ~3, os = (nwn + 3) & ~3;   // device strides: 16-byte rows
     const int64_t per_shot = 4LL * (is + os) + 5;
     int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(1 << 18, (64LL << 20) / per_shot));
+    if (const char *e = getenv("QD_HOST_CHUNK")) chunk = std::max<int64_t>(1, atoll(e));   // tests: many small chunks in flight
     chunk = std::min(chunk, std::max<int64_t>(shots, 1));
     for (int i = 0; i < 2; ++i) {
         if ((rc = d->d_in[i].ensure((size_t)chunk * is * 4))) return rc;
@@ -1628,6 +1631,8 @@ extern "C" int qd_osd_create(qd_graph *g, int32_t method, int32_t order, qd_osd 
     while (o->W % 4 != 2) ++o->W;           // rows of an odd number of 16-byte units: aligned, bank-conflict free 128-bit XORs
     o->P = 1;
     while (o->P < gd.n) o->P <<= 1;
+    // the (B, Y) pairs of the elimination (8 bytes per row) reuse the P * 8 bytes of the sort keys
+    if (gd.m > o->P) return fail(QD_EUNSUP, "OSD: more rows than the power of two >= the number of columns");
     if (o->method && (size_t)gd.m * 4 + (size_t)gd.n * 2 + 8 * 33 > (size_t)o->P * 8)
         return fail(QD_EUNSUP, "higher-order OSD: scratch for this shape does not fit");
     o->smem = osd_smem_layout(gd.m, o->W, o->P, gd.nwm, gd.nwn, true).total;
@@ -1715,18 +1720,23 @@ static int bposd_launch(qd_bp *d, qd_osd *o, const uint32_t *d_synd, int32_t syn
     const int64_t slice = std::max<int64_t>(1, std::min<int64_t>(shots, (1LL << 30) / (8LL * g.n)));
     if ((rc = o->d_soft.ensure((size_t)slice * g.n * 8))) return rc;
     if (!d_converged && (rc = o->d_conv.ensure((size_t)slice))) return rc;
+    // the OSD epilogue corrects the failure count by (new flag - BP's flag): it needs BP's flags even when the
+    // caller does not want them
+    const bool own_fail = d_err && d_counters && !d_fail;
+    if (own_fail && (rc = o->d_failbuf.ensure((size_t)slice))) return rc;
     const int saved = d->llr_mode;
     d->llr_mode = 1;
     for (int64_t s0 = 0; s0 < shots && !rc; s0 += slice) {
         const int64_t ns = std::min(slice, shots - s0);
         uint8_t *conv = d_converged ? d_converged + s0 : o->d_conv.as<uint8_t>();
+        uint8_t *flags = own_fail ? o->d_failbuf.as<uint8_t>() : (d_fail ? d_fail + s0 : nullptr);
         rc = bp_launch(d, d_synd + s0 * synd_stride, synd_stride, ns, d_corr + s0 * corr_stride, corr_stride, conv,
                        d_iters ? d_iters + s0 : nullptr, o->d_soft.as<double>(), d_err ? d_err + s0 * err_stride : nullptr,
-                       err_stride, logicals, d_fail ? d_fail + s0 : nullptr, d_counters, stream, queue);
+                       err_stride, logicals, flags, d_counters, stream, queue);
         if (!rc)
             rc = osd_launch(o, d->method == QD_BP_PRODUCT_SUM, d_synd + s0 * synd_stride, synd_stride, ns,
                             o->d_soft.as<double>(), conv, d_corr + s0 * corr_stride, corr_stride,
-                            d_err ? d_err + s0 * err_stride : nullptr, err_stride, logicals, d_fail ? d_fail + s0 : nullptr,
+                            d_err ? d_err + s0 * err_stride : nullptr, err_stride, logicals, flags,
                             d_counters, (cudaStream_t)stream, queue);
     }
     d->llr_mode = saved;

@@ -13,8 +13,16 @@ columns), with
   ``all_reduce(SUM)`` of ``int64[4] = {failures, shots, non_converged, iterations}`` per p-value.
 
 Supported ``decoder_mode``: ``'bp'`` (the first, pure-BP stage of the reference's
-``bposd_hybrid``), ``'bposd'``, ``'bposd_hybrid'``, ``'bposd_single_shot'`` (OSD = OSD-0; the
-reference's default ``osd_cs`` of order 7 raises ``NotImplementedError``) and ``'ssf'`` (rounds = 0).
+``bposd_hybrid``), ``'bposd'``, ``'bposd_hybrid'``, ``'bposd_single_shot'`` (``osd_method`` ``osd0``,
+``osd_e`` or ``osd_cs`` of any order, including the reference's default ``osd_cs`` of order 7) and
+``'ssf'`` (rounds = 0).
+
+Randomness.  Shots are drawn from a counter-based generator (Philox4x32-10 keyed by ``seed``, counter =
+global shot index ``shot0 + i``), so a ``(seed, shot0)`` pair names a fixed set of shots whatever the
+number of ranks.  ``p_sweep`` passes each rank its own ``shot0``.  ``run_simulation`` called WITHOUT
+``seed`` / ``shot0`` draws a fresh seed per call from the OS, like the reference (whose Stim sampler is
+seeded from entropy, ``_experiment.py:172``): repeated calls give independent shots and may be summed.
+Pass ``seed`` (and ``shot0``) to reproduce a run.
 For ``rounds > 0`` the noisy storage circuit is built (``exp_ldpc_b200.storage``) and sampled with Pauli
 frames on the device (:class:`StorageExperiment`); ``'bpd_detector'`` decodes on the circuit's detector
 error model (:class:`DetectorExperiment`).
@@ -159,14 +167,32 @@ class SpacetimeExperiment(CodeCapacityExperiment):
         return (x.sum(axis=1) % 2).astype(np.uint8)
 
 
+def syndrome_extraction_steps(code):
+    """``(x_steps, z_steps)`` the reference hands to the prior callables: the larger of the maximum row
+    and column weight of the X / Z check matrix (``_experiment.py:160-161``)."""
+    checks = code.checks
+    x_steps = int(max(checks.x.sum(axis=0).max(), checks.x.sum(axis=1).max()))
+    z_steps = int(max(checks.z.sum(axis=0).max(), checks.z.sum(axis=1).max()))
+    return x_steps, z_steps
+
+
+def fresh_seed() -> int:
+    """A 63-bit seed from the OS: what an unseeded ``run_simulation`` call uses (module docstring)."""
+    import os
+    return int.from_bytes(os.urandom(8), "little") >> 1
+
+
 def run_simulation(samples, code, meas_prior, data_prior, noise_model, noise_model_args, bp_osd_options, rounds,
-                   decoder_mode, seed: int = 0, shot0: int = 0, device: int = 0, precision: str = "f64"):
+                   decoder_mode, seed: Optional[int] = None, shot0: int = 0, device: int = 0, precision: str = "f64"):
     """``run_simulation`` of ``_experiment.py:154-210``: builds the storage-simulation circuit under
     ``noise_model`` (``rounds = 0``: its closed-form code-capacity equivalent), samples it on the device,
-    decodes with the ``decoder_mode`` recipe.  Returns ``list[bool]``: the logical-failure flag of every shot."""
-    checks = code.checks
-    x_steps = int(max(checks.x.sum(axis=0).max(), checks.x.sum(axis=1).max()))   # _experiment.py:160-161
-    z_steps = int(max(checks.z.sum(axis=0).max(), checks.z.sum(axis=1).max()))
+    decodes with the ``decoder_mode`` recipe.  Returns ``list[bool]``: the logical-failure flag of every shot.
+
+    ``seed=None`` (the default) draws a fresh seed per call, so repeated calls are independent as in the
+    reference; ``seed=<int>`` makes the call reproducible (shots ``shot0 .. shot0 + samples - 1`` of that stream)."""
+    if seed is None:
+        seed = fresh_seed()
+    x_steps, z_steps = syndrome_extraction_steps(code)                          # _experiment.py:160-161
     nm = noise_model(**noise_model_args)
     mprior = meas_prior(x_steps, z_steps)
     dprior = data_prior(x_steps, z_steps)
@@ -207,25 +233,29 @@ def p_sweep(samples, p_values, noise_model, noise_model_args, meas_prior, data_p
     if device is None:
         device = torch.cuda.current_device() if torch.cuda.is_available() else 0
     lo, hi = shard_range(int(samples), rank, world)
+    # the reference binds p into the prior callables (misc/p_sweep.py:28) and run_simulation calls them with
+    # the syndrome-extraction depths (_experiment.py:160-168)
+    x_steps, z_steps = syndrome_extraction_steps(code)
     rows = []
     for p_ph in p_values:
         t0 = time.time()
         nm = noise_model(**noise_model_args(p_ph))
+        dprior, mprior = data_prior(p_ph, x_steps, z_steps), meas_prior(p_ph, x_steps, z_steps)
         if shard_runner is None and decoder_mode == "bpd_detector":
             sim = build_storage_simulation(rounds, nm, code, use_x_logicals=False)
             exp = DetectorExperiment(sim.circuit, bp_osd_options, device=device, precision=precision)
             res = exp.run(hi - lo, seed=seed, shot0=lo) if hi > lo else dict(failures=0, shots=0, non_converged=0, iters_total=0)
         elif shard_runner is None and rounds != 0:
             sim = build_storage_simulation(rounds, nm, code, use_x_logicals=False)
-            exp = StorageExperiment(code, rounds, data_prior(p_ph, 0, 0), meas_prior(p_ph, 0, 0), decoder_mode,
+            exp = StorageExperiment(code, rounds, dprior, mprior, decoder_mode,
                                     bp_osd_options, device=device, precision=precision, circuit=sim.circuit)
             res = exp.run(hi - lo, seed=seed, shot0=lo) if hi > lo else dict(failures=0, shots=0, non_converged=0, iters_total=0)
         elif shard_runner is None:
-            exp = CodeCapacityExperiment(code, nm.code_capacity_flip_probability(), data_prior(p_ph, 0, 0), decoder_mode,
+            exp = CodeCapacityExperiment(code, nm.code_capacity_flip_probability(), dprior, decoder_mode,
                                          bp_osd_options, device=device, precision=precision)
             res = exp.run(hi - lo, seed=seed, shot0=lo)
         else:
-            res = shard_runner(p_ph, nm.code_capacity_flip_probability(), data_prior(p_ph, 0, 0), lo, hi)
+            res = shard_runner(p_ph, nm.code_capacity_flip_probability(), dprior, lo, hi)
         on_gpu = torch.cuda.is_available() and (not dist.is_initialized() or dist.get_backend(group) == "nccl")
         counters = torch.tensor([res["failures"], res["shots"], res["non_converged"], res["iters_total"]],
                                 dtype=torch.int64, device=f"cuda:{device}" if on_gpu else "cpu")

@@ -24,6 +24,7 @@ def test_reference_arm_line():
     d = _run("--impl", "reference", "--workload", "hgp_34_n225", "--steps", "1", "--warmup", "1", "--cpu-seconds", "0.3")
     assert BASE <= set(d) and d["impl"] == "reference"
     assert d["unit"] == "shots/s" and d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert isinstance(d["ms_per_step"], float) and d["ms_per_step"] > 0      # wall time of one step's bounded sample
     assert d["e2e"] == {"value": d["value"], "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "shots" in cb["sample"]

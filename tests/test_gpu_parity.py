@@ -963,3 +963,90 @@ def test_padded_strides_and_dirty_output_buffers(gpu, code225):
     out = d_cor.cpu().numpy().view(np.uint32)
     assert np.array_equal(unpack_bits(out[:, :row_words(n)], n), base)
     assert not out[:, (n + 31) // 32:].any()
+
+
+# ---------------------------------------------------------------------------------------------
+# regressions for the round-1 review
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", ["global", "auto"])
+def test_host_pipeline_many_chunks_in_flight(gpu, code225, kernel, monkeypatch):
+    """decode_batch over host buffers alternates chunks between two streams; the global-memory kernel's
+    message scratch must not be shared between the two launches in flight."""
+    from exp_ldpc_b200.decoders import bp_decoder
+    from oracle import pyoracle as po
+    hz = code225.checks.z
+    rng = np.random.default_rng(11)
+    shots = 1500
+    err = (rng.random((shots, hz.shape[1])) < 0.04).astype(np.uint8)
+    synd = ((err @ hz.T.toarray()) % 2).astype(np.uint8)
+    opts = dict(error_rate=0.03, max_iter=20, bp_method="ms", ms_scaling_factor=0.0)
+    monkeypatch.setenv("QD_HOST_CHUNK", "40")              # 38 chunks, two always in flight, grids smaller than the GPU
+    dec = bp_decoder(hz, kernel=kernel, **opts)
+    corr, conv, its = dec.decode_batch(synd)
+    monkeypatch.delenv("QD_HOST_CHUNK")
+    ref = po.OracleBP(hz, **opts)
+    for s in range(shots):
+        assert np.array_equal(corr[s], ref.decode(synd[s])), s
+        assert its[s] == ref.iter and conv[s] == ref.converge
+
+
+def test_bposd_counters_without_fail_buffer(gpu, code225):
+    """qd_bposd_decode_batch with counters and the fused epilogue but no per-shot flag buffer: failures of
+    unconverged shots are counted once (BP's count is replaced by OSD's, not added to)."""
+    import torch
+    from exp_ldpc_b200 import _lib
+    from exp_ldpc_b200.decoders import Logicals, Sampler, TannerGraph, bposd_decoder, row_words
+    hz = code225.checks.z
+    m, n = hz.shape
+    g = TannerGraph(hz)
+    dec = bposd_decoder(g, error_rate=0.04, max_iter=6, bp_method="ms", ms_scaling_factor=0.0, osd_method="osd0", osd_order=0)
+    lg = Logicals(code225.logicals.z)
+    shots, wn, wm = 4096, row_words(n), row_words(m)
+    dev = torch.device("cuda:0")
+    err = torch.zeros((shots, wn), dtype=torch.int32, device=dev)
+    synd = torch.zeros((shots, wm), dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    Sampler(0.06, n).run_device(3, 0, 0, shots, err, wn, st)
+    g.syndrome_batch_device(err, wn, shots, synd, wm, st)
+    out = {}
+    for with_fail in (True, False):
+        corr = torch.zeros((shots, wn), dtype=torch.int32, device=dev)
+        fail = torch.zeros(shots, dtype=torch.uint8, device=dev) if with_fail else None
+        counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        _lib.check(_lib.lib().qd_bposd_decode_batch(dec.handle, dec.osd_handle, _lib.ptr(synd), wm, shots, _lib.ptr(corr), wn,
+                                                    None, None, _lib.ptr(err), wn, lg.handle, _lib.ptr(fail), _lib.ptr(counters), st))
+        torch.cuda.synchronize()
+        out[with_fail] = counters.cpu().numpy().copy()
+        if with_fail:
+            assert int(fail.sum().item()) == int(counters[0].item())
+    assert out[True][2] > 0                                   # some shots did need OSD
+    assert np.array_equal(out[True], out[False])
+
+
+def test_osd_rejects_more_rows_than_key_slots(gpu):
+    """OSD keeps its (B, Y) pairs in the P * 8 bytes of the sort keys (P = power of two >= n): a redundant
+    check matrix with more rows than that is refused at construction instead of overrunning."""
+    from scipy import sparse
+    from exp_ldpc_b200.decoders import bposd_decoder
+    rng = np.random.default_rng(0)
+    a = (rng.random((40, 16)) < 0.3).astype(np.uint32)
+    a[:, 0] = 1
+    with pytest.raises((RuntimeError, ValueError, NotImplementedError)):
+        bposd_decoder(sparse.csr_matrix(a), error_rate=0.05, max_iter=4, bp_method="ms", osd_method="osd0", osd_order=0)
+    b = (rng.random((16, 16)) < 0.3).astype(np.uint32)      # m = P: accepted
+    b[:, 0] = 1
+    bposd_decoder(sparse.csr_matrix(b), error_rate=0.05, max_iter=4, bp_method="ms", osd_method="osd0", osd_order=0)
+
+
+def test_run_simulation_unseeded_calls_are_independent(gpu, code225):
+    """Without a seed every call draws fresh shots (the reference's Stim sampler is entropy-seeded); with a
+    seed the call is reproducible."""
+    from functools import partial
+    from exp_ldpc_b200.experiment import depolarizing_noise, run_simulation
+    p = 0.06
+    prior = lambda p_, *_: 2 / 3 * p_
+    opts = {"max_iter": 10, "bp_method": "ms", "ms_scaling_factor": 0.0}
+    args = (2000, code225, partial(prior, p), partial(prior, p), depolarizing_noise, {"p": p, "pm": p}, opts, 0, "bp")
+    a, b = run_simulation(*args), run_simulation(*args)
+    assert a != b and 0 < sum(a) < 2000
+    assert run_simulation(*args, seed=4) == run_simulation(*args, seed=4)

@@ -78,3 +78,27 @@ def test_reference_dataframe_columns(code225):
     # python/qldpc/misc/p_sweep.py:32-39: p_ph, failures, samples, walltime + the run options
     for col in ("p_ph", "failures", "samples", "walltime", "rounds", "decoder_mode", "max_iter", "bp_method", "ms_scaling_factor"):
         assert col in df.columns
+
+
+def test_p_sweep_hands_the_extraction_depths_to_the_priors(code225):
+    """The reference binds p (misc/p_sweep.py:28) and run_simulation calls prior(x_steps, z_steps) with the
+    code's syndrome-extraction depths (_experiment.py:160-168): a depth-dependent prior must see them."""
+    from exp_ldpc_b200.experiment import depolarizing_noise, p_sweep, syndrome_extraction_steps
+    steps = syndrome_extraction_steps(code225)
+    assert steps == (7, 7)                                  # (3,4) HGP: row weight 7, column weight <= 4
+    seen = []
+
+    def depth_prior(p, x_steps, z_steps):
+        seen.append((p, x_steps, z_steps))
+        return 0.5 - 0.5 * (1 - 2 * p) ** z_steps           # 0 for z_steps = 0: the decoder would reject it
+
+    priors = []
+
+    def runner(p_ph, q, prior, lo, hi):
+        priors.append(prior)
+        return dict(failures=0, shots=hi - lo, non_converged=0, iters_total=0)
+
+    p_sweep(10, [0.01], depolarizing_noise, lambda p: {"p": p, "pm": p}, depth_prior, depth_prior, code=code225, rounds=0,
+            decoder_mode="bp", bp_osd_options=OPTS, shard_runner=runner)
+    assert seen and all(s == (0.01, 7, 7) for s in seen)
+    assert priors == [pytest.approx(0.5 - 0.5 * 0.98 ** 7)]
