@@ -69,6 +69,7 @@ struct Bp7Ctl {
     int born[BP7_SMAX];         // see BpCtl::born
     unsigned unsat[2];          // bit s: slot s has an unsatisfied check (buffer T & 1)
     int pad[2];
+    double alpha[BP7_SMAX];     // min-sum scaling factor of slot s in the coming check pass
 };
 
 struct Bp7SmemLayout {
@@ -135,12 +136,15 @@ __device__ __forceinline__ void check_ms7(real (&v)[RD], unsigned sign0, real al
 #pragma unroll
     for (int k = 2; k < RD; ++k) pm[k] = mn_abs(pm[k - 1], v[k - 1]);
     real sm = A::big();                            // same among v[k+1..]
+    // the row's sign product rides on the multiplier: |pick| * (-al) = -(|pick| * al) bit for bit, so the
+    // per-edge sign costs one LOP3 (own sign bit) instead of two
+    const real als = xor_hi(al, sx & 0x80000000u);
 #pragma unroll
     for (int k = RD - 1; k >= 0; --k) {
         const real pick = k == RD - 1 ? pm[k] : (k == 0 ? sm : mn_abs(pm[k], sm));
         sm = k == RD - 1 ? v[k] : mn_abs(sm, v[k]);
-        const real mag = A::mul(fabs(pick), al);
-        v[k] = xor_hi(mag, (sx ^ hi_bits(v[k])) & 0x80000000u);
+        const real mag = A::mul(fabs(pick), als);
+        v[k] = xor_hi(mag, hi_bits(v[k]) & 0x80000000u);
     }
 }
 
@@ -395,6 +399,14 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
         }
     };
     load_slots(-1);
+    // scaling factor of slot s in check pass T (a slot born in b runs its iteration T - b there): one thread per
+    // slot writes it after the bit pass, the row owners read it instead of re-deriving it per row and slot
+    auto publish_alpha = [&](int T) {
+        if (METHOD == QD_BP_MIN_SUM_K && tid < S)
+            ctl->alpha[tid] = (double)(alpha_fixed != (real)0 ? alpha_fixed
+                                                              : A::sub((real)1, pow2_neg<real>(T - ctl->born[tid])));
+    };
+    publish_alpha(0);
     __syncthreads();
     bool any_shot = false;
 #pragma unroll
@@ -418,9 +430,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                 load_row(c, ra, dummy);
                 real va[RD], vb[RD];
                 unsigned long long fa = 0ULL, fbb = 0ULL;
-                auto alpha_of = [&](int s) -> real {
-                    return alpha_fixed != (real)0 ? alpha_fixed : A::sub((real)1, pow2_neg<real>(T - born[s]));
-                };
+                auto alpha_of = [&](int s) -> real { return METHOD == QD_BP_MIN_SUM_K ? (real)ctl->alpha[s] : (real)0; };
 #define QD_LD(n, buf, f) row_ld<real, METHOD, RD, (n) % S>(ra, fb, buf, f, dummy)
 #define QD_CS(n, buf, f) row_cs<real, METHOD, RD, S, (n) % S>(ra, fb, buf, f, i, valid, synbits, resbits, un, alpha_of((n) % S))
                 if (act == SMASK) {                             // steady state: straight line, two buffers
@@ -579,6 +589,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
             }
         }
         if (tid == 0) ctl->unsat[ub ^ 1] = 0u;              // buffer of the next check pass
+        publish_alpha(T + 1);
         __syncthreads();
     }
 
