@@ -21,6 +21,7 @@
 #include "frame_sim.cuh"
 #include "osd_kernel.cuh"
 #include "ssf_kernel.cuh"
+#include "syndrome_kernel.cuh"
 
 namespace qd {
 
@@ -284,7 +285,8 @@ struct qd_graph {
     std::vector<uint32_t> row_desc, col_desc, csc_pos, csc_row, fpos_of_pos;
     std::vector<uint8_t> csc_k;      // index of the edge within its row
     std::vector<int32_t> csc_edge;   // CSR edge id of every CSC entry
-    DevBuf d_col_ptr, d_csc_edge, d_ell;
+    DevBuf d_col_ptr, d_csc_edge, d_ell, d_syn_tbl;
+    int syn_q = 0, syn_ctas = 0;     // 128-shot syndrome kernel: uint4 table entries per check; resident CTAs per SM (0: not probed)
     int big = 0;                     // degrees / size beyond the shared-memory kernels: global-memory BP only
     // message placements of the thread-owned-state BP kernel, keyed by (banks, column tile)
     std::list<std::pair<int, Bp7Layout>> bp7_layouts;   // list: references stay valid
@@ -518,6 +520,20 @@ extern "C" int qd_graph_create(int32_t m, int32_t n, int64_t nnz, const int32_t 
         if ((rc = upload(g->d_ell, ell))) return rc;
         d.ell = g->d_ell.as<int32_t>(); d.ell_deg = max_row;
     }
+    if (max_row >= 1 && m >= 1) {
+        // the 128-shot kernel's view of H (syndrome_kernel.cuh): byte offsets of the 16-byte column slots, 4 edges
+        // per uint4, entry q of check c at [q * m + c]; missing edges point at the zero slot behind the columns
+        const int Q = (max_row + 3) / 4;
+        const uint32_t zero_off = (uint32_t)(33 * d.nwn) * 16u;
+        std::vector<uint32_t> tbl((size_t)Q * m * 4, zero_off);
+        for (int r = 0; r < m; ++r)
+            for (int e = h_row_ptr[r]; e < h_row_ptr[r + 1]; ++e) {
+                const int k = e - h_row_ptr[r], col = h_col_idx[e];
+                tbl[((size_t)(k >> 2) * m + r) * 4 + (k & 3)] = (uint32_t)(col + (col >> 5)) * 16u;
+            }
+        if ((rc = upload(g->d_syn_tbl, tbl))) return rc;
+        g->syn_q = Q;
+    }
     QD_CUDA(cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device));
     QD_CUDA(cudaDeviceGetAttribute(&g->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     *out = g.release();
@@ -621,6 +637,30 @@ extern "C" int qd_syndrome_batch(qd_graph *g, const uint32_t *d_vec, int32_t vec
     if (shots == 0) return 0;
     int rc = use_device(g->device);
     if (rc) return rc;
+    // 128-shot bit-sliced kernel whenever the column and check slots of a tile fit shared memory
+    const int xs = 33 * g->dev.nwn + 1, ys = 33 * g->dev.nwm;
+    const size_t smem128 = (size_t)(xs + ys) * 16;
+    if (g->syn_q > 0 && smem128 <= (size_t)g->smem_optin && !getenv("QD_SYNDROME_OLD")) {
+        auto kern = g->syn_q == 1 ? syndrome128_kernel<1> : g->syn_q == 2 ? syndrome128_kernel<2>
+                  : g->syn_q == 3 ? syndrome128_kernel<3> : g->syn_q == 4 ? syndrome128_kernel<4> : syndrome128_kernel<0>;
+        const int warps = std::max(1, std::min(8, (g->dev.nwn + 7) / 8));
+        if (g->syn_ctas == 0) {
+            QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128));
+            int nb = 0;
+            QD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps * 32, smem128));
+            g->syn_ctas = std::max(1, nb);
+        }
+        SynParams sp{};
+        sp.n = g->dev.n; sp.m = g->dev.m; sp.nwn = g->dev.nwn; sp.nwm = g->dev.nwm;
+        sp.xs = xs; sp.ys = ys; sp.Q = g->syn_q;
+        sp.tbl = g->d_syn_tbl.as<uint4>();
+        sp.vec = d_vec; sp.vstride = vec_stride; sp.shots = shots; sp.synd = d_synd; sp.sstride = synd_stride;
+        const long long tiles = (shots + 127) / 128;
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(tiles, (long long)g->sm_count * g->syn_ctas));
+        kern<<<grid, warps * 32, smem128, (cudaStream_t)stream>>>(sp);
+        QD_CUDA(cudaGetLastError());
+        return 0;
+    }
     const size_t per_warp = (size_t)g->dev.nwn * 33 * 4;
     if (per_warp <= 96u * 1024u && g->dev.ell && !getenv("QD_SYNDROME_GATHER")) {
         // bit-sliced kernel: as many warps per CTA as ~96 KB of shared memory hold (two CTAs per SM), at most 8
