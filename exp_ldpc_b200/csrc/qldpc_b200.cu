@@ -286,7 +286,7 @@ struct qd_graph {
     std::vector<uint8_t> csc_k;      // index of the edge within its row
     std::vector<int32_t> csc_edge;   // CSR edge id of every CSC entry
     DevBuf d_col_ptr, d_csc_edge, d_ell, d_syn_tbl;
-    int syn_q = 0, syn_ctas = 0;     // 128-shot syndrome kernel: uint4 table entries per check; resident CTAs per SM (0: not probed)
+    int syn_q = 0, syn_ctas[2] = {0, 0};     // 128-shot syndrome kernel: uint4 table entries per check; resident CTAs per SM (0: not probed)
     int big = 0;                     // degrees / size beyond the shared-memory kernels: global-memory BP only
     // message placements of the thread-owned-state BP kernel, keyed by (banks, column tile)
     std::list<std::pair<int, Bp7Layout>> bp7_layouts;   // list: references stay valid
@@ -637,26 +637,29 @@ extern "C" int qd_syndrome_batch(qd_graph *g, const uint32_t *d_vec, int32_t vec
     if (shots == 0) return 0;
     int rc = use_device(g->device);
     if (rc) return rc;
-    // 128-shot bit-sliced kernel whenever the column and check slots of a tile fit shared memory
+    // 128-shot bit-sliced kernel whenever the column and check slots of a tile fit shared memory; the tile's packed
+    // rows come in through one TMA bulk copy when they are 16-byte aligned and the staging buffer fits as well
     const int xs = 33 * g->dev.nwn + 1, ys = 33 * g->dev.nwm;
-    const size_t smem128 = (size_t)(xs + ys) * 16;
-    if (g->syn_q > 0 && smem128 <= (size_t)g->smem_optin && !getenv("QD_SYNDROME_OLD")) {
-        auto kern = g->syn_q == 1 ? syndrome128_kernel<1> : g->syn_q == 2 ? syndrome128_kernel<2>
-                  : g->syn_q == 3 ? syndrome128_kernel<3> : g->syn_q == 4 ? syndrome128_kernel<4> : syndrome128_kernel<0>;
+    const size_t smem_xy = ((size_t)xs + ys) * 16, smem_raw = (size_t)128 * vec_stride * 4;
+    if (g->syn_q > 0 && smem_xy + 64 <= (size_t)g->smem_optin && !getenv("QD_SYNDROME_OLD")) {
+        const bool tma = ((uintptr_t)d_vec & 15u) == 0 && (vec_stride & 3) == 0 && smem_xy + smem_raw + 64 <= (size_t)g->smem_optin &&
+                         !getenv("QD_SYNDROME_NO_TMA");
+        const size_t smem128 = smem_xy + (tma ? smem_raw : 0);
+        const int qt = g->syn_q <= 3 ? g->syn_q : 0;
+        void (*kern)(const SynParams) =
+            tma ? (qt == 1 ? syndrome128_kernel<true, 1> : qt == 2 ? syndrome128_kernel<true, 2> : qt == 3 ? syndrome128_kernel<true, 3> : syndrome128_kernel<true, 0>)
+                : (qt == 1 ? syndrome128_kernel<false, 1> : qt == 2 ? syndrome128_kernel<false, 2> : qt == 3 ? syndrome128_kernel<false, 3> : syndrome128_kernel<false, 0>);
         const int warps = std::max(1, std::min(8, (g->dev.nwn + 7) / 8));
-        if (g->syn_ctas == 0) {
-            QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128));
-            int nb = 0;
-            QD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps * 32, smem128));
-            g->syn_ctas = std::max(1, nb);
-        }
+        QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128));
+        int nb = 0;
+        QD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps * 32, smem128));
         SynParams sp{};
         sp.n = g->dev.n; sp.m = g->dev.m; sp.nwn = g->dev.nwn; sp.nwm = g->dev.nwm;
         sp.xs = xs; sp.ys = ys; sp.Q = g->syn_q;
         sp.tbl = g->d_syn_tbl.as<uint4>();
         sp.vec = d_vec; sp.vstride = vec_stride; sp.shots = shots; sp.synd = d_synd; sp.sstride = synd_stride;
         const long long tiles = (shots + 127) / 128;
-        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(tiles, (long long)g->sm_count * g->syn_ctas));
+        const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(tiles, (long long)g->sm_count * std::max(1, nb)));
         kern<<<grid, warps * 32, smem128, (cudaStream_t)stream>>>(sp);
         QD_CUDA(cudaGetLastError());
         return 0;

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """HBM roofline of the bit-packed syndrome kernel (qd_syndrome_batch): algorithmic bytes
 4 * (ceil(n/32) + ceil(m/32)) per shot over the CUDA-event time, against MEASURED_PEAKS.json.
-QD_SYNDROME_GATHER=1 selects the older one-thread-per-syndrome-word gather kernel for comparison."""
+QD_SYNDROME_OLD=1 selects the 32-shot-tile kernel of round 1, QD_SYNDROME_OLD=1 QD_SYNDROME_GATHER=1 the
+one-thread-per-syndrome-word gather kernel, for comparison.  Code names may be given as arguments."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
@@ -11,7 +12,7 @@ from exp_ldpc_b200.decoders import Sampler, TannerGraph, row_words
 
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 dev = torch.device("cuda:0")
-for name in ("hgp_34_n225", "hgp_34_n1600", "hgp_34_n6400"):
+for name in (sys.argv[1:] or ("hgp_34_n225", "hgp_34_n1600", "hgp_34_n6400")):
     code = load_code(os.path.join(ROOT, "codes", name + ".qecc"))
     hz = code.checks.z
     m, n = hz.shape
