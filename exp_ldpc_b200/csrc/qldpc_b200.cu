@@ -649,7 +649,9 @@ extern "C" int qd_syndrome_batch(qd_graph *g, const uint32_t *d_vec, int32_t vec
         void (*kern)(const SynParams) =
             tma ? (qt == 1 ? syndrome128_kernel<true, 1> : qt == 2 ? syndrome128_kernel<true, 2> : qt == 3 ? syndrome128_kernel<true, 3> : syndrome128_kernel<true, 0>)
                 : (qt == 1 ? syndrome128_kernel<false, 1> : qt == 2 ? syndrome128_kernel<false, 2> : qt == 3 ? syndrome128_kernel<false, 3> : syndrome128_kernel<false, 0>);
-        const int warps = std::max(1, std::min(8, (g->dev.nwn + 7) / 8));
+        // one warp per 8-word strip of the two transposes (in + out) when that is at most 10 warps, else 8
+        const int strips = (g->dev.nwn + 7) / 8 + (synd_stride + 7) / 8;
+        const int warps = strips <= 10 ? strips : 8;
         QD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128));
         int nb = 0;
         QD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, warps * 32, smem128));

@@ -112,7 +112,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 // QT:  compile-time number of uint4 table entries per check (1..3), 0 = run time.
 // Shot (4 s + g) of a tile is bit s of group g (interleaved groups spread the staging reads over the banks).
 template <bool TMA, int QT>
-__global__ void __launch_bounds__(256, 3) syndrome128_kernel(const SynParams p)
+__global__ void __launch_bounds__(320, 3) syndrome128_kernel(const SynParams p)
 {
     extern __shared__ uint4 syn_smem[];
     uint4 *X = syn_smem, *Y = syn_smem + p.xs;
@@ -141,15 +141,23 @@ __global__ void __launch_bounds__(256, 3) syndrome128_kernel(const SynParams p)
         acc.z ^= v0.z ^ v1.z ^ v2.z ^ v3.z; acc.w ^= v0.w ^ v1.w ^ v2.w ^ v3.w;
     };
 
+    // in-strips start behind the out-strips in the warps' round robin, except for the CTA's first tile
+    // (nothing to write out yet)
+    const int c_shift = nC % nwarps;
     uint32_t parity = 0u;
     if (TMA && tid == 0 && (long long)blockIdx.x < ntiles) fetch(blockIdx.x);
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long s0 = tile << 7;
         const int rows = rows_of(tile);
+        const int c_strips = tile == (long long)blockIdx.x ? 0 : c_shift;
         const int ns = (rows - g + 3) >> 2;                           // shots of this lane's group: 4 s + g < rows
-        // ---- A. packed error rows -> X
+        // ---- A. packed error rows -> X.  The strips (8 words) of both transposes are dealt out together: the out-strips of
+        // the previous tile come first in the list, so a CTA with as many warps as strips gives every warp one strip
         if (TMA) { mbar_wait(bar, parity); parity ^= 1u; }
-        for (int w = warp * 8 + wl; w < p.nwn; w += nwarps * 8) {
+        for (int t = warp - c_strips; t < nA; t += nwarps) {
+            if (t < 0) continue;
+            const int w = t * 8 + wl;
+            if (w >= p.nwn) continue;
             uint32_t a[32];
             if (TMA) {
                 const uint32_t *src = RAW + g * p.vstride + w;
@@ -194,7 +202,9 @@ __global__ void __launch_bounds__(256, 3) syndrome128_kernel(const SynParams p)
         }
         __syncthreads();
         // ---- C. Y -> packed syndrome rows (stride padding words are written as zeros)
-        for (int k = warp * 8 + wl; k < p.sstride; k += nwarps * 8) {
+        for (int t = warp; t < nC; t += nwarps) {
+            const int k = t * 8 + wl;
+            if (k >= p.sstride) continue;
             uint32_t o[32];
             if (k < p.nwm) {
                 const uint32_t *src = reinterpret_cast<const uint32_t *>(Y + k * 33) + g;
