@@ -1050,3 +1050,64 @@ def test_run_simulation_unseeded_calls_are_independent(gpu, code225):
     a, b = run_simulation(*args), run_simulation(*args)
     assert a != b and 0 < sum(a) < 2000
     assert run_simulation(*args, seed=4) == run_simulation(*args, seed=4)
+
+
+# ---------------------------------------------------------------------------------------------
+# 128-shot bit-sliced syndrome kernel (syndrome_kernel.cuh): ragged tiles, padded strides, rows that
+# are not 16-byte aligned (no TMA staging), irregular and long rows (run-time table length), n and m that are
+# not multiples of 32 — each against a dense numpy H e mod 2 and against the two older kernels
+# ---------------------------------------------------------------------------------------------
+def _random_sparse(rng, m, n, row_degrees):
+    from scipy import sparse
+    rows, cols = [], []
+    for r in range(m):
+        d = int(row_degrees(r))
+        for c in rng.choice(n, size=min(d, n), replace=False):
+            rows.append(r); cols.append(int(c))
+    return sparse.csr_matrix((np.ones(len(rows), dtype=np.uint32), (rows, cols)), shape=(m, n))
+
+
+@pytest.mark.parametrize("case", ["hgp225", "tiny", "ragged_words", "long_rows", "empty_rows"])
+def test_syndrome128_edge_cases(gpu, code225, case, monkeypatch):
+    import torch
+    from exp_ldpc_b200.decoders import TannerGraph, pack_bits, row_words, unpack_bits
+    rng = np.random.default_rng(11)
+    if case == "hgp225":
+        h = code225.checks.z
+    elif case == "tiny":
+        h = _random_sparse(rng, 3, 5, lambda r: 2)
+    elif case == "ragged_words":
+        h = _random_sparse(rng, 77, 333, lambda r: 1 + r % 9)            # row degrees 1..9: three table entries
+    elif case == "long_rows":
+        h = _random_sparse(rng, 40, 700, lambda r: 150 + r)              # run-time table length (Q = 48)
+    else:
+        h = _random_sparse(rng, 64, 96, lambda r: 0 if r % 3 == 0 else 4)
+    m, n = h.shape
+    hd = np.asarray(h.todense(), dtype=np.uint8) & 1
+    g = TannerGraph(h)
+    for shots, extra_e, extra_s, misalign in ((1, 0, 0, 0), (127, 0, 4, 0), (128, 4, 0, 0), (129, 0, 0, 0), (300, 8, 4, 0),
+                                              (300, 0, 0, 1), (1000, 4, 0, 2)):
+        es, ss = row_words(n) + extra_e, row_words(m) + extra_s
+        e = rng.integers(0, 2, size=(shots, n)).astype(np.uint8)
+        want = (e.astype(np.int64) @ hd.T.astype(np.int64)) % 2
+        packed = torch.from_numpy(pack_bits(e, es).view(np.int32))
+        if misalign:
+            # rows that start 4 * misalign bytes off a 16-byte boundary: the kernel must not use the bulk copy
+            flat = torch.zeros(shots * es + 4, dtype=torch.int32, device=gpu)
+            d_e = flat[misalign:misalign + shots * es].view(shots, es)
+            d_e.copy_(packed)
+        else:
+            d_e = packed.to(gpu)
+        for env in ({}, {"QD_SYNDROME_NO_TMA": "1"}, {"QD_SYNDROME_OLD": "1"}, {"QD_SYNDROME_OLD": "1", "QD_SYNDROME_GATHER": "1"}):
+            for k in ("QD_SYNDROME_NO_TMA", "QD_SYNDROME_OLD", "QD_SYNDROME_GATHER"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            d_s = torch.full((shots, ss), -1, dtype=torch.int32, device=gpu)
+            g.syndrome_batch_device(d_e, es, shots, d_s, ss)
+            torch.cuda.synchronize()
+            raw = d_s.cpu().numpy().view(np.uint32)
+            assert np.array_equal(unpack_bits(raw, m), want), (case, shots, env)
+            assert not raw[:, (m + 31) // 32:].any(), "stride padding words must be written as zeros"
+            if m % 32:
+                assert not (raw[:, m // 32] >> (m % 32)).any()
