@@ -410,6 +410,24 @@ def main():
                      "mean_iterations": mean_iters, "edge_updates_per_s": 2.0 * nnz * mean_iters * shots / (kernel_ms * 1e-3),
                      "peak_source": f"{sm_count} SMs x 128 B/clk x {sm_mhz:.0f} MHz (median SM clock during the timed region)"}
 
+    # the HBM-bound kernel of the path (H e mod 2 on the step's packed errors), timed alone: SURVEY.md §8(d) B_syn
+    # without the logical bits = 4 * (ceil(n/32) + ceil(m/32)) bytes per shot against the measured copy bandwidth
+    for _ in range(3):
+        graph.syndrome_batch_device(d_err, es, shots, d_syn, ss, stream)
+    s_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s_ev[0].record()
+    for _ in range(10):
+        graph.syndrome_batch_device(d_err, es, shots, d_syn, ss, stream)
+    s_ev[1].record()
+    torch.cuda.synchronize()
+    syn_ms = s_ev[0].elapsed_time(s_ev[1]) / 10
+    syn_bytes = 4 * ((n + 31) // 32 + (m + 31) // 32)
+    syn_achieved = syn_bytes * shots / (syn_ms * 1e-3) / 1e9
+    roofline_syndrome = {"bound": "hbm", "achieved": syn_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": syn_achieved / hbm_peak,
+                         "kernel": "syndrome128_kernel", "kernel_ms": syn_ms, "algorithmic_bytes_per_shot": syn_bytes,
+                         "note": "inputs of one step (larger than L2 at the default shot count); not part of `value`"}
+
     cpu = None
     if not args.no_cpu_baseline:
         v, cores, sample, cpu_iters = cpu_port_throughput(code, p, opts, target_seconds=args.cpu_seconds or 12.0, decoder=args.decoder,
@@ -423,7 +441,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": config, "e2e": e2e, "gpu_launches": args.steps * (2 if osd else 1), "clocks": clk, "roofline": roofline,
-            "roofline_smem": roofline_smem, "cpu_baseline": cpu,
+            "roofline_smem": roofline_smem, "roofline_syndrome": roofline_syndrome, "cpu_baseline": cpu,
             "counters": {"failures": int(cnt[0]), "shots": int(cnt[1]), "non_converged": int(cnt[2]),
                          "iterations": int(cnt[3])},
             "wall_s_timed_region": t_wall}

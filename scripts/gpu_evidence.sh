@@ -9,8 +9,8 @@ OUT=gpurun_out
 mkdir -p $OUT
 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"
 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"
-b() { name=$1; shift; python bench.py "$@" > $OUT/${TAG}_bench_${name}.json 2>> $OUT/${TAG}_bench.err; echo "bench $name rc=$?"; }
-b hgp_34_n1600
+b() { name=$1; shift; python bench.py --cpu-seconds ${CPU_S:-4} "$@" > $OUT/${TAG}_bench_${name}.json 2>> $OUT/${TAG}_bench.err; echo "bench $name rc=$?"; }
+CPU_S=12 b hgp_34_n1600
 b hgp_34_n1600_reference --impl reference --steps 2 --warmup 1
 b hgp_34_n1600_f32 --precision f32
 b hgp_34_n225 --workload hgp_34_n225
@@ -38,3 +38,5 @@ cap bp7_n1600 bp7 --shots 131072
 cap osd_n1600 osd --decoder bposd --shots 16384
 cap ssf_n1600 ssf --decoder ssf --shots 131072
 cap bpc_st1600 bpc --workload st_hgp1600_T3 --shots 16384
+cap syn128_n1600 syndrome128 --shots 1048576
+python scripts/microbench/syndrome_bw.py > $OUT/${TAG}_syndrome_microbench.txt 2>&1
