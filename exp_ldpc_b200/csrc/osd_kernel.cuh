@@ -85,14 +85,15 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
     uint16_t *pcol = reinterpret_cast<uint16_t *>(smem_raw + L.pcol);
     uint32_t *dec = reinterpret_cast<uint32_t *>(smem_raw + L.dec);
     __shared__ long long sh_shot;
-    __shared__ int cand[64];
+    __shared__ unsigned candrow[3][32];                       // pivot round r, slot r % 3: lowest unused row whose lowest set bit is column c
     __shared__ int sh_k;
     __shared__ int red32[32];
     __shared__ unsigned long long red64[32];
     const int W = p.W, W2 = p.W / 2, m = p.m, n = p.n;
     long long c_delta = 0;                                    // thread 0: change of the failure count
+    int rbuf = 0;                                             // slot of candrow[] the next pivot round nominates into
 
-    if (tid < 64) cand[tid] = 0x7fffffff;                     // entries of absent warps stay "no candidate"
+    for (int i = tid; i < 96; i += NT) candrow[i >> 5][i & 31] = 0xFFFFFFFFu;
     for (int x = tid; x < W2 * (OSD_BLOCK / 4); x += NT)      // entry 0 of every nibble table: the empty XOR
         reinterpret_cast<ulonglong2 *>(smem_raw + L.tables)[x * 16] = make_ulonglong2(0ULL, 0ULL);
 
@@ -196,38 +197,61 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                     }
                     avail[q] = isused[q] ? 0u : B[q];
                 }
-                // One barrier per PIVOT: every thread proposes (lowest block column in which one of its unused
-                // rows has a bit, that row); the minimum over the CTA is the next independent column in ranking
-                // order together with a pivot row for it.  Columns that depend on earlier ones never show a bit in
-                // an unused row (and keep none), so they cost nothing.
+                // One barrier per BATCH of pivots.  Any unused row whose block word is non-zero can serve as a pivot for the
+                // column of its lowest set bit, as long as it is reduced against the pivots already chosen — the set of pivot
+                // columns (leading positions of the span of the unused rows) does not depend on the order.  So a round nominates,
+                // for EVERY block column at once, the lowest unused row whose lowest set bit is that column (one shared
+                // atomicMin per warp and column value); after the barrier lane c of every warp holds the candidate of column c
+                // and its (B, Y) pair, and the candidates are applied from the highest column down: a row with lowest bit c has
+                // no bits below c, so applying it never disturbs the lowest bit of a candidate still to come, while that
+                // candidate's bits at the higher pivot columns are cleared before its turn (the lanes reduce their candidates
+                // in step, lane = column, so nothing is computed twice).  Rows with independent random words have
+                // geometrically distributed lowest bits: a round yields ~log2(#unused rows) pivots instead of one.
                 int npiv = 0;
-                auto pivot_round = [&](int *cd) -> bool {       // false: the block is finished
-                    int key = 0x7fffffff;
-#pragma unroll
-                    for (int q = 0; q < RPT; ++q)
-                        if (avail[q]) key = min(key, ((__ffs((int)avail[q]) - 1) << 16) | (tid + q * NT));
-                    key = __reduce_min_sync(0xffffffffu, key);
-                    if (lane == 0) cd[warp] = key;
-                    __syncthreads();
-                    const int best = __reduce_min_sync(0xffffffffu, cd[lane]);
-                    if (best == 0x7fffffff) return false;       // the rest of the block depends on earlier columns
-                    const int j = best >> 16, piv = best & 0xffff;
-                    const uint2 pv = BY[piv];
-                    if (lane == npiv) myprow = piv;             // lane i of every warp remembers the block's i-th pivot row
+                auto pivot_round = [&]() -> bool {              // false: the block is finished
+                    const int buf = rbuf, nxt = buf == 2 ? 0 : buf + 1;
+                    rbuf = nxt;
 #pragma unroll
                     for (int q = 0; q < RPT; ++q) {
-                        if (tid + q * NT == piv) { isused[q] = true; mypcol[q] = t0 + j; }
-                        else if ((B[q] >> j) & 1u) {
-                            B[q] ^= pv.x; Y[q] ^= pv.y ^ (1u << npiv);
-                            BY[tid + q * NT] = make_uint2(B[q], Y[q]);
+                        const int c = avail[q] ? __ffs((int)avail[q]) - 1 : 32;
+                        const unsigned grp = __match_any_sync(0xffffffffu, c);
+                        if (c < 32 && (grp & ((1u << lane) - 1u)) == 0u) atomicMin(&candrow[buf][c], (unsigned)(tid + q * NT));
+                    }
+                    if (tid < 32) candrow[nxt][tid] = 0xFFFFFFFFu;   // the slots of the next round (last read two barriers ago)
+                    __syncthreads();
+                    const unsigned prw = candrow[buf][lane];
+                    unsigned todo = __ballot_sync(0xffffffffu, prw != 0xFFFFFFFFu);
+                    if (!todo) return false;                    // the rest of the block depends on earlier columns
+                    uint32_t pb = 0u, py = 0u;
+                    if (prw != 0xFFFFFFFFu) { const uint2 pv = BY[prw]; pb = pv.x; py = pv.y; }
+                    bool changed[RPT], chosen[RPT];
+#pragma unroll
+                    for (int q = 0; q < RPT; ++q) changed[q] = chosen[q] = false;
+                    while (todo) {
+                        const int c = 31 - __clz((int)todo);
+                        todo &= ~(1u << c);
+                        const uint32_t vb = __shfl_sync(0xffffffffu, pb, c);
+                        const uint32_t vy = __shfl_sync(0xffffffffu, py, c) ^ (1u << npiv);
+                        const unsigned vr = __shfl_sync(0xffffffffu, prw, c);
+                        if (lane < c && ((pb >> c) & 1u)) { pb ^= vb; py ^= vy; }     // candidates of lower columns absorb it
+                        if (lane == npiv) myprow = (int)vr;     // lane i of every warp remembers the block's i-th pivot row
+#pragma unroll
+                        for (int q = 0; q < RPT; ++q) {
+                            if (tid + q * NT == (int)vr) { isused[q] = true; chosen[q] = true; mypcol[q] = t0 + c; }
+                            else if ((B[q] >> c) & 1u) { B[q] ^= vb; Y[q] ^= vy; changed[q] = true; }
                         }
+                        ++npiv; ++rank;
+                    }
+#pragma unroll
+                    for (int q = 0; q < RPT; ++q) {
+                        // (a row chosen in this round keeps its published pair: others may still be reading it, and a used
+                        // row is never nominated again)
+                        if (changed[q] && !chosen[q]) BY[tid + q * NT] = make_uint2(B[q], Y[q]);
                         avail[q] = isused[q] ? 0u : B[q];
                     }
-                    ++npiv;
-                    return ++rank < p.rank;
+                    return rank < p.rank;
                 };
-                // cand[] is double-buffered: a warp that runs ahead into the next round never overwrites a slot early
-                while (pivot_round(cand) && pivot_round(cand + 32)) { }
+                while (pivot_round()) { }
                 if (warp == 0 && lane < npiv) prow[lane] = (uint16_t)myprow;
                 __syncthreads();
                 if (npiv == 0) continue;
