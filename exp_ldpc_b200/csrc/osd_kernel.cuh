@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                 isused[q] = false;
                 mypcol[q] = 0xFFFF;
             }
-            int rank = 0, myprow = 0;
+            int rank = 0;
             for (int t0 = 0; t0 < n && rank < p.rank; t0 += OSD_BLOCK) {
 #pragma unroll
                 for (int q = 0; q < RPT; ++q) {
@@ -224,35 +224,46 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                     if (!todo) return false;                    // the rest of the block depends on earlier columns
                     uint32_t pb = 0u, py = 0u;
                     if (prw != 0xFFFFFFFFu) { const uint2 pv = BY[prw]; pb = pv.x; py = pv.y; }
-                    bool changed[RPT], chosen[RPT];
+                    // a row knows by itself whether it was chosen: it is the candidate of the column it nominated itself for
+                    int mycol[RPT];
+                    bool changed[RPT];
 #pragma unroll
-                    for (int q = 0; q < RPT; ++q) changed[q] = chosen[q] = false;
+                    for (int q = 0; q < RPT; ++q) {
+                        const int c = avail[q] ? __ffs((int)avail[q]) - 1 : 0;
+                        mycol[q] = (avail[q] && candrow[buf][c] == (unsigned)(tid + q * NT)) ? c : -1;
+                        changed[q] = false;
+                    }
+                    // pivot i of the block = the i-th candidate from the top: warp 0 files the rows for the table pass
+                    if (warp == 0 && prw != 0xFFFFFFFFu) prow[npiv + __popc(todo >> lane) - 1] = (uint16_t)prw;
+                    uint32_t nbit = 1u << npiv;
+                    const int k = __popc(todo);
                     while (todo) {
                         const int c = 31 - __clz((int)todo);
-                        todo &= ~(1u << c);
+                        todo ^= 1u << c;
                         const uint32_t vb = __shfl_sync(0xffffffffu, pb, c);
-                        const uint32_t vy = __shfl_sync(0xffffffffu, py, c) ^ (1u << npiv);
-                        const unsigned vr = __shfl_sync(0xffffffffu, prw, c);
-                        if (lane < c && ((pb >> c) & 1u)) { pb ^= vb; py ^= vy; }     // candidates of lower columns absorb it
-                        if (lane == npiv) myprow = (int)vr;     // lane i of every warp remembers the block's i-th pivot row
+                        const uint32_t vy = __shfl_sync(0xffffffffu, py, c) ^ nbit;
+                        nbit <<= 1;
+                        const uint32_t lm = (lane < c && ((pb >> c) & 1u)) ? 0xFFFFFFFFu : 0u;   // candidates of lower columns absorb it
+                        pb ^= vb & lm; py ^= vy & lm;
 #pragma unroll
                         for (int q = 0; q < RPT; ++q) {
-                            if (tid + q * NT == (int)vr) { isused[q] = true; chosen[q] = true; mypcol[q] = t0 + c; }
-                            else if ((B[q] >> c) & 1u) { B[q] ^= vb; Y[q] ^= vy; changed[q] = true; }
+                            const uint32_t hm = (mycol[q] != c && ((B[q] >> c) & 1u)) ? 0xFFFFFFFFu : 0u;
+                            B[q] ^= vb & hm; Y[q] ^= vy & hm;
+                            changed[q] |= hm != 0u;
                         }
-                        ++npiv; ++rank;
                     }
+                    npiv += k; rank += k;
 #pragma unroll
                     for (int q = 0; q < RPT; ++q) {
                         // (a row chosen in this round keeps its published pair: others may still be reading it, and a used
                         // row is never nominated again)
-                        if (changed[q] && !chosen[q]) BY[tid + q * NT] = make_uint2(B[q], Y[q]);
+                        if (mycol[q] >= 0) { isused[q] = true; mypcol[q] = t0 + mycol[q]; }
+                        else if (changed[q]) BY[tid + q * NT] = make_uint2(B[q], Y[q]);
                         avail[q] = isused[q] ? 0u : B[q];
                     }
                     return rank < p.rank;
                 };
                 while (pivot_round()) { }
-                if (warp == 0 && lane < npiv) prow[lane] = (uint16_t)myprow;
                 __syncthreads();
                 if (npiv == 0) continue;
                 const int jc0 = p.method == 0 ? min((t0 + OSD_BLOCK) >> 7, n >> 7) : 0;
