@@ -112,7 +112,10 @@ int qd_circuit_sample(qd_circuit *c, uint64_t seed, int64_t shot0, int64_t shots
 int qd_circuit_propagate_faults(qd_circuit *c, int64_t num_faults, const int32_t *d_site_and_pauli,
                                 uint32_t *d_records, int32_t stride, void *stream);
 
-/* ---- H @ v mod 2, batched and bit-packed --------------------------------------------------- */
+/* ---- H @ v mod 2, batched and bit-packed (python/qldpc/misc/_experiment.py:47,58,124;
+ *      python/qldpc/spacetime_code.py:109).  All words of d_synd up to synd_stride are written (padding
+ *      words as zeros); d_vec is only read.  Any strides >= the packed row lengths are accepted; rows that
+ *      are 16-byte aligned (d_vec 16-byte aligned, vec_stride a multiple of 4 words) take the TMA path. */
 int qd_syndrome_batch(qd_graph *g, const uint32_t *d_vec, int32_t vec_stride, int64_t shots,
                       uint32_t *d_synd, int32_t synd_stride, void *stream);
 
