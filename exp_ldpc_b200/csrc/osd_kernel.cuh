@@ -127,15 +127,13 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
         __syncthreads();
         for (int k2 = 2; k2 <= p.P; k2 <<= 1)
             for (int j = k2 >> 1; j > 0; j >>= 1) {
-                for (int i = tid; i < p.P; i += NT) {
-                    const int l = i ^ j;
-                    if (l > i) {
-                        const unsigned long long ka = keys[i], kb = keys[l];
-                        const uint16_t ia = idx[i], ib = idx[l];
-                        const bool a_gt_b = ka > kb || (ka == kb && ia > ib);
-                        const bool up = (i & k2) == 0;
-                        if (a_gt_b == up) { keys[i] = kb; keys[l] = ka; idx[i] = ib; idx[l] = ia; }
-                    }
+                for (int pr = tid; pr < p.P / 2; pr += NT) {           // one compare-exchange per thread and step: pair (i, i | j)
+                    const int i = ((pr & ~(j - 1)) << 1) | (pr & (j - 1)), l = i | j;
+                    const unsigned long long ka = keys[i], kb = keys[l];
+                    const uint16_t ia = idx[i], ib = idx[l];
+                    const bool a_gt_b = ka > kb || (ka == kb && ia > ib);
+                    const bool up = (i & k2) == 0;
+                    if (a_gt_b == up) { keys[i] = kb; keys[l] = ka; idx[i] = ib; idx[l] = ia; }
                 }
                 __syncthreads();
             }
