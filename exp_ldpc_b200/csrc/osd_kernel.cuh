@@ -125,8 +125,33 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
             idx[i] = (uint16_t)i;
         }
         __syncthreads();
-        for (int k2 = 2; k2 <= p.P; k2 <<= 1)
-            for (int j = k2 >> 1; j > 0; j >>= 1) {
+        // bitonic network over (key, column).  Steps with a partner distance below 32 stay inside an aligned run of 32
+        // elements: a warp takes such a run into registers (lane = position) and does ALL consecutive short steps with
+        // shuffles, so only the steps with distance >= 32 go through shared memory and cost a barrier (21 of 66 at P = 2048).
+        auto run_steps = [&](int k2, int jtop) {                  // steps j = jtop, jtop/2, ..., 1 of stage k2 on every run of 32
+            for (int r = warp; r < p.P / 32; r += nwarps) {
+                const int i = r * 32 + lane;
+                unsigned long long key = keys[i];
+                uint32_t ix = idx[i];
+                for (int kk = k2, j0 = jtop; ; ) {
+                    for (int j = j0; j > 0; j >>= 1) {
+                        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, j);
+                        const uint32_t oi = __shfl_xor_sync(0xffffffffu, ix, j);
+                        const bool mine_gt = key > ok || (key == ok && ix > oi);
+                        const bool up = (i & kk) == 0, low = (lane & j) == 0;
+                        if (mine_gt == (up == low)) { key = ok; ix = oi; }   // the lower position keeps the smaller one when ascending
+                    }
+                    if (kk >= 32 || kk >= p.P) break;             // stages 2..32 run back to back inside the registers
+                    kk <<= 1; j0 = kk >> 1;
+                }
+                keys[i] = key;
+                idx[i] = (uint16_t)ix;
+            }
+        };
+        run_steps(2, 1);                                          // stages k2 = 2 .. 32 completely
+        __syncthreads();
+        for (int k2 = 64; k2 <= p.P; k2 <<= 1) {
+            for (int j = k2 >> 1; j >= 32; j >>= 1) {
                 for (int pr = tid; pr < p.P / 2; pr += NT) {           // one compare-exchange per thread and step: pair (i, i | j)
                     const int i = ((pr & ~(j - 1)) << 1) | (pr & (j - 1)), l = i | j;
                     const unsigned long long ka = keys[i], kb = keys[l];
@@ -137,6 +162,9 @@ __global__ void __launch_bounds__(1024, 1) osd0_kernel(const OsdParams p)
                 }
                 __syncthreads();
             }
+            run_steps(k2, 16);
+            __syncthreads();
+        }
 
         // ---- 2. [H | s] with the columns in ranked order: column idx[t] sits at bit position t, s at position n
         {

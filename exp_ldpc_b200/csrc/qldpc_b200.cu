@@ -1674,7 +1674,7 @@ extern "C" int qd_osd_create(qd_graph *g, int32_t method, int32_t order, qd_osd 
     o->method = order > 0 ? method : 0; o->order = method ? order : 0;
     o->W = (gd.n + 1 + 63) / 64;
     while (o->W % 4 != 2) ++o->W;           // rows of an odd number of 16-byte units: aligned, bank-conflict free 128-bit XORs
-    o->P = 1;
+    o->P = 32;                              // (the ranking network works on runs of 32)
     while (o->P < gd.n) o->P <<= 1;
     // the (B, Y) pairs of the elimination (8 bytes per row) reuse the P * 8 bytes of the sort keys
     if (gd.m > o->P) return fail(QD_EUNSUP, "OSD: more rows than the power of two >= the number of columns");
