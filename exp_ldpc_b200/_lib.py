@@ -48,6 +48,7 @@ SIGNATURES = {
     "qd_bp_get_config": (C.c_int, [vp, P(i32), P(i32), P(i32), P(i32), P(i32), P(i32)]),
     "qd_bp_select_kernel": (C.c_int, [vp, i32]),
     "qd_bp_get_kernel": (C.c_int, [vp, P(i32), P(i32), P(i32)]),
+    "qd_bp_cluster_plan_check": (C.c_int, [i32, i32, vp, vp, i32, i32, vp]),
     "qd_bp_decode_batch": (C.c_int, [vp, vp, i32, i64, vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, vp]),
     "qd_bp_decode_batch_host": (C.c_int, [vp, vp, i32, i64, vp, i32, vp, vp]),
     "qd_bp_decode_one": (C.c_int, [vp, vp, vp, P(i32), P(i32), vp]),

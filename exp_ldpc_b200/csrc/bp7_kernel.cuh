@@ -29,6 +29,7 @@
 #pragma once
 
 #include "bp_kernel.cuh"
+#include "cluster.cuh"
 
 namespace qd {
 
@@ -62,6 +63,15 @@ struct Bp7Params {
     uint8_t *fail;
     long long *counters;        // {failures, shots, non_converged, iterations}
     unsigned long long *next_shot;
+    // cluster mode (template flag CL): a thread-block cluster of cl_C CTAs decodes S shots together.  CTA `rank` owns a
+    // contiguous share of the rows and keeps their messages; every per-CTA table above is an array over the ranks
+    // (stride = the common, padded size), m / m32 / nrec / lines are those common sizes.
+    int cl_C;
+    const int32_t *cl_row0;     // [C] first (global) row of the share
+    const int32_t *cl_rows;     // [C] rows of the share
+    const int32_t *cl_nexp;     // [C] export entries
+    const uint2 *cl_export;     // [C][cl_exp_stride]: x = local message element | mailbox element << 16, y = destination rank
+    int cl_exp_stride;
 };
 
 struct Bp7Ctl {
@@ -284,7 +294,15 @@ __device__ __forceinline__ void col_update(const uint32_t (&ea)[VMAX], const uin
 #undef QD_CS
 }
 
-template <typename real, int METHOD, int RD, int VMAX, int S, bool IRREG, int MAXT, int MINB>
+// CL (cluster mode): the Tanner graph is too large for one SM.  The rows are split over the CTAs of a cluster; a column
+// whose edges all lie in one share is updated there, a column cut by the split has a replica record in every CTA that
+// holds one of its edges.  A replica reads the check->bit messages of its remote edges from a MAILBOX (message elements
+// nobody's rows own) that the row owners fill through distributed shared memory after the check pass ("export"), runs
+// the same serial sums as every other replica of the column, and keeps the outputs of its local edges.  Everything else
+// — in-place message array, conflict-free placement, thread-owned state, slot refill — is the single-CTA kernel; the
+// slot control block is replicated and advanced identically in every CTA (CTA 0 draws from the shot queue and assembles
+// the outputs).  Arithmetic and its order are unchanged, so results are bit-identical to the single-CTA kernels.
+template <typename real, int METHOD, int RD, int VMAX, int S, bool IRREG, int MAXT, int MINB, bool CL = false>
 __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
 {
     using A = Ar<real>;
@@ -306,22 +324,40 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
     uint32_t *outbits = reinterpret_cast<uint32_t *>(smem_raw + p.off_out);      // [S][nwn]
     Bp7Ctl *ctl = reinterpret_cast<Bp7Ctl *>(smem_raw + p.off_ctl);
     const int max_iter = p.max_iter;
-    const real *prior_rec = static_cast<const real *>(p.prior_rec);
     const real alpha_fixed = (real)p.alpha_fixed;
     const bool staged = p.staged != 0;
+    // this CTA's tables and share of the rows (cluster mode: indexed by the rank within the cluster)
+    const uint32_t rank = CL ? cl_rank() : 0u;
+    const uint32_t NC = CL ? (uint32_t)p.cl_C : 1u;
+    const uint4 *const tbl = p.table + (CL ? (size_t)rank * p.nrec * (VMAX / 4) : 0);
+    const uint4 *const rtbl = p.row_table + (CL ? (size_t)rank * p.m32 * RQ : 0);
+    const uint8_t *const cdeg = p.chunk_deg + (CL ? (size_t)rank * (p.nrec / 32) : 0);
+    const real *const prior_rec = static_cast<const real *>(p.prior_rec) + (CL ? (size_t)rank * p.nrec : 0);
+    const uint16_t *const colid = p.col_id + (CL ? (size_t)rank * p.nrec : 0);
+    const int my_m = CL ? p.cl_rows[rank] : p.m;
+    const int row0 = CL ? p.cl_row0[rank] : 0;
+    // slot control: one copy per CTA, written identically everywhere (cluster mode: by CTA 0 through the cluster window)
+    auto set_slot = [&](int s, long long shot, int born) {
+        if (!CL) { ctl->shot[s] = shot; ctl->born[s] = born; }
+        else
+            for (uint32_t r = 0; r < NC; ++r) {
+                cl_st_s64(cl_map(smem_u32(&ctl->shot[s]), r), shot);
+                cl_st_u32(cl_map(smem_u32(&ctl->born[s]), r), (uint32_t)born);
+            }
+    };
 
     if (staged) {
         uint4 *st = reinterpret_cast<uint4 *>(smem_raw + p.off_table);
-        for (int i = tid; i < p.nrec * (VMAX / 4); i += NT) st[i] = p.table[i];
+        for (int i = tid; i < p.nrec * (VMAX / 4); i += NT) st[i] = tbl[i];
     }
-    if (tid < S) {
+    if (CL) cluster_sync_once_fenced();                // every CTA of the cluster runs before its shared memory is written
+    if ((!CL || rank == 0) && tid < S) {
         const unsigned long long id = atomicAdd(p.next_shot, 1ULL);
         const bool more = id < (unsigned long long)p.shots;
-        ctl->shot[tid] = more ? (long long)id : -1;
-        ctl->born[tid] = more ? -1 : BP_IDLE;          // -1: takes part in iteration 0 in full
+        set_slot(tid, more ? (long long)id : -1, more ? -1 : BP_IDLE);     // -1: takes part in iteration 0 in full
     }
     if (tid == 0) ctl->unsat[0] = ctl->unsat[1] = 0u;
-    __syncthreads();
+    if (CL) cluster_sync_once_fenced(); else __syncthreads();
 
     // ---- thread-owned state, bit (i * S + s): i-th owned row / column record, slot s
     unsigned synbits = 0u, resbits = 0u, decbits = 0u;
@@ -333,7 +369,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
 #pragma unroll
         for (int q = 0; q < VMAX / 4; ++q) {
             const uint4 x = staged ? lds_v4(a_tab + (uint32_t)(r * (VMAX / 4) + q) * 16u)
-                                   : __ldg(p.table + (size_t)r * (VMAX / 4) + q);
+                                   : __ldg(tbl + (size_t)r * (VMAX / 4) + q);
             w[4 * q + 0] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
         }
 #pragma unroll
@@ -348,7 +384,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
         uint32_t w[4 * RQ];
 #pragma unroll
         for (int q = 0; q < RQ; ++q) {
-            const uint4 x = __ldg(p.row_table + (size_t)c * RQ + q);
+            const uint4 x = __ldg(rtbl + (size_t)c * RQ + q);
             w[4 * q + 0] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
         }
         dummy = 0u;
@@ -368,14 +404,15 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
         if (!fresh) return;
         int i = 0;
         for (int c = tid; c < p.m32; c += NT, ++i) {
-            const bool valid = c < p.m;
+            const bool valid = c < my_m;
             const uint32_t fb = a_flags + (uint32_t)(valid ? c : p.m) * FP;
+            const int gc = row0 + c;                                  // the row's index in the syndrome
 #pragma unroll
             for (int s = 0; s < S; ++s)
                 if ((fresh >> s) & 1u) {
                     const int bi = i * S + s;
                     unsigned b = 0u;
-                    if (valid) b = (p.synd[ctl->shot[s] * (long long)p.synd_stride + (c >> 5)] >> (c & 31)) & 1u;
+                    if (valid) b = (p.synd[ctl->shot[s] * (long long)p.synd_stride + (gc >> 5)] >> (gc & 31)) & 1u;
                     synbits = (synbits & ~(1u << bi)) | (b << bi);
                     resbits = (resbits & ~(1u << bi)) | (b << bi);
                     sts_u64(fb + s * FB, 0ULL);
@@ -386,7 +423,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
         for (int r = tid; r < p.nrec; r += NT, ++i) {
             uint32_t ea[VMAX], fa[VMAX];
             load_record(r, ea, fa);
-            const int deg = p.chunk_deg[r >> 5];
+            const int deg = cdeg[r >> 5];
             const real pj = prior_of(r);
 #pragma unroll
             for (int s = 0; s < S; ++s)
@@ -412,8 +449,15 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
 #pragma unroll
     for (int s = 0; s < S; ++s) any_shot |= ctl->born[s] != BP_IDLE;
 
+#ifdef QD_BP7_TIMING
+    long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64(), n_iter = 0;
+#define QD_TICK7(k) do { const long long now_ = clock64(); tacc[k] += now_ - tlast; tlast = now_; } while (0)
+#else
+#define QD_TICK7(k) do { } while (0)
+#endif
     for (int T = 0; any_shot; ++T) {
         const int ub = T & 1;
+        QD_TICK7(5);
         // ================================================================== check pass
         {
             int born[S];
@@ -423,7 +467,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
             unsigned un = 0u;
             int i = 0;
             for (int c = tid; c < p.m32; c += NT, ++i) {
-                const bool valid = c < p.m;
+                const bool valid = c < my_m;
                 const uint32_t fb = a_flags + (uint32_t)(valid ? c : p.m) * FP;
                 uint32_t ra[RD];
                 unsigned dummy;
@@ -464,9 +508,33 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
 #undef QD_CS
             }
             un = __reduce_or_sync(0xffffffffu, un);
-            if (lane == 0 && un) atomicOr(&ctl->unsat[ub], un);
+            if (lane == 0 && un) {
+                if (!CL) atomicOr(&ctl->unsat[ub], un);
+                else for (uint32_t r = 0; r < NC; ++r) cl_red_or_u32(cl_map(smem_u32(&ctl->unsat[ub]), r), un);
+            }
         }
         __syncthreads();
+        QD_TICK7(0);
+        if (CL) {
+            // ============================================================== export: check->bit messages of cut columns
+            // into the mailboxes of the other CTAs that hold a replica of the column (consecutive entries fill
+            // consecutive elements of a destination line)
+            unsigned act = 0u;
+#pragma unroll
+            for (int s = 0; s < S; ++s) act |= (unsigned)(ctl->born[s] != BP_IDLE) << s;
+            const int nexp = p.cl_nexp[rank];
+            const uint2 *ex = p.cl_export + (size_t)rank * p.cl_exp_stride;
+            for (int x = tid; x < nexp; x += NT) {
+                const uint2 e = __ldg(ex + x);
+                const uint32_t src = a_msg + (e.x & 0xffffu) * RB;
+                const uint32_t dst = cl_map(a_msg + (e.x >> 16) * RB, e.y);
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    if ((act >> s) & 1u) cl_st(dst + s * LINE, lds_real(src + s * LINE, real()));
+            }
+            cluster_sync_once_fenced();
+        }
+        QD_TICK7(1);
 
         // ================================================================== retire / refill
         {
@@ -481,27 +549,37 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
             }
             if (done) {
                 // the queue's answer is not needed before the epilogue is through: ask first
+                // (cluster mode: CTA 0 holds the output words, every CTA adds the decisions of the columns it owns)
+                const bool lead = !CL || rank == 0;
                 unsigned long long next_id = 0ULL;
-                if (tid < S && ((done >> tid) & 1u)) next_id = atomicAdd(p.next_shot, 1ULL);
-                if (tid == 0) ctl->pad[0] = 0;                  // bit s: the residual of slot s anticommutes with a logical
-                // hard decisions of the finished slots, back in column order
-                for (int w = tid; w < S * p.nwn; w += NT) outbits[w] = p.const_bits[w % p.nwn];
-                __syncthreads();
+                if (lead && tid < S && ((done >> tid) & 1u)) next_id = atomicAdd(p.next_shot, 1ULL);
+                if (lead) {
+                    if (tid == 0) ctl->pad[0] = 0;              // bit s: the residual of slot s anticommutes with a logical
+                    // hard decisions of the finished slots, back in column order
+                    for (int w = tid; w < S * p.nwn; w += NT) outbits[w] = p.const_bits[w % p.nwn];
+                }
+                if (CL) cluster_sync_once_fenced(); else __syncthreads();
+                QD_TICK7(6);
                 {
                     int i = 0;
                     for (int r = tid; r < p.nrec; r += NT, ++i) {
                         const unsigned bits = (decbits >> (i * S)) & done;
                         if (bits) {
-                            const unsigned col = p.col_id[r];
+                            const unsigned col = colid[r];
                             if (col != 0xFFFFu) {
 #pragma unroll
                                 for (int s = 0; s < S; ++s)
-                                    if ((bits >> s) & 1u) atomicOr(&outbits[s * p.nwn + (col >> 5)], 1u << (col & 31));
+                                    if ((bits >> s) & 1u) {
+                                        if (!CL) atomicOr(&outbits[s * p.nwn + (col >> 5)], 1u << (col & 31));
+                                        else cl_red_or_u32(cl_map(smem_u32(&outbits[s * p.nwn + (col >> 5)]), 0u), 1u << (col & 31));
+                                    }
                             }
                         }
                     }
                 }
-                __syncthreads();
+                if (CL) cluster_sync_once_fenced(); else __syncthreads();
+                QD_TICK7(7);
+                if (lead) {
                 // all finished slots together: corrections out, residuals in place (each word by one thread)
                 for (int x = tid; x < S * p.corr_stride; x += NT) {
                     const int s = x / p.corr_stride, w = x - s * p.corr_stride;
@@ -524,6 +602,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                     }
                 }
                 __syncthreads();
+                QD_TICK7(8);
                 if (tid == 0) {
                     const unsigned failing = (unsigned)ctl->pad[0];
                     for (int s = 0; s < S; ++s) {
@@ -538,13 +617,15 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                         c_fail += f; c_shots += 1; c_nc += !conv; c_it += it;
                     }
                 }
+                }   // lead
                 __syncthreads();
-                if (tid < S && ((done >> tid) & 1u)) {
+                QD_TICK7(9);
+                if (lead && tid < S && ((done >> tid) & 1u)) {
                     const bool more = next_id < (unsigned long long)p.shots;
-                    ctl->shot[tid] = more ? (long long)next_id : -1;
-                    ctl->born[tid] = more ? T : BP_IDLE;
+                    set_slot(tid, more ? (long long)next_id : -1, more ? T : BP_IDLE);
                 }
-                __syncthreads();
+                if (CL) cluster_sync_once_fenced(); else __syncthreads();
+                QD_TICK7(10);
                 bool any_active = false;
 #pragma unroll
                 for (int s = 0; s < S; ++s) any_active |= ctl->born[s] != BP_IDLE;
@@ -554,6 +635,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
             }
         }
 
+        QD_TICK7(2);
         // ================================================================== bit pass
         {
             unsigned run = 0u, want = 0u;        // slots to update; slots whose soft output is written in this pass
@@ -571,8 +653,8 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                 uint32_t ea[VMAX], fa[VMAX];
                 load_record(r, ea, fa);
                 const real pj = prior_of(r);
-                const int deg = __shfl_sync(0xffffffffu, (int)__ldg(p.chunk_deg + (r >> 5)), 0);
-                const Bp7LlrOut lo{want ? p.llr : nullptr, p.col_id, p.n, p.llr_mode, want, ctl->shot};
+                const int deg = __shfl_sync(0xffffffffu, (int)__ldg(cdeg + (r >> 5)), 0);
+                const Bp7LlrOut lo{want ? p.llr : nullptr, colid, p.n, p.llr_mode, want, ctl->shot};
 #define QD_COL(D_) col_update<real, METHOD, (D_), VMAX, S, FB>(ea, fa, pj, i, run, decbits, lo, r)
                 switch (deg) {
                 case 1: QD_COL(1); break;
@@ -588,10 +670,23 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
 #undef QD_COL
             }
         }
+        QD_TICK7(3);
         if (tid == 0) ctl->unsat[ub ^ 1] = 0u;              // buffer of the next check pass
         publish_alpha(T + 1);
-        __syncthreads();
+        // (cluster mode: nobody exports into a mailbox that is still being read, nobody sets a flag that is being reset)
+        if (CL) cluster_sync_once_fenced(); else __syncthreads();
+        QD_TICK7(4);
+#ifdef QD_BP7_TIMING
+        ++n_iter;
+#endif
     }
+#ifdef QD_BP7_TIMING
+    if (blockIdx.x < 8 && (tid == 0 || tid == NT - 1))
+        printf("bp7 timing cta %d tid %d: check %lld export+bar %lld retire[pre %lld init %lld scatter %lld corr+logical %lld outputs %lld setslot %lld "
+               "refill %lld] bit %lld endbar %lld (iters %lld)\n", (int)blockIdx.x, tid,
+               tacc[0], tacc[1], tacc[2] - tacc[2], tacc[6], tacc[7], tacc[8], tacc[9], tacc[10], tacc[2], tacc[3], tacc[4], n_iter);
+#endif
+    if (CL) cluster_sync_once_fenced();                     // no CTA leaves while its shared memory may still be addressed
 
     if (tid == 0 && p.counters && c_shots) {
         atomicAdd((unsigned long long *)&p.counters[0], (unsigned long long)c_fail);

@@ -39,6 +39,48 @@ struct Bp7LayoutProblem {
     int vmax = 4, nb = 16;
 };
 
+// Kempe-chain edge colouring of a bipartite multigraph with maximum degree <= NB: edge e joins left vertex lv[e] and
+// right vertex rv[e]; returns a colour in [0, NB) per edge, no colour twice at a vertex (Koenig).
+inline std::vector<int> bp7_colour_bipartite(int nnz, int nleft, int nright, const std::vector<int> &lv, const std::vector<int> &rv,
+                                             int NB)
+{
+    std::vector<int> at_l((size_t)std::max(nleft, 1) * NB, -1), at_r((size_t)std::max(nright, 1) * NB, -1);   // edge using colour c at a vertex
+    std::vector<int> col(std::max(nnz, 1), -1);
+    auto free_colour = [&](const std::vector<int> &at, int v) {
+        for (int c = 0; c < NB; ++c) if (at[(size_t)v * NB + c] < 0) return c;
+        return -1;
+    };
+    std::vector<int> path;
+    for (int e = 0; e < nnz; ++e) {
+        const int u = lv[e], v = rv[e];
+        const int a = free_colour(at_l, u), b = free_colour(at_r, v);
+        if (a != b && at_r[(size_t)v * NB + a] >= 0) {
+            // colour a is taken at v: swap a <-> b along the alternating path that starts at v with
+            // its a-edge (it cannot reach u: u has no a-edge and the graph is bipartite)
+            path.clear();
+            int side = 1, w = v, c = a;                            // side 1: w is a right vertex
+            for (;;) {
+                const int f = side ? at_r[(size_t)w * NB + c] : at_l[(size_t)w * NB + c];
+                if (f < 0) break;
+                path.push_back(f);
+                w = side ? lv[f] : rv[f];
+                side ^= 1;
+                c = c == a ? b : a;
+            }
+            for (int f : path) { at_l[(size_t)lv[f] * NB + col[f]] = -1; at_r[(size_t)rv[f] * NB + col[f]] = -1; }
+            for (int f : path) {
+                col[f] = col[f] == a ? b : a;
+                at_l[(size_t)lv[f] * NB + col[f]] = f;
+                at_r[(size_t)rv[f] * NB + col[f]] = f;
+            }
+        }
+        col[e] = a;
+        at_l[(size_t)u * NB + a] = e;
+        at_r[(size_t)v * NB + a] = e;
+    }
+    return col;
+}
+
 inline Bp7Layout bp7_colour_layout(const Bp7LayoutProblem &P)
 {
     Bp7Layout L;
@@ -76,41 +118,7 @@ inline Bp7Layout bp7_colour_layout(const Bp7LayoutProblem &P)
                 rv[e] = (L.rec_of_col[j] / NB) * V + t;
             }
     }
-    // Kempe-chain edge colouring of the bipartite multigraph
-    std::vector<int> at_l((size_t)nleft * NB, -1), at_r((size_t)nright * NB, -1);   // edge using colour c at a vertex
-    std::vector<int> col(nnz, -1);
-    auto free_colour = [&](const std::vector<int> &at, int v) {
-        for (int c = 0; c < NB; ++c) if (at[(size_t)v * NB + c] < 0) return c;
-        return -1;
-    };
-    std::vector<int> path;
-    for (int e = 0; e < nnz; ++e) {
-        const int u = lv[e], v = rv[e];
-        const int a = free_colour(at_l, u), b = free_colour(at_r, v);
-        if (a != b && at_r[(size_t)v * NB + a] >= 0) {
-            // colour a is taken at v: swap a <-> b along the alternating path that starts at v with
-            // its a-edge (it cannot reach u: u has no a-edge and the graph is bipartite)
-            path.clear();
-            int side = 1, w = v, c = a;                            // side 1: w is a right vertex
-            for (;;) {
-                const int f = side ? at_r[(size_t)w * NB + c] : at_l[(size_t)w * NB + c];
-                if (f < 0) break;
-                path.push_back(f);
-                w = side ? lv[f] : rv[f];
-                side ^= 1;
-                c = c == a ? b : a;
-            }
-            for (int f : path) { at_l[(size_t)lv[f] * NB + col[f]] = -1; at_r[(size_t)rv[f] * NB + col[f]] = -1; }
-            for (int f : path) {
-                col[f] = col[f] == a ? b : a;
-                at_l[(size_t)lv[f] * NB + col[f]] = f;
-                at_r[(size_t)rv[f] * NB + col[f]] = f;
-            }
-        }
-        col[e] = a;
-        at_l[(size_t)u * NB + a] = e;
-        at_r[(size_t)v * NB + a] = e;
-    }
+    const std::vector<int> col = bp7_colour_bipartite(nnz, nleft, nright, lv, rv, NB);
     std::vector<int> used(NB, 0);
     for (int e = 0; e < nnz; ++e) {
         L.colour[e] = (uint8_t)col[e];

@@ -40,10 +40,26 @@ static bp7_kernel_fn pick7_s(int slots)
     }
 }
 
-bp7_kernel_fn QD_CAT(pick_bp7_, QD_INST_TAG)(int rd, int vmax, int slots, int irregular)
+// cluster mode (rows split over the CTAs of a thread-block cluster): the padded row degree 9 covers the spacetime
+// matrices it exists for, and any graph with rows up to 9 and columns up to 4 for the tests
+template <typename real, int M>
+static bp7_kernel_fn pick7_cluster(int rd, int vmax, int slots)
+{
+    if (rd != 9 || vmax != 4) return nullptr;
+    switch (slots) {
+    case 1: return bp7_kernel<real, M, 9, 4, 1, true, BP7_MAXT, 1, true>;
+    case 2: return bp7_kernel<real, M, 9, 4, 2, true, BP7_MAXT, 1, true>;
+    case 3: return bp7_kernel<real, M, 9, 4, 3, true, BP7_MAXT, 1, true>;
+    case 4: return bp7_kernel<real, M, 9, 4, 4, true, BP7_MAXT, 1, true>;
+    default: return nullptr;
+    }
+}
+
+bp7_kernel_fn QD_CAT(pick_bp7_, QD_INST_TAG)(int rd, int vmax, int slots, int irregular, int cluster)
 {
     typedef QD_INST_REAL real;
     constexpr int M = QD_INST_METHOD;
+    if (cluster) return pick7_cluster<real, M>(rd, vmax, slots);
     switch ((irregular ? 10000 : 0) + rd * 100 + vmax) {
     case 704: return pick7_s<real, M, 7, 4, false>(slots);
     case 10904: return pick7_s<real, M, 9, 4, true>(slots);      // spacetime matrices of (3,4) HGP codes

@@ -15,6 +15,7 @@
 
 #include "bp7_kernel.cuh"
 #include "bp7_layout.h"
+#include "bp7_cluster_layout.h"
 #include "bp_pick.h"
 #include "bpg_kernel.cuh"
 #include "bpc_kernel.cuh"
@@ -328,6 +329,10 @@ struct qd_bp {
     // cluster kernel (bpc_kernel.cuh): messages spread over the shared memories of `cl_C` CTAs
     int cluster = 0, cl_C = 0, cl_max_edges = 0, cl_max_rows = 0, cl_max_cols = 0, cl_max_cedges = 0, cl_nwpos = 0, cl_clusters = 0;
     DevBuf dc_row_lo, dc_row_start, dc_edge_pos, dc_lc_lo, dc_lc_col, dc_lc_ptr, dc_desc, dc_word_lo, dc_col_pos, dc_prior;
+    // cluster mode of the row-regular kernel (bp7_kernel.cuh, CL): rows split over `cl7_C` CTAs, replicas + mailboxes for cut columns
+    int cl7 = 0, cl7_C = 0, cl7_clusters = 0;
+    Bp7ClusterPlan cl7_plan;
+    DevBuf d7c_row0, d7c_rows, d7c_nexp, d7c_export;
     int llr_mode = 0;      // what d_llr receives (0: log-ratio every iteration, 1: raw soft output of the last iteration)
     DevBuf d7_table, d7_row_table, d7_chunk_deg, d7_prior_rec, d7_col_id, d7_const_bits;
     // host-buffer pipeline state
@@ -713,10 +718,10 @@ static bp_kernel_fn bp_kernel_for(const qd_bp *d)
 static bp7_kernel_fn bp7_kernel_for(const qd_bp *d, int slots)
 {
     if (d->precision == QD_PREC_F64)
-        return d->method == QD_BP_MIN_SUM ? pick_bp7_f64_ms(d->rd, d->vmax, slots, d->v7_irreg)
-                                          : pick_bp7_f64_ps(d->rd, d->vmax, slots, d->v7_irreg);
-    return d->method == QD_BP_MIN_SUM ? pick_bp7_f32_ms(d->rd, d->vmax, slots, d->v7_irreg)
-                                      : pick_bp7_f32_ps(d->rd, d->vmax, slots, d->v7_irreg);
+        return d->method == QD_BP_MIN_SUM ? pick_bp7_f64_ms(d->rd, d->vmax, slots, d->v7_irreg, d->cl7)
+                                          : pick_bp7_f64_ps(d->rd, d->vmax, slots, d->v7_irreg, d->cl7);
+    return d->method == QD_BP_MIN_SUM ? pick_bp7_f32_ms(d->rd, d->vmax, slots, d->v7_irreg, d->cl7)
+                                      : pick_bp7_f32_ps(d->rd, d->vmax, slots, d->v7_irreg, d->cl7);
 }
 
 static size_t bp_smem(const qd_bp *d, int slots, bool stage)
@@ -955,6 +960,218 @@ static int bp7_configure(qd_bp *d, int threads, int slots, int ctas)
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// cluster mode of the row-regular kernel (bp7_kernel.cuh, CL; plan: bp7_cluster_layout.h)
+// ---------------------------------------------------------------------------------------------
+static const int kBp7cSlots[] = {4, 3, 2, 1};
+constexpr int BP7C_RD = 9, BP7C_V = 4;
+
+static bool bp7c_graph_ok(const qd_bp *d)
+{
+    const GraphDev &gd = d->g->dev;
+    return !d->g->big && gd.max_row_deg >= 2 && gd.max_row_deg <= BP7C_RD && gd.max_col_deg >= 1 && gd.max_col_deg <= BP7C_V &&
+           gd.m >= 64 && gd.n < 65535;
+}
+
+static Bp7ClusterPlan bp7c_plan(qd_bp *d, int C)
+{
+    qd_graph *g = d->g;
+    Bp7ClusterProblem P;
+    P.m = g->dev.m; P.n = g->dev.n;
+    P.row_ptr = g->row_ptr.data(); P.col_idx = g->col_idx.data(); P.col_ptr = g->col_ptr.data();
+    P.csc_row = reinterpret_cast<const int32_t *>(g->csc_row.data()); P.csc_k = g->csc_k.data();
+    P.vmax = BP7C_V; P.rd = BP7C_RD; P.nb = d->precision == QD_PREC_F64 ? 16 : 32;
+    return bp7_cluster_plan(P, C);
+}
+
+static size_t bp7c_smem(const qd_bp *d, const Bp7ClusterPlan &plan, int slots, bool staged)
+{
+    return bp7_smem_layout(plan.m_max, plan.nrec, d->g->dev.nwn, plan.lines, BP7C_RD, BP7C_V, slots,
+                           d->precision == QD_PREC_F64 ? 8 : 4, staged).total;
+}
+
+static bool bp7c_geometry_ok(const qd_bp *d, const Bp7ClusterPlan &plan, int slots, int threads)
+{
+    const Bp7SmemLayout SL = bp7_smem_layout(plan.m_max, plan.nrec, d->g->dev.nwn, plan.lines, BP7C_RD, BP7C_V, slots,
+                                             d->precision == QD_PREC_F64 ? 8 : 4, false);
+    if (SL.msg_elems > 65535 || (plan.m_max + 1) * bp7_flag_pitch(slots, BP7C_RD) > 65535) return false;
+    if (threads < 32 || threads > BP7_MAXT || threads % 32) return false;
+    if (((plan.m32 + threads - 1) / threads) * slots > 32) return false;
+    if (((plan.nrec + threads - 1) / threads) * slots > 32) return false;
+    return true;
+}
+
+static int bp7c_pick_threads(const qd_bp *d, const Bp7ClusterPlan &plan, int S)
+{
+    int best = 0; long best_cost = -1;
+    for (int t = 32; t <= BP7_MAXT; t += 32) {
+        if (!bp7c_geometry_ok(d, plan, S, t)) continue;
+        const long cost = (long)((plan.m32 + t - 1) / t) * 4 * BP7C_RD + (long)((plan.nrec + t - 1) / t) * 9;
+        const long score = cost * 4096 + t;
+        if (best_cost < 0 || score < best_cost) { best_cost = score; best = t; }
+    }
+    return best;
+}
+
+// rough throughput of a geometry: shots in flight per SM, discounted for the shallow software pipeline of few slots
+static double bp7_geometry_score(int slots, int ctas_per_cluster)
+{
+    static const double eff[5] = {0.0, 0.70, 0.88, 0.96, 1.0};
+    return (double)slots / ctas_per_cluster * eff[std::min(slots, 4)];
+}
+
+// build and upload the per-rank tables of the plan for `slots` shots per cluster
+static int bp7c_prepare(qd_bp *d, int slots)
+{
+    qd_graph *g = d->g;
+    const GraphDev &gd = g->dev;
+    const Bp7ClusterPlan &plan = d->cl7_plan;
+    const int C = plan.C, V = BP7C_V, RD = BP7C_RD, S = slots, NB = plan.nb, RB = 128 / NB;
+    const int FP = bp7_flag_pitch(S, RD), FB = bp7_flag_record(RD), RQ = (RD + 3) / 4;
+    const int nrec = plan.nrec, m32 = plan.m32, M = plan.m_max;
+    auto elem = [&](const Bp7Pos &ps) { return ps.line * NB * S + ps.colour; };
+    auto scratch = [&](int lane) { return plan.lines * NB * S + (lane % NB); };
+    std::vector<uint32_t> const_bits(std::max(gd.nwn, 1), 0u);
+    for (int j = 0; j < gd.n; ++j)
+        if (g->col_ptr[j + 1] == g->col_ptr[j]) {
+            const double pr = d->prior_dom[j];
+            if (d->method == QD_BP_MIN_SUM ? pr <= 0.0 : pr >= 1.0) const_bits[j >> 5] |= 1u << (j & 31);
+        }
+    std::vector<uint16_t> table((size_t)C * nrec * 2 * V, 0), col_id((size_t)C * nrec, 0xFFFF);
+    std::vector<uint8_t> chunk_deg((size_t)C * (nrec / 32), 0);
+    std::vector<double> prior_rec((size_t)C * nrec, d->prior_dom[0]);
+    std::vector<uint32_t> row_table((size_t)C * m32 * RQ * 4, 0u);
+    std::vector<int32_t> row0(C), rows(C), nexp(C);
+    const int exp_stride = std::max(plan.nexp_max, 1);
+    std::vector<uint2> exports((size_t)C * exp_stride, make_uint2(0u, 0u));
+    for (int c = 0; c < C; ++c) {
+        const Bp7ClusterRank &R = plan.rank[c];
+        row0[c] = R.row0; rows[c] = R.rows; nexp[c] = (int)R.exports.size();
+        for (int r = 0; r < nrec; ++r) {
+            uint16_t *mq = &table[((size_t)c * nrec + r) * 2 * V], *fq = mq + V;
+            const int j = r < R.nrec ? R.rec_col[r] : -1;
+            for (int t = 0; t < V; ++t) {
+                const Bp7Pos ps = r < R.nrec ? R.rec_pos[(size_t)r * V + t] : Bp7Pos();
+                mq[t] = (uint16_t)(ps.line >= 0 ? elem(ps) : scratch(r));
+                const int fr = r < R.nrec ? R.rec_flag_row[(size_t)r * V + t] : -1;
+                fq[t] = (uint16_t)(fr >= 0 ? fr * FP + R.rec_flag_k[(size_t)r * V + t] : M * FP + (t % FB));
+            }
+            if (j >= 0) {
+                if (R.rec_owner[r]) col_id[(size_t)c * nrec + r] = (uint16_t)j;
+                prior_rec[(size_t)c * nrec + r] = d->prior_dom[j];
+            }
+        }
+        for (int q = 0; q < R.nrec / 32; ++q) chunk_deg[(size_t)c * (nrec / 32) + q] = R.chunk_deg[q];
+        for (int r = 0; r < m32; ++r)
+            for (int k = 0; k < RQ * 4; ++k) {
+                const Bp7Pos ps = (r < R.rows && k < RD) ? R.row_pos[(size_t)r * RD + k] : Bp7Pos();
+                uint32_t v = (uint32_t)((ps.line >= 0 ? elem(ps) : scratch(r)) * RB);
+                if (r < R.rows && ps.line < 0) v |= 0x80000000u;       // no such edge: reads as the neutral message
+                row_table[((size_t)c * m32 + r) * RQ * 4 + k] = v;
+            }
+        for (size_t x = 0; x < R.exports.size(); ++x) {
+            const auto &e = R.exports[x];
+            exports[(size_t)c * exp_stride + x] = make_uint2((uint32_t)elem(e.src) | ((uint32_t)elem(e.dst) << 16), (uint32_t)e.rank);
+        }
+    }
+    d->v7_nrec = nrec;
+    d->v7_lines = plan.lines;
+    int rc;
+    if ((rc = upload(d->d7_table, table)) || (rc = upload(d->d7_row_table, row_table)) || (rc = upload(d->d7_col_id, col_id)) ||
+        (rc = upload(d->d7_chunk_deg, chunk_deg)) || (rc = upload(d->d7_const_bits, const_bits)) || (rc = upload(d->d7c_row0, row0)) ||
+        (rc = upload(d->d7c_rows, rows)) || (rc = upload(d->d7c_nexp, nexp)) || (rc = upload(d->d7c_export, exports)))
+        return rc;
+    if (d->precision == QD_PREC_F64) {
+        if ((rc = upload(d->d7_prior_rec, prior_rec))) return rc;
+    } else {
+        std::vector<float> pf(prior_rec.begin(), prior_rec.end());
+        if ((rc = upload(d->d7_prior_rec, pf))) return rc;
+    }
+    return 0;
+}
+
+static void bp7c_launch_config(const qd_bp *d, int C, int threads, size_t smem, unsigned grid, cudaStream_t st, cudaLaunchConfig_t &cfg,
+                               cudaLaunchAttribute *attr)
+{
+    (void)d;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+}
+
+// choose (cluster size, slots, threads) for the cluster mode (0 = choose) and upload its tables.  On success d->cl7 = 1 and
+// d->rd / vmax / v7_irreg describe the compiled cluster variant; *score (optional) receives bp7_geometry_score.
+static int bp7c_configure(qd_bp *d, int want_C, int want_slots, int want_threads, double *score, bool any_cut = false)
+{
+    if (!bp7c_graph_ok(d)) return fail(QD_EUNSUP, "cluster mode of the row-regular BP kernel: rows up to 9, columns up to 4 edges");
+    const size_t budget = (size_t)d->g->smem_optin;
+    const bool dbg = getenv("QD_BPC_DEBUG") != nullptr;
+    const int save_rd = d->rd, save_vmax = d->vmax, save_irreg = d->v7_irreg, save_cl7 = d->cl7;
+    d->rd = BP7C_RD; d->vmax = BP7C_V; d->v7_irreg = 1; d->cl7 = 1;
+    auto restore = [&]() { d->rd = save_rd; d->vmax = save_vmax; d->v7_irreg = save_irreg; d->cl7 = save_cl7; };
+    double best_score = -1.0;
+    int best_C = 0, best_S = 0, best_T = 0, best_staged = 0, best_clusters = 0;
+    size_t best_smem = 0;
+    Bp7ClusterPlan best_plan;
+    for (int C = 2; C <= 8; ++C) {
+        if (want_C > 0 && C != want_C) continue;
+        if (d->g->dev.m < 32 * C) continue;
+        Bp7ClusterPlan plan = bp7c_plan(d, C);
+        if (!plan.ok) continue;
+        {
+            qd_graph *g = d->g;
+            Bp7ClusterProblem P;
+            P.m = g->dev.m; P.n = g->dev.n;
+            P.row_ptr = g->row_ptr.data(); P.col_idx = g->col_idx.data(); P.col_ptr = g->col_ptr.data();
+            P.csc_row = reinterpret_cast<const int32_t *>(g->csc_row.data()); P.csc_k = g->csc_k.data();
+            P.vmax = BP7C_V; P.rd = BP7C_RD; P.nb = plan.nb;
+            if (bp7_cluster_plan_errors(P, plan) != 0) { restore(); return fail(QD_ECUDA, "cluster plan failed its self-check"); }
+        }
+        // a split that cuts a large part of the columns moves the messages through the cluster window instead of shared
+        // memory: only splits along the block structure of the matrix are worth it (unless the caller insists)
+        if (!any_cut && want_C <= 0 && plan.mailbox_elems * 3 > plan.local_edges) continue;
+        for (int S : kBp7cSlots) {
+            if (want_slots > 0 && S != want_slots) continue;
+            if (!bp7_kernel_for(d, S)) continue;
+            int staged = 1;
+            size_t smem = bp7c_smem(d, plan, S, true);
+            if (smem > budget) { staged = 0; smem = bp7c_smem(d, plan, S, false); }
+            if (smem > budget) continue;
+            const int T = want_threads > 0 ? want_threads : bp7c_pick_threads(d, plan, S);
+            if (!T || !bp7c_geometry_ok(d, plan, S, T)) continue;
+            bp7_kernel_fn fn = bp7_kernel_for(d, S);
+            if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
+            cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+            bp7c_launch_config(d, C, T, smem, (unsigned)(C * std::max(1, d->g->sm_count / C)), nullptr, cfg, attr);
+            int nclusters = 0;
+            const cudaError_t oe = cudaOccupancyMaxActiveClusters(&nclusters, fn, &cfg);
+            if (dbg) fprintf(stderr, "bp7c: C=%d S=%d T=%d smem=%zu staged=%d cut=%ld/%ld clusters=%d (%s)\n", C, S, T, smem, staged,
+                             plan.mailbox_elems, plan.local_edges, nclusters, cudaGetErrorString(oe));
+            if (oe != cudaSuccess || nclusters < 1) { cudaGetLastError(); continue; }
+            // SMs actually used by whole clusters count, not the nominal S / C
+            const double sc = bp7_geometry_score(S, C) * ((double)nclusters * C / std::max(1, d->g->sm_count));
+            if (sc > best_score) {
+                best_score = sc; best_C = C; best_S = S; best_T = T; best_staged = staged; best_smem = smem; best_clusters = nclusters;
+                best_plan = plan;
+            }
+            break;                                                // fewer slots of the same split are never better
+        }
+    }
+    if (best_C == 0) { restore(); return fail(QD_EUNSUP, "cluster mode of the row-regular BP kernel: no split of the rows fits"); }
+    d->cl7_plan = std::move(best_plan);
+    d->cl7_C = best_C; d->cl7_clusters = best_clusters;
+    int rc = bp7c_prepare(d, best_S);
+    if (rc) { restore(); return rc; }
+    d->threads = best_T; d->slots = best_S; d->ctas_per_sm = 1; d->groups = 1; d->smem = best_smem; d->v7_staged = best_staged;
+    if (score) *score = best_score;
+    return 0;
+}
+
 
 template <typename real, int METHOD>
 static void (*bpc_fn())(const BpcParams) { return bpc_kernel<real, METHOD>; }
@@ -1094,12 +1311,22 @@ static int bpc_prepare(qd_bp *d)
 // pick the kernel family and its default launch geometry.  Row-regular graphs with a compiled
 // (row degree, column tile) pair take the thread-owned-state kernel (bp7_kernel.cuh) when they fit;
 // everything else the generic kernel (bp_kernel.cuh).
-static int bp_choose_kernel(qd_bp *d, bool allow_regular, bool family_global = false, bool family_cluster = false)
+// regular_cluster: 1 = force the cluster mode of the row-regular kernel, -1 = never use it, 0 = when it pays
+static int bp_choose_kernel(qd_bp *d, bool allow_regular, bool family_global = false, bool family_cluster = false,
+                            int regular_cluster = 0)
 {
+    const bool family_regular_cluster = regular_cluster > 0;
     const GraphDev &gd = d->g->dev;
     int rc;
     d->v7 = 0;
+    d->cl7 = 0;
     d->global_mem = 0;
+    d->cluster = 0;
+    if (family_regular_cluster) {
+        if ((rc = bp7c_configure(d, 0, 0, 0, nullptr, true))) return rc;       // forced: any graph the kernel can hold
+        d->v7 = 1;
+        return 0;
+    }
     const bool shared_ok = !d->g->big && gd.max_col_deg <= 16 && !(d->method == QD_BP_PRODUCT_SUM && gd.max_row_deg > 16);
     if (family_global || family_cluster || !shared_ok) { d->global_mem = 1; }
     else if (allow_regular && gd.max_row_deg >= 2 && gd.max_col_deg >= 1 && gd.max_col_deg <= 8) {
@@ -1121,6 +1348,24 @@ static int bp_choose_kernel(qd_bp *d, bool allow_regular, bool family_global = f
             d->slots = 0;
             d->d7_table.alloc(0);
             if (bp7_configure(d, 0, 0, 0) != 0) d->v7 = 0;     // does not fit: generic kernel
+        }
+        // Graphs that leave one SM with one or two shots in flight, or none: split the rows over a thread-block cluster
+        // when the matrix has the block structure for it (spacetime matrices) and more shots per SM come out of it.
+        if (regular_cluster == 0 && (!d->v7 || d->slots <= 2) && bp7c_graph_ok(d)) {
+            const double single = d->v7 ? bp7_geometry_score(d->slots, 1) : 0.0;
+            const int save_threads = d->threads, save_slots = d->slots, save_ctas = d->ctas_per_sm, save_staged = d->v7_staged;
+            const int save_rd = d->rd, save_vmax = d->vmax, save_irreg = d->v7_irreg;
+            const size_t save_smem = d->smem;
+            double sc = 0.0;
+            if (bp7c_configure(d, 0, 0, 0, &sc) == 0 && sc > 1.1 * single) {
+                d->v7 = 1;                                        // bp7c_configure left d->cl7 = 1 and the cluster tables
+            } else {
+                d->cl7 = 0;
+                d->rd = save_rd; d->vmax = save_vmax; d->v7_irreg = save_irreg;
+                d->threads = save_threads; d->slots = save_slots; d->ctas_per_sm = save_ctas; d->v7_staged = save_staged; d->smem = save_smem;
+                // the two modes share the table buffers: put the single-CTA tables back
+                if (d->v7 && (rc = bp7_prepare(d, d->slots))) return rc;
+            }
         }
     }
     if (!d->v7 && !d->global_mem) {
@@ -1147,14 +1392,50 @@ static int bp_choose_kernel(qd_bp *d, bool allow_regular, bool family_global = f
     return 0;
 }
 
+// host-only: plan the cluster split of a graph and run the plan's self-check (no device needed)
+extern "C" int qd_bp_cluster_plan_check(int32_t m, int32_t n, const int32_t *row_ptr, const int32_t *col_idx, int32_t ctas,
+                                        int32_t banks, int64_t *stats)
+{
+    if (m <= 0 || n <= 0 || !row_ptr || !col_idx || !stats) return fail(QD_EINVAL, "bad arguments");
+    if (banks != 16 && banks != 32) return fail(QD_EINVAL, "banks must be 16 (8-byte messages) or 32 (4-byte messages)");
+    const int nnz = row_ptr[m];
+    std::vector<int32_t> col_ptr(n + 1, 0), csc_row(std::max(nnz, 1));
+    std::vector<uint8_t> csc_k(std::max(nnz, 1));
+    for (int r = 0; r < m; ++r)
+        for (int e = row_ptr[r]; e < row_ptr[r + 1]; ++e) {
+            if (col_idx[e] < 0 || col_idx[e] >= n) return fail(QD_EINVAL, "column index out of range");
+            if (e > row_ptr[r] && col_idx[e] <= col_idx[e - 1]) return fail(QD_EINVAL, "column indices must be sorted and distinct within a row");
+            ++col_ptr[col_idx[e] + 1];
+        }
+    for (int j = 0; j < n; ++j) col_ptr[j + 1] += col_ptr[j];
+    {
+        std::vector<int32_t> fill(col_ptr.begin(), col_ptr.end() - 1);
+        for (int r = 0; r < m; ++r)
+            for (int e = row_ptr[r]; e < row_ptr[r + 1]; ++e) {
+                const int at = fill[col_idx[e]]++;
+                csc_row[at] = r; csc_k[at] = (uint8_t)(e - row_ptr[r]);
+            }
+    }
+    Bp7ClusterProblem P;
+    P.m = m; P.n = n; P.row_ptr = row_ptr; P.col_idx = col_idx; P.col_ptr = col_ptr.data(); P.csc_row = csc_row.data(); P.csc_k = csc_k.data();
+    P.vmax = BP7C_V; P.rd = BP7C_RD; P.nb = banks;
+    const Bp7ClusterPlan plan = bp7_cluster_plan(P, ctas);
+    if (!plan.ok) return fail(QD_EUNSUP, "no cluster plan: rows up to 9 and columns up to 4 edges, 2 <= ctas <= rows");
+    stats[0] = bp7_cluster_plan_errors(P, plan);
+    stats[1] = plan.local_edges; stats[2] = plan.mailbox_elems; stats[3] = plan.lines;
+    stats[4] = plan.nrec; stats[5] = plan.m_max; stats[6] = plan.nexp_max; stats[7] = 0;
+    return 0;
+}
+
 extern "C" int qd_bp_select_kernel(qd_bp *d, int32_t family)
 {
     if (!d) return fail(QD_EINVAL, "NULL handle");
-    if (family != 0 && family != 5 && family != 6 && family != 7 && family != 8)
-        return fail(QD_EINVAL, "kernel family must be 0 (automatic), 5 (global memory), 6 (generic), 7 (thread-owned state) or 8 (cluster)");
+    if (family != 0 && family != 5 && family != 6 && family != 7 && family != 8 && family != 9)
+        return fail(QD_EINVAL, "kernel family must be 0 (automatic), 5 (global memory), 6 (generic), 7 (thread-owned state), 8 (cluster) "
+                               "or 9 (thread-owned state over a cluster)");
     int rc = use_device(d->g->device);
     if (rc) return rc;
-    if ((rc = bp_choose_kernel(d, family != 6, family == 5, family == 8))) return rc;
+    if ((rc = bp_choose_kernel(d, family != 6, family == 5, family == 8, family == 9 ? 1 : (family == 7 ? -1 : 0)))) return rc;
     if (family == 8 && !d->cluster) return fail(QD_EUNSUP, "the cluster BP kernel does not support this graph");
     if (family == 7 && !d->v7) return fail(QD_EUNSUP, "the thread-owned-state BP kernel does not support this graph");
     if (family == 6 && d->global_mem) return fail(QD_EUNSUP, "the generic shared-memory BP kernel does not support this graph");
@@ -1164,7 +1445,7 @@ extern "C" int qd_bp_select_kernel(qd_bp *d, int32_t family)
 extern "C" int qd_bp_get_kernel(qd_bp *d, int32_t *family, int32_t *row_degree, int32_t *column_tile)
 {
     if (!d) return fail(QD_EINVAL, "NULL handle");
-    if (family) *family = d->cluster ? 8 : (d->global_mem ? 5 : (d->v7 ? 7 : 6));
+    if (family) *family = d->cluster ? 8 : (d->global_mem ? 5 : (d->v7 ? (d->cl7 ? 9 : 7) : 6));
     if (row_degree) *row_degree = d->rd;
     if (column_tile) *column_tile = d->vmax;
     return 0;
@@ -1242,6 +1523,9 @@ extern "C" int qd_bp_configure(qd_bp *d, int32_t threads, int32_t slots, int32_t
         if (teams > 1) return fail(QD_EINVAL, "the row-regular BP kernel runs one team per CTA");
         int rc = use_device(d->g->device);
         if (rc) return rc;
+        if (d->cl7)          // cluster mode: `ctas_per_sm` is read as the cluster size (CTAs per shot group)
+            return bp7c_configure(d, ctas_per_sm > 0 ? ctas_per_sm : d->cl7_C, slots > 0 ? slots : d->slots,
+                                  threads > 0 ? threads : (slots > 0 ? 0 : d->threads), nullptr, true);
         return bp7_configure(d, threads > 0 ? threads : (slots > 0 ? 0 : d->threads), slots > 0 ? slots : d->slots,
                              ctas_per_sm > 0 ? ctas_per_sm : (slots > 0 || threads > 0 ? 0 : d->ctas_per_sm));
     }
@@ -1267,7 +1551,8 @@ extern "C" int qd_bp_get_config(qd_bp *d, int32_t *threads, int32_t *slots, int3
     if (slots) *slots = d->slots;
     if (ctas_per_sm) *ctas_per_sm = d->ctas_per_sm;
     if (smem_bytes) *smem_bytes = (int32_t)d->smem;
-    if (grid) *grid = d->g->sm_count * d->ctas_per_sm;
+    if (grid) *grid = d->cl7 ? d->cl7_clusters * d->cl7_C : d->g->sm_count * d->ctas_per_sm;
+    if (ctas_per_sm && d->cl7) *ctas_per_sm = d->cl7_C;       // cluster mode: CTAs per cluster
     return 0;
 }
 
@@ -1351,12 +1636,17 @@ static int bp_launch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int6
     }
     if (d->v7) {
         Bp7Params q{};
-        q.m = g.m; q.n = g.n; q.nwm = g.nwm; q.nwn = g.nwn;
-        q.m32 = (g.m + 31) / 32 * 32;
+        q.m = d->cl7 ? d->cl7_plan.m_max : g.m; q.n = g.n; q.nwm = g.nwm; q.nwn = g.nwn;
+        q.m32 = (q.m + 31) / 32 * 32;
         q.nrec = d->v7_nrec;
         q.lines = d->v7_lines;
+        if (d->cl7) {
+            q.cl_C = d->cl7_C;
+            q.cl_row0 = d->d7c_row0.as<int32_t>(); q.cl_rows = d->d7c_rows.as<int32_t>(); q.cl_nexp = d->d7c_nexp.as<int32_t>();
+            q.cl_export = d->d7c_export.as<uint2>(); q.cl_exp_stride = std::max(d->cl7_plan.nexp_max, 1);
+        }
         {
-            const Bp7SmemLayout SL = bp7_smem_layout(g.m, d->v7_nrec, g.nwn, d->v7_lines, d->rd, d->vmax, d->slots,
+            const Bp7SmemLayout SL = bp7_smem_layout(q.m, d->v7_nrec, g.nwn, d->v7_lines, d->rd, d->vmax, d->slots,
                                                      d->precision == QD_PREC_F64 ? 8 : 4, d->v7_staged != 0);
             q.off_flags = (int)SL.flags; q.off_table = (int)SL.table; q.off_out = (int)SL.out; q.off_ctl = (int)SL.ctl;
         }
@@ -1386,6 +1676,13 @@ static int bp_launch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int6
         QD_CUDA(cudaFuncSetAttribute(fn7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem));
         QD_CUDA(cudaMemsetAsync(q.next_shot, 0, sizeof(unsigned long long), st));
         const long long want7 = (shots + d->slots - 1) / d->slots;
+        if (d->cl7) {
+            const long long nclusters = std::min<long long>(d->cl7_clusters, want7);
+            cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+            bp7c_launch_config(d, d->cl7_C, d->threads, d->smem, (unsigned)(nclusters * d->cl7_C), st, cfg, attr);
+            QD_CUDA(cudaLaunchKernelEx(&cfg, fn7, q));
+            return 0;
+        }
         const unsigned grid7 = (unsigned)std::min<long long>((long long)d->g->sm_count * d->ctas_per_sm, want7);
         fn7<<<grid7, d->threads, d->smem, st>>>(q);
         QD_CUDA(cudaGetLastError());

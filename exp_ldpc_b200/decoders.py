@@ -170,7 +170,7 @@ class bp_decoder:
 
     Extra keywords: ``precision`` ('f64' reproduces the reference's double-precision operation
     order bit for bit; 'f32' is faster, not reproducible), ``device``, ``kernel`` ('auto' |
-    'regular' | 'generic' | 'cluster' | 'global': which CUDA kernel family decodes; the results are identical).
+    'regular' | 'regular_cluster' | 'generic' | 'cluster' | 'global': which CUDA kernel family decodes; the results are identical).
     """
 
     def __init__(self, parity_check_matrix, error_rate=None, max_iter=0, bp_method=0, ms_scaling_factor=1.0,
@@ -205,7 +205,7 @@ class bp_decoder:
         _lib.check(_lib.lib().qd_bp_create(self.graph.handle, _lib.ptr(self.channel_probs), int(max_iter), self.bp_method,
                                            self.ms_scaling_factor, self.precision, C.byref(self._h)))
         if kernel != "auto":
-            _lib.check(_lib.lib().qd_bp_select_kernel(self._h, {"global": 5, "generic": 6, "regular": 7, "cluster": 8}[kernel]))
+            _lib.check(_lib.lib().qd_bp_select_kernel(self._h, {"global": 5, "generic": 6, "regular": 7, "cluster": 8, "regular_cluster": 9}[kernel]))
         self.converge = 0
         self.iter = 0
         self.bp_decoding = np.zeros(self.n, dtype=np.int64)
@@ -238,7 +238,7 @@ class bp_decoder:
         out = dict(zip(("threads", "slots", "ctas_per_sm", "teams", "smem_bytes", "grid"), (x.value for x in v)))
         k = [C.c_int32() for _ in range(3)]
         _lib.check(_lib.lib().qd_bp_get_kernel(self._h, *[C.byref(x) for x in k]))
-        out["kernel"] = {5: "global", 6: "generic", 7: "regular", 8: "cluster"}[k[0].value]
+        out["kernel"] = {5: "global", 6: "generic", 7: "regular", 8: "cluster", 9: "regular_cluster"}[k[0].value]
         return out
 
     # ---- the ldpc call

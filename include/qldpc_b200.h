@@ -150,9 +150,21 @@ int qd_bp_get_config(qd_bp *d, int32_t *threads, int32_t *slots, int32_t *ctas_p
 /* Kernel family (testing / tuning).  qd_bp_create picks automatically: 7 = thread-owned-state
  * shared-memory kernel (a variant is compiled for the graph's degrees), 6 = generic shared-memory
  * kernel, 8 = messages spread over the shared memories of a thread-block cluster of 2 / 4 / 8 SMs
- * (graphs too large or too dense for one SM), 5 = messages in global memory (graphs beyond that; slower).
- * select: 0 = automatic, 5 / 6 / 7 / 8 = force; resets the launch geometry. */
+ * (graphs too large or too dense for one SM), 5 = messages in global memory (graphs beyond that; slower),
+ * 9 = the thread-owned-state kernel over a thread-block cluster: the rows are split over 2..8 CTAs, columns cut by the
+ * split are updated redundantly in every CTA that holds one of their edges and their check->bit messages travel through
+ * distributed shared memory (block-structured matrices that leave one SM with at most two shots in flight: the
+ * spacetime matrices of spacetime_code.py:46-75; rows up to 9, columns up to 4 edges).  In that family qd_bp_configure /
+ * qd_bp_get_config read `ctas_per_sm` as the cluster size.
+ * select: 0 = automatic, 5 / 6 / 7 / 8 / 9 = force; resets the launch geometry. */
 int qd_bp_select_kernel(qd_bp *d, int32_t family);
+/* Host-only self-check of family 9's plan (no device needed): split the rows of the CSR graph over `ctas` CTAs, place the
+ * messages, and verify the plan (every edge local to exactly one CTA, every remote edge of a replica fed by exactly one
+ * export, every access bank-conflict free).  banks = 16 (8-byte messages) or 32 (4-byte).
+ * stats[8] = {errors (0 = consistent), local edges, mailbox elements, message lines per CTA, records per CTA,
+ *             rows per CTA, exports per CTA (largest), 0}. */
+int qd_bp_cluster_plan_check(int32_t m, int32_t n, const int32_t *row_ptr, const int32_t *col_idx, int32_t ctas,
+                             int32_t banks, int64_t *stats);
 int qd_bp_get_kernel(qd_bp *d, int32_t *family, int32_t *row_degree, int32_t *column_tile);
 
 /* Decode `shots` packed syndromes.  Required: d_synd, d_corr.  Optional (NULL to skip):

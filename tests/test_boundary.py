@@ -142,3 +142,53 @@ def test_p_sweep_cli_options_match_reference():
     for bad in ("0.1,0.2,3", "(0.2,0.1,3)", "(0.1,0.2,0)"):
         with pytest.raises(RuntimeError):
             parse_sweep_spec(bad)
+
+
+# ---- cluster mode of the row-regular BP kernel (family 9): the host-side plan checks itself without a GPU
+def _plan_check(h, ctas, banks=16):
+    import ctypes as C
+    from scipy import sparse
+    from exp_ldpc_b200 import _lib
+    h = sparse.csr_matrix(h)
+    h.sort_indices()
+    rp = np.ascontiguousarray(h.indptr, dtype=np.int32)
+    ci = np.ascontiguousarray(h.indices, dtype=np.int32)
+    stats = np.zeros(8, dtype=np.int64)
+    rc = _lib.lib().qd_bp_cluster_plan_check(h.shape[0], h.shape[1], _lib.ptr(rp), _lib.ptr(ci), ctas, banks, _lib.ptr(stats))
+    return rc, dict(zip(("errors", "local_edges", "mailbox", "lines", "nrec", "rows", "exports", "_"), stats.tolist()))
+
+
+@pytest.mark.parametrize("rounds,ctas", [(1, 2), (3, 2), (3, 4), (2, 3), (3, 3), (7, 8)])
+def test_cluster_plan_of_spacetime_matrices_is_consistent(built, code225, rounds, ctas):
+    """Rows of [blockdiag(H x (T+1)) | M] (spacetime_code.py:46-75) split over the CTAs of a cluster: every edge is local to
+    one CTA, every remote edge of a replica is fed by one export, all accesses are bank-conflict free; a split along the
+    rounds cuts only measurement columns."""
+    from exp_ldpc_b200.spacetime import SpacetimeCode
+    hz = code225.checks.z
+    m, n = hz.shape
+    h = SpacetimeCode(hz, rounds).spacetime_check_matrix
+    for banks in (16, 32):
+        rc, st = _plan_check(h, ctas, banks)
+        assert rc == 0 and st["errors"] == 0, st
+        assert st["local_edges"] == h.nnz
+        if (rounds + 1) % ctas == 0:
+            assert st["mailbox"] == 2 * (ctas - 1) * m       # one measurement column per check and boundary, a replica on either side
+            assert st["rows"] == (rounds + 1) // ctas * m
+
+
+def test_cluster_plan_of_an_unstructured_split_is_consistent(built, code225):
+    """A plain (3,4) HGP check matrix has no block structure: the split cuts most columns (replicas with several remote
+    edges, columns spanning three CTAs).  Slow on the GPU, but the plan must still be right."""
+    hz = code225.checks.z
+    for ctas in (2, 3):
+        rc, st = _plan_check(hz, ctas)
+        assert rc == 0 and st["errors"] == 0, st
+        assert st["local_edges"] == hz.nnz and st["mailbox"] > hz.nnz // 4
+
+
+def test_cluster_plan_rejects_what_the_kernel_cannot_hold(built):
+    from scipy import sparse
+    from exp_ldpc_b200 import _lib
+    dense_row = sparse.csr_matrix(np.ones((4, 12), dtype=np.uint8))      # rows of 12 edges > 9
+    rc, _ = _plan_check(dense_row, 2)
+    assert rc == _lib.QD_EUNSUP

@@ -93,9 +93,14 @@ def _run_gpu_case(name, codes, precision="f64", config=None, kernel="auto"):
     if decoder == "bp" and kernel != "auto":
         assert exp.decoder.config()["kernel"] == kernel
     if config and decoder == "bp":
+        from exp_ldpc_b200._lib import QdError, QD_EUNSUP
         try:
             exp.decoder.configure(**config)
         except ValueError as e:          # geometry not representable for this graph
+            pytest.skip(str(e))
+        except QdError as e:             # (cluster mode: too few rows for that many CTAs, or no room)
+            if e.code != QD_EUNSUP:
+                raise
             pytest.skip(str(e))
     return exp.run(shots, seed=seed, per_shot=True)
 
@@ -374,10 +379,12 @@ def test_spacetime_experiment_against_live_oracle(gpu, code225, rounds, method):
     opts = dict(max_iter=30, bp_method=method, ms_scaling_factor=0.0)
     shots = 256
     data_prior, meas_prior = 0.012, 0.02
-    for kernel in ("auto", "generic"):
+    for kernel in ("auto", "generic") + (("regular_cluster",) if rounds else ()):
         exp = SpacetimeExperiment(code225, rounds, data_prior, meas_prior, opts, kernel=kernel)
         if kernel == "auto":
             assert exp.decoder.config()["kernel"] == "regular"      # padded-row variant for T = 3
+        if kernel == "regular_cluster":
+            assert exp.decoder.config()["ctas_per_sm"] == 2          # two rounds per CTA for T = 3: only measurement columns are cut
         got = exp.run(shots, seed=21, per_shot=True)
         h_st = exp.spacetime.spacetime_check_matrix
         n, m = code225.num_qubits, code225.checks.z.shape[0]
@@ -823,16 +830,72 @@ def test_cluster_bp_kernel_matches_committed_golden_vectors(gpu, codes, name):
     assert np.array_equal(out["converged"], g[name + "_conv"])
 
 
-@pytest.mark.parametrize("kernel", ["auto", "global"])
+@pytest.mark.parametrize("name", _bp_case_names())
+def test_regular_cluster_bp_kernel_matches_committed_golden_vectors(gpu, codes, name):
+    """Every golden BP case replayed by the thread-owned-state kernel in cluster mode (forced).  These check matrices have
+    no block structure, so the row split cuts most columns: replicas with several remote edges, columns spanning three
+    CTAs, mailboxes as large as the local message arrays."""
+    g = np.load(os.path.join(GOLDEN, "decoder_vectors.npz"))
+    out = _run_gpu_case(name, codes, kernel="regular_cluster")
+    assert np.array_equal(np.packbits(out["decodings"], axis=1), g[name + "_dec"])
+    assert np.array_equal(out["iters"], g[name + "_iters"])
+    assert np.array_equal(out["fail"], g[name + "_fail"])
+    assert np.array_equal(out["converged"], g[name + "_conv"])
+
+
+@pytest.mark.parametrize("name", ["ms_sched_225", "ps_225", "ms_sched_1600"])
+@pytest.mark.parametrize("config", [dict(ctas_per_sm=2, slots=1), dict(ctas_per_sm=2, slots=4), dict(ctas_per_sm=3, slots=2),
+                                    dict(ctas_per_sm=4, slots=3), dict(ctas_per_sm=8, slots=2, threads=128),
+                                    dict(ctas_per_sm=5, slots=1, threads=64)])
+def test_regular_cluster_kernel_independent_of_cluster_geometry(gpu, codes, name, config):
+    """Cluster size (read from `ctas_per_sm` in this family), slots and threads change where the messages live and which
+    CTA updates which column, never the bits."""
+    g = np.load(os.path.join(GOLDEN, "decoder_vectors.npz"))
+    out = _run_gpu_case(name, codes, config=config, kernel="regular_cluster")
+    assert np.array_equal(np.packbits(out["decodings"], axis=1), g[name + "_dec"])
+    assert np.array_equal(out["iters"], g[name + "_iters"])
+    assert np.array_equal(out["fail"], g[name + "_fail"])
+
+
+def test_regular_cluster_kernel_soft_outputs_and_priors(gpu, code225):
+    """Per-column priors, product-sum and min-sum, soft outputs of the single-shot call, fp32: cluster mode equals the
+    single-CTA kernel bit for bit (same arithmetic, different placement)."""
+    from exp_ldpc_b200.decoders import bp_decoder
+    from exp_ldpc_b200.spacetime import SpacetimeCode
+    rng = np.random.default_rng(5)
+    h = SpacetimeCode(code225.checks.z, 1).spacetime_check_matrix
+    probs = rng.uniform(0.004, 0.05, h.shape[1])
+    err = (rng.random((300, h.shape[1])) < probs).astype(np.uint8)
+    synd = (err @ h.T.toarray()) % 2
+    for precision in ("f64", "f32"):
+        for method in ("ms", "ps"):
+            a = bp_decoder(h, channel_probs=probs, max_iter=12, bp_method=method, ms_scaling_factor=0.0, kernel="regular", precision=precision)
+            b = bp_decoder(h, channel_probs=probs, max_iter=12, bp_method=method, ms_scaling_factor=0.0, kernel="regular_cluster",
+                           precision=precision)
+            assert b.config()["kernel"] == "regular_cluster" and b.config()["ctas_per_sm"] == 2
+            ca, va, ia = a.decode_batch(synd)
+            cb, vb, ib = b.decode_batch(synd)
+            assert np.array_equal(ca, cb) and np.array_equal(va, vb) and np.array_equal(ia, ib), (precision, method)
+            assert 0 < int(va.sum()) < synd.shape[0] or method == "ps"
+            for s in (0, 7):
+                da, db = a.decode(synd[s]), b.decode(synd[s])
+                assert np.array_equal(da, db) and a.iter == b.iter and a.converge == b.converge
+                assert np.array_equal(a.log_prob_ratios, b.log_prob_ratios)
+
+
+@pytest.mark.parametrize("kernel", ["auto", "cluster", "global"])
 def test_large_graphs_take_the_cluster_kernel(gpu, code1600, kernel):
-    """Spacetime matrix of the n = 1600 code, T = 3: 26 k edges do not fit one SM in fp64; they are spread over
-    a cluster (automatic choice) or, forced, kept in global memory."""
+    """Spacetime matrix of the n = 1600 code, T = 3: 26 k edges do not fit one SM in fp64; the rows are split over a
+    cluster along the rounds and decoded by the thread-owned-state kernel (automatic choice), or, forced, by the generic
+    cluster kernel or out of global memory."""
     from exp_ldpc_b200.experiment import SpacetimeExperiment
     from oracle import pyoracle as po
     opts = dict(max_iter=8, bp_method="ms", ms_scaling_factor=0.0)
     exp = SpacetimeExperiment(code1600, 3, 0.004, 0.006, opts, kernel=kernel)
-    assert exp.decoder.config()["kernel"] == ("cluster" if kernel == "auto" else "global")
-    shots = 24
+    assert exp.decoder.config()["kernel"] == ("regular_cluster" if kernel == "auto" else kernel)
+    if kernel == "auto":
+        assert exp.decoder.config()["ctas_per_sm"] == 4              # one round per CTA
+    shots = 24 if kernel != "auto" else 2000                         # auto: more shots than slots in flight (refill path)
     got = exp.run(shots, seed=2, per_shot=True)
     h_st = exp.spacetime.spacetime_check_matrix
     m, n = code1600.checks.z.shape
