@@ -39,7 +39,7 @@ struct Bp7Params {
     int m, n, nwm, nwn;
     int m32;                    // rows rounded up to a multiple of 32
     int lines;                  // 128-byte message lines per slot
-    int off_flags, off_table, off_out, off_ctl;   // shared-memory carve-up (bp7_smem_layout), bytes
+    int off_flags, off_table, off_out, off_ctl, off_syn, off_cb;   // shared-memory carve-up (bp7_smem_layout), bytes
     int nrec;                   // column records (degree classes padded to multiples of 32)
     int max_iter;
     int staged;                 // record table copied to shared memory
@@ -49,7 +49,8 @@ struct Bp7Params {
     double prior0;              // the common prior (decoder domain) when uniform_prior
     double alpha_fixed;         // 0 => alpha_it = 1 - 2^-it
     const uint4 *table;         // VMAX/4 uint4 per record: u16 message element indices, then u16 flag offsets
-    const uint4 *row_table;     // (RD+3)/4 uint4 per row (m32 rows): byte offsets of the row's messages (slot 0)
+    const uint4 *row_table;     // bp7_row_quads uint4 per row (m32 rows): u16 element indices of the row's messages (slot 0),
+                                // then (rows of different degrees) a u16 mask of the missing edges
     const uint8_t *chunk_deg;   // [nrec / 32]
     const void *prior_rec;      // real[nrec], decoder domain
     const uint16_t *col_id;     // [nrec]; 0xFFFF = padding record
@@ -78,14 +79,22 @@ struct Bp7Ctl {
     long long shot[BP7_SMAX];
     int born[BP7_SMAX];         // see BpCtl::born
     unsigned unsat[2];          // bit s: slot s has an unsatisfied check (buffer T & 1)
-    int pad[2];
+    int pad[2];                 // pad[0] bit s: the residual of the shot draining from slot s anticommutes with a logical
     double alpha[BP7_SMAX];     // min-sum scaling factor of slot s in the coming check pass
+    long long resv[BP7_SMAX];   // the slot's next shot, drawn from the queue ahead of time (-1: none)
+    long long drain_shot[BP7_SMAX];   // the finished shot whose outputs are draining from slot s
+    int drain_it[BP7_SMAX], drain_conv[BP7_SMAX];
+    unsigned need_resv, fresh_resv;   // bit s: slot s wants a reservation / got one in this iteration (syndrome not staged yet)
+    int pad2[2];
 };
 
 struct Bp7SmemLayout {
-    size_t msg, flags, table, out, ctl, total;
+    size_t msg, flags, table, out, ctl, syn, cb, total;
     int msg_elems;              // elements of the message array (incl. scratch row)
 };
+
+// uint4 per row-table entry: RD 16-bit message positions, one more 16-bit word for the missing-edge mask of irregular rows
+__host__ __device__ constexpr int bp7_row_quads(int rd, bool irregular) { return (rd + (irregular ? 1 : 0) + 7) / 8; }
 
 // flag bytes of a row: S records of 8 (row degree <= 8) or 16 bytes; the pitch is an odd number of
 // 8-byte words, which keeps the check pass conflict free
@@ -93,7 +102,7 @@ __host__ __device__ inline int bp7_flag_record(int rd) { return rd <= 8 ? 8 : 16
 __host__ __device__ inline int bp7_flag_pitch(int s, int rd) { return ((s * bp7_flag_record(rd) / 8) | 1) * 8; }
 
 // lines: 128-byte lines per slot (from the layout); one more line group is scratch for padding lanes
-__host__ __device__ inline Bp7SmemLayout bp7_smem_layout(int m, int nrec, int nwn, int lines, int rd, int vmax, int s,
+__host__ __device__ inline Bp7SmemLayout bp7_smem_layout(int m, int nrec, int nwn, int nwm, int lines, int rd, int vmax, int s,
                                                          int real_bytes, bool staged)
 {
     Bp7SmemLayout L;
@@ -104,6 +113,8 @@ __host__ __device__ inline Bp7SmemLayout bp7_smem_layout(int m, int nrec, int nw
     o = (o + 15) & ~(size_t)15;
     L.table = o; o += staged ? (size_t)nrec * vmax * 4 : 0;
     L.out = o;   o += ((size_t)s * nwn * 4 + 15) & ~(size_t)15;
+    L.syn = o;   o += ((size_t)s * nwm * 4 + 15) & ~(size_t)15;     // staged syndromes of the slots' next shots
+    L.cb = o;    o += ((size_t)nwn * 4 + 15) & ~(size_t)15;         // decisions of columns without edges
     L.ctl = o;   o += sizeof(Bp7Ctl);
     L.total = o;
     return L;
@@ -158,6 +169,33 @@ __device__ __forceinline__ void check_ms7(real (&v)[RD], unsigned sign0, real al
     }
 }
 
+// Long rows (RD >= 8: spacetime matrices): smallest and second-smallest magnitude plus the position of the first
+// smallest.  The value edge k receives is the minimum over the OTHER edges either way (second smallest at that position,
+// smallest elsewhere; equal magnitudes are equal values), so the outputs are bit-identical to the two sweeps above; this
+// form keeps RD + 2 values live instead of 2 RD + 1 and multiplies twice per row instead of once per edge.
+template <typename real, int RD>
+__device__ __forceinline__ void check_ms_m12(real (&v)[RD], unsigned sign0, real al)
+{
+    using A = Ar<real>;
+    unsigned sx = sign0;
+#pragma unroll
+    for (int k = 0; k < RD; ++k) sx ^= hi_bits(v[k]);
+    real m1 = v[0], m2 = A::big();
+    int arg = 0;
+#pragma unroll
+    for (int k = 1; k < RD; ++k) {
+        const bool lt1 = fabs(v[k]) < fabs(m1);
+        const bool lt2 = fabs(v[k]) < fabs(m2);
+        m2 = lt1 ? m1 : (lt2 ? v[k] : m2);
+        m1 = lt1 ? v[k] : m1;
+        arg = lt1 ? k : arg;
+    }
+    const real als = xor_hi(al, sx & 0x80000000u);
+    const real o1 = A::mul(fabs(m1), als), o2 = A::mul(fabs(m2), als);
+#pragma unroll
+    for (int k = 0; k < RD; ++k) v[k] = xor_hi(k == arg ? o2 : o1, hi_bits(v[k]) & 0x80000000u);
+}
+
 // ---- product-sum check update in the probability-ratio domain, register resident
 template <typename real, int RD>
 __device__ __forceinline__ void check_ps7(real (&v)[RD], unsigned sbit)
@@ -202,7 +240,7 @@ __device__ __forceinline__ void row_ld(const uint32_t (&ra)[RD], uint32_t fb, re
     }
 }
 
-template <typename real, int METHOD, int RD, int S, int s>
+template <typename real, int METHOD, int RD, int S, int s, bool LONGROWS>
 __device__ __forceinline__ void row_cs(const uint32_t (&ra)[RD], uint32_t fb, real (&v)[RD], unsigned long long f, int i,
                                        bool valid, unsigned synbits, unsigned &resbits, unsigned &un, real al)
 {
@@ -215,7 +253,10 @@ __device__ __forceinline__ void row_cs(const uint32_t (&ra)[RD], uint32_t fb, re
     }
     un |= (valid ? (resbits >> bi) & 1u : 0u) << s;
     const unsigned sbit = (synbits >> bi) & 1u;
-    if (METHOD == QD_BP_MIN_SUM_K) check_ms7<real, RD>(v, sbit << 31, al);
+    if (METHOD == QD_BP_MIN_SUM_K) {
+        if (LONGROWS) check_ms_m12<real, RD>(v, sbit << 31, al);
+        else check_ms7<real, RD>(v, sbit << 31, al);
+    }
     else check_ps7<real, RD>(v, sbit);
 #pragma unroll
     for (int k = 0; k < RD; ++k) sts_off<s * 128>(ra[k], v[k]);
@@ -228,7 +269,19 @@ __device__ __forceinline__ void col_ld(const uint32_t (&ea)[VMAX], real (&cv)[D]
     for (int t = 0; t < D; ++t) cv[t] = lds_off<s * 128>(ea[t], real());
 }
 
-struct Bp7LlrOut { double *llr; const uint16_t *col_id; int n; int raw; unsigned want; const long long *shot; };
+// Soft output of one (column record, slot): rare (single-shot calls, the first stage of bposd), so it lives out of line
+// and re-derives everything it needs from the kernel parameters instead of holding registers through the bit pass.
+struct Bp7LlrOut { unsigned want; const Bp7Params *p; const long long *shot; uint32_t rank; };
+
+template <typename real, int METHOD>
+__device__ __forceinline__ void bp7_write_llr(const Bp7Params *p, const long long *shots, uint32_t rank, int r, int s, real soft)
+{
+    using A = Ar<real>;
+    const unsigned col = p->col_id[(size_t)rank * p->nrec + r];            // (rank = 0 outside cluster mode)
+    if (col != 0xFFFFu)
+        p->llr[shots[s] * (long long)p->n + col] =
+            (METHOD == QD_BP_MIN_SUM_K || p->llr_mode) ? (double)soft : (double)A::lg(A::div((real)1, soft));
+}
 
 template <typename real, int METHOD, int D, int VMAX, int S, int FB, int s>
 __device__ __forceinline__ void col_cs(const uint32_t (&ea)[VMAX], const uint32_t (&fa)[VMAX], real (&cv)[D], real pj, int i,
@@ -246,12 +299,7 @@ __device__ __forceinline__ void col_cs(const uint32_t (&ea)[VMAX], const uint32_
         for (int t = 0; t < D; ++t) sts_u8_off<s * FB>(fa[t], 1u);
     }
     decbits ^= flip << bi;
-    if (lo.llr && ((lo.want >> s) & 1u)) {                   // rare: soft output requested for this slot and pass
-        const unsigned col = lo.col_id[r];
-        if (col != 0xFFFFu)
-            lo.llr[lo.shot[s] * (long long)lo.n + col] =
-                (METHOD == QD_BP_MIN_SUM_K || lo.raw) ? (double)soft : (double)A::lg(A::div((real)1, soft));
-    }
+    if ((lo.want >> s) & 1u) bp7_write_llr<real, METHOD>(lo.p, lo.shot, lo.rank, r, s, soft);   // rare
 }
 
 // all slots of one column record of compile-time degree D
@@ -303,7 +351,7 @@ __device__ __forceinline__ void col_update(const uint32_t (&ea)[VMAX], const uin
 // slot control block is replicated and advanced identically in every CTA (CTA 0 draws from the shot queue and assembles
 // the outputs).  Arithmetic and its order are unchanged, so results are bit-identical to the single-CTA kernels.
 template <typename real, int METHOD, int RD, int VMAX, int S, bool IRREG, int MAXT, int MINB, bool CL = false>
-__global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
+__global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const __grid_constant__ Bp7Params p)
 {
     using A = Ar<real>;
     static_assert(VMAX == 4 || VMAX == 8, "column tile");
@@ -312,8 +360,10 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
     constexpr int LINE = 128;                            // bytes between the slots of one message
     constexpr int FB = RD <= 8 ? 8 : 16;                 // flag bytes per (row, slot)
     constexpr int FP = ((S * FB / 8) | 1) * 8;           // flag bytes per row (bp7_flag_pitch)
-    constexpr int RQ = (RD + 3) / 4;                     // uint4 per row-table entry
+    constexpr int RQ = bp7_row_quads(RD, IRREG);         // uint4 per row-table entry
     constexpr unsigned SMASK = (1u << S) - 1u;
+    constexpr bool PREFETCH = S == 1;                    // table entries a turn ahead (see the check pass)
+    constexpr bool LONGROWS = IRREG && RD >= 8;          // spacetime matrices: min / second-min check update, one row buffer
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = (int)threadIdx.x, NT = (int)blockDim.x, lane = tid & 31;
 
@@ -346,32 +396,68 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
             }
     };
 
+    uint32_t *synbuf = reinterpret_cast<uint32_t *>(smem_raw + p.off_syn);       // [S][nwm] syndrome of the slot's NEXT shot
+    uint32_t *cbits = reinterpret_cast<uint32_t *>(smem_raw + p.off_cb);         // [nwn] decisions of columns without edges
+    const bool lead = !CL || rank == 0;                                          // the CTA that talks to the queue and writes outputs
+    const int warp = tid >> 5, svc_warp = (NT >> 5) - 1;                         // service warp: the one with the fewest rows
+
     if (staged) {
         uint4 *st = reinterpret_cast<uint4 *>(smem_raw + p.off_table);
         for (int i = tid; i < p.nrec * (VMAX / 4); i += NT) st[i] = tbl[i];
     }
-    if (CL) cluster_sync_once_fenced();                // every CTA of the cluster runs before its shared memory is written
-    if ((!CL || rank == 0) && tid < S) {
+    for (int w = tid; w < p.nwn; w += NT) cbits[w] = p.const_bits[w];
+    for (int w = tid; w < S * p.nwn; w += NT) outbits[w] = 0u;
+    if (tid < BP7_SMAX) { ctl->resv[tid] = -1; ctl->drain_shot[tid] = -1; }
+    if (tid == 0) { ctl->unsat[0] = ctl->unsat[1] = 0u; ctl->pad[0] = 0; ctl->need_resv = 0u; ctl->fresh_resv = 0u; }
+    if (CL) cluster_sync_once_fenced(); else __syncthreads();      // (cluster: every CTA runs before its shared memory is written)
+    if (lead && tid < S) {
         const unsigned long long id = atomicAdd(p.next_shot, 1ULL);
         const bool more = id < (unsigned long long)p.shots;
         set_slot(tid, more ? (long long)id : -1, more ? -1 : BP_IDLE);     // -1: takes part in iteration 0 in full
     }
-    if (tid == 0) ctl->unsat[0] = ctl->unsat[1] = 0u;
     if (CL) cluster_sync_once_fenced(); else __syncthreads();
+    if (tid == 0) {                                                // slots that hold a shot reserve their next one
+        unsigned need = 0u;
+#pragma unroll
+        for (int s = 0; s < S; ++s) need |= (unsigned)(ctl->born[s] != BP_IDLE) << s;
+        ctl->need_resv = need;
+    }
+
+    // the slots' birth stamps, one or two 128-bit broadcast loads (the control block is read by every thread)
+    auto read_born = [&](int (&born)[S]) {
+        int b[BP7_SMAX];
+        const uint4 lo4 = lds_v4(smem_u32(&ctl->born[0]));
+        b[0] = (int)lo4.x; b[1] = (int)lo4.y; b[2] = (int)lo4.z; b[3] = (int)lo4.w;
+        if (S > 4) {
+            const uint4 hi4 = lds_v4(smem_u32(&ctl->born[4]));
+            b[4] = (int)hi4.x; b[5] = (int)hi4.y; b[6] = (int)hi4.z; b[7] = (int)hi4.w;
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) born[s] = b[s];
+    };
+    auto active_mask = [&]() -> unsigned {
+        int born[S];
+        read_born(born);
+        unsigned act = 0u;
+#pragma unroll
+        for (int s = 0; s < S; ++s) act |= (unsigned)(born[s] != BP_IDLE) << s;
+        return act;
+    };
 
     // ---- thread-owned state, bit (i * S + s): i-th owned row / column record, slot s
     unsigned synbits = 0u, resbits = 0u, decbits = 0u;
     long long c_fail = 0, c_shots = 0, c_nc = 0, c_it = 0;      // thread 0 only
 
     // record -> shared addresses of its edges (slot 0) and of their flip-flag bytes (slot 0)
-    auto load_record = [&](int r, uint32_t (&ea)[VMAX], uint32_t (&fa)[VMAX]) {
-        uint32_t w[VMAX];                                        // VMAX/2 words of mq, then VMAX/2 of fq
+    auto fetch_record = [&](int r, uint32_t (&w)[VMAX]) {       // VMAX/2 words of mq, then VMAX/2 of fq
 #pragma unroll
         for (int q = 0; q < VMAX / 4; ++q) {
             const uint4 x = staged ? lds_v4(a_tab + (uint32_t)(r * (VMAX / 4) + q) * 16u)
                                    : __ldg(tbl + (size_t)r * (VMAX / 4) + q);
             w[4 * q + 0] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
         }
+    };
+    auto decode_record = [&](const uint32_t (&w)[VMAX], uint32_t (&ea)[VMAX], uint32_t (&fa)[VMAX]) {
 #pragma unroll
         for (int t = 0; t < VMAX; ++t) {
             const uint32_t mw = w[t >> 1], fw = w[VMAX / 2 + (t >> 1)];
@@ -379,25 +465,31 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
             fa[t] = a_flags + ((t & 1) ? (fw >> 16) : (fw & 0xffffu));
         }
     };
+    auto load_record = [&](int r, uint32_t (&ea)[VMAX], uint32_t (&fa)[VMAX]) {
+        uint32_t w[VMAX];
+        fetch_record(r, w);
+        decode_record(w, ea, fa);
+    };
     // row -> shared addresses of its messages (slot 0), in column order
-    auto load_row = [&](int c, uint32_t (&ra)[RD], unsigned &dummy) {
-        uint32_t w[4 * RQ];
+    auto fetch_row = [&](int c, uint32_t (&w)[4 * RQ]) {
 #pragma unroll
         for (int q = 0; q < RQ; ++q) {
             const uint4 x = __ldg(rtbl + (size_t)c * RQ + q);
             w[4 * q + 0] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w;
         }
-        dummy = 0u;
+    };
+    auto decode_row = [&](const uint32_t (&w)[4 * RQ], uint32_t (&ra)[RD], unsigned &dummy) {
 #pragma unroll
-        for (int k = 0; k < RD; ++k) {
-            ra[k] = a_msg + (IRREG ? (w[k] & 0x7fffffffu) : w[k]);
-            if (IRREG) dummy |= (w[k] >> 31) << k;          // bit 31 of an entry: no such edge in this row
-        }
+        for (int k = 0; k < RD; ++k) ra[k] = a_msg + ((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu)) * RB;
+        // the 16-bit entry after the last edge: bit k set = no k-th edge in this row
+        dummy = IRREG ? ((RD & 1) ? (w[RD >> 1] >> 16) : (w[RD >> 1] & 0xffffu)) : 0u;
     };
     auto prior_of = [&](int r) -> real { return p.uniform_prior ? (real)p.prior0 : prior_rec[r]; };
 
-    // ---- (re)load every slot born in `stamp`
-    auto load_slots = [&](int stamp) {
+    // ---- (re)load every slot born in `stamp`.  The first shots read their syndromes from global memory; later ones find
+    // them in shared memory (synbuf, staged while the slot's previous shot was running).  The previous shot's decisions
+    // (decbits) stay: the bit pass of the same iteration files them and clears the bits.
+    auto load_slots = [&](int stamp, bool from_global) {
         unsigned fresh = 0u;
 #pragma unroll
         for (int s = 0; s < S; ++s) fresh |= (ctl->born[s] == stamp ? 1u : 0u) << s;
@@ -412,15 +504,18 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                 if ((fresh >> s) & 1u) {
                     const int bi = i * S + s;
                     unsigned b = 0u;
-                    if (valid) b = (p.synd[ctl->shot[s] * (long long)p.synd_stride + (gc >> 5)] >> (gc & 31)) & 1u;
+                    if (valid) {
+                        const uint32_t word = from_global ? p.synd[ctl->shot[s] * (long long)p.synd_stride + (gc >> 5)]
+                                                          : synbuf[s * p.nwm + (gc >> 5)];
+                        b = (word >> (gc & 31)) & 1u;
+                    }
                     synbits = (synbits & ~(1u << bi)) | (b << bi);
                     resbits = (resbits & ~(1u << bi)) | (b << bi);
                     sts_u64(fb + s * FB, 0ULL);
                     if (FB > 8) sts_u64(fb + s * FB + 8, 0ULL);
                 }
         }
-        i = 0;
-        for (int r = tid; r < p.nrec; r += NT, ++i) {
+        for (int r = tid; r < p.nrec; r += NT) {
             uint32_t ea[VMAX], fa[VMAX];
             load_record(r, ea, fa);
             const int deg = cdeg[r >> 5];
@@ -428,14 +523,13 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
 #pragma unroll
             for (int s = 0; s < S; ++s)
                 if ((fresh >> s) & 1u) {
-                    decbits &= ~(1u << (i * S + s));
 #pragma unroll
                     for (int t = 0; t < VMAX; ++t)
                         if (t < deg) sts_real(ea[t] + s * LINE, pj);
                 }
         }
     };
-    load_slots(-1);
+    load_slots(-1, true);
     // scaling factor of slot s in check pass T (a slot born in b runs its iteration T - b there): one thread per
     // slot writes it after the bit pass, the row owners read it instead of re-deriving it per row and slot
     auto publish_alpha = [&](int T) {
@@ -445,9 +539,10 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
     };
     publish_alpha(0);
     __syncthreads();
-    bool any_shot = false;
-#pragma unroll
-    for (int s = 0; s < S; ++s) any_shot |= ctl->born[s] != BP_IDLE;
+    // warp-uniform copies of the control state every thread would otherwise re-read each pass: the slots holding a shot,
+    // and the slots retired one / two iterations ago (their outputs are draining)
+    unsigned act = active_mask(), d1 = 0u, d2 = 0u;
+    const bool any_shot = act != 0u;
 
 #ifdef QD_BP7_TIMING
     long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64(), n_iter = 0;
@@ -455,29 +550,91 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
 #else
 #define QD_TICK7(k) do { } while (0)
 #endif
+    // A finished shot leaves its slot at once (the slot's next shot and its syndrome are already in shared memory), and
+    // its outputs drain over the following two iterations beside the decoding of the other slots:
+    //   iteration T   (shot found finished after the check pass)  bit pass: the column owners file its decisions into
+    //                                                              the output words; its error words are requested
+    //   iteration T+1 check pass: correction written, residual formed;   bit pass: logical parities of the residual
+    //   iteration T+2 check pass: per-shot outputs and counters, output words cleared
+    // Meanwhile the service warp draws the slot's next-but-one shot from the queue and stages its syndrome.
+    uint32_t err_pf = 0u;                                      // error word (slot, word) = tid of a shot retired in the last iteration
+    // corrections of the slots in `mask` out, their residuals in place (each word by one thread)
+    auto drain_corrections = [&](unsigned mask) {
+        if (!lead || !mask) return;
+        for (int x = tid; x < S * p.corr_stride; x += NT) {
+            const int s = x / p.corr_stride, w = x - s * p.corr_stride;
+            if (!((mask >> s) & 1u)) continue;
+            const long long shot = ctl->drain_shot[s];
+            const uint32_t v = w < p.nwn ? (outbits[s * p.nwn + w] | cbits[w]) : 0u;
+            p.corr[shot * (long long)p.corr_stride + w] = v;
+            if (p.err && w < p.nwn)
+                outbits[s * p.nwn + w] = v ^ (x == tid ? err_pf : p.err[shot * (long long)p.err_stride + w]);
+        }
+    };
+    bool b2_pending = false;                                   // cluster mode: arrived at the end-of-iteration barrier, not yet waited
     for (int T = 0; any_shot; ++T) {
         const int ub = T & 1;
         QD_TICK7(5);
         // ================================================================== check pass
         {
-            int born[S];
-            unsigned act = 0u;
-#pragma unroll
-            for (int s = 0; s < S; ++s) { born[s] = ctl->born[s]; act |= (unsigned)(born[s] != BP_IDLE) << s; }
+            // ---- drain steps due now (lead CTA): d1 = slots retired in T - 1, d2 = in T - 2
+            if (!CL) drain_corrections(d1);                   // (cluster mode: after the wait below, the decisions come from all CTAs)
+            if (lead && d2) {
+                for (int x = tid; x < S * p.nwn; x += NT)
+                    if ((d2 >> (x / p.nwn)) & 1u) outbits[x] = 0u;
+                if (tid == 0) {
+                    const unsigned failing = (unsigned)ctl->pad[0];
+                    for (int s = 0; s < S; ++s) {
+                        if (!((d2 >> s) & 1u)) continue;
+                        const int it = ctl->drain_it[s], conv = ctl->drain_conv[s];
+                        const int f = (int)((failing >> s) & 1u);
+                        const long long shot = ctl->drain_shot[s];
+                        if (p.conv) p.conv[shot] = (uint8_t)conv;
+                        if (p.iters) p.iters[shot] = it;
+                        if (p.fail) p.fail[shot] = (uint8_t)f;
+                        c_fail += f; c_shots += 1; c_nc += !conv; c_it += it;
+                    }
+                    ctl->pad[0] = (int)(failing & ~d2);
+                }
+            }
+            // ---- queue service: the syndromes requested in the last bit pass have landed; draw the next shots
+            long long resv_new = -1;
+            bool resv_have = false;
+            if (warp == svc_warp) {
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                const unsigned need = ctl->need_resv;
+                if (need) {
+                    if (lead && lane < S && ((need >> lane) & 1u)) {
+                        const unsigned long long id = atomicAdd(p.next_shot, 1ULL);
+                        resv_new = id < (unsigned long long)p.shots ? (long long)id : -1;
+                        resv_have = true;
+                        if (!CL) ctl->resv[lane] = resv_new;  // (cluster mode: sent to every CTA after the wait below)
+                    }
+                    __syncwarp();
+                    if (lane == 0) { ctl->fresh_resv = need; ctl->need_resv = 0u; }
+                }
+            }
             unsigned un = 0u;
             int i = 0;
+            // single-slot geometries (graphs that fill an SM: tables in global memory, several rows and records per thread,
+            // no second slot to overlap with): the table entry of the thread's NEXT row / record is requested a turn ahead
+            uint32_t wrow[4 * RQ];
+            if (PREFETCH && tid < p.m32) fetch_row(tid, wrow);
             for (int c = tid; c < p.m32; c += NT, ++i) {
                 const bool valid = c < my_m;
                 const uint32_t fb = a_flags + (uint32_t)(valid ? c : p.m) * FP;
                 uint32_t ra[RD];
                 unsigned dummy;
-                load_row(c, ra, dummy);
+                if (!PREFETCH) fetch_row(c, wrow);
+                decode_row(wrow, ra, dummy);
+                if (PREFETCH && c + NT < p.m32) fetch_row(c + NT, wrow);
                 real va[RD], vb[RD];
                 unsigned long long fa = 0ULL, fbb = 0ULL;
                 auto alpha_of = [&](int s) -> real { return METHOD == QD_BP_MIN_SUM_K ? (real)ctl->alpha[s] : (real)0; };
 #define QD_LD(n, buf, f) row_ld<real, METHOD, RD, (n) % S>(ra, fb, buf, f, dummy)
-#define QD_CS(n, buf, f) row_cs<real, METHOD, RD, S, (n) % S>(ra, fb, buf, f, i, valid, synbits, resbits, un, alpha_of((n) % S))
-                if (act == SMASK) {                             // steady state: straight line, two buffers
+#define QD_CS(n, buf, f) row_cs<real, METHOD, RD, S, (n) % S, LONGROWS>(ra, fb, buf, f, i, valid, synbits, resbits, un, alpha_of((n) % S))
+                if (act == SMASK && !LONGROWS) {                // steady state: straight line, two buffers (long rows: one
+                                                                // buffer, two would not fit the register file)
                     QD_LD(0, va, fa);
                     if (S > 1) QD_LD(1, vb, fbb);
                     QD_CS(0, va, fa);
@@ -508,20 +665,26 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
 #undef QD_CS
             }
             un = __reduce_or_sync(0xffffffffu, un);
-            if (lane == 0 && un) {
-                if (!CL) atomicOr(&ctl->unsat[ub], un);
-                else for (uint32_t r = 0; r < NC; ++r) cl_red_or_u32(cl_map(smem_u32(&ctl->unsat[ub]), r), un);
+            if (!CL) {
+                if (lane == 0 && un) atomicOr(&ctl->unsat[ub], un);
+            } else {
+                // Cluster mode: everything that touches another CTA waits for the end-of-iteration barrier of the previous
+                // iteration, which this CTA only ARRIVED at: the check pass above ran in its shadow.
+                __syncthreads();
+                if (b2_pending) { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); b2_pending = false; }
+                if (lane == 0 && un)
+                    for (uint32_t r = 0; r < NC; ++r) cl_red_or_u32(cl_map(smem_u32(&ctl->unsat[ub]), r), un);
+                if (resv_have)
+                    for (uint32_t r = 0; r < NC; ++r) cl_st_s64(cl_map(smem_u32(&ctl->resv[lane]), r), resv_new);
+                drain_corrections(d1);
             }
         }
-        __syncthreads();
+        if (!CL) __syncthreads();
         QD_TICK7(0);
         if (CL) {
             // ============================================================== export: check->bit messages of cut columns
             // into the mailboxes of the other CTAs that hold a replica of the column (consecutive entries fill
             // consecutive elements of a destination line)
-            unsigned act = 0u;
-#pragma unroll
-            for (int s = 0; s < S; ++s) act |= (unsigned)(ctl->born[s] != BP_IDLE) << s;
             const int nexp = p.cl_nexp[rank];
             const uint2 *ex = p.cl_export + (size_t)rank * p.cl_exp_stride;
             for (int x = tid; x < nexp; x += NT) {
@@ -536,101 +699,35 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
         }
         QD_TICK7(1);
 
-        // ================================================================== retire / refill
+        // ================================================================== retire / refill: nothing here touches global memory
+        unsigned done = 0u;
         {
             const unsigned unsat = ctl->unsat[ub];
-            unsigned done = 0u;
+            int born[S];
+            read_born(born);
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-                const int b = ctl->born[s], it = T - b - 1;
+                const int b = born[s], it = T - b - 1;
                 const unsigned fin = (unsigned)(b != BP_IDLE) & (unsigned)(it >= 1) &
                                      ((~(unsat >> s) & 1u) | (unsigned)(it >= max_iter));
                 done |= fin << s;
             }
             if (done) {
-                // the queue's answer is not needed before the epilogue is through: ask first
-                // (cluster mode: CTA 0 holds the output words, every CTA adds the decisions of the columns it owns)
-                const bool lead = !CL || rank == 0;
-                unsigned long long next_id = 0ULL;
-                if (lead && tid < S && ((done >> tid) & 1u)) next_id = atomicAdd(p.next_shot, 1ULL);
-                if (lead) {
-                    if (tid == 0) ctl->pad[0] = 0;              // bit s: the residual of slot s anticommutes with a logical
-                    // hard decisions of the finished slots, back in column order
-                    for (int w = tid; w < S * p.nwn; w += NT) outbits[w] = p.const_bits[w % p.nwn];
-                }
-                if (CL) cluster_sync_once_fenced(); else __syncthreads();
-                QD_TICK7(6);
-                {
-                    int i = 0;
-                    for (int r = tid; r < p.nrec; r += NT, ++i) {
-                        const unsigned bits = (decbits >> (i * S)) & done;
-                        if (bits) {
-                            const unsigned col = colid[r];
-                            if (col != 0xFFFFu) {
-#pragma unroll
-                                for (int s = 0; s < S; ++s)
-                                    if ((bits >> s) & 1u) {
-                                        if (!CL) atomicOr(&outbits[s * p.nwn + (col >> 5)], 1u << (col & 31));
-                                        else cl_red_or_u32(cl_map(smem_u32(&outbits[s * p.nwn + (col >> 5)]), 0u), 1u << (col & 31));
-                                    }
-                            }
-                        }
-                    }
-                }
-                if (CL) cluster_sync_once_fenced(); else __syncthreads();
-                QD_TICK7(7);
-                if (lead) {
-                // all finished slots together: corrections out, residuals in place (each word by one thread)
-                for (int x = tid; x < S * p.corr_stride; x += NT) {
-                    const int s = x / p.corr_stride, w = x - s * p.corr_stride;
-                    if (!((done >> s) & 1u)) continue;
-                    const long long shot = ctl->shot[s];
-                    const uint32_t v = w < p.nwn ? outbits[s * p.nwn + w] : 0u;
-                    p.corr[shot * (long long)p.corr_stride + w] = v;
-                    if (p.err && w < p.nwn) outbits[s * p.nwn + w] = v ^ p.err[shot * (long long)p.err_stride + w];
-                }
-                if (p.err) {
-                    __syncthreads();
-                    // logical parities: a thread per (slot, logical); consecutive threads read consecutive logicals
-                    for (int item = tid; item < S * p.k; item += NT) {
-                        const int s = item / p.k, i = item - s * p.k;
-                        if (!((done >> s) & 1u)) continue;
-                        const uint32_t *D = outbits + s * p.nwn;
-                        uint32_t acc = 0u;
-                        for (int w = 0; w < p.nwn; ++w) acc ^= __ldg(p.lzT + (size_t)w * p.k + i) & D[w];
-                        if (__popc(acc) & 1) atomicOr(&ctl->pad[0], 1 << s);
-                    }
+                // every CTA of a cluster holds the same control block and advances it in the same way
+                if (tid < S && ((done >> tid) & 1u)) {
+                    const int s = tid;
+                    ctl->drain_shot[s] = ctl->shot[s];
+                    ctl->drain_it[s] = T - ctl->born[s] - 1;
+                    ctl->drain_conv[s] = (int)(~(unsat >> s) & 1u);
+                    const long long nx = ctl->resv[s];
+                    ctl->resv[s] = -1;
+                    ctl->shot[s] = nx;
+                    ctl->born[s] = nx >= 0 ? T : BP_IDLE;
+                    if (nx >= 0) atomicOr(&ctl->need_resv, 1u << s);      // (an empty queue stays empty)
                 }
                 __syncthreads();
-                QD_TICK7(8);
-                if (tid == 0) {
-                    const unsigned failing = (unsigned)ctl->pad[0];
-                    for (int s = 0; s < S; ++s) {
-                        if (!((done >> s) & 1u)) continue;
-                        const int it = T - ctl->born[s] - 1;
-                        const int conv = !((unsat >> s) & 1u);
-                        const int f = (int)((failing >> s) & 1u);
-                        const long long shot = ctl->shot[s];
-                        if (p.conv) p.conv[shot] = (uint8_t)conv;
-                        if (p.iters) p.iters[shot] = it;
-                        if (p.fail) p.fail[shot] = (uint8_t)f;
-                        c_fail += f; c_shots += 1; c_nc += !conv; c_it += it;
-                    }
-                }
-                }   // lead
-                __syncthreads();
-                QD_TICK7(9);
-                if (lead && tid < S && ((done >> tid) & 1u)) {
-                    const bool more = next_id < (unsigned long long)p.shots;
-                    set_slot(tid, more ? (long long)next_id : -1, more ? T : BP_IDLE);
-                }
-                if (CL) cluster_sync_once_fenced(); else __syncthreads();
-                QD_TICK7(10);
-                bool any_active = false;
-#pragma unroll
-                for (int s = 0; s < S; ++s) any_active |= ctl->born[s] != BP_IDLE;
-                if (!any_active) break;
-                load_slots(T);
+                act = active_mask();
+                load_slots(T, false);
                 // no barrier: the bit pass below skips slots born in T and ends with a barrier
             }
         }
@@ -638,23 +735,83 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
         QD_TICK7(2);
         // ================================================================== bit pass
         {
-            unsigned run = 0u, want = 0u;        // slots to update; slots whose soft output is written in this pass
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-                const int b = ctl->born[s];
-                const unsigned on = (unsigned)(b != BP_IDLE) & (unsigned)(b != T);
-                run |= on << s;
-                // mode 1: only the iteration that hits the cap
-                want |= (on & ((unsigned)(p.llr_mode == 0) | (unsigned)(T - b == max_iter))) << s;
+            // ---- drain: logical parities of the residuals formed in this iteration's check pass (8 lanes per logical)
+            if (lead && p.err) {
+                if (d1) {
+                    const int total = S * p.k * 8;
+                    for (int base = warp * 32; base < total; base += NT) {
+                        const int item = base + lane, g = item >> 3, j = item & 7;
+                        const int s = g / p.k, i = g - s * p.k;
+                        uint32_t acc = 0u;
+                        if (item < total && ((d1 >> s) & 1u)) {
+                            const uint32_t *D = outbits + s * p.nwn;
+                            for (int w = j; w < p.nwn; w += 8) acc ^= __ldg(p.lzT + (size_t)w * p.k + i) & D[w];
+                        }
+                        acc ^= __shfl_xor_sync(0xffffffffu, acc, 1);
+                        acc ^= __shfl_xor_sync(0xffffffffu, acc, 2);
+                        acc ^= __shfl_xor_sync(0xffffffffu, acc, 4);
+                        if (j == 0 && (__popc(acc) & 1)) atomicOr(&ctl->pad[0], 1 << s);
+                    }
+                }
             }
-            if (!p.llr) want = 0u;
+            // ---- queue service: request the syndromes of the shots drawn in this iteration's check pass
+            if (warp == svc_warp) {
+                const unsigned fr = ctl->fresh_resv;
+                if (fr) {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        const long long shot = ((fr >> s) & 1u) ? ctl->resv[s] : -1;
+                        if (shot < 0) continue;
+                        const uint32_t *src = p.synd + shot * (long long)p.synd_stride;
+                        for (int w = lane; w < p.nwm; w += 32)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(synbuf + s * p.nwm + w)), "l"(src + w) : "memory");
+                    }
+                    __syncwarp();
+                    if (lane == 0) ctl->fresh_resv = 0u;
+                }
+            }
+            // ---- drain: decisions of the shots retired in this iteration, back in column order
+            if (done) {
+                int i = 0;
+                for (int r = tid; r < p.nrec; r += NT, ++i) {
+                    const unsigned bits = (decbits >> (i * S)) & done;
+                    if (bits) {
+                        const unsigned col = colid[r];
+                        if (col != 0xFFFFu) {
+#pragma unroll
+                            for (int s = 0; s < S; ++s)
+                                if ((bits >> s) & 1u) {
+                                    if (!CL) atomicOr(&outbits[s * p.nwn + (col >> 5)], 1u << (col & 31));
+                                    else cl_red_or_u32(cl_map(smem_u32(&outbits[s * p.nwn + (col >> 5)]), 0u), 1u << (col & 31));
+                                }
+                        }
+                        decbits &= ~(done << (i * S));
+                    }
+                }
+            }
+            // slots to update: the ones holding a shot that was not loaded in this iteration; slots whose soft output is
+            // written in this pass (mode 1: only the iteration that hits the cap)
+            const unsigned run = act & ~done;
+            unsigned want = 0u;
+            if (p.llr) {
+                int born[S];
+                read_born(born);
+#pragma unroll
+                for (int s = 0; s < S; ++s)
+                    want |= (((run >> s) & 1u) & ((unsigned)(p.llr_mode == 0) | (unsigned)(T - born[s] == max_iter))) << s;
+            }
             int i = 0;
+            uint32_t wrec[VMAX];
+            int degn = 0;
+            if (PREFETCH && tid < p.nrec) { fetch_record(tid, wrec); degn = (int)__ldg(cdeg + (tid >> 5)); }
             for (int r = tid; r < p.nrec; r += NT, ++i) {
                 uint32_t ea[VMAX], fa[VMAX];
-                load_record(r, ea, fa);
+                if (!PREFETCH) { fetch_record(r, wrec); degn = (int)__ldg(cdeg + (r >> 5)); }
+                decode_record(wrec, ea, fa);
                 const real pj = prior_of(r);
-                const int deg = __shfl_sync(0xffffffffu, (int)__ldg(cdeg + (r >> 5)), 0);
-                const Bp7LlrOut lo{want ? p.llr : nullptr, colid, p.n, p.llr_mode, want, ctl->shot};
+                const int deg = __shfl_sync(0xffffffffu, degn, 0);
+                if (PREFETCH && r + NT < p.nrec) { fetch_record(r + NT, wrec); degn = (int)__ldg(cdeg + ((r + NT) >> 5)); }
+                const Bp7LlrOut lo{want, &p, ctl->shot, rank};
 #define QD_COL(D_) col_update<real, METHOD, (D_), VMAX, S, FB>(ea, fa, pj, i, run, decbits, lo, r)
                 switch (deg) {
                 case 1: QD_COL(1); break;
@@ -669,24 +826,40 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const Bp7Params p)
                 }
 #undef QD_COL
             }
+            // ---- drain: ask for the error words of the shots retired in this iteration (used at the top of the next one)
+            if (lead && done && p.err && tid < S * p.corr_stride) {
+                const int s = tid / p.corr_stride, w = tid - s * p.corr_stride;
+                if (((done >> s) & 1u) && w < p.nwn) err_pf = p.err[ctl->drain_shot[s] * (long long)p.err_stride + w];
+            }
         }
         QD_TICK7(3);
         if (tid == 0) ctl->unsat[ub ^ 1] = 0u;              // buffer of the next check pass
         publish_alpha(T + 1);
-        // (cluster mode: nobody exports into a mailbox that is still being read, nobody sets a flag that is being reset)
-        if (CL) cluster_sync_once_fenced(); else __syncthreads();
+        // (cluster mode: nobody exports into a mailbox that is still being read, nobody sets a flag that is being reset —
+        // but this CTA only arrives here and waits after its next check pass, which touches no other CTA)
+        __syncthreads();
+        if (CL) {
+            if (tid == 0) asm volatile("fence.acq_rel.cluster;" ::: "memory");
+            asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+            b2_pending = true;
+        }
         QD_TICK7(4);
 #ifdef QD_BP7_TIMING
         ++n_iter;
 #endif
+        // go on while a slot decodes or drains
+        d2 = d1; d1 = done;
+        if (!(act | d1 | d2)) break;
     }
 #ifdef QD_BP7_TIMING
     if (blockIdx.x < 8 && (tid == 0 || tid == NT - 1))
-        printf("bp7 timing cta %d tid %d: check %lld export+bar %lld retire[pre %lld init %lld scatter %lld corr+logical %lld outputs %lld setslot %lld "
-               "refill %lld] bit %lld endbar %lld (iters %lld)\n", (int)blockIdx.x, tid,
-               tacc[0], tacc[1], tacc[2] - tacc[2], tacc[6], tacc[7], tacc[8], tacc[9], tacc[10], tacc[2], tacc[3], tacc[4], n_iter);
+        printf("bp7 timing cta %d tid %d: check %lld export+bar %lld retire %lld bit %lld endbar %lld (iters %lld)\n", (int)blockIdx.x, tid,
+               tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], n_iter);
 #endif
-    if (CL) cluster_sync_once_fenced();                     // no CTA leaves while its shared memory may still be addressed
+    if (CL) {                                               // no CTA leaves while its shared memory may still be addressed
+        if (b2_pending) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        cluster_sync_once_fenced();
+    }
 
     if (tid == 0 && p.counters && c_shots) {
         atomicAdd((unsigned long long *)&p.counters[0], (unsigned long long)c_fail);

@@ -15,7 +15,7 @@ constexpr int BP7_MAXT = QD_BP7_MAXT;   // launch bound of the row-regular kerne
 
 #define QD_DECL_PICK(tag)                                        \
     bp_kernel_fn pick_bp6_##tag(int vmax, int threads);          \
-    bp7_kernel_fn pick_bp7_##tag(int rd, int vmax, int slots, int irregular, int cluster);
+    bp7_kernel_fn pick_bp7_##tag(int rd, int vmax, int slots, int irregular, int cluster, int threads);
 QD_DECL_PICK(f64_ms)
 QD_DECL_PICK(f64_ps)
 QD_DECL_PICK(f32_ms)

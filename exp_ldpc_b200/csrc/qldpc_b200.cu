@@ -715,13 +715,16 @@ static bp_kernel_fn bp_kernel_for(const qd_bp *d)
     return d->method == QD_BP_MIN_SUM ? pick_bp6_f32_ms(d->vmax, t) : pick_bp6_f32_ps(d->vmax, t);
 }
 
-static bp7_kernel_fn bp7_kernel_for(const qd_bp *d, int slots)
+// threads: the CTA size the kernel will be launched with (0: any — existence checks); wide column tiles are compiled for
+// several launch bounds (bp_inst.cu)
+static bp7_kernel_fn bp7_kernel_for(const qd_bp *d, int slots, int threads = 0)
 {
+    const int t = threads > 0 ? threads : BP7_MAXT;
     if (d->precision == QD_PREC_F64)
-        return d->method == QD_BP_MIN_SUM ? pick_bp7_f64_ms(d->rd, d->vmax, slots, d->v7_irreg, d->cl7)
-                                          : pick_bp7_f64_ps(d->rd, d->vmax, slots, d->v7_irreg, d->cl7);
-    return d->method == QD_BP_MIN_SUM ? pick_bp7_f32_ms(d->rd, d->vmax, slots, d->v7_irreg, d->cl7)
-                                      : pick_bp7_f32_ps(d->rd, d->vmax, slots, d->v7_irreg, d->cl7);
+        return d->method == QD_BP_MIN_SUM ? pick_bp7_f64_ms(d->rd, d->vmax, slots, d->v7_irreg, d->cl7, t)
+                                          : pick_bp7_f64_ps(d->rd, d->vmax, slots, d->v7_irreg, d->cl7, t);
+    return d->method == QD_BP_MIN_SUM ? pick_bp7_f32_ms(d->rd, d->vmax, slots, d->v7_irreg, d->cl7, t)
+                                      : pick_bp7_f32_ps(d->rd, d->vmax, slots, d->v7_irreg, d->cl7, t);
 }
 
 static size_t bp_smem(const qd_bp *d, int slots, bool stage)
@@ -812,7 +815,7 @@ static size_t bp7_smem(qd_bp *d, int slots, bool staged)
 {
     const GraphDev &g = d->g->dev;
     const Bp7Layout &L = bp7_layout_of(d);
-    return bp7_smem_layout(g.m, L.nrec, g.nwn, L.lines, d->rd, d->vmax, slots, d->precision == QD_PREC_F64 ? 8 : 4, staged).total;
+    return bp7_smem_layout(g.m, L.nrec, g.nwn, g.nwm, L.lines, d->rd, d->vmax, slots, d->precision == QD_PREC_F64 ? 8 : 4, staged).total;
 }
 
 // can a (slots, threads) geometry be represented?  per-thread state is one bit per owned
@@ -822,7 +825,7 @@ static bool bp7_geometry_ok(qd_bp *d, int slots, int threads)
     const GraphDev &g = d->g->dev;
     const Bp7Layout &L = bp7_layout_of(d);
     const int m32 = (g.m + 31) / 32 * 32;
-    const Bp7SmemLayout SL = bp7_smem_layout(g.m, L.nrec, g.nwn, L.lines, d->rd, d->vmax, slots, d->precision == QD_PREC_F64 ? 8 : 4, false);
+    const Bp7SmemLayout SL = bp7_smem_layout(g.m, L.nrec, g.nwn, g.nwm, L.lines, d->rd, d->vmax, slots, d->precision == QD_PREC_F64 ? 8 : 4, false);
     if (SL.msg_elems > 65535 || (g.m + 1) * bp7_flag_pitch(slots, d->rd) > 65535 || g.n >= 65535) return false;
     if (threads < 32 || threads > BP7_MAXT || threads % 32) return false;
     if (((m32 + threads - 1) / threads) * slots > 32) return false;
@@ -837,7 +840,8 @@ static int bp7_prepare(qd_bp *d, int slots)
     const GraphDev &gd = g->dev;
     const Bp7Layout &L = bp7_layout_of(d);
     const int V = d->vmax, S = slots, RD = d->rd, NB = L.nb, RB = 128 / NB, FP = bp7_flag_pitch(S, RD), FB = bp7_flag_record(RD);
-    const int m32 = (gd.m + 31) / 32 * 32, RQ = (RD + 3) / 4;
+    const int m32 = (gd.m + 31) / 32 * 32, RQ = bp7_row_quads(RD, d->v7_irreg != 0);
+    (void)RB;
     // element index (slot 0) of a CSR edge; scratch elements live in the extra line group
     auto elem = [&](int e) { return L.index[e] * NB * S + L.colour[e]; };
     auto scratch = [&](int lane) { return L.lines * NB * S + (lane % NB); };
@@ -876,14 +880,16 @@ static int bp7_prepare(qd_bp *d, int slots)
         }
         r0 += padded;
     }
-    std::vector<uint32_t> row_table((size_t)m32 * RQ * 4, 0u);
+    std::vector<uint16_t> row_table((size_t)m32 * RQ * 8, 0);
     for (int c = 0; c < m32; ++c) {
         const int deg = c < gd.m ? g->row_ptr[c + 1] - g->row_ptr[c] : 0;
-        for (int k = 0; k < RQ * 4; ++k) {
-            uint32_t v = (uint32_t)((k < deg ? elem(g->row_ptr[c] + k) : scratch(c)) * RB);
-            if (d->v7_irreg && c < gd.m && k >= deg) v |= 0x80000000u;     // no such edge: reads as the neutral message
-            row_table[(size_t)c * RQ * 4 + k] = v;
+        uint16_t *row = &row_table[(size_t)c * RQ * 8];
+        unsigned missing = 0u;
+        for (int k = 0; k < RD; ++k) {
+            row[k] = (uint16_t)(k < deg ? elem(g->row_ptr[c] + k) : scratch(c));
+            if (c < gd.m && k >= deg) missing |= 1u << k;         // no such edge: reads as the neutral message
         }
+        if (d->v7_irreg) row[RD] = (uint16_t)missing;
     }
     d->v7_nrec = L.nrec;
     d->v7_lines = L.lines;
@@ -951,7 +957,9 @@ static int bp7_configure(qd_bp *d, int threads, int slots, int ctas)
     }
     if (C <= 0) {
         C = (int)std::max<size_t>(1, per_sm / (smem + 1024));
-        C = std::min(C, std::max(1, BP7_MAXT / T));               // 80 registers x 800 threads fill the register file
+        // the register file holds one launch bound's worth of threads (wide column tiles: see pick7_wide in bp_inst.cu)
+        const int bound = d->vmax == 8 && !d->v7_irreg && T <= 640 ? 640 : BP7_MAXT;
+        C = std::min(C, std::max(1, bound / T));
         C = std::min(C, 8);
     }
     int rc;
@@ -986,13 +994,13 @@ static Bp7ClusterPlan bp7c_plan(qd_bp *d, int C)
 
 static size_t bp7c_smem(const qd_bp *d, const Bp7ClusterPlan &plan, int slots, bool staged)
 {
-    return bp7_smem_layout(plan.m_max, plan.nrec, d->g->dev.nwn, plan.lines, BP7C_RD, BP7C_V, slots,
+    return bp7_smem_layout(plan.m_max, plan.nrec, d->g->dev.nwn, d->g->dev.nwm, plan.lines, BP7C_RD, BP7C_V, slots,
                            d->precision == QD_PREC_F64 ? 8 : 4, staged).total;
 }
 
 static bool bp7c_geometry_ok(const qd_bp *d, const Bp7ClusterPlan &plan, int slots, int threads)
 {
-    const Bp7SmemLayout SL = bp7_smem_layout(plan.m_max, plan.nrec, d->g->dev.nwn, plan.lines, BP7C_RD, BP7C_V, slots,
+    const Bp7SmemLayout SL = bp7_smem_layout(plan.m_max, plan.nrec, d->g->dev.nwn, d->g->dev.nwm, plan.lines, BP7C_RD, BP7C_V, slots,
                                              d->precision == QD_PREC_F64 ? 8 : 4, false);
     if (SL.msg_elems > 65535 || (plan.m_max + 1) * bp7_flag_pitch(slots, BP7C_RD) > 65535) return false;
     if (threads < 32 || threads > BP7_MAXT || threads % 32) return false;
@@ -1027,8 +1035,9 @@ static int bp7c_prepare(qd_bp *d, int slots)
     const GraphDev &gd = g->dev;
     const Bp7ClusterPlan &plan = d->cl7_plan;
     const int C = plan.C, V = BP7C_V, RD = BP7C_RD, S = slots, NB = plan.nb, RB = 128 / NB;
-    const int FP = bp7_flag_pitch(S, RD), FB = bp7_flag_record(RD), RQ = (RD + 3) / 4;
+    const int FP = bp7_flag_pitch(S, RD), FB = bp7_flag_record(RD), RQ = bp7_row_quads(RD, true);
     const int nrec = plan.nrec, m32 = plan.m32, M = plan.m_max;
+    (void)RB;
     auto elem = [&](const Bp7Pos &ps) { return ps.line * NB * S + ps.colour; };
     auto scratch = [&](int lane) { return plan.lines * NB * S + (lane % NB); };
     std::vector<uint32_t> const_bits(std::max(gd.nwn, 1), 0u);
@@ -1040,7 +1049,7 @@ static int bp7c_prepare(qd_bp *d, int slots)
     std::vector<uint16_t> table((size_t)C * nrec * 2 * V, 0), col_id((size_t)C * nrec, 0xFFFF);
     std::vector<uint8_t> chunk_deg((size_t)C * (nrec / 32), 0);
     std::vector<double> prior_rec((size_t)C * nrec, d->prior_dom[0]);
-    std::vector<uint32_t> row_table((size_t)C * m32 * RQ * 4, 0u);
+    std::vector<uint16_t> row_table((size_t)C * m32 * RQ * 8, 0);
     std::vector<int32_t> row0(C), rows(C), nexp(C);
     const int exp_stride = std::max(plan.nexp_max, 1);
     std::vector<uint2> exports((size_t)C * exp_stride, make_uint2(0u, 0u));
@@ -1062,13 +1071,16 @@ static int bp7c_prepare(qd_bp *d, int slots)
             }
         }
         for (int q = 0; q < R.nrec / 32; ++q) chunk_deg[(size_t)c * (nrec / 32) + q] = R.chunk_deg[q];
-        for (int r = 0; r < m32; ++r)
-            for (int k = 0; k < RQ * 4; ++k) {
-                const Bp7Pos ps = (r < R.rows && k < RD) ? R.row_pos[(size_t)r * RD + k] : Bp7Pos();
-                uint32_t v = (uint32_t)((ps.line >= 0 ? elem(ps) : scratch(r)) * RB);
-                if (r < R.rows && ps.line < 0) v |= 0x80000000u;       // no such edge: reads as the neutral message
-                row_table[((size_t)c * m32 + r) * RQ * 4 + k] = v;
+        for (int r = 0; r < m32; ++r) {
+            uint16_t *row = &row_table[((size_t)c * m32 + r) * RQ * 8];
+            unsigned missing = 0u;
+            for (int k = 0; k < RD; ++k) {
+                const Bp7Pos ps = r < R.rows ? R.row_pos[(size_t)r * RD + k] : Bp7Pos();
+                row[k] = (uint16_t)(ps.line >= 0 ? elem(ps) : scratch(r));
+                if (r < R.rows && ps.line < 0) missing |= 1u << k;     // no such edge: reads as the neutral message
             }
+            row[RD] = (uint16_t)missing;
+        }
         for (size_t x = 0; x < R.exports.size(); ++x) {
             const auto &e = R.exports[x];
             exports[(size_t)c * exp_stride + x] = make_uint2((uint32_t)elem(e.src) | ((uint32_t)elem(e.dst) << 16), (uint32_t)e.rank);
@@ -1144,7 +1156,7 @@ static int bp7c_configure(qd_bp *d, int want_C, int want_slots, int want_threads
             if (smem > budget) continue;
             const int T = want_threads > 0 ? want_threads : bp7c_pick_threads(d, plan, S);
             if (!T || !bp7c_geometry_ok(d, plan, S, T)) continue;
-            bp7_kernel_fn fn = bp7_kernel_for(d, S);
+            bp7_kernel_fn fn = bp7_kernel_for(d, S, T);
             if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
             cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
             bp7c_launch_config(d, C, T, smem, (unsigned)(C * std::max(1, d->g->sm_count / C)), nullptr, cfg, attr);
@@ -1646,9 +1658,10 @@ static int bp_launch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int6
             q.cl_export = d->d7c_export.as<uint2>(); q.cl_exp_stride = std::max(d->cl7_plan.nexp_max, 1);
         }
         {
-            const Bp7SmemLayout SL = bp7_smem_layout(q.m, d->v7_nrec, g.nwn, d->v7_lines, d->rd, d->vmax, d->slots,
+            const Bp7SmemLayout SL = bp7_smem_layout(q.m, d->v7_nrec, g.nwn, g.nwm, d->v7_lines, d->rd, d->vmax, d->slots,
                                                      d->precision == QD_PREC_F64 ? 8 : 4, d->v7_staged != 0);
             q.off_flags = (int)SL.flags; q.off_table = (int)SL.table; q.off_out = (int)SL.out; q.off_ctl = (int)SL.ctl;
+            q.off_syn = (int)SL.syn; q.off_cb = (int)SL.cb;
         }
         q.row_table = d->d7_row_table.as<uint4>();
         q.max_iter = d->max_iter;
@@ -1671,7 +1684,7 @@ static int bp_launch(qd_bp *d, const uint32_t *d_synd, int32_t synd_stride, int6
         q.fail = d_fail;
         q.counters = (long long *)d_counters;
         q.next_shot = d->d_next.as<unsigned long long>() + queue;
-        bp7_kernel_fn fn7 = bp7_kernel_for(d, d->slots);
+        bp7_kernel_fn fn7 = bp7_kernel_for(d, d->slots, d->threads);
         if (!fn7) return fail(QD_EUNSUP, "no row-regular BP kernel compiled for this geometry");
         QD_CUDA(cudaFuncSetAttribute(fn7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d->smem));
         QD_CUDA(cudaMemsetAsync(q.next_shot, 0, sizeof(unsigned long long), st));
