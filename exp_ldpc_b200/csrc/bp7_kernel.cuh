@@ -98,8 +98,20 @@ __host__ __device__ constexpr int bp7_row_quads(int rd, bool irregular) { return
 
 // flag bytes of a row: S records of 8 (row degree <= 8) or 16 bytes; the pitch is an odd number of
 // 8-byte words, which keeps the check pass conflict free
-__host__ __device__ inline int bp7_flag_record(int rd) { return rd <= 8 ? 8 : 16; }
+// (rows of 9 edges: the ninth edge's flag byte lives in a second array behind the records, one byte per (row, slot), rows
+// interleaved in blocks of 8 so that the slots of a row stay 8 bytes apart like everywhere else)
+__host__ __device__ inline int bp7_flag_record(int rd) { (void)rd; return 8; }
 __host__ __device__ inline int bp7_flag_pitch(int s, int rd) { return ((s * bp7_flag_record(rd) / 8) | 1) * 8; }
+// byte offset (from the flag area) of the flag of edge k of `row`, slot 0; rows = rows incl. the scratch row (m + 1)
+__host__ __device__ inline int bp7_flag_offset(int row, int k, int rows, int s, int rd)
+{
+    if (k < 8) return row * bp7_flag_pitch(s, rd) + k;
+    return rows * bp7_flag_pitch(s, rd) + (row >> 3) * 8 * s + (row & 7);
+}
+__host__ __device__ inline int bp7_flag_bytes(int rows, int s, int rd)
+{
+    return rows * bp7_flag_pitch(s, rd) + (rd > 8 ? ((rows + 7) / 8) * 8 * s : 0);
+}
 
 // lines: 128-byte lines per slot (from the layout); one more line group is scratch for padding lanes
 __host__ __device__ inline Bp7SmemLayout bp7_smem_layout(int m, int nrec, int nwn, int nwm, int lines, int rd, int vmax, int s,
@@ -109,7 +121,7 @@ __host__ __device__ inline Bp7SmemLayout bp7_smem_layout(int m, int nrec, int nw
     L.msg_elems = (lines + 1) * s * (128 / real_bytes);
     size_t o = 0;
     L.msg = o;   o += (size_t)(lines + 1) * s * 128;
-    L.flags = o; o += (size_t)(m + 1) * bp7_flag_pitch(s, rd);
+    L.flags = o; o += (size_t)bp7_flag_bytes(m + 1, s, rd);
     o = (o + 15) & ~(size_t)15;
     L.table = o; o += staged ? (size_t)nrec * vmax * 4 : 0;
     L.out = o;   o += ((size_t)s * nwn * 4 + 15) & ~(size_t)15;
@@ -221,15 +233,19 @@ __device__ __forceinline__ void check_ps7(real (&v)[RD], unsigned sbit)
 // ---- one slot of one row: load, and compute + store.  The shared-memory accesses are volatile asm
 // and keep their program order, so the callers issue the loads of the next slots by hand before the
 // arithmetic of the current one (software pipeline over the slots).
+template <int OFF> __device__ __forceinline__ uint32_t lds_u8_off(uint32_t a)
+{ uint32_t v; asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF)); return v; }
+
+// fb: the row's flag record, f9: its ninth-edge flag byte (RD > 8), both for slot 0
 template <typename real, int METHOD, int RD, int s>
-__device__ __forceinline__ void row_ld(const uint32_t (&ra)[RD], uint32_t fb, real (&v)[RD], unsigned long long &f,
+__device__ __forceinline__ void row_ld(const uint32_t (&ra)[RD], uint32_t fb, uint32_t f9, real (&v)[RD], unsigned long long &f,
                                        unsigned dummy)
 {
-    constexpr int FB = RD <= 8 ? 8 : 16;
+    constexpr int FB = 8;
     f = lds_u64_off<s * FB>(fb);
-    if (RD > 8) {                       // second flag word: fold it in, keep "any flag set" in bit 63
-        const unsigned long long g = lds_u64_off<s * FB + (RD > 8 ? 8 : 0)>(fb);
-        f = ((unsigned long long)((__popcll(f) + __popcll(g)) & 1)) | ((f | g) ? 0x8000000000000002ULL : 0ULL);
+    if (RD > 8) {                       // ninth flag: fold it in, keep "any flag set" in bit 63
+        const unsigned g = lds_u8_off<s * FB>(f9);
+        f = ((unsigned long long)((__popcll(f) + (int)g) & 1)) | ((f | g) ? 0x8000000000000002ULL : 0ULL);
     }
 #pragma unroll
     for (int k = 0; k < RD; ++k) v[k] = lds_off<s * 128>(ra[k], real());
@@ -241,15 +257,15 @@ __device__ __forceinline__ void row_ld(const uint32_t (&ra)[RD], uint32_t fb, re
 }
 
 template <typename real, int METHOD, int RD, int S, int s, bool LONGROWS>
-__device__ __forceinline__ void row_cs(const uint32_t (&ra)[RD], uint32_t fb, real (&v)[RD], unsigned long long f, int i,
+__device__ __forceinline__ void row_cs(const uint32_t (&ra)[RD], uint32_t fb, uint32_t f9, real (&v)[RD], unsigned long long f, int i,
                                        bool valid, unsigned synbits, unsigned &resbits, unsigned &un, real al)
 {
-    constexpr int FB = RD <= 8 ? 8 : 16;
+    constexpr int FB = 8;
     const int bi = i * S + s;
     resbits ^= ((unsigned)__popcll(f) & 1u) << bi;      // RD > 8: f was folded by row_ld (even popcount pad)
     if (f) {
         sts_u64_off<s * FB>(fb, 0ULL);
-        if (RD > 8) sts_u64_off<s * FB + (RD > 8 ? 8 : 0)>(fb, 0ULL);
+        if (RD > 8) sts_u8_off<s * FB>(f9, 0u);
     }
     un |= (valid ? (resbits >> bi) & 1u : 0u) << s;
     const unsigned sbit = (synbits >> bi) & 1u;
@@ -358,7 +374,8 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const __grid_constant__
     static_assert(S >= 1 && S <= BP7_SMAX, "slots");
     constexpr int RB = (int)sizeof(real);
     constexpr int LINE = 128;                            // bytes between the slots of one message
-    constexpr int FB = RD <= 8 ? 8 : 16;                 // flag bytes per (row, slot)
+    static_assert(RD <= 9, "flag layout: eight flags in the row's record, one more in the second array");
+    constexpr int FB = 8;                                // flag bytes per (row, slot)
     constexpr int FP = ((S * FB / 8) | 1) * 8;           // flag bytes per row (bp7_flag_pitch)
     constexpr int RQ = bp7_row_quads(RD, IRREG);         // uint4 per row-table entry
     constexpr unsigned SMASK = (1u << S) - 1u;
@@ -498,6 +515,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const __grid_constant__
         for (int c = tid; c < p.m32; c += NT, ++i) {
             const bool valid = c < my_m;
             const uint32_t fb = a_flags + (uint32_t)(valid ? c : p.m) * FP;
+            const uint32_t f9 = a_flags + (uint32_t)bp7_flag_offset(valid ? c : p.m, 8, p.m + 1, S, RD);
             const int gc = row0 + c;                                  // the row's index in the syndrome
 #pragma unroll
             for (int s = 0; s < S; ++s)
@@ -512,7 +530,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const __grid_constant__
                     synbits = (synbits & ~(1u << bi)) | (b << bi);
                     resbits = (resbits & ~(1u << bi)) | (b << bi);
                     sts_u64(fb + s * FB, 0ULL);
-                    if (FB > 8) sts_u64(fb + s * FB + 8, 0ULL);
+                    if (RD > 8) sts_u8(f9 + s * FB, 0u);
                 }
         }
         for (int r = tid; r < p.nrec; r += NT) {
@@ -623,6 +641,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const __grid_constant__
             for (int c = tid; c < p.m32; c += NT, ++i) {
                 const bool valid = c < my_m;
                 const uint32_t fb = a_flags + (uint32_t)(valid ? c : p.m) * FP;
+                const uint32_t f9 = RD > 8 ? a_flags + (uint32_t)bp7_flag_offset(valid ? c : p.m, 8, p.m + 1, S, RD) : 0u;
                 uint32_t ra[RD];
                 unsigned dummy;
                 if (!PREFETCH) fetch_row(c, wrow);
@@ -631,8 +650,8 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const __grid_constant__
                 real va[RD], vb[RD];
                 unsigned long long fa = 0ULL, fbb = 0ULL;
                 auto alpha_of = [&](int s) -> real { return METHOD == QD_BP_MIN_SUM_K ? (real)ctl->alpha[s] : (real)0; };
-#define QD_LD(n, buf, f) row_ld<real, METHOD, RD, (n) % S>(ra, fb, buf, f, dummy)
-#define QD_CS(n, buf, f) row_cs<real, METHOD, RD, S, (n) % S, LONGROWS>(ra, fb, buf, f, i, valid, synbits, resbits, un, alpha_of((n) % S))
+#define QD_LD(n, buf, f) row_ld<real, METHOD, RD, (n) % S>(ra, fb, f9, buf, f, dummy)
+#define QD_CS(n, buf, f) row_cs<real, METHOD, RD, S, (n) % S, LONGROWS>(ra, fb, f9, buf, f, i, valid, synbits, resbits, un, alpha_of((n) % S))
                 if (act == SMASK && !LONGROWS) {                // steady state: straight line, two buffers (long rows: one
                                                                 // buffer, two would not fit the register file)
                     QD_LD(0, va, fa);

@@ -826,7 +826,7 @@ static bool bp7_geometry_ok(qd_bp *d, int slots, int threads)
     const Bp7Layout &L = bp7_layout_of(d);
     const int m32 = (g.m + 31) / 32 * 32;
     const Bp7SmemLayout SL = bp7_smem_layout(g.m, L.nrec, g.nwn, g.nwm, L.lines, d->rd, d->vmax, slots, d->precision == QD_PREC_F64 ? 8 : 4, false);
-    if (SL.msg_elems > 65535 || (g.m + 1) * bp7_flag_pitch(slots, d->rd) > 65535 || g.n >= 65535) return false;
+    if (SL.msg_elems > 65535 || bp7_flag_bytes(g.m + 1, slots, d->rd) > 65535 || g.n >= 65535) return false;
     if (threads < 32 || threads > BP7_MAXT || threads % 32) return false;
     if (((m32 + threads - 1) / threads) * slots > 32) return false;
     if (((L.nrec + threads - 1) / threads) * slots > 32) return false;
@@ -840,6 +840,7 @@ static int bp7_prepare(qd_bp *d, int slots)
     const GraphDev &gd = g->dev;
     const Bp7Layout &L = bp7_layout_of(d);
     const int V = d->vmax, S = slots, RD = d->rd, NB = L.nb, RB = 128 / NB, FP = bp7_flag_pitch(S, RD), FB = bp7_flag_record(RD);
+    (void)FP;
     const int m32 = (gd.m + 31) / 32 * 32, RQ = bp7_row_quads(RD, d->v7_irreg != 0);
     (void)RB;
     // element index (slot 0) of a CSR edge; scratch elements live in the extra line group
@@ -869,10 +870,10 @@ static int bp7_prepare(qd_bp *d, int slots)
                 if (j >= 0 && t < dg) {
                     const int ce = g->col_ptr[j] + t;
                     mq[t] = (uint16_t)elem(csr_edge[ce]);
-                    fq[t] = (uint16_t)((int)g->csc_row[ce] * FP + g->csc_k[ce]);
+                    fq[t] = (uint16_t)bp7_flag_offset((int)g->csc_row[ce], g->csc_k[ce], gd.m + 1, S, RD);
                 } else {
                     mq[t] = (uint16_t)scratch(r);
-                    fq[t] = (uint16_t)(gd.m * FP + (t % FB));
+                    fq[t] = (uint16_t)bp7_flag_offset(gd.m, t % FB, gd.m + 1, S, RD);
                 }
             }
             if (j >= 0) { col_id[r] = (uint16_t)j; prior_rec[r] = d->prior_dom[j]; }
@@ -1002,7 +1003,7 @@ static bool bp7c_geometry_ok(const qd_bp *d, const Bp7ClusterPlan &plan, int slo
 {
     const Bp7SmemLayout SL = bp7_smem_layout(plan.m_max, plan.nrec, d->g->dev.nwn, d->g->dev.nwm, plan.lines, BP7C_RD, BP7C_V, slots,
                                              d->precision == QD_PREC_F64 ? 8 : 4, false);
-    if (SL.msg_elems > 65535 || (plan.m_max + 1) * bp7_flag_pitch(slots, BP7C_RD) > 65535) return false;
+    if (SL.msg_elems > 65535 || bp7_flag_bytes(plan.m_max + 1, slots, BP7C_RD) > 65535) return false;
     if (threads < 32 || threads > BP7_MAXT || threads % 32) return false;
     if (((plan.m32 + threads - 1) / threads) * slots > 32) return false;
     if (((plan.nrec + threads - 1) / threads) * slots > 32) return false;
@@ -1036,6 +1037,7 @@ static int bp7c_prepare(qd_bp *d, int slots)
     const Bp7ClusterPlan &plan = d->cl7_plan;
     const int C = plan.C, V = BP7C_V, RD = BP7C_RD, S = slots, NB = plan.nb, RB = 128 / NB;
     const int FP = bp7_flag_pitch(S, RD), FB = bp7_flag_record(RD), RQ = bp7_row_quads(RD, true);
+    (void)FP;
     const int nrec = plan.nrec, m32 = plan.m32, M = plan.m_max;
     (void)RB;
     auto elem = [&](const Bp7Pos &ps) { return ps.line * NB * S + ps.colour; };
@@ -1063,7 +1065,8 @@ static int bp7c_prepare(qd_bp *d, int slots)
                 const Bp7Pos ps = r < R.nrec ? R.rec_pos[(size_t)r * V + t] : Bp7Pos();
                 mq[t] = (uint16_t)(ps.line >= 0 ? elem(ps) : scratch(r));
                 const int fr = r < R.nrec ? R.rec_flag_row[(size_t)r * V + t] : -1;
-                fq[t] = (uint16_t)(fr >= 0 ? fr * FP + R.rec_flag_k[(size_t)r * V + t] : M * FP + (t % FB));
+                fq[t] = (uint16_t)(fr >= 0 ? bp7_flag_offset(fr, R.rec_flag_k[(size_t)r * V + t], M + 1, S, RD)
+                                           : bp7_flag_offset(M, t % FB, M + 1, S, RD));
             }
             if (j >= 0) {
                 if (R.rec_owner[r]) col_id[(size_t)c * nrec + r] = (uint16_t)j;
