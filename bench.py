@@ -48,6 +48,8 @@ WORKLOADS = {
     # the decoder's priors (data and measurement 2p/3); Stim circuit-level sampling is a "next" row
     "st_hgp225_T3": ("spacetime:hgp_34_n225.qecc:3", 0.02, _BP, "spacetime (T=3) of the (3,4) HGP [[225,9]] code"),
     "st_hgp1600_T3": ("spacetime:hgp_34_n1600.qecc:3", 0.02, _BP, "spacetime (T=3) of the (3,4) HGP n=1600 code"),
+    # the reference's default number of rounds (misc/p_sweep.py:62) on the BASELINE configs[1] code
+    "st_hgp1600_T1": ("spacetime:hgp_34_n1600.qecc:1", 0.02, _BP, "spacetime (T=1) of the (3,4) HGP n=1600 code"),
 }
 SSF_DEFAULT_P = 0.01
 
@@ -177,6 +179,8 @@ def main():
     ap.add_argument("--slots", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--teams", type=int, default=0)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "regular", "regular_cluster", "generic", "cluster", "global"],
+                    help="force a BP kernel family (tuning / comparison); the default is the library's own choice")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=None,
                     help="wall seconds of CPU work per reference-arm step / for the cpu_baseline sample (default: bounded automatically)")
@@ -268,7 +272,8 @@ def main():
         dec = ssf_decoder(graph, code.checks.x)
         cfg = {"kernel": "ssf"}
     else:
-        dec = (bposd_decoder if osd else bp_decoder)(graph, channel_probs=prior_vec, precision=args.precision, **opts)
+        dec = (bposd_decoder if osd else bp_decoder)(graph, channel_probs=prior_vec, precision=args.precision, kernel=args.kernel,
+                                                     **opts)
         if args.threads or args.slots or args.ctas or args.teams:
             dec.configure(args.threads, args.slots, args.ctas, args.teams)
         cfg = dec.config()
@@ -386,7 +391,8 @@ def main():
     sm_mhz = clk.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
     smem_peak = sm_count * 128 * sm_mhz * 1e6 / 1e9
     smem_achieved = smem_bytes_per_shot * shots / (kernel_ms * 1e-3) / 1e9
-    kernel_name = {"regular": "bp7_kernel", "ssf": "ssf_kernel", "cluster": "bpc_kernel", "global": "bpg_kernel"}.get(cfg.get("kernel"), "bp_kernel")
+    kernel_name = {"regular": "bp7_kernel", "regular_cluster": "bp7_kernel (cluster mode)", "ssf": "ssf_kernel", "cluster": "bpc_kernel",
+                   "global": "bpg_kernel"}.get(cfg.get("kernel"), "bp_kernel")
     if osd:
         kernel_name += " + osd0_kernel"
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full`

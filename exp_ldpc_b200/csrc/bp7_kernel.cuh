@@ -426,13 +426,13 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const __grid_constant__
     for (int w = tid; w < S * p.nwn; w += NT) outbits[w] = 0u;
     if (tid < BP7_SMAX) { ctl->resv[tid] = -1; ctl->drain_shot[tid] = -1; }
     if (tid == 0) { ctl->unsat[0] = ctl->unsat[1] = 0u; ctl->pad[0] = 0; ctl->need_resv = 0u; ctl->fresh_resv = 0u; }
-    if (CL) cluster_sync_once_fenced(); else __syncthreads();      // (cluster: every CTA runs before its shared memory is written)
+    if (CL) cluster_sync_release_all(); else __syncthreads();      // (cluster: every CTA runs before its shared memory is written)
     if (lead && tid < S) {
         const unsigned long long id = atomicAdd(p.next_shot, 1ULL);
         const bool more = id < (unsigned long long)p.shots;
         set_slot(tid, more ? (long long)id : -1, more ? -1 : BP_IDLE);     // -1: takes part in iteration 0 in full
     }
-    if (CL) cluster_sync_once_fenced(); else __syncthreads();
+    if (CL) cluster_sync_release_all(); else __syncthreads();
     if (tid == 0) {                                                // slots that hold a shot reserve their next one
         unsigned need = 0u;
 #pragma unroll
@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const __grid_constant__
                 for (int s = 0; s < S; ++s)
                     if ((act >> s) & 1u) cl_st(dst + s * LINE, lds_real(src + s * LINE, real()));
             }
-            cluster_sync_once_fenced();
+            cluster_sync_release_all();
         }
         QD_TICK7(1);
 
@@ -807,6 +807,9 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const __grid_constant__
                         decbits &= ~(done << (i * S));
                     }
                 }
+                // (cluster mode: the decisions sent to CTA 0 are released by the threads that sent them; the barrier at the
+                // end of the iteration is arrived at relaxed, behind thread 0's fence only)
+                if (CL) asm volatile("fence.acq_rel.cluster;" ::: "memory");
             }
             // slots to update: the ones holding a shot that was not loaded in this iteration; slots whose soft output is
             // written in this pass (mode 1: only the iteration that hits the cap)
@@ -877,7 +880,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const __grid_constant__
 #endif
     if (CL) {                                               // no CTA leaves while its shared memory may still be addressed
         if (b2_pending) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-        cluster_sync_once_fenced();
+        cluster_sync_release_all();
     }
 
     if (tid == 0 && p.counters && c_shots) {

@@ -41,4 +41,14 @@ __device__ __forceinline__ void cluster_sync_once_fenced()
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// Cluster-wide barrier after which every CTA sees the distributed-shared-memory stores and reductions that ANY thread of
+// any CTA issued before it: each thread releases its own remote accesses (a single thread's fence, as above, orders what
+// that thread has observed; stores other threads sent into another SM's shared memory may still be in flight).
+__device__ __forceinline__ void cluster_sync_release_all()
+{
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 }  // namespace qd

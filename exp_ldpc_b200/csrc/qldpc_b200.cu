@@ -1366,7 +1366,10 @@ static int bp_choose_kernel(qd_bp *d, bool allow_regular, bool family_global = f
         }
         // Graphs that leave one SM with one or two shots in flight, or none: split the rows over a thread-block cluster
         // when the matrix has the block structure for it (spacetime matrices) and more shots per SM come out of it.
-        if (regular_cluster == 0 && (!d->v7 || d->slots <= 2) && bp7c_graph_ok(d)) {
+        // (Measured at n=1600, T=1: one shot per SM in the single-CTA kernel, 2.98 M shots/s, still beats three shots per
+        // two-CTA cluster, 2.70 M — barriers and the export cost more than the extra shots in flight bring. So: only
+        // when the graph does not fit one SM.)
+        if (regular_cluster == 0 && !d->v7 && bp7c_graph_ok(d)) {
             const double single = d->v7 ? bp7_geometry_score(d->slots, 1) : 0.0;
             const int save_threads = d->threads, save_slots = d->slots, save_ctas = d->ctas_per_sm, save_staged = d->v7_staged;
             const int save_rd = d->rd, save_vmax = d->vmax, save_irreg = d->v7_irreg;

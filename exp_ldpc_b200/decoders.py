@@ -239,6 +239,8 @@ class bp_decoder:
         k = [C.c_int32() for _ in range(3)]
         _lib.check(_lib.lib().qd_bp_get_kernel(self._h, *[C.byref(x) for x in k]))
         out["kernel"] = {5: "global", 6: "generic", 7: "regular", 8: "cluster", 9: "regular_cluster"}[k[0].value]
+        if out["kernel"] == "regular_cluster":      # in this family `ctas_per_sm` carries the cluster size (CTAs per group of shots)
+            out["cluster_ctas"] = out["ctas_per_sm"]
         return out
 
     # ---- the ldpc call

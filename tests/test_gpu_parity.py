@@ -928,6 +928,30 @@ def test_dense_rows_take_a_multi_sm_kernel(gpu):
             assert its[s] == ref.iter and conv[s] == ref.converge
 
 
+def test_global_memory_kernel_long_columns(gpu):
+    """Columns of ~18 and ~60 edges (beyond the register-resident column update of the global-memory kernel), rows of
+    60..200 edges: the literal serial sweeps must equal the serial decoder."""
+    from scipy import sparse
+    from exp_ldpc_b200.decoders import bp_decoder
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(11)
+    for rows, cols, density in ((60, 200, 0.3), (120, 90, 0.5)):        # column degrees ~18 (<= 32) and ~60 (> 32)
+        a = (rng.random((rows, cols)) < density).astype(np.uint32)
+        a[:, 0] = 1
+        a[0, :] = 1
+        h = sparse.csr_matrix(a)
+        probs = rng.uniform(0.01, 0.06, cols)
+        err = (rng.random((24, cols)) < probs).astype(np.int64)
+        synd = (err @ a.T.astype(np.int64)) % 2
+        dec = bp_decoder(h, channel_probs=probs, max_iter=12, bp_method="ms", ms_scaling_factor=0.0, kernel="global")
+        ref = po.OracleBP(h, channel_probs=probs, max_iter=12, bp_method="ms", ms_scaling_factor=0.0)
+        corr, conv, its = dec.decode_batch(synd)
+        for s in range(synd.shape[0]):
+            assert np.array_equal(corr[s], ref.decode(synd[s])), (rows, cols, s)
+            assert its[s] == ref.iter and conv[s] == ref.converge
+        want = ref.decode(synd[3])
+        assert np.array_equal(dec.decode(synd[3]), want) and np.allclose(dec.log_prob_ratios, ref.log_prob_ratios, rtol=1e-12, atol=1e-12)
+
 
 @pytest.mark.parametrize("which,method,osd,order,p", [("hgp225", "ms", "osd_cs", 7, 0.04), ("hgp225", "ps", "osd_cs", 10, 0.03),
                                                       ("hgp225", "ms", "osd_e", 6, 0.05), ("hgp1600", "ms", "osd_cs", 7, 0.025)])
