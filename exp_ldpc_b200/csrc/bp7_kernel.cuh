@@ -25,7 +25,15 @@
 //   * min-sum check update = exclusive prefix/suffix minima, exactly the two sweeps of the serial
 //     decoder (3(RD-2) minima per row instead of min/second-min bookkeeping);
 //   * fp64: every operation is an explicitly rounded intrinsic issued in the serial order, so
-//     decisions, iteration counts and soft outputs are bit-identical to the CPU restatement.
+//     decisions, iteration counts and soft outputs are bit-identical to the CPU restatement;
+//   * a finished shot leaves its slot at once: the slot's next shot was drawn from the queue ahead of
+//     time and its syndrome staged in shared memory by a service warp, and the finished shot's
+//     outputs (decisions back in column order, correction, residual, logical parities, counters)
+//     drain over the next two iterations beside the decoding — no global round trip and a single
+//     CTA barrier on the critical path of a retire;
+//   * cluster mode (template flag CL): graphs that exceed one SM but are block structured (the
+//     multi-round matrices of spacetime_code.py:46-75) are split by rows over a thread-block
+//     cluster; see the comment at the kernel and bp7_cluster_layout.h.
 #pragma once
 
 #include "bp_kernel.cuh"
@@ -379,7 +387,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const __grid_constant__
     constexpr int FP = ((S * FB / 8) | 1) * 8;           // flag bytes per row (bp7_flag_pitch)
     constexpr int RQ = bp7_row_quads(RD, IRREG);         // uint4 per row-table entry
     constexpr unsigned SMASK = (1u << S) - 1u;
-    constexpr bool PREFETCH = S == 1;                    // table entries a turn ahead (see the check pass)
+    constexpr bool PREFETCH = S == 1;                    // table entries a turn ahead (see the check pass; no gain in cluster mode)
     constexpr bool LONGROWS = IRREG && RD >= 8;          // spacetime matrices: min / second-min check update, one row buffer
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = (int)threadIdx.x, NT = (int)blockDim.x, lane = tid & 31;

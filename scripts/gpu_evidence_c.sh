@@ -34,7 +34,12 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py $SHORT > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "launch list rc=$?"
 cap() { name=$1; k=$2; shift 2; timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $OUT/${TAG}_${name} \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e "$@" > $OUT/${TAG}_ncu_${name}.log 2>&1; echo "ncu $name rc=$?"; }
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e "$@" > $OUT/${TAG}_ncu_${name}.log 2>&1; echo "ncu $name rc=$?"
+    # the reports are large (gpurun brings back at most 64 MiB): summarise here, keep the text only
+    { python scripts/ncu_summary.py $OUT/${TAG}_${name}.ncu-rep; echo "--- hottest source lines (samples / instructions / shared wavefronts)";
+      python scripts/ncu_lines.py $OUT/${TAG}_${name}.ncu-rep 24; } > $OUT/${TAG}_${name}_ncu_full_summary.txt 2>&1
+    rm -f $OUT/${TAG}_${name}.ncu-rep; }
 cap bp7_n1600 bp7 --shots 131072
 cap bp7c_st1600 bp7 --workload st_hgp1600_T3 --shots 16384
 cap osd_n1600 osd --decoder bposd --shots 16384
+du -sh $OUT
