@@ -815,9 +815,6 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const __grid_constant__
                         decbits &= ~(done << (i * S));
                     }
                 }
-                // (cluster mode: the decisions sent to CTA 0 are released by the threads that sent them; the barrier at the
-                // end of the iteration is arrived at relaxed, behind thread 0's fence only)
-                if (CL) asm volatile("fence.acq_rel.cluster;" ::: "memory");
             }
             // slots to update: the ones holding a shot that was not loaded in this iteration; slots whose soft output is
             // written in this pass (mode 1: only the iteration that hits the cap)
@@ -869,8 +866,7 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const __grid_constant__
         // but this CTA only arrives here and waits after its next check pass, which touches no other CTA)
         __syncthreads();
         if (CL) {
-            if (tid == 0) asm volatile("fence.acq_rel.cluster;" ::: "memory");
-            asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // every thread releases what it sent to CTA 0
             b2_pending = true;
         }
         QD_TICK7(4);

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(800, 1) bpc_kernel(const BpcParams p)
             for (int k = 0; k < deg; ++k) s_epos[lo + k] = p.edge_pos[e + k];
         }
     }
-    cluster_sync_once_fenced();                 // every CTA of the cluster is running before its shared memory is written remotely
+    cluster_sync_release_all();                 // every CTA of the cluster is running before its shared memory is written remotely
 
     for (;;) {
         if (rank == 0 && tid == 0) {
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(800, 1) bpc_kernel(const BpcParams p)
             const uint32_t sa = (uint32_t)__cvta_generic_to_shared(&sh_shot);
             for (int r = 0; r < C; ++r) cl_st_s64(cl_map(sa, (uint32_t)r), s);
         }
-        cluster_sync_once_fenced();
+        cluster_sync_release_all();
         const long long shot = sh_shot;
         if (shot < 0) break;
         const uint32_t *sw = p.synd + shot * (long long)p.synd_stride;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(800, 1) bpc_kernel(const BpcParams p)
             const real pj = s_prior[i];
             for (int t = s_lcptr[i]; t < s_lcptr[i + 1]; ++t) st_msg(b2c, b2c_sa, s_desc[t], pj);
         }
-        cluster_sync_once_fenced();
+        cluster_sync_release_all();
         // Iteration it + 1's check pass also tests iteration it's decisions (H dec == s ?, decisions are replicated:
         // local reads), so an iteration costs two cluster barriers; the check pass that discovers convergence is
         // wasted, its messages are never used.  it = iterations completed.
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(800, 1) bpc_kernel(const BpcParams p)
                 unsat = __syncthreads_or(unsat);
                 if (tid < C) cl_st_u32(cl_map((uint32_t)__cvta_generic_to_shared(&sh_unsat[it & 1][rank]), (uint32_t)tid), (uint32_t)unsat);
             }
-            cluster_sync_once_fenced();
+            cluster_sync_release_all();
             QD_TICK(2);
             if (test) {
                 int any = 0;
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(800, 1) bpc_kernel(const BpcParams p)
                 if (lane < C) cl_st_u32(cl_map(decw_sa + (uint32_t)(w0 + (i >> 5)) * 4u, (uint32_t)lane), word);
             }
             QD_TICK(3);
-            cluster_sync_once_fenced();
+            cluster_sync_release_all();
             QD_TICK(4);
         }
         // ---- outputs (CTA 0 holds every decision)
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(800, 1) bpc_kernel(const BpcParams p)
             }
         }
         // the next shot's setup overwrites sh_shot / messages / decisions of other CTAs: everyone must be done
-        cluster_sync_once_fenced();
+        cluster_sync_release_all();
     }
 #ifdef QD_BPC_TIMING
     if (blockIdx.x < (unsigned)C && (tid == 0 || tid == NT - 1))

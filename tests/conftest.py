@@ -22,7 +22,8 @@ def pytest_collection_modifyitems(config, items):
         return
     for item in items:
         if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
-            item.add_marker(pytest.mark.timeout(300))
+            # method "thread": the main thread of a hung test sits inside a CUDA call and never returns to the interpreter
+            item.add_marker(pytest.mark.timeout(300, method="thread"))
 
 
 @pytest.fixture(scope="session")
