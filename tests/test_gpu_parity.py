@@ -883,6 +883,29 @@ def test_regular_cluster_kernel_soft_outputs_and_priors(gpu, code225):
                 assert np.array_equal(a.log_prob_ratios, b.log_prob_ratios)
 
 
+def test_bposd_over_the_cluster_mode_equals_the_single_cta_kernel(gpu, code225):
+    """BP + OSD on a spacetime matrix with the BP stage in cluster mode: the soft outputs that rank the columns for OSD are
+    written by the CTA that owns a column, so corrections, convergence flags and iteration counts must equal the
+    single-CTA run bit for bit (osd0 and the reference's default osd_cs 7)."""
+    from exp_ldpc_b200.decoders import bposd_decoder
+    from exp_ldpc_b200.spacetime import SpacetimeCode
+    rng = np.random.default_rng(8)
+    h = SpacetimeCode(code225.checks.z, 1).spacetime_check_matrix
+    probs = np.full(h.shape[1], 0.03)
+    err = (rng.random((200, h.shape[1])) < probs).astype(np.uint8)
+    synd = (err @ h.T.toarray()) % 2
+    for method, osd, order in (("ms", "osd0", 0), ("ps", "osd_cs", 7)):
+        opts = dict(channel_probs=probs, max_iter=10, bp_method=method, ms_scaling_factor=0.0, osd_method=osd, osd_order=order)
+        a = bposd_decoder(h, kernel="regular", **opts)
+        b = bposd_decoder(h, kernel="regular_cluster", **opts)
+        assert b.config()["kernel"] == "regular_cluster"
+        ca, va, ia = a.decode_batch(synd)
+        cb, vb, ib = b.decode_batch(synd)
+        assert 0 < int(va.sum()) < synd.shape[0]                     # both the BP and the OSD branch are exercised
+        assert np.array_equal(ca, cb) and np.array_equal(va, vb) and np.array_equal(ia, ib), (method, osd)
+        assert np.array_equal((cb @ h.T.toarray()) % 2, synd)        # BP + OSD always returns a correction with the right syndrome
+
+
 @pytest.mark.parametrize("kernel", ["auto", "cluster", "global"])
 def test_large_graphs_take_the_cluster_kernel(gpu, code1600, kernel):
     """Spacetime matrix of the n = 1600 code, T = 3: 26 k edges do not fit one SM in fp64; the rows are split over a
