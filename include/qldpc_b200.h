@@ -151,7 +151,7 @@ int qd_bp_get_config(qd_bp *d, int32_t *threads, int32_t *slots, int32_t *ctas_p
  * shared-memory kernel (a variant is compiled for the graph's degrees), 6 = generic shared-memory
  * kernel, 8 = messages spread over the shared memories of a thread-block cluster of 2 / 4 / 8 SMs
  * (graphs too large or too dense for one SM), 5 = messages in global memory (graphs beyond that; slower),
- * 9 = the thread-owned-state kernel over a thread-block cluster: the rows are split over 2..8 CTAs, columns cut by the
+ * 9 = the thread-owned-state kernel over a thread-block cluster: the rows are split over 2, 4 or 8 CTAs, columns cut by the
  * split are updated redundantly in every CTA that holds one of their edges and their check->bit messages travel through
  * distributed shared memory (block-structured matrices that leave one SM with at most two shots in flight: the
  * spacetime matrices of spacetime_code.py:46-75; rows up to 9, columns up to 4 edges).  In that family qd_bp_configure /
