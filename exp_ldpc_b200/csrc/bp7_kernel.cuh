@@ -868,6 +868,10 @@ __global__ void __launch_bounds__(MAXT, MINB) bp7_kernel(const __grid_constant__
         if (CL) {
             asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // every thread releases what it sent to CTA 0
             b2_pending = true;
+#ifdef QD_BP7_NO_SPLIT_BARRIER                                  // (experiments: wait at once)
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+            b2_pending = false;
+#endif
         }
         QD_TICK7(4);
 #ifdef QD_BP7_TIMING
