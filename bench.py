@@ -44,6 +44,8 @@ WORKLOADS = {
     "lp_882": ("builder:pk19_b1_882", 0.05, _BP, "QC lifted product [[882,24]]"),        # BASELINE configs[2]
     "qclp_1054": ("builder:pk20_qc_1054", 0.05, _BP, "QC lifted product [[1054,140]]"),
     "a5lp_2700": ("builder:a5_lift_2700", 0.05, _BP, "PSL(2,5) lifted product n=2700"),  # BASELINE configs[3]
+    # BASELINE configs[3] as a Cayley-graph Tanner code: PSL(2,4) ~ A5, Morgenstern B generators, [6,3,3] local codes
+    "cayley_lp_4320": ("builder:psl2_tanner_lp_4320", 0.05, _BP, "PSL(2,4) Cayley-graph Tanner lifted product [[4320,28]]"),
     # BASELINE configs[4]: spacetime matrix of the [[225,9]] code, T rounds, phenomenological faults drawn from
     # the decoder's priors (data and measurement 2p/3); Stim circuit-level sampling is a "next" row
     "st_hgp225_T3": ("spacetime:hgp_34_n225.qecc:3", 0.02, _BP, "spacetime (T=3) of the (3,4) HGP [[225,9]] code"),
@@ -77,8 +79,9 @@ def load_workload(name):
         from exp_ldpc_b200.codes import load_code
         return load_code(os.path.join(ROOT, "codes", src.split(":")[1]))
     if src.startswith("builder:"):
-        from exp_ldpc_b200 import code_builders
-        return getattr(code_builders, src.split(":", 1)[1])()
+        from exp_ldpc_b200 import cayley_codes, code_builders
+        name = src.split(":", 1)[1]
+        return getattr(code_builders if hasattr(code_builders, name) else cayley_codes, name)()
     from exp_ldpc_b200.codes import load_code
     return load_code(os.path.join(ROOT, "codes", src))
 

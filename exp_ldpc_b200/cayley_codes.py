@@ -39,7 +39,7 @@ from .codes import QuantumCode
 __all__ = [
     "Field", "FiniteGroup", "pgl2_group", "psl2_group", "get_psl2", "zqm_group", "random_check_matrix",
     "random_abelian_generators", "morgenstern_matrices", "morgenstern_generators", "lifted_product_code",
-    "lifted_product_code_cyclic", "lifted_product_code_pgl2",
+    "lifted_product_code_cyclic", "lifted_product_code_pgl2", "psl2_tanner_lp_4320",
 ]
 
 
@@ -454,3 +454,17 @@ def lifted_product_code_pgl2(l, i, r, compute_logicals=None, seed=None, check_co
     group, gens = morgenstern_generators(l, i)
     double_cover = True if double_cover is None else double_cover
     return _wrapper(group, gens, r, compute_logicals, seed, check_complex, r2=r2, double_cover=double_cover)
+
+
+def psl2_tanner_lp_4320(compute_logicals: bool = True) -> QuantumCode:
+    """[[4320, 28]]: a decodable instance of BASELINE.json configs[3] — the lifted product over the
+    Cayley graph of PGL(2,4) = PSL(2,4) ~ A5 (order 60) on the six Morgenstern "B" generators
+    ``{a b : a != b}`` (double cover D_6), both local codes the [6,3,3] shortened Hamming code.
+    n = (6^2 + 4 * 3^2) * 60; X and Z checks of weight 5 / 7, qubits in 2..4 checks of either type.
+    (``lifted_product_code_pgl2(1, 2, 5)`` of the reference's tests draws 5 x 3 local codes at random:
+    all-zero checks and untouched qubits — it pins the construction, not a code one would decode.)"""
+    local = np.array([[1, 1, 0, 1, 0, 0], [0, 1, 1, 0, 1, 0], [1, 0, 1, 0, 0, 1]], dtype=np.uint8)
+    group, gens = morgenstern_generators(1, 2, use_B_generators=True, symmetric=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return lifted_product_code(group, gens, local, local, compute_logicals=compute_logicals, double_cover=True)

@@ -346,6 +346,34 @@ def test_ssf_code_families_against_live_oracle(gpu, family_codes, name, p):
     assert np.array_equal(got["converged"], ref["converged"])
 
 
+def test_cayley_tanner_lp_against_live_oracle(gpu):
+    """BASELINE configs[3]: the [[4320, 28]] Cayley-graph Tanner lifted product over PSL(2,4) (check degrees 5 / 7,
+    qubit degrees 2..4; cayley_codes.psl2_tanner_lp_4320) — BP (min-sum, product-sum) and small-set-flip."""
+    from exp_ldpc_b200.cayley_codes import psl2_tanner_lp_4320
+    from exp_ldpc_b200.experiment import CodeCapacityExperiment
+    from oracle import pyoracle as po
+    code = psl2_tanner_lp_4320()
+    hz, lz, hx = code.checks.z, code.logicals.z, code.checks.x
+    shots = 256
+    for method, alpha, p in (("ms", 0.0, 0.03), ("ms", 0.75, 0.06), ("ps", 0.0, 0.04)):
+        q, prior = 2 * p / 3 + p - 4 / 3 * p * p, 2 * p / 3
+        opts = dict(max_iter=24, bp_method=method, ms_scaling_factor=alpha)
+        ref = po.run_code_capacity(hz, lz, q, prior, decoder="bp", max_iter=24, bp_method=method, ms_scaling_factor=alpha,
+                                   seed=11, shots=shots, per_shot=True)
+        got = CodeCapacityExperiment(code, q, prior, "bp", opts).run(shots, seed=11, per_shot=True)
+        assert (got["decodings"] == ref["decodings"]).all(), (method, alpha, "hard decisions differ")
+        assert np.array_equal(got["iters"], ref["iters"]) and np.array_equal(got["fail"], ref["fail"])
+        assert np.array_equal(got["converged"], ref["converged"])
+    p = 0.008
+    q = prior = 2 * p / 3
+    got = CodeCapacityExperiment(code, q, prior, "ssf", {}).run(shots, seed=3, per_shot=True)
+    ref = po.run_code_capacity(hz, lz, q, prior, decoder="ssf", hx=hx, seed=3, shots=shots, per_shot=True)
+    assert (got["decodings"] == ref["decodings"]).all()
+    assert np.array_equal(got["iters"], ref["iters"]) and np.array_equal(got["fail"], ref["fail"])
+    assert np.array_equal(got["converged"], ref["converged"])
+    assert 0 < int(ref["converged"].sum()) and int(ref["iters"].max()) > 1
+
+
 def test_bp_per_bit_priors_match_oracle(gpu, code225):
     """channel_probs vector (the hybrid decoder's data / measurement priors, _experiment.py:106-113)."""
     from exp_ldpc_b200.decoders import bp_decoder
