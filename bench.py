@@ -149,7 +149,9 @@ def cpu_port_throughput(code, p, opts, target_seconds=12.0, threads=0, decoder="
     hz, lz, q, prior = problem
     cores = po.num_threads() if threads <= 0 else threads
     osd_dec = {"osd0": "bposd0", "osd_e": "bposd_e", "osd_cs": "bposd_cs"}[opts.get("osd_method", "osd0")]
-    kw = dict(decoder={"bposd": osd_dec}.get(decoder, decoder), hx=code.checks.x, osd_order=opts.get("osd_order", 0), max_iter=opts["max_iter"], bp_method=opts["bp_method"],
+    kw = dict(decoder={"bposd": osd_dec}.get(decoder, decoder), hx=code.checks.x, osd_order=opts.get("osd_order", 0),
+              max_iter=0 if decoder == "ssf" else opts["max_iter"],        # SSF: no round cap, like ssf_decoder's default
+              bp_method=opts["bp_method"],
               ms_scaling_factor=opts["ms_scaling_factor"], seed=0, threads=cores)
     probe = 64 * cores
     t0 = time.perf_counter()
@@ -226,7 +228,7 @@ def main():
     config = {"workload": f"{args.workload}: {family} n={n} m={m} nnz={nnz} k={code.num_logicals}, "
                           f"{'phenomenological faults' if WORKLOADS[args.workload][0].startswith('spacetime:') else 'code capacity'}, "
                           f"{how}, p={p} (flip q={q:.5f}, prior 2p/3)",
-              "shots_per_step_per_gpu": args.shots, "p": p, "decoder": args.decoder, "max_iter": opts["max_iter"],
+              "shots_per_step_per_gpu": args.shots, "p": p, "decoder": args.decoder, "max_iter": 0 if ssf else opts["max_iter"],
               "bp_method": opts["bp_method"], "precision": dtype, "parallelism": f"shots sharded over {world} rank(s), one all-reduce of int64[4] per step",
               "l2": "inputs larger than L2 (no flush needed)"}
 
