@@ -31,6 +31,14 @@ def test_reference_arm_line():
     assert d["config"]["workload"].startswith("hgp_34_n225") and "model" not in d["config"]
 
 
+def test_reference_arm_ssf_runs_without_the_bp_round_cap():
+    """The SSF baseline must do the GPU decoder's work: no round cap (it once inherited BP's max_iter = 32)."""
+    d = _run("--impl", "reference", "--workload", "hgp_34_n225", "--decoder", "ssf", "--steps", "1", "--warmup", "1",
+             "--cpu-seconds", "0.3")
+    assert d["impl"] == "reference" and "SSF" in d["metric"] and d["dtype"] == "u32"
+    assert d["config"]["decoder"] == "ssf" and d["config"]["max_iter"] == 0 and d["value"] > 0
+
+
 @pytest.mark.gpu
 def test_b200_arm_line(built):
     d = _run("--workload", "hgp_34_n225", "--shots", "65536", "--steps", "2", "--warmup", "3", "--cpu-seconds", "0.5")
