@@ -21,7 +21,7 @@ _EXPORTS = {
     "build_storage_simulation": "storage", "build_perfect_circuit": "storage", "CircuitTargets": "storage",
     "StorageSim": "storage", "schedule_checks": "storage",
     # spacetime codes  (spacetime_code.py)
-    "SpacetimeCode": "spacetime", "SpacetimeCodeSingleShot": "spacetime",
+    "SpacetimeCode": "spacetime", "SpacetimeCodeSingleShot": "spacetime", "DetectorSpacetimeCode": "spacetime",
     "DetectorErrorModel": "circuits", "detector_error_model": "circuits", "CircuitSampler": "circuits",
     # decoders and experiments  (ldpc's duck type; misc/_experiment.py, misc/p_sweep.py)
     "bp_decoder": "decoders", "bposd_decoder": "decoders", "ssf_decoder": "decoders",

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Decode the shots of a GPU p-sweep CSV (scripts/p_sweep.py, code capacity, --decoder_mode bp | ssf) again on the CPU
+"""Decode the shots of a GPU p-sweep CSV (scripts/p_sweep.py, code capacity, --decoder_mode bp | ssf | bposd) again on the CPU
 oracle — same seed, same global shot indices, the flip probability and the prior computed exactly as p_sweep does — and
 print both sets of counters side by side.  The fp64 BP path and SSF are bit-exact, so failures, non-converged shots
 and the iteration total must be IDENTICAL.  Test infrastructure: this script may import oracle/.
@@ -32,9 +32,11 @@ for _, r in df.iloc[:rows].iterrows():
     q = depolarizing_noise(p, p).code_capacity_flip_probability()       # scripts/p_sweep.py: pm = p
     prior = 2 / 3 * p                                                   # constant_pheno_prior
     dec = r.decoder_mode
+    oracle_dec = {"bposd": {"osd0": "bposd0", "osd_e": "bposd_e", "osd_cs": "bposd_cs"}[r.osd_method]}.get(dec, dec)
     t = time.time()
-    c = po.run_code_capacity(hz, lz, q, prior, seed=0, shots=int(r.samples), decoder=dec, hx=hx,
-                             max_iter=int(r.max_iter) if dec == "bp" else 0, bp_method=r.bp_method,
+    c = po.run_code_capacity(hz, lz, q, prior, seed=0, shots=int(r.samples), decoder=oracle_dec, hx=hx,
+                             max_iter=0 if dec == "ssf" else int(r.max_iter), bp_method=r.bp_method,
+                             osd_order=0 if r.osd_method == "osd0" else int(r.osd_order),
                              ms_scaling_factor=float(r.ms_scaling_factor))
     same = (c["failures"], c["non_converged"], c["iters_total"]) == (int(r.failures), int(r.non_converged), int(r.iters_total))
     print(f"{dec},{p!r},{int(r.samples)},{int(r.failures)},{c['failures']},{int(r.non_converged)},{c['non_converged']},"
