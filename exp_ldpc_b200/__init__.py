@@ -26,6 +26,8 @@ _EXPORTS = {
     # decoders and experiments  (ldpc's duck type; misc/_experiment.py, misc/p_sweep.py)
     "bp_decoder": "decoders", "bposd_decoder": "decoders", "ssf_decoder": "decoders",
     "run_simulation": "experiment", "p_sweep": "experiment",
+    "BPOSDCorrect": "wrappers", "BPOSDHybridCorrect": "wrappers", "BPOSDCorrectSingleShot": "wrappers",
+    "BPDetectorCorrect": "wrappers",
 }
 _MODULES = {"noise_model": "storage"}        # `noise_model.trivial_noise()` etc. live in storage.py
 
