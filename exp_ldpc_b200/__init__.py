@@ -19,7 +19,7 @@ _EXPORTS = {
     "lifted_product_code": "cayley_codes", "random_check_matrix": "cayley_codes",
     # storage simulation and noise  (storage_sim.py, noise_model.py, qecc_util.py:120-155)
     "build_storage_simulation": "storage", "build_perfect_circuit": "storage", "CircuitTargets": "storage",
-    "StorageSim": "storage", "schedule_checks": "storage",
+    "StorageSim": "storage", "schedule_checks": "storage", "edge_color_bipartite": "storage",
     # spacetime codes  (spacetime_code.py)
     "SpacetimeCode": "spacetime", "SpacetimeCodeSingleShot": "spacetime", "DetectorSpacetimeCode": "spacetime",
     "DetectorErrorModel": "circuits", "detector_error_model": "circuits", "CircuitSampler": "circuits",

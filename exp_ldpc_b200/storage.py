@@ -25,7 +25,7 @@ import numpy as np
 
 from .codes import QuantumCode, canonical_csr
 
-__all__ = ["CircuitTargets", "NoiseRewriter", "StorageSim", "schedule_checks", "build_perfect_circuit",
+__all__ = ["CircuitTargets", "NoiseRewriter", "StorageSim", "schedule_checks", "edge_color_bipartite", "build_perfect_circuit",
            "build_storage_simulation", "trivial_noise", "depolarizing_noise", "circuit_noise", "circuit_ticks"]
 
 
@@ -103,6 +103,48 @@ def schedule_checks(checks) -> List[Dict[int, int]]:
             at_check[c, a] = q
             at_data[q, a] = c
     return [{int(c): int(at_check[c, col]) for c in range(m) if at_check[c, col] >= 0} for col in range(deg)]
+
+
+def edge_color_bipartite(biadjacency) -> List[set]:
+    """Proper edge colouring of a bipartite (multi)graph with maximum-degree many colours (Koenig): the counterpart
+    of the reference's ``edge_color_bipartite`` (``edge_coloring.py:17-88``) on a biadjacency matrix instead of a
+    networkx graph.  ``biadjacency[u, v]`` = number of parallel edges between left vertex u and right vertex v;
+    returns one set per colour of edges ``(u, v, key)``, ``key`` numbering the parallel edges of a pair.
+    Same alternating-path argument as :func:`schedule_checks`, kept separate because that one fixes the gate order
+    of the storage circuits."""
+    a = np.asarray(biadjacency.toarray() if hasattr(biadjacency, "toarray") else biadjacency).astype(np.int64)
+    if a.ndim != 2 or (a < 0).any():
+        raise RuntimeError("biadjacency must be a matrix of non-negative edge multiplicities")
+    nl, nr = a.shape
+    deg = int(max(a.sum(axis=1).max(initial=0), a.sum(axis=0).max(initial=0)))
+    edges = [(u, v, k) for u in range(nl) for v in np.flatnonzero(a[u]) for k in range(a[u, v])]
+    colour = -np.ones(len(edges), dtype=np.int64)
+    at_left = -np.ones((nl, deg), dtype=np.int64)       # at_left[u, colour] = edge id
+    at_right = -np.ones((nr, deg), dtype=np.int64)
+    for e, (u, v, _) in enumerate(edges):
+        ca = int(np.flatnonzero(at_left[u] < 0)[0])     # free at u
+        cb = int(np.flatnonzero(at_right[v] < 0)[0])    # free at v
+        if ca != cb and at_right[v, ca] >= 0:
+            # walk the ca / cb alternating path that leaves v by its ca-edge (it cannot reach u) and swap the colours
+            path, on_right, x, col = [], True, int(v), ca
+            while True:
+                f = int(at_right[x, col]) if on_right else int(at_left[x, col])
+                if f < 0:
+                    break
+                path.append(f)
+                x = edges[f][0] if on_right else edges[f][1]
+                on_right, col = not on_right, (cb if col == ca else ca)
+            for f in path:
+                at_left[edges[f][0], colour[f]] = -1
+                at_right[edges[f][1], colour[f]] = -1
+            for f in path:
+                colour[f] = cb if colour[f] == ca else ca
+                at_left[edges[f][0], colour[f]] = f
+                at_right[edges[f][1], colour[f]] = f
+        colour[e] = ca
+        at_left[u, ca] = e
+        at_right[v, ca] = e
+    return [{edges[e] for e in np.flatnonzero(colour == c)} for c in range(deg)]
 
 
 def build_perfect_circuit(code: QuantumCode):

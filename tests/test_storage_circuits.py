@@ -52,6 +52,50 @@ def test_schedule_is_a_proper_colouring(seed):
     assert len(seen) == h.nnz
 
 
+def _check_colouring(a, colours):
+    """tests/test_edge_coloring.py:6-18: max-degree many colours, every edge once, no vertex twice in a colour."""
+    a = np.asarray(a)
+    assert len(colours) == max(a.sum(axis=0).max(), a.sum(axis=1).max())
+    edges = [e for c in colours for e in c]
+    assert len(edges) == len(set(edges)) == a.sum()
+    for u in range(a.shape[0]):
+        for v in range(a.shape[1]):
+            assert sorted(k for (x, y, k) in edges if (x, y) == (u, v)) == list(range(a[u, v]))
+    for c in colours:
+        assert len({u for u, _, _ in c}) == len(c) and len({v for _, v, _ in c}) == len(c)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_bipartite_edge_colouring(seed):                           # tests/test_edge_coloring.py:21-28
+    rng = np.random.default_rng(seed)
+    nl, nr, degree = int(rng.integers(10, 40)), int(rng.integers(10, 40)), int(rng.integers(4, 12))
+    a = (rng.random((nl, nr)) < degree / np.sqrt(nl * nr)).astype(np.int64)
+    _check_colouring(a, storage.edge_color_bipartite(a))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_bipartite_multigraph_edge_colouring(seed):                # tests/test_edge_coloring.py:30-46
+    rng = np.random.default_rng(100 + seed)
+    nl, nr = int(rng.integers(6, 25)), int(rng.integers(6, 25))
+    a = np.zeros((nl, nr), dtype=np.int64)
+    for u in range(nl):                                            # configuration model: stubs of u land anywhere, repeats allowed
+        for v in rng.integers(0, nr, size=int(rng.integers(4, 12))):
+            a[u, v] += 1
+    assert a.max() >= 2                                            # parallel edges are present
+    colours = storage.edge_color_bipartite(a)
+    _check_colouring(a, colours)
+    from scipy import sparse
+    assert storage.edge_color_bipartite(sparse.csr_matrix(a)) == colours
+
+
+def test_edge_colouring_degenerate_inputs():
+    assert storage.edge_color_bipartite(np.zeros((3, 4), dtype=int)) == []
+    assert storage.edge_color_bipartite(np.array([[3]])) == [{(0, 0, 0)}, {(0, 0, 1)}, {(0, 0, 2)}] or \
+        sorted(map(sorted, storage.edge_color_bipartite(np.array([[3]])))) == [[(0, 0, 0)], [(0, 0, 1)], [(0, 0, 2)]]
+    with pytest.raises(RuntimeError):
+        storage.edge_color_bipartite(np.array([[1, -1]]))
+
+
 def test_ancilla_targets_reconstruct_the_checks(code225):
     """tests/test_storage_sim.py:79-105."""
     targets, circuit = storage.build_perfect_circuit(code225)
