@@ -314,31 +314,39 @@ def unpack_bposd_args(parsed_args, code) -> dict:
     }
 
 
-def p_sweep_main(noise_model_args, noise_model, meas_prior, data_prior, argv=None):
-    """Same command line as the reference's ``p_sweep_main``; prints the result CSV on rank 0.
-    ``--decoder_mode`` additionally accepts ``bp`` and ``ssf`` (the modes this engine decodes);
-    ``--rounds`` defaults to 0 (code capacity), the case the engine covers."""
-    import sys
+def p_sweep_parser():
+    """The reference's command line (``misc/p_sweep.py:57-65``: same flags, same defaults — ``--rounds 1``,
+    ``--decoder_mode bposd``) plus what this engine adds: the modes ``bp`` and ``ssf``, ``--precision``, ``--seed``."""
     from argparse import ArgumentParser
     from pathlib import Path
-
-    import torch
-
-    from .codes import load_code
     parser = ArgumentParser(description='Sweep the physical error rate for the given quantum code on the GPU(s)')
     parser.add_argument('code', type=Path)
     parser.add_argument('--samples', type=int, help='Number of samples to take', required=True)
     parser.add_argument('--p_sweep', type=parse_sweep_spec, required=True,
                         help='lower and upper bounds of the sweep + number of points in the form (lower, upper, points)')
-    parser.add_argument('--rounds', type=int, help='Number of rounds of syndrome extraction', default=0)
-    parser.add_argument('--decoder_mode', default='bp',
-                        choices=['bp', 'ssf', 'bposd', 'bposd_single_shot', 'bposd_hybrid', 'bpd_detector'],
-                        help="OSD-based modes need --bposd_osd_method osd0")
+    parser.add_argument('--rounds', type=int, default=1,
+                        help='Number of rounds of syndrome extraction (0: code capacity)')
+    parser.add_argument('--decoder_mode', default='bposd',
+                        choices=['bposd', 'bposd_single_shot', 'bposd_hybrid', 'bpd_detector', 'bp', 'ssf'],
+                        help='BP+OSD, BP+OSD (single shot), hybrid BP + (BP+OSD), BP on the detector error model; '
+                             'bp: the pure-BP first stage of the hybrid; ssf: small-set-flip (rounds = 0 only)')
     parser.add_argument('--linspace', type=bool, default=False,
                         help='linearly spaced points (default: uniform spacing in log space)')
     parser.add_argument('--precision', default='f64', choices=['f64', 'f32'])
     parser.add_argument('--seed', type=int, default=0)
     add_bposd_args(parser)
+    return parser
+
+
+def p_sweep_main(noise_model_args, noise_model, meas_prior, data_prior, argv=None):
+    """Same command line as the reference's ``p_sweep_main`` (:func:`p_sweep_parser`); prints the result CSV on
+    rank 0.  Under ``torchrun`` the shots of every p are sharded over the ranks."""
+    import sys
+
+    import torch
+
+    from .codes import load_code
+    parser = p_sweep_parser()
     args = parser.parse_args(sys.argv[1:] if argv is None else argv)
     code = load_code(args.code)
     bp_osd_options = unpack_bposd_args(args, code)

@@ -19,13 +19,13 @@ for name in ("pk19_b1_882", "a5_lift_2700"):
 PY
 SW='(0.01,0.1,10)'
 s() { name=$1; shift; python scripts/p_sweep.py "$@" > $OUT/${TAG}_sweep_${name}.csv 2>> $OUT/${TAG}_sweep.err; echo "sweep $name rc=$?"; }
-s hgp1600_bp_ms32_1e7 codes/hgp_34_n1600.qecc --samples 10000000 --p_sweep "$SW" --decoder_mode bp --bposd_bp_method ms --bposd_max_iter 32
-s hgp1600_ssf_1e7 codes/hgp_34_n1600.qecc --samples 10000000 --p_sweep "$SW" --decoder_mode ssf
-s hgp6400_bp_ms32_2e6 codes/hgp_34_n6400.qecc --samples 2000000 --p_sweep "$SW" --decoder_mode bp --bposd_bp_method ms --bposd_max_iter 32
-s hgp6400_ssf_1e6 codes/hgp_34_n6400.qecc --samples 1000000 --p_sweep "$SW" --decoder_mode ssf
-s lp882_bp_ms32_1e8 $OUT/codes/pk19_b1_882.qecc --samples 100000000 --p_sweep "(0.05,0.05,1)" --decoder_mode bp --bposd_bp_method ms --bposd_max_iter 32
-s lp882_bp_ms32_sweep_1e7 $OUT/codes/pk19_b1_882.qecc --samples 10000000 --p_sweep "$SW" --decoder_mode bp --bposd_bp_method ms --bposd_max_iter 32
-s a5lp2700_ssf_1e6 $OUT/codes/a5_lift_2700.qecc --samples 1000000 --p_sweep "$SW" --decoder_mode ssf
-s hgp1600_bposd_cs7_ms32_1e6 codes/hgp_34_n1600.qecc --samples 1000000 --p_sweep "$SW" --decoder_mode bposd --bposd_bp_method ms --bposd_max_iter 32
+s hgp1600_bp_ms32_1e7 codes/hgp_34_n1600.qecc --samples 10000000 --p_sweep "$SW" --decoder_mode bp --bposd_bp_method ms --bposd_max_iter 32 --rounds 0
+s hgp1600_ssf_1e7 codes/hgp_34_n1600.qecc --samples 10000000 --p_sweep "$SW" --decoder_mode ssf --rounds 0
+s hgp6400_bp_ms32_2e6 codes/hgp_34_n6400.qecc --samples 2000000 --p_sweep "$SW" --decoder_mode bp --bposd_bp_method ms --bposd_max_iter 32 --rounds 0
+s hgp6400_ssf_1e6 codes/hgp_34_n6400.qecc --samples 1000000 --p_sweep "$SW" --decoder_mode ssf --rounds 0
+s lp882_bp_ms32_1e8 $OUT/codes/pk19_b1_882.qecc --samples 100000000 --p_sweep "(0.05,0.05,1)" --decoder_mode bp --bposd_bp_method ms --bposd_max_iter 32 --rounds 0
+s lp882_bp_ms32_sweep_1e7 $OUT/codes/pk19_b1_882.qecc --samples 10000000 --p_sweep "$SW" --decoder_mode bp --bposd_bp_method ms --bposd_max_iter 32 --rounds 0
+s a5lp2700_ssf_1e6 $OUT/codes/a5_lift_2700.qecc --samples 1000000 --p_sweep "$SW" --decoder_mode ssf --rounds 0
+s hgp1600_bposd_cs7_ms32_1e6 codes/hgp_34_n1600.qecc --samples 1000000 --p_sweep "$SW" --decoder_mode bposd --bposd_bp_method ms --bposd_max_iter 32 --rounds 0
 python scripts/ler_ci_check.py > $OUT/${TAG}_ler_ci_hgp1600_bp.csv 2>> $OUT/${TAG}_sweep.err; echo "ci bp rc=$?"
 python scripts/ler_ci_check.py --decoder ssf --cpu-shots 20000 --same-shots 5000 > $OUT/${TAG}_ler_ci_hgp1600_ssf.csv 2>> $OUT/${TAG}_sweep.err; echo "ci ssf rc=$?"

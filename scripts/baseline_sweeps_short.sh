@@ -16,8 +16,8 @@ with open("gpurun_out/codes/pk19_b1_882.qecc", "w") as f:
 PY
 SW='(0.01,0.1,10)'
 s() { name=$1; shift; timeout 400 python scripts/p_sweep.py "$@" > $OUT/${TAG}_sweep_${name}.csv 2>> $OUT/${TAG}_sweep.err; echo "sweep $name rc=$?"; }
-s hgp1600_bp_ms32_1e7 codes/hgp_34_n1600.qecc --samples 10000000 --p_sweep "$SW" --decoder_mode bp --bposd_bp_method ms --bposd_max_iter 32
-s lp882_bp_ms32_1e8 $OUT/codes/pk19_b1_882.qecc --samples 100000000 --p_sweep "(0.05,0.05,1)" --decoder_mode bp --bposd_bp_method ms --bposd_max_iter 32
+s hgp1600_bp_ms32_1e7 codes/hgp_34_n1600.qecc --samples 10000000 --p_sweep "$SW" --decoder_mode bp --bposd_bp_method ms --bposd_max_iter 32 --rounds 0
+s lp882_bp_ms32_1e8 $OUT/codes/pk19_b1_882.qecc --samples 100000000 --p_sweep "(0.05,0.05,1)" --decoder_mode bp --bposd_bp_method ms --bposd_max_iter 32 --rounds 0
 # the reference's multi-round pipeline on the 1600-qubit code: storage circuit of 3 rounds under depolarizing_noise, sampled by
 # Pauli frames, BP over the spacetime matrix (thread-block-cluster kernel), fold, logical flag
 s hgp1600_rounds3_bp_2e5 codes/hgp_34_n1600.qecc --samples 200000 --p_sweep "(0.002,0.008,4)" --rounds 3 --decoder_mode bp --bposd_bp_method ms --bposd_max_iter 32

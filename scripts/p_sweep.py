@@ -2,7 +2,8 @@
 """GPU counterpart of the reference's scripts/p_sweep.py (same noise model, priors and CLI):
 
     python scripts/p_sweep.py codes/hgp_34_n1600.qecc --samples 10000000 --p_sweep "(0.01,0.1,10)" \
-        --bposd_bp_method ms --bposd_max_iter 32
+        --bposd_bp_method ms --bposd_max_iter 32 --decoder_mode bp --rounds 0
+    (defaults as in the reference: --rounds 1 --decoder_mode bposd, i.e. BP + osd_cs order 7 over one extraction round)
     torchrun --nproc-per-node 8 --master-addr 127.0.0.1 scripts/p_sweep.py ...      # shots sharded over 8 GPUs
 """
 import os

@@ -144,6 +144,20 @@ def test_p_sweep_cli_options_match_reference():
             parse_sweep_spec(bad)
 
 
+def test_p_sweep_command_line_defaults_match_reference():
+    """misc/p_sweep.py:57-65: a bare `p_sweep.py code --samples N --p_sweep (..)` means one round of syndrome
+    extraction decoded with BP+OSD (osd_cs, order 7), as in the reference."""
+    from exp_ldpc_b200.experiment import p_sweep_parser
+    a = p_sweep_parser().parse_args(["code.qecc", "--samples", "10", "--p_sweep", "(0.01,0.1,3)"])
+    assert a.rounds == 1 and a.decoder_mode == "bposd" and a.linspace is False
+    assert a.bposd_osd_method == "osd_cs" and a.bposd_osd_order == 7 and a.bposd_bp_method == "ps"
+    assert str(a.code) == "code.qecc" and a.samples == 10 and a.p_sweep == (0.01, 0.1, 3)
+    for mode in ("bposd", "bposd_single_shot", "bposd_hybrid", "bpd_detector", "bp", "ssf"):
+        assert p_sweep_parser().parse_args(["c", "--samples", "1", "--p_sweep", "(1,1,1)", "--decoder_mode", mode]).decoder_mode == mode
+    with pytest.raises(SystemExit):
+        p_sweep_parser().parse_args(["c", "--samples", "1", "--p_sweep", "(1,1,1)", "--decoder_mode", "nope"])
+
+
 # ---- cluster mode of the row-regular BP kernel (family 9): the host-side plan checks itself without a GPU
 def _plan_check(h, ctas, banks=16):
     import ctypes as C
