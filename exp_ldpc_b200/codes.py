@@ -221,6 +221,9 @@ def write_quantum_code(stream, code: QuantumCode) -> None:
 
 
 def load_code(path) -> QuantumCode:
-    """``load_code`` of ``misc/_experiment.py:231-235`` taking a path instead of argparse args."""
+    """``load_code`` of ``misc/_experiment.py:231-235``: a path, or — as there — parsed command-line
+    arguments whose ``code`` attribute is the path."""
+    if not isinstance(path, (str, bytes)) and not hasattr(path, "__fspath__") and hasattr(path, "code"):
+        path = path.code
     with open(path, "r") as fh:
         return read_quantum_code(fh, validate_stabilizer_code=True)

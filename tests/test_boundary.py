@@ -144,6 +144,18 @@ def test_p_sweep_cli_options_match_reference():
             parse_sweep_spec(bad)
 
 
+def test_load_code_takes_a_path_or_parsed_arguments():
+    """_experiment.py:231-235 hands load_code the argparse namespace."""
+    import os
+    from argparse import Namespace
+    from pathlib import Path
+    from exp_ldpc_b200.codes import load_code
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "codes", "hgp_34_n225.qecc")
+    a, b, c = load_code(path), load_code(Path(path)), load_code(Namespace(code=Path(path)))
+    assert a.num_qubits == b.num_qubits == c.num_qubits == 225
+    assert (a.checks.z != c.checks.z).nnz == 0
+
+
 def test_p_sweep_command_line_defaults_match_reference():
     """misc/p_sweep.py:57-65: a bare `p_sweep.py code --samples N --p_sweep (..)` means one round of syndrome
     extraction decoded with BP+OSD (osd_cs, order 7), as in the reference."""
