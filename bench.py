@@ -164,6 +164,15 @@ def cpu_port_throughput(code, p, opts, target_seconds=12.0, threads=0, decoder="
     return shots / dt, cores, f"{shots} shots of the same workload, {dt:.1f} s wall on {cores} threads", r["iters_total"] / shots
 
 
+def single_core_baseline(code, p, opts, args, problem):
+    """the port on ONE core beside the all-core figure (a short bounded sample), and what the figure means."""
+    v1, _, sample1, _ = cpu_port_throughput(code, p, opts, target_seconds=min(3.0, max(0.2, (args.cpu_seconds or 12.0) / 4.0)),
+                                            threads=1, decoder=args.decoder, problem=problem)
+    return {"single_core": {"value": v1, "unit": "shots/s", "sample": sample1},
+            "note": "C port of the decoder alone: the reference adds a Python call, GF(2) array construction and slicing per shot "
+                    "(_experiment.py:200-209), so this is an upper bound on its throughput"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -253,7 +262,8 @@ def main():
                 "dtype": "u32" if ssf else "f64",
                 "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "shots/s", "cores": cores, "kind": "port",
-                                 "sample": sample + " per step (oracle/qldpc_oracle.c; the reference's own decoder `ldpc` is not installable here)"},
+                                 "sample": sample + " per step (oracle/qldpc_oracle.c; the reference's own decoder `ldpc` is not installable here)",
+                                 **single_core_baseline(code, p, opts, args, problem)},
                 "e2e": {"value": v, "unit": "shots/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -445,6 +455,7 @@ def main():
                                                           problem=problem)
         cpu = {"value": v, "unit": "shots/s", "cores": cores, "kind": "port", "sample": sample,
                "mean_iterations": cpu_iters}
+        cpu.update(single_core_baseline(code, p, opts, args, problem))
 
     if ssf:
         roofline_smem = None

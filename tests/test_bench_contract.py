@@ -29,6 +29,8 @@ def test_reference_arm_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "shots" in cb["sample"]
     assert d["config"]["workload"].startswith("hgp_34_n225") and "model" not in d["config"]
+    one = cb["single_core"]                                                  # all cores and one core
+    assert one["unit"] == "shots/s" and one["value"] > 0 and "1 threads" in one["sample"] and "upper bound" in cb["note"]
 
 
 def test_reference_arm_ssf_runs_without_the_bp_round_cap():
