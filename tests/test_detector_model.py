@@ -76,3 +76,17 @@ def test_decoder_inputs_line_up():
     c = DetectorSpacetimeCode(DEM)
     assert c.fault_priors.shape == (c.fault_check_matrix.shape[1],) == (c.fault_map.shape[1],)
     assert c.fault_check_matrix.has_sorted_indices
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_models_survive_the_text_round_trip(seed):
+    from scipy import sparse
+    rng = np.random.default_rng(seed)
+    nd, no, nf = int(rng.integers(1, 40)), int(rng.integers(0, 6)), int(rng.integers(1, 60))
+    fc = sparse.csr_matrix((rng.random((nd, nf)) < 0.1).astype(np.uint32))
+    fm = sparse.csr_matrix((rng.random((no, nf)) < 0.2).astype(np.uint32))
+    pr = rng.uniform(1e-6, 0.4, nf)
+    c = DetectorSpacetimeCode(detector_model_text(fc, fm, pr))
+    assert c.fault_check_matrix.shape == (nd, nf) and c.fault_map.shape == (no, nf)
+    assert (c.fault_check_matrix != fc).nnz == 0 and (c.fault_map != fm).nnz == 0
+    assert np.array_equal(c.fault_priors, pr)                    # repr() of a double parses back to the same double
