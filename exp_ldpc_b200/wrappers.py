@@ -17,7 +17,7 @@ Two deviations, both deliberate and the same as in ``StorageExperiment``:
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, Optional, Tuple
+from typing import Callable, Dict, Tuple
 
 import numpy as np
 
