@@ -19,7 +19,6 @@ import ctypes as C
 from typing import Optional
 
 import numpy as np
-from scipy import sparse
 
 from . import _lib
 from .codes import canonical_csr

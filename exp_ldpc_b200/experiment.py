@@ -32,7 +32,6 @@ from __future__ import annotations
 import ctypes as C
 import math
 import time
-from dataclasses import dataclass
 from typing import Callable, Dict, Optional
 
 import numpy as np
