@@ -104,3 +104,15 @@ def test_recipes_on_the_gpu_decoders(built, code225, mode, cls):
     for s in range(faults.shape[0]):
         readout, history = _record_of(code225, rounds, faults[s])
         assert np.array_equal(w.readout_correction(history, readout), want[s]), (mode, s)
+
+
+def test_no_cpu_fallback_behind_the_wrappers(built, code225):
+    """Without a CUDA device the default (GPU) decoders refuse loudly; nothing decodes on the host instead."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from exp_ldpc_b200._lib import QdError
+    with pytest.raises(QdError, match="no usable CUDA device"):
+        wrappers.BPOSDHybridCorrect(code225, 1, OPTS, (0.01, 0.01))
+    with pytest.raises(QdError, match="no usable CUDA device"):
+        wrappers.BPDetectorCorrect("error(0.1) D0 L0\n", OPTS)
