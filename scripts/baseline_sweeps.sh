@@ -3,7 +3,7 @@
 #   configs[1]  (3,4) HGP n=1600 and n=6400, BP (min-sum, 32 iterations) and SSF, p in geomspace(0.01, 0.10, 10), 1e7 shots per p
 #   configs[2]  QC lifted product [[882,24]], BP, 1e8 shots (one GPU here; shots shard over ranks under torchrun)
 #   configs[3]  PSL(2,5) lifted product n=2700, SSF sweep
-# plus the LER-inside-the-oracle's-CI check (scripts/ler_ci_check.py).  CSVs go to gpurun_out/<tag>_*.
+# plus the LER-inside-the-oracle's-CI check (tests/tools/ler_ci_check.py).  CSVs go to gpurun_out/<tag>_*.
 set -u
 TAG=${1:-base}
 OUT=gpurun_out
@@ -27,5 +27,5 @@ s lp882_bp_ms32_1e8 $OUT/codes/pk19_b1_882.qecc --samples 100000000 --p_sweep "(
 s lp882_bp_ms32_sweep_1e7 $OUT/codes/pk19_b1_882.qecc --samples 10000000 --p_sweep "$SW" --decoder_mode bp --bposd_bp_method ms --bposd_max_iter 32 --rounds 0
 s a5lp2700_ssf_1e6 $OUT/codes/a5_lift_2700.qecc --samples 1000000 --p_sweep "$SW" --decoder_mode ssf --rounds 0
 s hgp1600_bposd_cs7_ms32_1e6 codes/hgp_34_n1600.qecc --samples 1000000 --p_sweep "$SW" --decoder_mode bposd --bposd_bp_method ms --bposd_max_iter 32 --rounds 0
-python scripts/ler_ci_check.py > $OUT/${TAG}_ler_ci_hgp1600_bp.csv 2>> $OUT/${TAG}_sweep.err; echo "ci bp rc=$?"
-python scripts/ler_ci_check.py --decoder ssf --cpu-shots 20000 --same-shots 5000 > $OUT/${TAG}_ler_ci_hgp1600_ssf.csv 2>> $OUT/${TAG}_sweep.err; echo "ci ssf rc=$?"
+python tests/tools/ler_ci_check.py > $OUT/${TAG}_ler_ci_hgp1600_bp.csv 2>> $OUT/${TAG}_sweep.err; echo "ci bp rc=$?"
+python tests/tools/ler_ci_check.py --decoder ssf --cpu-shots 20000 --same-shots 5000 > $OUT/${TAG}_ler_ci_hgp1600_ssf.csv 2>> $OUT/${TAG}_sweep.err; echo "ci ssf rc=$?"

@@ -3,13 +3,13 @@
 inside the 95 % binomial (Wilson) interval of the CPU oracle's, measured on INDEPENDENT shots (different seed),
 and — fp64 path — the hard decisions on identical shots are bit-identical (fp32: agreement fraction printed).
 
-    python scripts/ler_ci_check.py [--code codes/hgp_34_n1600.qecc] [--gpu-shots 1000000] [--cpu-shots 50000]
-Prints one CSV row per (precision, p).  Test infrastructure: this script may import oracle/."""
+    python tests/tools/ler_ci_check.py [--code codes/hgp_34_n1600.qecc] [--gpu-shots 1000000] [--cpu-shots 50000]
+Prints one CSV row per (precision, p).  Test infrastructure (it lives under tests/): it may import oracle/."""
 import argparse
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 

@@ -2,14 +2,14 @@
 """Decode the shots of a GPU p-sweep CSV (scripts/p_sweep.py, code capacity, --decoder_mode bp | ssf | bposd) again on the CPU
 oracle — same seed, same global shot indices, the flip probability and the prior computed exactly as p_sweep does — and
 print both sets of counters side by side.  The fp64 BP path and SSF are bit-exact, so failures, non-converged shots
-and the iteration total must be IDENTICAL.  Test infrastructure: this script may import oracle/.
+and the iteration total must be IDENTICAL.  Test infrastructure (it lives under tests/): it may import oracle/.
 
-    python scripts/replicate_sweep_on_oracle.py <builder-or-qecc> <sweep.csv> [max_rows]"""
+    python tests/tools/replicate_sweep_on_oracle.py <builder-or-qecc> <sweep.csv> [max_rows]"""
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import pandas as pd  # noqa: E402
 
