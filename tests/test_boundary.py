@@ -84,6 +84,12 @@ def test_product_never_imports_the_oracle():
                 code = re.sub(r"/\*(.|\n)*?\*/", "", open(path).read())
                 code = re.sub(r"//.*", "", code)
                 assert not re.search(r"oracle|orc_", code), path
+    # the user-facing scripts are product too (checker scripts that call the oracle live under tests/tools)
+    for f in os.listdir(os.path.join(ROOT, "scripts")):
+        if f.endswith(".py"):
+            code = re.sub(r'"""(.|\n)*?"""', "", open(os.path.join(ROOT, "scripts", f)).read())
+            code = re.sub(r"#.*", "", code)
+            assert not re.search(r"pyoracle|libqldpc_oracle|import\s+oracle\b|from\s+oracle\b|orc_", code), f
     # and the built library does not link it
     from exp_ldpc_b200 import _lib
     if os.path.exists(_lib.LIB_PATH):
